@@ -1,0 +1,248 @@
+// vanrijn.hpp -- C++ host-side mirror of the reference's library API for the render loop.
+//
+// The reference is a Rust crate and the Rust toolchain is not available in the build image, so
+// the host side above the C ABI (include/vanrijn_cuda.h) is written in C++ with the reference's
+// names, argument meaning and error behaviour; INTEGRATION.md shows the equivalent Rust binding.
+// Paths below are relative to /root/reference/src/.
+//
+//   vanrijn::Scene                       scene.rs:5-8
+//   vanrijn::Sphere / Plane / Triangle   raycasting/{sphere,plane,triangle}.rs
+//   vanrijn::BoundingVolumeHierarchy     raycasting/bounding_volume_hierarchy.rs:18-75 (median split)
+//   vanrijn::PrimitiveList               Vec<Box<dyn Primitive>> (raycasting/vec_aggregate.rs)
+//   vanrijn::{Lambertian,Phong,Reflective}Material, SmoothTransparentDialectric   materials/*.rs
+//   vanrijn::Spectrum, ColourRgbF, NamedColour                                    colour/*.rs
+//   vanrijn::Tile, TileIterator          util/tile_iterator.rs
+//   vanrijn::AccumulationBuffer          accumulation_buffer.rs:6-85
+//   vanrijn::load_obj                    mesh.rs:74-88
+//   vanrijn::partial_render_scene        camera.rs:95-130  <- the drop-in entry point
+//
+// Types are unchanged in meaning; the only additions are the `flatten` hooks that emit the
+// 16-byte-aligned SoA layout uploaded once per scene (the "one additive trait method" of
+// SURVEY.md section 7), and RenderOptions for the parameters the reference hard-codes.
+#ifndef VANRIJN_HPP
+#define VANRIJN_HPP
+
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vanrijn_cuda.h"
+
+namespace vanrijn {
+
+struct Vec3 {
+    double x = 0, y = 0, z = 0;
+    Vec3() = default;
+    Vec3(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {}
+};
+
+enum class NamedColour { Black, White, Red, Lime, Blue, Yellow, Cyan, Magenta, Gray, Maroon, Olive, Green, Purple, Teal, Navy };
+
+struct ColourRgbF {
+    double red = 0, green = 0, blue = 0;
+    ColourRgbF() = default;
+    ColourRgbF(double r, double g, double b) : red(r), green(g), blue(b) {}
+    static ColourRgbF from_named(NamedColour name); // colour/colour_rgb.rs:17-35
+};
+
+// colour/spectrum.rs:6-176 -- uniform samples over [shortest, longest]
+struct Spectrum {
+    double shortest_wavelength = 380.0, longest_wavelength = 740.0;
+    std::vector<double> samples;
+    static Spectrum black();
+    static Spectrum grey(double brightness);
+    static Spectrum diamond_index_of_refraction();
+    static Spectrum reflection_from_linear_rgb(const ColourRgbF &colour);
+};
+
+class FlatSceneBuilder;
+
+// materials/mod.rs:25-34.  The BSDFs themselves run on the device; the host objects carry parameters.
+struct Material {
+    virtual ~Material() = default;
+    virtual uint32_t flatten(FlatSceneBuilder &out) const = 0; // returns the material index
+};
+struct LambertianMaterial : Material {
+    Spectrum colour;
+    double diffuse_strength = 1.0;
+    LambertianMaterial(Spectrum c, double d) : colour(std::move(c)), diffuse_strength(d) {}
+    uint32_t flatten(FlatSceneBuilder &out) const override;
+};
+struct PhongMaterial : Material {
+    Spectrum colour;
+    double diffuse_strength, specular_strength, smoothness;
+    PhongMaterial(Spectrum c, double d, double s, double sm) : colour(std::move(c)), diffuse_strength(d), specular_strength(s), smoothness(sm) {}
+    uint32_t flatten(FlatSceneBuilder &out) const override;
+};
+struct ReflectiveMaterial : Material {
+    Spectrum colour;
+    double diffuse_strength, reflection_strength;
+    ReflectiveMaterial(Spectrum c, double d, double r) : colour(std::move(c)), diffuse_strength(d), reflection_strength(r) {}
+    uint32_t flatten(FlatSceneBuilder &out) const override;
+};
+struct SmoothTransparentDialectric : Material {
+    Spectrum eta;
+    explicit SmoothTransparentDialectric(Spectrum e) : eta(std::move(e)) {}
+    uint32_t flatten(FlatSceneBuilder &out) const override;
+};
+
+// raycasting/mod.rs:135-142
+struct Primitive {
+    virtual ~Primitive() = default;
+    // append this primitive as a top-level traversal item of object `object_id`
+    virtual void flatten(FlatSceneBuilder &out, uint32_t object_id, uint32_t prim_id) const = 0;
+};
+struct Sphere : Primitive {
+    Vec3 centre;
+    double radius;
+    std::shared_ptr<Material> material;
+    Sphere(Vec3 c, double r, std::shared_ptr<Material> m) : centre(c), radius(r), material(std::move(m)) {}
+    void flatten(FlatSceneBuilder &out, uint32_t object_id, uint32_t prim_id) const override;
+};
+struct Plane : Primitive {
+    Vec3 normal, tangent, cotangent;
+    double distance_from_origin;
+    std::shared_ptr<Material> material;
+    Plane(Vec3 normal, double distance_from_origin, std::shared_ptr<Material> m); // plane.rs:17-32
+    void flatten(FlatSceneBuilder &out, uint32_t object_id, uint32_t prim_id) const override;
+};
+struct Triangle : Primitive {
+    std::array<Vec3, 3> vertices, normals;
+    std::shared_ptr<Material> material;
+    Triangle(std::array<Vec3, 3> v, std::array<Vec3, 3> n, std::shared_ptr<Material> m) : vertices(v), normals(n), material(std::move(m)) {}
+    void flatten(FlatSceneBuilder &out, uint32_t object_id, uint32_t prim_id) const override;
+};
+
+// raycasting/mod.rs:144-145
+struct Aggregate {
+    virtual ~Aggregate() = default;
+    virtual void flatten(FlatSceneBuilder &out, uint32_t object_id) const = 0;
+};
+// Vec<Box<dyn Primitive>> as an Aggregate (vec_aggregate.rs:11-24)
+struct PrimitiveList : Aggregate {
+    std::vector<std::shared_ptr<Primitive>> primitives;
+    void flatten(FlatSceneBuilder &out, uint32_t object_id) const override;
+};
+// bounding_volume_hierarchy.rs:18-75.  Only triangles may be stored (what load_obj produces).
+class BoundingVolumeHierarchy : public Aggregate {
+  public:
+    // reorders `primitives` in place, as the reference's build(&mut [Arc<dyn Primitive>]) does
+    static std::unique_ptr<BoundingVolumeHierarchy> build(std::vector<std::shared_ptr<Primitive>> &primitives);
+    void flatten(FlatSceneBuilder &out, uint32_t object_id) const override;
+    uint32_t depth() const { return depth_; }
+    size_t triangle_count() const { return tri_v_.size() / 9; }
+
+  private:
+    friend class FlatSceneBuilder;
+    std::vector<double> tri_v_, tri_n_;       // 9 doubles per triangle, leaf (DFS) order
+    std::vector<uint32_t> tri_prim_id_;       // original index of each triangle
+    std::vector<std::shared_ptr<Material>> tri_material_;
+    std::vector<double> node_min_, node_max_; // 3 per node, DFS pre-order
+    std::vector<int32_t> node_child_;         // 2 per node, indices local to this BVH
+    uint32_t depth_ = 0;
+};
+
+// scene.rs:5-8
+struct Scene {
+    Vec3 camera_location;
+    std::vector<std::unique_ptr<Aggregate>> objects;
+    Scene() = default;
+    Scene(Scene &&) = default;
+    ~Scene();
+    // device copy, created on first use and reused (the scene is immutable while it renders)
+    struct DeviceCache;
+    mutable std::shared_ptr<DeviceCache> device_cache;
+};
+
+// util/tile_iterator.rs:2-67
+struct Tile {
+    size_t start_column, end_column, start_row, end_row;
+    size_t width() const { return end_column - start_column; }
+    size_t height() const { return end_row - start_row; }
+};
+class TileIterator {
+  public:
+    TileIterator(size_t total_width, size_t total_height, size_t tile_size);
+    bool next(Tile &tile);
+
+  private:
+    size_t tile_size_, total_height_, total_width_, current_column_ = 0, current_row_ = 0;
+};
+
+// accumulation_buffer.rs:6-85: five row-major arrays
+class AccumulationBuffer {
+  public:
+    AccumulationBuffer(size_t width, size_t height);
+    size_t width() const { return width_; }
+    size_t height() const { return height_; }
+    // accumulation_buffer.rs:62-85 -- touches only colour and weight of the destination
+    void merge_tile(const Tile &tile, const AccumulationBuffer &src);
+    std::vector<double> colour, colour_sum, colour_bias; // 3 per pixel (XYZ)
+    std::vector<double> weight, weight_bias;             // 1 per pixel
+
+  private:
+    size_t width_, height_;
+};
+
+// mesh.rs:74-88
+std::vector<std::shared_ptr<Primitive>> load_obj(const std::string &filename, std::shared_ptr<Material> material);
+
+// The parameters partial_render_scene hard-codes (camera.rs:69,103), made explicit.
+struct DirectionalLight {
+    Vec3 direction;
+    Spectrum spectrum;
+};
+struct RenderOptions {
+    uint32_t spp = 1;
+    uint32_t max_depth = 128;
+    uint64_t sample_offset = 0;
+    uint64_t seed = 1;
+    uint32_t integrator = VRJ_INTEGRATOR_SIMPLE_RANDOM;
+    uint32_t bvh_filter = VRJ_FILTER_F32;
+    uint32_t sample_stride = 1;
+    int device = 0;
+    std::vector<DirectionalLight> lights; // Whitted
+    Spectrum ambient_light = Spectrum::black();
+    VrjStats *stats = nullptr;
+};
+
+// camera.rs:95-100.  Throws std::runtime_error where the reference would panic or when CUDA fails.
+AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width);
+AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &options);
+
+// Collects the flattened SoA arrays and exposes them as a VrjSceneDesc.
+class FlatSceneBuilder {
+  public:
+    uint32_t add_spectrum(const Spectrum &s);
+    uint32_t add_material(uint32_t kind, uint32_t spectrum, double p0, double p1, double p2);
+    void add_sphere(const Sphere &s, uint32_t material, uint32_t object_id, uint32_t prim_id);
+    void add_plane(const Plane &p, uint32_t material, uint32_t object_id, uint32_t prim_id);
+    void add_triangle(const Triangle &t, uint32_t material, uint32_t object_id, uint32_t prim_id);
+    void add_bvh(const BoundingVolumeHierarchy &bvh, uint32_t object_id);
+    const VrjSceneDesc &desc(const Vec3 &camera);
+    uint32_t material_index(const Material *m);
+
+  private:
+    std::vector<VrjSpectrum> spectra_;
+    std::vector<double> samples_;
+    std::vector<VrjMaterial> materials_;
+    std::vector<std::pair<const Material *, uint32_t>> material_cache_;
+    std::vector<VrjSphere> spheres_;
+    std::vector<VrjPlane> planes_;
+    std::vector<VrjBvh> bvhs_;
+    std::vector<VrjItem> items_;
+    std::vector<double> tri_[6];
+    std::vector<uint32_t> tri_material_, tri_prim_id_;
+    std::vector<double> node_min_, node_max_;
+    std::vector<int32_t> node_child_;
+    VrjSceneDesc desc_{};
+};
+
+// Flatten + upload (cached on the scene).  Exposed for callers that want the raw C ABI.
+const VrjScene *device_scene(const Scene &scene, int device = 0);
+
+} // namespace vanrijn
+#endif

@@ -1,0 +1,383 @@
+"""Pins the CPU oracle against the known-answer and property tests the reference itself holds
+for the hot path.  Each test names the reference test it restates.
+Paths are relative to /root/reference/src/.  CPU only.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oraclelib as O
+from oraclelib import dp, vec
+
+L = O.lib()
+ZN = np.zeros(9)
+RNG = np.random.default_rng(20261018)
+
+
+def tri_hit(v, o, d, n=ZN):
+    return O.hit16(L.orc_triangle_intersect, np.asarray(v, float).ravel(), np.asarray(n, float).ravel(), vec(*o), vec(*d))
+
+
+# ---------------------------------------------------------------- raycasting/triangle.rs:396-496
+@pytest.mark.parametrize("v,o,d", [
+    ([[0, 1, 1], [1, -1, 1], [-1, -1, 1]], (0, 0, 0), (0, 0, 1)),          # z axis, ccw
+    ([[0, 1, 1], [-1, -1, 1], [1, -1, 1]], (0, 0, 0), (0, 0, 1)),          # z axis, cw
+    ([[0, 1, -1], [1, -1, -1], [-1, -1, -1]], (0, 0, 0), (0, 0, -1)),      # -z axis, ccw
+    ([[0, 1, -1], [-1, -1, -1], [1, -1, -1]], (0, 0, 0), (0, 0, -1)),      # -z axis, cw
+    ([[5, 6, 6], [6, 4, 6], [4, 4, 6]], (5, 5, 5), (0, 0, 1)),             # translated
+    ([[6, 6.5, 6], [7, 4.5, 6], [5, 4.5, 6]], (5, 5, 5), (1, 0.5, 1)),     # oblique, translated
+])
+def test_triangle_fixed_hits(v, o, d):
+    assert tri_hit(v, o, d) is not None
+
+
+def _rand_tri_cases(n):
+    for _ in range(n):
+        v = RNG.normal(scale=10.0, size=(3, 3))
+        o = RNG.normal(scale=10.0, size=3)
+        yield v, o
+
+
+def _bary():
+    e = 1e-7  # triangle.rs:664-671
+    a = RNG.random() * (1 - e) + e
+    b = RNG.random() * (1 - a) + e
+    return a, b, 1.0 - (a + b)
+
+
+def test_triangle_centroid_properties():
+    """triangle.rs:531-655: centroid ray hits; location/distance/normal/retro within 1e-7."""
+    checked = 0
+    for v, o in _rand_tri_cases(400):
+        c = v.sum(0) / 3.0
+        d = (c - o) / np.linalg.norm(c - o)
+        nrm = np.cross(v[1] - v[0], v[2] - v[0])
+        nrm /= np.linalg.norm(nrm)
+        if abs(nrm @ d) < 1e-7:
+            continue
+        h = tri_hit(v, o, d, np.tile(nrm, 3))
+        assert h is not None
+        assert np.linalg.norm(h["location"] - c) < 1e-7 * max(1.0, np.linalg.norm(c))
+        assert abs(h["distance"] - np.linalg.norm(c - o)) < 1e-7 * max(1.0, np.linalg.norm(c - o))
+        assert np.linalg.norm(h["normal"] - nrm) < 1e-7
+        assert np.linalg.norm(h["retro"] + d) < 1e-7
+        checked += 1
+    assert checked > 300
+
+
+def test_triangle_barycentric_properties():
+    """triangle.rs:707-805: arbitrary interior point hits; normal/distance/retro within 1e-5."""
+    for v, o in _rand_tri_cases(400):
+        a, b, g = _bary()
+        p = v[0] * a + v[1] * b + v[2] * g
+        d = (p - o) / np.linalg.norm(p - o)
+        nrm = np.cross(v[1] - v[0], v[2] - v[0])
+        nrm /= np.linalg.norm(nrm)
+        if abs(nrm @ d) < 1e-7 or min(a, b, g) < 1e-6:
+            continue
+        h = tri_hit(v, o, d, np.tile(nrm, 3))
+        assert h is not None
+        assert np.linalg.norm(h["normal"] - nrm) < 1e-5
+        assert abs(h["distance"] - np.linalg.norm(p - o)) < 1e-5 * max(1.0, np.linalg.norm(p - o))
+        assert np.linalg.norm(h["retro"] + d) < 1e-5
+
+
+@pytest.mark.parametrize("edge", [0, 1, 2])
+def test_triangle_outside_edge_misses(edge):
+    """triangle.rs:807-889: a target point strictly outside one edge (in the triangle's plane) misses."""
+    for v, o in _rand_tri_cases(300):
+        a, b, c = v[edge], v[(edge + 1) % 3], v[(edge + 2) % 3]
+        u_axis = (b - a) / np.linalg.norm(b - a)
+        w_axis = np.cross(c - a, u_axis)
+        w_axis /= np.linalg.norm(w_axis)
+        v_axis = np.cross(w_axis, u_axis)  # points away from c
+        uv = RNG.normal(scale=5.0, size=2)
+        if abs(uv[1]) < 1e-6:
+            continue
+        target = a + u_axis * uv[0] + v_axis * abs(uv[1])
+        d = (target - o) / np.linalg.norm(target - o)
+        nrm = np.cross(b - a, c - a)
+        if abs(nrm @ d) / np.linalg.norm(nrm) < 1e-6:
+            continue
+        assert tri_hit(v, o, d) is None
+
+
+def test_triangle_behind_ray_misses():
+    """triangle.rs:891-915."""
+    for v, o in _rand_tri_cases(300):
+        a, b, g = _bary()
+        p = v[0] * a + v[1] * b + v[2] * g
+        d = (o - p) / np.linalg.norm(o - p)
+        assert tri_hit(v, o, d) is None
+
+
+def test_triangle_helpers():
+    """triangle.rs:249-388: valid permutation with the largest component last; shear zeroes x,y."""
+    for _ in range(500):
+        d = RNG.normal(size=3)
+        perm = (C.c_int * 3)()
+        shear = np.zeros(2)
+        L.orc_triangle_helpers(d.ctypes.data_as(dp), perm, shear.ctypes.data_as(dp))
+        p = [perm[0], perm[1], perm[2]]
+        assert sorted(p) == [0, 1, 2]
+        assert d[p[2]] >= d.max() - 0.0
+        pd = d[p]
+        if pd[2] > 1e-3:
+            assert abs(pd[0] + shear[0] * pd[2]) < 1e-5 and abs(pd[1] + shear[1] * pd[2]) < 1e-5
+
+
+# ---------------------------------------------------------------- raycasting/sphere.rs:112-184
+def sph(c, r, o, d):
+    return O.hit16(L.orc_sphere_intersect, vec(*c), float(r), vec(*o), vec(*d))
+
+
+def test_sphere_fixed_cases():
+    assert sph((1.5, 1.5, 15.0), 5.0, (1, 2, 3), (0, 0, 1)) is not None
+    assert sph((-5.0, 1.5, 15.0), 5.0, (1, 2, 3), (0, 0, 1)) is None
+    assert sph((1.5, 1.5, -15.0), 5.0, (1, 2, 3), (0, 0, 1)) is None
+    assert sph((1.5, 1.5, 2.0), 5.0, (1, 2, 3), (0, 0, 1)) is not None  # origin inside
+
+
+def test_sphere_distance_to_centre():
+    n = 0
+    for _ in range(400):
+        o, c = RNG.normal(scale=10, size=3), RNG.normal(scale=10, size=3)
+        r = abs(RNG.normal(scale=3))
+        if r <= 0 or r + 1e-6 >= np.linalg.norm(o - c):
+            continue
+        h = sph(c, r, o, c - o)
+        assert h is not None
+        assert abs(np.linalg.norm(c - o) - (h["distance"] + r)) < 1e-5
+        n += 1
+    assert n > 100
+
+
+# ---------------------------------------------------------------- raycasting/plane.rs:118-164
+def test_plane_fixed_cases():
+    assert O.hit16(L.orc_plane_intersect, vec(1, 0, 0), -5.0, vec(1, 2, 3), vec(-1, 0, 1)) is not None
+    assert O.hit16(L.orc_plane_intersect, vec(1, 0, 0), -5.0, vec(1, 2, 3), vec(1, 0, 1)) is None
+    h = O.hit16(L.orc_plane_intersect, vec(1, 0, 0), -5.0, vec(1, 2, 3), vec(-1, 0, 1))
+    assert abs(h["location"][0] - (-5.0)) < 1e-10
+
+
+# ---------------------------------------------------------------- raycasting/axis_aligned_bounding_box.rs:59-123
+def aabb(lo, hi, o, d):
+    return bool(L.orc_aabb_intersect(*[np.asarray(a, float).ctypes.data_as(dp) for a in (lo, hi, o, d)]))
+
+
+def _wrap(p, lo, hi):
+    frac = np.abs(p - lo) / (hi - lo)
+    return lo + (frac - np.floor(frac)) * (hi - lo)
+
+
+def test_aabb_properties_line_semantics():
+    for _ in range(400):
+        c1, c2, o, p = (RNG.normal(scale=10, size=3) for _ in range(4))
+        lo, hi = np.minimum(c1, c2), np.maximum(c1, c2)
+        inside = _wrap(p, lo, hi)
+        assert aabb(c1, c2, o, inside - o)              # :59-70 ray towards an interior point hits
+        oi = _wrap(o, lo, hi)
+        assert aabb(c1, c2, oi, oi - p)                  # :72-83 origin inside always hits
+        if not np.all((o >= lo) & (o <= hi)):
+            assert aabb(c1, c2, o, o - inside)           # :85-99 box BEHIND the ray still reports a hit (line test)
+
+
+def test_aabb_axis_parallel():
+    lo, hi = (1.0, 2.0, 3.0), (4.0, 5.0, 6.0)
+    assert aabb(lo, hi, (0, 3, 4), (1, 0, 0)) and aabb(lo, hi, (2, 0, 4), (0, 1, 0)) and aabb(lo, hi, (2, 3, 0), (0, 0, 1))
+    assert not aabb(lo, hi, (0, 0, 0), (1, 0, 0))
+    assert not aabb(lo, hi, (0, 0, 0), (0, 1, 0))
+    assert not aabb(lo, hi, (0, 0, 0), (0, 0, 1))
+
+
+def test_largest_dimension():
+    """util/axis_aligned_bounding_box.rs:76-99 and its tests :108-239."""
+    ld = lambda lo, hi: L.orc_largest_dimension(vec(*lo).ctypes.data_as(dp), vec(*hi).ctypes.data_as(dp))
+    assert ld((0, 0, 0), (3, 2, 1)) == 0
+    assert ld((0, 0, 0), (1, 3, 2)) == 1
+    assert ld((0, 0, 0), (1, 2, 3)) == 2
+    assert ld((0, 0, 0), (2, 2, 1)) == 0      # first strictly-largest wins
+    assert ld((0, 0, 0), (0, 0, 0)) == 0      # all degenerate -> 0
+
+
+# ---------------------------------------------------------------- colour/spectrum.rs:427-488
+def spectrum(lo, hi, samples, w):
+    s = np.asarray(samples, float)
+    return L.orc_spectrum_intensity(lo, hi, len(s), s.ctypes.data_as(dp), w)
+
+
+def test_spectrum_kats():
+    s = [0.5, 1.0, 0.75, 1.5]
+    assert spectrum(400.5, 700.25, s, 400.5) == 0.5
+    assert spectrum(400.5, 700.25, s, 700.25) == 1.5
+    assert spectrum(400.0, 700.0, s, 500.0) == 1.0
+    assert spectrum(400.0, 700.0, s, 600.0) == 0.75
+    assert spectrum(400.0, 700.0, s, 450.0) == 0.75
+    assert spectrum(400.0, 700.0, s, 550.0) == 0.875
+    assert spectrum(400.0, 700.0, s, 650.0) == 1.125
+    assert spectrum(400.0, 700.0, s, 399.9999) == 0.0
+    assert spectrum(400.0, 700.0, s, 700.0001) == 0.0
+
+
+def test_rgb_spectrum_branches():
+    """spectrum.rs:81-165: white reproduces the WHITE basis; pure channels reproduce theirs."""
+    out = np.zeros(32)
+    L.orc_rgb_to_spectrum(1.0, 1.0, 1.0, out.ctypes.data_as(dp))
+    assert abs(out[0] - 1.0618958571272863) < 1e-15
+    L.orc_rgb_to_spectrum(0.0, 0.0, 0.0, out.ctypes.data_as(dp))
+    assert np.all(out == 0.0)
+    # sky colour (y, y, 1) with y < 0: red == green < blue branch -> white*y + 0*cyan + (1-y)*blue
+    L.orc_rgb_to_spectrum(-0.25, -0.25, 1.0, out.ctypes.data_as(dp))
+    white = np.zeros(32)
+    blue = np.zeros(32)
+    L.orc_rgb_to_spectrum(1.0, 1.0, 1.0, white.ctypes.data_as(dp))
+    L.orc_rgb_to_spectrum(0.0, 0.0, 1.0, blue.ctypes.data_as(dp))
+    assert np.allclose(out, -0.25 * white + 1.25 * blue, rtol=0, atol=1e-15)
+
+
+# ---------------------------------------------------------------- colour/colour_xyz.rs:109-133
+def test_xyz_rgb_round_trip():
+    for _ in range(100):
+        xyz = RNG.random(3)
+        rgb = np.zeros(3)
+        back = np.zeros(3)
+        L.orc_xyz_to_linear_rgb(xyz.ctypes.data_as(dp), rgb.ctypes.data_as(dp))
+        L.orc_linear_rgb_to_xyz(rgb.ctypes.data_as(dp), back.ctypes.data_as(dp))
+        assert np.max(np.abs(back - xyz)) < 1e-7
+
+
+def test_cmf_peaks():
+    xyz = np.zeros(3)
+    L.orc_cmf_xyz(599.8, xyz.ctypes.data_as(dp))
+    assert abs(xyz[0] - 1.056) < 0.01
+    L.orc_cmf_xyz(0.0, xyz.ctypes.data_as(dp))
+    assert np.all(np.abs(xyz) < 1e-30)   # wavelength 0 (depth-limited paths) contributes ~nothing
+
+
+def test_srgb_gamma_constants_as_written():
+    assert L.orc_srgb_gamma(0.001) == 12.98 * 0.001
+    assert abs(L.orc_srgb_gamma(0.5) - (1.005 * 0.5 ** (1 / 2.4) - 0.055)) < 1e-15
+
+
+# ---------------------------------------------------------------- accumulation_buffer.rs:91-327
+def _xyz(w, i):
+    out = np.zeros(3)
+    L.orc_cmf_xyz(w, out.ctypes.data_as(dp))
+    return out * i
+
+
+def test_accum_first_update_exact():
+    st = np.zeros(11)
+    L.orc_accum_update(st.ctypes.data_as(dp), 589.0, 1.5, 0.8)
+    assert np.array_equal(st[0:3], _xyz(589.0, 1.5))
+    assert st[9] == 0.8
+
+
+def test_accum_two_and_three_updates_exact():
+    c1, c2, c3 = _xyz(589.0, 0.5), _xyz(656.0, 1.5), _xyz(393.0, 1.2)
+    st = np.zeros(11)
+    L.orc_accum_update(st.ctypes.data_as(dp), 589.0, 0.5, 1.0)
+    L.orc_accum_update(st.ctypes.data_as(dp), 656.0, 1.5, 1.0)
+    assert np.array_equal(st[0:3], (c1 + c2) / 2.0)
+    st = np.zeros(11)
+    w1, w2, w3 = 0.75, 1.25, 0.5
+    L.orc_accum_update(st.ctypes.data_as(dp), 589.0, 0.5, w1)
+    L.orc_accum_update(st.ctypes.data_as(dp), 656.0, 1.5, w2)
+    assert np.array_equal(st[0:3], (c1 * w1 + c2 * w2) / (w1 + w2))
+    L.orc_accum_update(st.ctypes.data_as(dp), 393.0, 1.2, w3)
+    assert np.array_equal(st[0:3], (c1 * w1 + c2 * w2 + c3 * w3) / (w1 + w2 + w3))
+
+
+def test_accum_merge_matches_direct():
+    """accumulation_buffer.rs:254-327 on a single pixel: blend(colour,weight) == sequential updates within 1e-10."""
+    for i in range(5):
+        for j in range(4):
+            wl1, wl2 = 350.0 + i * j, 700.0 - i * j
+            w = 0.2 + i * 0.02 + j * 0.3
+            single = np.zeros(11)
+            L.orc_accum_update(single.ctypes.data_as(dp), wl1, 1.0, w)
+            L.orc_accum_update(single.ctypes.data_as(dp), wl2, 1.0, w)
+            a, b = np.zeros(11), np.zeros(11)
+            L.orc_accum_update(a.ctypes.data_as(dp), wl1, 1.0, w)
+            L.orc_accum_update(b.ctypes.data_as(dp), wl2, 1.0, w)
+            out = np.zeros(3)
+            L.orc_accum_blend(a[0:3].copy().ctypes.data_as(dp), a[9], b[0:3].copy().ctypes.data_as(dp), b[9], out.ctypes.data_as(dp))
+            assert np.linalg.norm(out - single[0:3]) < 1e-10
+            assert a[9] + b[9] == single[9]
+
+
+# ---------------------------------------------------------------- util/tile_iterator.rs:76-154
+@pytest.mark.parametrize("w,h,ts", [(20, 15, 5), (21, 15, 5), (20, 16, 5), (1, 1, 5), (640, 480, 32), (7, 3, 2048)])
+def test_tile_iterator_covers_every_pixel_once(w, h, ts):
+    cap = 4096
+    tiles = (C.c_uint64 * (4 * cap))()
+    n = L.orc_tile_iterator(w, h, ts, tiles, cap)
+    assert n == -(-w // ts) * -(-h // ts)
+    cover = np.zeros((h, w), int)
+    for i in range(n):
+        sc, ec, sr, er = tiles[4 * i:4 * i + 4]
+        cover[sr:er, sc:ec] += 1
+    assert np.all(cover == 1)
+
+
+# ---------------------------------------------------------------- camera.rs:143-182
+def test_camera_ray_hits_film_location():
+    o, d = np.zeros(3), np.zeros(3)
+    cam = vec(0, 0, 0)
+    L.orc_camera_ray(800, 600, cam.ctypes.data_as(dp), 100, 200, 0.5, 0.5, o.ctypes.data_as(dp), d.ctypes.data_as(dp))
+    p = d / d[2]   # film plane z = 1
+    fw, fh = 800 / 600, 1.0
+    assert abs(p[0] - ((200 + 0.5) * fw / 800 - fw / 2)) < 0.5 / 200.0
+    assert abs(p[1] - (-(100 + 0.5) * fh / 600 + fh / 2)) < 0.5 / 800.0
+    assert abs(np.linalg.norm(d) - 1.0) < 1e-15
+    # portrait branch of camera.rs:29-33 (film height = w/h < 1)
+    L.orc_camera_ray(600, 800, cam.ctypes.data_as(dp), 0, 0, 0.0, 0.0, o.ctypes.data_as(dp), d.ctypes.data_as(dp))
+    p = d / d[2]
+    assert abs(p[0] + 0.5) < 1e-12 and abs(p[1] - (0.75 * 799 / 800 - 0.375)) < 1e-12
+
+
+# ---------------------------------------------------------------- math/mat3.rs:189-356
+def test_mat3_kats():
+    m = np.array([1, 3, 2, 4, 5, 6, 7, 8, 9], float)
+    assert L.orc_mat3_determinant(m.ctypes.data_as(dp)) == 9.0
+    out = np.zeros(9)
+    sing = np.array([1, 2, 3, 4, 5, 6, 7, 8, 9], float)
+    assert L.orc_mat3_inverse(sing.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+    ident = np.eye(3).ravel()
+    assert L.orc_mat3_inverse(ident.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 1
+    assert np.array_equal(out, ident)
+    m = np.array([4, -5, -2, 5, -6, -2, -8, 9, 3], float)   # det == 1, which is why cof^T * det passes upstream
+    assert L.orc_mat3_inverse(m.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 1
+    assert np.array_equal(out, np.array([0, -3, -2, 1, -4, -2, -3, 4, 1], float))
+    # the quirk itself: det != 1 gives inverse * det^2
+    m = np.diag([2.0, 2.0, 2.0]).ravel()
+    L.orc_mat3_inverse(m.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert np.array_equal(out, np.diag([32.0, 32.0, 32.0]).ravel())
+
+
+# ---------------------------------------------------------------- counter RNG (Random123 known answers)
+@pytest.mark.parametrize("ctr,key,expect", [
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+])
+def test_philox_known_answers(ctr, key, expect):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    out = (C.c_uint32 * 4)()
+    L.orc_philox4x32_10(c, k, out)
+    assert tuple(out) == expect
+
+
+def test_rng_ranges_and_stream_layout():
+    u = np.array([L.orc_rng_f64(1, 7, 3, i) for i in range(2000)])
+    assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.03
+    v = np.array([L.orc_rng_open01(1, 7, 3, i) for i in range(2000)])
+    assert v.min() > 0.0 and v.max() < 1.0
+    b = np.array([L.orc_rng_bool(1, 7, 3, i) for i in range(2000)])
+    assert 0.45 < b.mean() < 0.55
+    # different pixel / sample / seed give different streams
+    assert L.orc_rng_f64(1, 7, 3, 0) != L.orc_rng_f64(1, 8, 3, 0) != L.orc_rng_f64(2, 7, 3, 0)
+    assert L.orc_rng_f64(1, 7, 3, 0) != L.orc_rng_f64(1, 7, 4, 0)

@@ -1,0 +1,467 @@
+// vanrijn_host.cpp -- host side of the drop-in: scene types, OBJ loading, the reference-topology
+// BVH build, flattening to the SoA layout of include/vanrijn_cuda.h, and partial_render_scene.
+// No ray is ever traced on the host: everything below either prepares data or calls the C ABI.
+// Reference paths are relative to /root/reference/src/.
+#include "../../../include/vanrijn.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <numeric>
+
+namespace vanrijn {
+
+namespace {
+const double kRgbBasis[7][32] = {
+#include "../rgb_basis_tables.inc"
+};
+enum { B_WHITE = 0, B_CYAN, B_MAGENTA, B_YELLOW, B_RED, B_GREEN, B_BLUE };
+
+inline Vec3 sub(Vec3 a, Vec3 b) { return Vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline double dot(Vec3 a, Vec3 b) { return ((0.0 + a.x * b.x) + a.y * b.y) + a.z * b.z; }
+inline Vec3 cross(Vec3 a, Vec3 b) { return Vec3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline Vec3 normalize(Vec3 a) {
+    double inv = 1.0 / std::sqrt(dot(a, a));
+    return Vec3(a.x * inv, a.y * inv, a.z * inv);
+}
+} // namespace
+
+// ------------------------------------------------------------------------------ colour
+ColourRgbF ColourRgbF::from_named(NamedColour name) {
+    switch (name) {
+    case NamedColour::Black: return {0.0, 0.0, 0.0};
+    case NamedColour::White: return {1.0, 1.0, 1.0};
+    case NamedColour::Red: return {1.0, 0.0, 0.0};
+    case NamedColour::Lime: return {0.0, 1.0, 0.0};
+    case NamedColour::Blue: return {0.0, 0.0, 1.0};
+    case NamedColour::Yellow: return {1.0, 1.0, 0.0};
+    case NamedColour::Cyan: return {0.0, 1.0, 1.0};
+    case NamedColour::Magenta: return {1.0, 0.0, 1.0};
+    case NamedColour::Gray: return {0.5, 0.5, 0.5};
+    case NamedColour::Maroon: return {0.5, 0.0, 0.0};
+    case NamedColour::Olive: return {0.5, 0.5, 0.0};
+    case NamedColour::Green: return {0.0, 0.5, 0.0};
+    case NamedColour::Purple: return {0.5, 0.0, 0.5};
+    case NamedColour::Teal: return {0.0, 0.5, 0.5};
+    case NamedColour::Navy: return {0.0, 0.0, 0.5};
+    }
+    return {};
+}
+
+Spectrum Spectrum::black() { return grey(0.0); }
+Spectrum Spectrum::grey(double brightness) {
+    Spectrum s;
+    s.samples = {brightness, brightness};
+    return s;
+}
+Spectrum Spectrum::diamond_index_of_refraction() { // spectrum.rs:29-48
+    Spectrum s;
+    s.shortest_wavelength = 326.27, s.longest_wavelength = 774.9;
+    s.samples = {2.505813241, 2.487866556, 2.473323675, 2.464986815, 2.455051934, 2.441251728,
+                 2.431478974, 2.427076431, 2.420857286, 2.411429037, 2.406543164, 2.406202402};
+    return s;
+}
+Spectrum Spectrum::reflection_from_linear_rgb(const ColourRgbF &c) { // spectrum.rs:81-165
+    const double r = c.red, g = c.green, b = c.blue;
+    int mid, last;
+    double k0, k1, k2;
+    if (r <= g && r <= b) {
+        mid = B_CYAN, k0 = r;
+        if (g <= b) last = B_BLUE, k1 = g - r, k2 = b - g;
+        else last = B_GREEN, k1 = b - r, k2 = g - b;
+    } else if (g <= r && g < b) {
+        mid = B_MAGENTA, k0 = g;
+        if (r <= b) last = B_BLUE, k1 = r - g, k2 = b - r;
+        else last = B_RED, k1 = b - g, k2 = r - b;
+    } else {
+        mid = B_YELLOW, k0 = b;
+        if (r <= g) last = B_GREEN, k1 = r - b, k2 = g - r;
+        else last = B_RED, k1 = g - b, k2 = r - g;
+    }
+    Spectrum s;
+    s.shortest_wavelength = 380.0, s.longest_wavelength = 720.0;
+    s.samples.resize(32);
+    for (int i = 0; i < 32; i++) s.samples[i] = k0 * kRgbBasis[B_WHITE][i] + k1 * kRgbBasis[mid][i] + k2 * kRgbBasis[last][i];
+    return s;
+}
+
+// ------------------------------------------------------------------------------ materials
+uint32_t LambertianMaterial::flatten(FlatSceneBuilder &out) const {
+    return out.add_material(VRJ_MAT_LAMBERTIAN, out.add_spectrum(colour), diffuse_strength, 0.0, 0.0);
+}
+uint32_t PhongMaterial::flatten(FlatSceneBuilder &out) const {
+    return out.add_material(VRJ_MAT_PHONG, out.add_spectrum(colour), diffuse_strength, specular_strength, smoothness);
+}
+uint32_t ReflectiveMaterial::flatten(FlatSceneBuilder &out) const {
+    return out.add_material(VRJ_MAT_REFLECTIVE, out.add_spectrum(colour), diffuse_strength, reflection_strength, 0.0);
+}
+uint32_t SmoothTransparentDialectric::flatten(FlatSceneBuilder &out) const {
+    return out.add_material(VRJ_MAT_DIELECTRIC, out.add_spectrum(eta), 0.0, 0.0, 0.0);
+}
+
+// ------------------------------------------------------------------------------ primitives
+Plane::Plane(Vec3 n, double d, std::shared_ptr<Material> m) : distance_from_origin(d), material(std::move(m)) {
+    normal = normalize(n);
+    // vec3.rs:112-127 smallest_coord
+    double ax = std::fabs(normal.x), ay = std::fabs(normal.y), az = std::fabs(normal.z);
+    int smallest = ax < ay ? (ax < az ? 0 : 2) : (ay < az ? 1 : 2);
+    Vec3 axis(smallest == 0 ? 1.0 : 0.0, smallest == 1 ? 1.0 : 0.0, smallest == 2 ? 1.0 : 0.0);
+    cotangent = normalize(cross(normal, axis));
+    tangent = cross(normal, cotangent);
+}
+void Sphere::flatten(FlatSceneBuilder &out, uint32_t object_id, uint32_t prim_id) const {
+    out.add_sphere(*this, out.material_index(material.get()), object_id, prim_id);
+}
+void Plane::flatten(FlatSceneBuilder &out, uint32_t object_id, uint32_t prim_id) const {
+    out.add_plane(*this, out.material_index(material.get()), object_id, prim_id);
+}
+void Triangle::flatten(FlatSceneBuilder &out, uint32_t object_id, uint32_t prim_id) const {
+    out.add_triangle(*this, out.material_index(material.get()), object_id, prim_id);
+}
+void PrimitiveList::flatten(FlatSceneBuilder &out, uint32_t object_id) const {
+    for (size_t i = 0; i < primitives.size(); i++) primitives[i]->flatten(out, object_id, (uint32_t)i);
+}
+
+// ------------------------------------------------------------------------------ BVH build
+namespace {
+struct BuildCtx {
+    const std::vector<double> *v;  // 9 per triangle (input order)
+    std::vector<double> lo, hi, centre; // 3 per triangle
+    std::vector<uint32_t> order;
+    std::vector<double> node_min, node_max;
+    std::vector<int32_t> node_child;
+    uint32_t depth = 0;
+
+    // util/axis_aligned_bounding_box.rs:76-99: first strictly-largest extent; degenerate extents count as -1
+    static int largest_dimension(const double lo[3], const double hi[3]) {
+        int dim = 0;
+        double best = 0.0;
+        for (int k = 0; k < 3; k++) {
+            double extent = (lo[k] == hi[k]) ? -1.0 : hi[k] - lo[k];
+            if (extent > best) dim = k, best = extent;
+        }
+        return dim;
+    }
+    // bounding_volume_hierarchy.rs:49-75.  Returns the node index.  Node boxes are unions of
+    // triangle boxes (min/max are exact, so bottom-up equals the reference's fold over the slice).
+    int32_t build(size_t begin, size_t end, uint32_t level) {
+        depth = std::max(depth, level + 1);
+        int32_t me = (int32_t)(node_child.size() / 2);
+        node_child.push_back(0), node_child.push_back(0);
+        node_min.insert(node_min.end(), 3, std::numeric_limits<double>::infinity());
+        node_max.insert(node_max.end(), 3, -std::numeric_limits<double>::infinity());
+        double blo[3], bhi[3];
+        for (int k = 0; k < 3; k++) blo[k] = std::numeric_limits<double>::infinity(), bhi[k] = -blo[k];
+        for (size_t i = begin; i < end; i++) {
+            uint32_t t = order[i];
+            for (int k = 0; k < 3; k++) blo[k] = std::fmin(blo[k], lo[3 * t + k]), bhi[k] = std::fmax(bhi[k], hi[3 * t + k]);
+        }
+        for (int k = 0; k < 3; k++) node_min[3 * me + k] = blo[k], node_max[3 * me + k] = bhi[k];
+        if (end - begin <= 1) {
+            node_child[2 * me] = ~(int32_t)begin; // leaf: ~first triangle (BVH-local, leaf order)
+            node_child[2 * me + 1] = (int32_t)(end - begin);
+            return me;
+        }
+        int axis = largest_dimension(blo, bhi);
+        // bounding_volume_hierarchy.rs:38-46: sort by box centre on that axis.  The reference uses
+        // sort_unstable_by (order among equal keys unspecified); a stable sort makes the tree deterministic.
+        std::stable_sort(order.begin() + begin, order.begin() + end,
+                         [this, axis](uint32_t a, uint32_t b) { return centre[3 * a + axis] < centre[3 * b + axis]; });
+        size_t pivot = begin + (end - begin) / 2;
+        int32_t l = build(begin, pivot, level + 1);
+        int32_t r = build(pivot, end, level + 1);
+        node_child[2 * me] = l, node_child[2 * me + 1] = r;
+        return me;
+    }
+};
+} // namespace
+
+std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vector<std::shared_ptr<Primitive>> &primitives) {
+    std::unique_ptr<BoundingVolumeHierarchy> bvh(new BoundingVolumeHierarchy());
+    const size_t n = primitives.size();
+    std::vector<double> v(n * 9), nr(n * 9);
+    for (size_t i = 0; i < n; i++) {
+        const Triangle *t = dynamic_cast<const Triangle *>(primitives[i].get());
+        if (!t) throw std::runtime_error("BoundingVolumeHierarchy::build: only Triangle primitives can be stored on the device BVH");
+        for (int k = 0; k < 3; k++) {
+            v[i * 9 + 3 * k] = t->vertices[k].x, v[i * 9 + 3 * k + 1] = t->vertices[k].y, v[i * 9 + 3 * k + 2] = t->vertices[k].z;
+            nr[i * 9 + 3 * k] = t->normals[k].x, nr[i * 9 + 3 * k + 1] = t->normals[k].y, nr[i * 9 + 3 * k + 2] = t->normals[k].z;
+        }
+    }
+    BuildCtx cx;
+    cx.v = &v;
+    cx.lo.resize(3 * n), cx.hi.resize(3 * n), cx.centre.resize(3 * n);
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            double a = v[i * 9 + k], b = v[i * 9 + 3 + k], c = v[i * 9 + 6 + k];
+            double mn = std::fmin(std::fmin(a, b), c), mx = std::fmax(std::fmax(a, b), c);
+            cx.lo[3 * i + k] = mn, cx.hi[3 * i + k] = mx;
+            cx.centre[3 * i + k] = (mn + mx) / 2.0; // bounding_volume_hierarchy.rs:30-36
+        }
+    cx.order.resize(n);
+    std::iota(cx.order.begin(), cx.order.end(), 0u);
+    cx.node_child.reserve(4 * n + 2);
+    cx.build(0, n, 0);
+    bvh->depth_ = cx.depth;
+    bvh->node_min_ = std::move(cx.node_min), bvh->node_max_ = std::move(cx.node_max), bvh->node_child_ = std::move(cx.node_child);
+    bvh->tri_v_.resize(n * 9), bvh->tri_n_.resize(n * 9), bvh->tri_prim_id_.resize(n), bvh->tri_material_.resize(n);
+    std::vector<std::shared_ptr<Primitive>> reordered(n);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t src = cx.order[i];
+        std::memcpy(&bvh->tri_v_[i * 9], &v[(size_t)src * 9], 72);
+        std::memcpy(&bvh->tri_n_[i * 9], &nr[(size_t)src * 9], 72);
+        bvh->tri_prim_id_[i] = src;
+        bvh->tri_material_[i] = static_cast<const Triangle *>(primitives[src].get())->material;
+        reordered[i] = primitives[src];
+    }
+    primitives.swap(reordered); // the reference sorts the caller's slice in place
+    return bvh;
+}
+void BoundingVolumeHierarchy::flatten(FlatSceneBuilder &out, uint32_t object_id) const { out.add_bvh(*this, object_id); }
+
+// ------------------------------------------------------------------------------ flattening
+uint32_t FlatSceneBuilder::add_spectrum(const Spectrum &s) {
+    VrjSpectrum d;
+    d.shortest_wavelength = s.shortest_wavelength, d.longest_wavelength = s.longest_wavelength;
+    d.first_sample = (uint32_t)samples_.size(), d.n_samples = (uint32_t)s.samples.size();
+    samples_.insert(samples_.end(), s.samples.begin(), s.samples.end());
+    spectra_.push_back(d);
+    return (uint32_t)spectra_.size() - 1;
+}
+uint32_t FlatSceneBuilder::add_material(uint32_t kind, uint32_t spectrum, double p0, double p1, double p2) {
+    materials_.push_back(VrjMaterial{kind, spectrum, p0, p1, p2});
+    return (uint32_t)materials_.size() - 1;
+}
+uint32_t FlatSceneBuilder::material_index(const Material *m) {
+    if (!m) throw std::runtime_error("primitive without a material");
+    for (auto &e : material_cache_)
+        if (e.first == m) return e.second;
+    uint32_t id = m->flatten(*this);
+    material_cache_.push_back({m, id});
+    return id;
+}
+void FlatSceneBuilder::add_sphere(const Sphere &s, uint32_t material, uint32_t object_id, uint32_t prim_id) {
+    spheres_.push_back(VrjSphere{{s.centre.x, s.centre.y, s.centre.z}, s.radius, material, 0});
+    items_.push_back(VrjItem{VRJ_ITEM_SPHERE, (uint32_t)spheres_.size() - 1, object_id, prim_id});
+}
+void FlatSceneBuilder::add_plane(const Plane &p, uint32_t material, uint32_t object_id, uint32_t prim_id) {
+    VrjPlane d{};
+    d.normal[0] = p.normal.x, d.normal[1] = p.normal.y, d.normal[2] = p.normal.z;
+    d.tangent[0] = p.tangent.x, d.tangent[1] = p.tangent.y, d.tangent[2] = p.tangent.z;
+    d.cotangent[0] = p.cotangent.x, d.cotangent[1] = p.cotangent.y, d.cotangent[2] = p.cotangent.z;
+    d.distance_from_origin = p.distance_from_origin, d.material = material;
+    planes_.push_back(d);
+    items_.push_back(VrjItem{VRJ_ITEM_PLANE, (uint32_t)planes_.size() - 1, object_id, prim_id});
+}
+void FlatSceneBuilder::add_triangle(const Triangle &t, uint32_t material, uint32_t object_id, uint32_t prim_id) {
+    for (int k = 0; k < 3; k++) {
+        const Vec3 &v = t.vertices[k], &n = t.normals[k];
+        tri_[k].insert(tri_[k].end(), {v.x, v.y, v.z, 0.0});
+        tri_[3 + k].insert(tri_[3 + k].end(), {n.x, n.y, n.z, 0.0});
+    }
+    tri_material_.push_back(material), tri_prim_id_.push_back(prim_id);
+    items_.push_back(VrjItem{VRJ_ITEM_TRIANGLE, (uint32_t)tri_material_.size() - 1, object_id, prim_id});
+}
+void FlatSceneBuilder::add_bvh(const BoundingVolumeHierarchy &b, uint32_t object_id) {
+    VrjBvh d{};
+    d.first_node = node_child_.size() / 2, d.n_nodes = b.node_child_.size() / 2;
+    d.first_triangle = tri_material_.size(), d.n_triangles = b.triangle_count();
+    d.depth = b.depth_;
+    const size_t nt = b.triangle_count();
+    for (int k = 0; k < 6; k++) tri_[k].reserve(tri_[k].size() + 4 * nt);
+    for (size_t i = 0; i < nt; i++) {
+        for (int k = 0; k < 3; k++) {
+            const double *v = &b.tri_v_[i * 9 + 3 * k], *n = &b.tri_n_[i * 9 + 3 * k];
+            tri_[k].insert(tri_[k].end(), {v[0], v[1], v[2], 0.0});
+            tri_[3 + k].insert(tri_[3 + k].end(), {n[0], n[1], n[2], 0.0});
+        }
+        tri_material_.push_back(material_index(b.tri_material_[i].get()));
+        tri_prim_id_.push_back(b.tri_prim_id_[i]);
+    }
+    for (size_t n = 0; n < d.n_nodes; n++) {
+        for (int k = 0; k < 3; k++) node_min_.push_back(b.node_min_[3 * n + k]), node_max_.push_back(b.node_max_[3 * n + k]);
+        node_min_.push_back(0.0), node_max_.push_back(0.0);
+        int32_t l = b.node_child_[2 * n], r = b.node_child_[2 * n + 1];
+        if (l >= 0) {
+            node_child_.push_back(l + (int32_t)d.first_node), node_child_.push_back(r + (int32_t)d.first_node);
+        } else {
+            node_child_.push_back(~((~l) + (int32_t)d.first_triangle)), node_child_.push_back(r);
+        }
+    }
+    bvhs_.push_back(d);
+    items_.push_back(VrjItem{VRJ_ITEM_BVH, (uint32_t)bvhs_.size() - 1, object_id, 0});
+}
+const VrjSceneDesc &FlatSceneBuilder::desc(const Vec3 &camera) {
+    VrjSceneDesc &d = desc_;
+    d = VrjSceneDesc{};
+    d.abi_version = VRJ_ABI_VERSION;
+    d.camera_location[0] = camera.x, d.camera_location[1] = camera.y, d.camera_location[2] = camera.z;
+    d.n_spectra = (uint32_t)spectra_.size(), d.n_spectrum_samples = (uint32_t)samples_.size();
+    d.spectra = spectra_.data(), d.spectrum_samples = samples_.data();
+    d.n_materials = (uint32_t)materials_.size(), d.materials = materials_.data();
+    d.n_spheres = (uint32_t)spheres_.size(), d.spheres = spheres_.data();
+    d.n_planes = (uint32_t)planes_.size(), d.planes = planes_.data();
+    d.n_bvhs = (uint32_t)bvhs_.size(), d.bvhs = bvhs_.data();
+    d.n_triangles = tri_material_.size();
+    d.tri_v0 = tri_[0].data(), d.tri_v1 = tri_[1].data(), d.tri_v2 = tri_[2].data();
+    d.tri_n0 = tri_[3].data(), d.tri_n1 = tri_[4].data(), d.tri_n2 = tri_[5].data();
+    d.tri_material = tri_material_.data(), d.tri_prim_id = tri_prim_id_.data();
+    d.n_nodes = node_child_.size() / 2;
+    d.node_min = node_min_.data(), d.node_max = node_max_.data(), d.node_child = node_child_.data();
+    d.n_items = (uint32_t)items_.size(), d.items = items_.data();
+    return d;
+}
+
+// ------------------------------------------------------------------------------ OBJ loading
+// mesh.rs:13-88 over the behaviour of obj 0.9's Obj::<SimplePolygon>::load: `v`, `vn`, `f`
+// (a, a/b, a//c, a/b/c; 1-based, negative = relative to the end), f32 parse then widen,
+// fan triangulation around the polygon's first vertex, zero normal when a vertex has none.
+std::vector<std::shared_ptr<Primitive>> load_obj(const std::string &filename, std::shared_ptr<Material> material) {
+    FILE *f = std::fopen(filename.c_str(), "r");
+    if (!f) throw std::runtime_error("load_obj: cannot open " + filename);
+    std::vector<float> positions, normals;
+    std::vector<std::shared_ptr<Primitive>> out;
+    std::vector<long> vi, ni;
+    char line[8192];
+    auto is_space = [](char c) { return c == ' ' || c == '\t'; };
+    while (std::fgets(line, sizeof line, f)) {
+        const char *p = line;
+        while (is_space(*p)) p++;
+        if (p[0] == 'v' && is_space(p[1])) {
+            char *q = const_cast<char *>(p + 1);
+            for (int k = 0; k < 3; k++) positions.push_back(std::strtof(q, &q));
+        } else if (p[0] == 'v' && p[1] == 'n' && is_space(p[2])) {
+            char *q = const_cast<char *>(p + 2);
+            for (int k = 0; k < 3; k++) normals.push_back(std::strtof(q, &q));
+        } else if (p[0] == 'f' && is_space(p[1])) {
+            vi.clear(), ni.clear();
+            char *q = const_cast<char *>(p + 1);
+            const long np = (long)positions.size() / 3, nn = (long)normals.size() / 3;
+            while (true) {
+                while (is_space(*q)) q++;
+                if (*q == '\0' || *q == '\n' || *q == '\r' || *q == '#') break;
+                long v = std::strtol(q, &q, 10), n = 0;
+                bool has_normal = false;
+                if (*q == '/') {
+                    q++;
+                    if (*q != '/') (void)std::strtol(q, &q, 10);
+                    if (*q == '/') {
+                        q++;
+                        n = std::strtol(q, &q, 10);
+                        has_normal = true;
+                    }
+                }
+                vi.push_back(v < 0 ? np + v : v - 1);
+                ni.push_back(has_normal ? (n < 0 ? nn + n : n - 1) : -1);
+            }
+            auto vertex = [&](size_t k) { return Vec3(positions[3 * vi[k]], positions[3 * vi[k] + 1], positions[3 * vi[k] + 2]); };
+            auto normal = [&](size_t k) {
+                return ni[k] < 0 ? Vec3() : Vec3(normals[3 * ni[k]], normals[3 * ni[k] + 1], normals[3 * ni[k] + 2]);
+            };
+            for (size_t k = 1; k + 1 < vi.size(); k++)
+                out.push_back(std::make_shared<Triangle>(std::array<Vec3, 3>{vertex(0), vertex(k), vertex(k + 1)},
+                                                         std::array<Vec3, 3>{normal(0), normal(k), normal(k + 1)}, material));
+        }
+    }
+    std::fclose(f);
+    return out;
+}
+
+// ------------------------------------------------------------------------------ tiles, accumulation buffer
+TileIterator::TileIterator(size_t total_width, size_t total_height, size_t tile_size)
+    : tile_size_(tile_size), total_height_(total_height), total_width_(total_width) {
+    if (!(tile_size > 0 && tile_size * 2 < std::numeric_limits<size_t>::max())) throw std::runtime_error("TileIterator: bad tile size");
+}
+bool TileIterator::next(Tile &tile) { // tile_iterator.rs:41-66
+    if (current_row_ >= total_height_) return false;
+    tile.start_column = current_column_, tile.end_column = std::min(total_width_, current_column_ + tile_size_);
+    tile.start_row = current_row_, tile.end_row = std::min(total_height_, current_row_ + tile_size_);
+    current_column_ += tile_size_;
+    if (current_column_ >= total_width_) current_row_ += tile_size_, current_column_ = 0;
+    return true;
+}
+
+AccumulationBuffer::AccumulationBuffer(size_t width, size_t height)
+    : colour(3 * width * height, 0.0), colour_sum(3 * width * height, 0.0), colour_bias(3 * width * height, 0.0),
+      weight(width * height, 0.0), weight_bias(width * height, 0.0), width_(width), height_(height) {}
+
+void AccumulationBuffer::merge_tile(const Tile &tile, const AccumulationBuffer &src) {
+    if (tile.width() != src.width() || tile.height() != src.height()) throw std::runtime_error("merge_tile: tile and source sizes differ");
+    if (tile.end_row > height_ || tile.end_column > width_) throw std::runtime_error("merge_tile: tile outside the buffer");
+    for (size_t i = 0; i < tile.height(); i++)
+        for (size_t j = 0; j < tile.width(); j++) {
+            size_t d = (tile.start_row + i) * width_ + tile.start_column + j, s = i * src.width_ + j;
+            double w1 = weight[d], w2 = src.weight[s];
+            double inv = 1.0 / (w1 + w2); // accumulation_buffer.rs:81-85
+            for (int k = 0; k < 3; k++) colour[3 * d + k] = (colour[3 * d + k] * w1 + src.colour[3 * s + k] * w2) * inv;
+            weight[d] += w2;
+        }
+}
+
+// ------------------------------------------------------------------------------ device scene + render
+struct Scene::DeviceCache {
+    std::mutex mutex;
+    std::vector<std::pair<int, VrjScene *>> scenes;
+    ~DeviceCache() {
+        for (auto &e : scenes) vrj_scene_destroy(e.second);
+    }
+};
+Scene::~Scene() = default;
+
+const VrjScene *device_scene(const Scene &scene, int device) {
+    static std::mutex create_mutex;
+    {
+        std::lock_guard<std::mutex> g(create_mutex);
+        if (!scene.device_cache) scene.device_cache = std::make_shared<Scene::DeviceCache>();
+    }
+    std::lock_guard<std::mutex> g(scene.device_cache->mutex);
+    for (auto &e : scene.device_cache->scenes)
+        if (e.first == device) return e.second;
+    FlatSceneBuilder fb;
+    for (size_t i = 0; i < scene.objects.size(); i++) scene.objects[i]->flatten(fb, (uint32_t)i);
+    VrjScene *dev = nullptr;
+    if (vrj_scene_create(&fb.desc(scene.camera_location), device, &dev) != VRJ_OK)
+        throw std::runtime_error(std::string("vrj_scene_create: ") + vrj_last_error());
+    scene.device_cache->scenes.push_back({device, dev});
+    return dev;
+}
+
+AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width) {
+    return partial_render_scene(scene, tile, height, width, RenderOptions());
+}
+
+AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &o) {
+    AccumulationBuffer buffer(tile.width(), tile.height());
+    VrjRenderParams p{};
+    p.spp = o.spp, p.max_depth = o.max_depth, p.sample_offset = o.sample_offset, p.seed = o.seed;
+    p.integrator = o.integrator, p.bvh_filter = o.bvh_filter, p.bias = 0.0000001, p.sample_stride = o.sample_stride;
+    auto as_data = [](const Spectrum &s) {
+        return VrjSpectrumData{s.shortest_wavelength, s.longest_wavelength, (uint32_t)s.samples.size(), 0u, s.samples.data()};
+    };
+    std::vector<VrjLight> lights;
+    VrjSpectrumData ambient = as_data(o.ambient_light);
+    if (o.integrator == VRJ_INTEGRATOR_WHITTED) { // WhittedIntegrator { ambient_light, lights }
+        for (const DirectionalLight &l : o.lights) {
+            VrjLight d{};
+            d.direction[0] = l.direction.x, d.direction[1] = l.direction.y, d.direction[2] = l.direction.z;
+            d.spectrum = as_data(l.spectrum);
+            lights.push_back(d);
+        }
+        p.lights = lights.data(), p.n_lights = (uint32_t)lights.size(), p.ambient_light = &ambient;
+    }
+    const VrjScene *dev = device_scene(scene, o.device);
+    VrjTile t{tile.start_column, tile.end_column, tile.start_row, tile.end_row};
+    VrjAccumOut out{};
+    out.memory = VRJ_MEM_HOST;
+    out.colour = buffer.colour.data(), out.colour_sum = buffer.colour_sum.data(), out.colour_bias = buffer.colour_bias.data();
+    out.weight = buffer.weight.data(), out.weight_bias = buffer.weight_bias.data();
+    out.stats = o.stats;
+    if (vrj_render_tile(dev, &t, height, width, &p, &out) != VRJ_OK) throw std::runtime_error(std::string("vrj_render_tile: ") + vrj_last_error());
+    return buffer;
+}
+
+} // namespace vanrijn

@@ -1,0 +1,667 @@
+// vanrijn_cuda.cu -- C ABI (include/vanrijn_cuda.h) over the sm_100a wavefront kernels.
+// There is no CPU fallback anywhere in this library: without a CUDA device every entry
+// point that computes returns VRJ_ERR_CUDA.
+#include "../../include/vanrijn_cuda.h"
+#include "vrj_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace vrj;
+
+namespace {
+
+thread_local std::string g_error;
+VrjStatus fail(VrjStatus code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+#define VRJ_CUDA(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(e_ == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA,             \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                                \
+    } while (0)
+
+struct DeviceBuffer {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DeviceBuffer() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t n) {
+        bytes = n;
+        return cudaMalloc(&p, std::max<size_t>(n, 16));
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+// per-call scratch: path queues, photon results, accumulators, counters
+struct Scratch {
+    size_t capacity = 0; // paths
+    size_t npix = 0;
+    uint32_t steps = 0;
+    DeviceBuffer queues[2][6];
+    DeviceBuffer photons, counters, stats;
+    DeviceBuffer acc_colour, acc_sum, acc_bias, acc_weight, acc_wbias;
+    DeviceBuffer lights, light_samples;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> marks; // per-launch boundaries, reused across calls
+    std::vector<int> mark_class;    // class of the launch that ENDS at mark i (-1: start of a batch)
+    size_t n_marks = 0;
+    uint32_t *host_count = nullptr; // pinned
+    ~Scratch() {
+        if (stream) cudaStreamDestroy(stream);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t e : marks) cudaEventDestroy(e);
+        if (host_count) cudaFreeHost(host_count);
+    }
+    // record a boundary event on the stream; cls = class of the launch it closes
+    cudaError_t mark(int cls) {
+        if (n_marks == marks.size()) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
+            marks.push_back(e), mark_class.push_back(cls);
+        }
+        mark_class[n_marks] = cls;
+        return cudaEventRecord(marks[n_marks++], stream);
+    }
+    PathQueue queue(int i) const {
+        PathQueue q;
+        q.q0 = queues[i][0].as<double2>(), q.q1 = queues[i][1].as<double2>(), q.q2 = queues[i][2].as<double2>();
+        q.q3 = queues[i][3].as<double2>(), q.q4 = queues[i][4].as<double2>(), q.q5 = queues[i][5].as<uint4>();
+        return q;
+    }
+};
+
+} // namespace
+
+struct VrjScene {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t device_bytes = 0;
+    DevScene dev{};
+    std::vector<DeviceBuffer *> owned;
+    std::mutex pool_mutex;
+    std::vector<Scratch *> pool;
+    uint32_t n_spectra = 0;
+    ~VrjScene() {
+        for (auto *s : pool) delete s;
+        for (auto *b : owned) delete b;
+    }
+};
+
+namespace {
+
+template <typename T, typename P>
+VrjStatus upload(VrjScene *sc, const std::vector<T> &host, P &dev_ptr) {
+    DeviceBuffer *b = new DeviceBuffer();
+    sc->owned.push_back(b);
+    VRJ_CUDA(b->alloc(host.size() * sizeof(T)));
+    if (!host.empty()) VRJ_CUDA(cudaMemcpy(b->p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    sc->device_bytes += host.size() * sizeof(T);
+    dev_ptr = b->as<T>();
+    return VRJ_OK;
+}
+
+float round_down_f32(double v) {
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+    return f;
+}
+float round_up_f32(double v) {
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return f;
+}
+
+// Re-express one reference-topology BVH (a box per node) as "wide" nodes that carry the boxes of
+// both children, so one fetch decides both; leaves (<= 1 triangle) live in the child references.
+struct WideBuilder {
+    const VrjSceneDesc *d;
+    std::vector<float> n32;   // 16 floats per wide node
+    std::vector<double> n64;  // 14 doubles per wide node
+    void box_of(int64_t node, double lo[3], double hi[3]) const {
+        for (int k = 0; k < 3; k++) lo[k] = d->node_min[node * 4 + k], hi[k] = d->node_max[node * 4 + k];
+    }
+    bool is_leaf(int64_t node) const { return d->node_child[2 * node] < 0; }
+    // reference for a child: wide index if internal, ~triangle if a 1-triangle leaf; false if empty leaf
+    void put_child(size_t w, int which, int64_t node, int32_t ref, bool empty) {
+        double lo[3], hi[3];
+        if (empty) {
+            for (int k = 0; k < 3; k++) lo[k] = std::numeric_limits<double>::infinity(), hi[k] = -lo[k];
+        } else {
+            box_of(node, lo, hi);
+        }
+        // f32 layout: [c0.lox c0.hix c0.loy c0.hiy][c1.lox c1.hix c1.loy c1.hiy][c0.loz c0.hiz c1.loz c1.hiz][l r 0 0]
+        float *f = &n32[w * 16];
+        float flo[3], fhi[3];
+        for (int k = 0; k < 3; k++) flo[k] = empty ? (float)lo[k] : round_down_f32(lo[k]), fhi[k] = empty ? (float)hi[k] : round_up_f32(hi[k]);
+        f[which * 4 + 0] = flo[0], f[which * 4 + 1] = fhi[0], f[which * 4 + 2] = flo[1], f[which * 4 + 3] = fhi[1];
+        f[8 + which * 2 + 0] = flo[2], f[8 + which * 2 + 1] = fhi[2];
+        std::memcpy(&f[12 + which], &ref, 4);
+        // f64 layout: c0 {lox hix loy hiy loz hiz} c1 {...} {bits(l,r), 0}
+        double *g = &n64[w * 14];
+        for (int k = 0; k < 3; k++) g[which * 6 + 2 * k] = lo[k], g[which * 6 + 2 * k + 1] = hi[k];
+        int32_t pair[2];
+        std::memcpy(pair, &g[12], 8);
+        pair[which] = ref;
+        std::memcpy(&g[12], pair, 8);
+    }
+    size_t new_node() {
+        size_t w = n32.size() / 16;
+        n32.resize(n32.size() + 16, 0.0f);
+        n64.resize(n64.size() + 14, 0.0);
+        return w;
+    }
+    // returns the reference to use for `node` from its parent
+    int32_t child_ref(int64_t node, bool *empty) {
+        *empty = false;
+        if (is_leaf(node)) {
+            if (d->node_child[2 * node + 1] == 0) {
+                *empty = true;
+                return -1;
+            }
+            return d->node_child[2 * node]; // ~first_triangle, already absolute
+        }
+        return (int32_t)build(node);
+    }
+    size_t build(int64_t node) { // node is internal
+        size_t w = new_node();
+        int64_t l = d->node_child[2 * node], r = d->node_child[2 * node + 1];
+        bool el, er;
+        int32_t rl = child_ref(l, &el);
+        put_child(w, 0, l, rl, el);
+        int32_t rr = child_ref(r, &er);
+        put_child(w, 1, r, rr, er);
+        return w;
+    }
+};
+
+VrjStatus validate(const VrjSceneDesc *d) {
+    if (!d) return fail(VRJ_ERR_INVALID_ARGUMENT, "scene description is NULL");
+    if (d->abi_version != VRJ_ABI_VERSION) return fail(VRJ_ERR_INVALID_ARGUMENT, "VrjSceneDesc.abi_version mismatch");
+    if (d->n_triangles > 0x7ffffff0ull || d->n_nodes > 0x7ffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "scene too large for 31-bit indices");
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        if (d->materials[i].kind > VRJ_MAT_DIELECTRIC) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown material kind");
+        if (d->materials[i].spectrum >= d->n_spectra) return fail(VRJ_ERR_INVALID_ARGUMENT, "material spectrum out of range");
+    }
+    for (uint32_t i = 0; i < d->n_spectra; i++) {
+        const VrjSpectrum &s = d->spectra[i];
+        if (s.n_samples < 2 || (uint64_t)s.first_sample + s.n_samples > d->n_spectrum_samples)
+            return fail(VRJ_ERR_INVALID_ARGUMENT, "spectrum sample range out of bounds (need >= 2 samples)");
+    }
+    for (uint32_t i = 0; i < d->n_spheres; i++)
+        if (d->spheres[i].material >= d->n_materials) return fail(VRJ_ERR_INVALID_ARGUMENT, "sphere material out of range");
+    for (uint32_t i = 0; i < d->n_planes; i++)
+        if (d->planes[i].material >= d->n_materials) return fail(VRJ_ERR_INVALID_ARGUMENT, "plane material out of range");
+    for (uint64_t i = 0; i < d->n_triangles; i++)
+        if (d->tri_material[i] >= d->n_materials) return fail(VRJ_ERR_INVALID_ARGUMENT, "triangle material out of range");
+    for (uint32_t i = 0; i < d->n_items; i++) {
+        const VrjItem &it = d->items[i];
+        uint64_t lim = it.kind == VRJ_ITEM_SPHERE ? d->n_spheres : it.kind == VRJ_ITEM_PLANE ? d->n_planes
+                     : it.kind == VRJ_ITEM_TRIANGLE ? d->n_triangles : it.kind == VRJ_ITEM_BVH ? d->n_bvhs : 0;
+        if (it.index >= lim) return fail(VRJ_ERR_INVALID_ARGUMENT, "item index out of range");
+    }
+    for (uint32_t i = 0; i < d->n_bvhs; i++) {
+        const VrjBvh &b = d->bvhs[i];
+        if (b.first_node + b.n_nodes > d->n_nodes || b.first_triangle + b.n_triangles > d->n_triangles)
+            return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh range out of bounds");
+        if (b.depth > 31) return fail(VRJ_ERR_UNSUPPORTED, "bvh deeper than the 32-entry traversal stack");
+        for (uint64_t n = b.first_node; n < b.first_node + b.n_nodes; n++) {
+            int32_t l = d->node_child[2 * n], r = d->node_child[2 * n + 1];
+            if (l >= 0) {
+                if ((uint64_t)l >= d->n_nodes || r < 0 || (uint64_t)r >= d->n_nodes) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh child out of range");
+            } else {
+                if (r < 0 || r > 1) return fail(VRJ_ERR_UNSUPPORTED, "bvh leaves hold at most one triangle (as the reference builds them)");
+                if (r == 1 && (uint64_t)(~l) >= d->n_triangles) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh leaf triangle out of range");
+            }
+        }
+    }
+    return VRJ_OK;
+}
+
+Scratch *acquire_scratch(VrjScene *sc) {
+    std::lock_guard<std::mutex> g(sc->pool_mutex);
+    if (sc->pool.empty()) return new Scratch();
+    Scratch *s = sc->pool.back();
+    sc->pool.pop_back();
+    return s;
+}
+void release_scratch(VrjScene *sc, Scratch *s) {
+    std::lock_guard<std::mutex> g(sc->pool_mutex);
+    if (sc->pool.size() < 4) sc->pool.push_back(s);
+    else delete s;
+}
+
+VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t steps, uint32_t n_lights, size_t n_light_samples) {
+    if (!s->stream) {
+        VRJ_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        VRJ_CUDA(cudaEventCreate(&s->ev0));
+        VRJ_CUDA(cudaEventCreate(&s->ev1));
+        VRJ_CUDA(cudaMallocHost(&s->host_count, 64 * sizeof(uint32_t)));
+    }
+    if (s->capacity < capacity) {
+        for (int i = 0; i < 2; i++)
+            for (int k = 0; k < 6; k++) {
+                if (s->queues[i][k].p) cudaFree(s->queues[i][k].p), s->queues[i][k].p = nullptr;
+                VRJ_CUDA(s->queues[i][k].alloc(capacity * 16));
+            }
+        if (s->photons.p) cudaFree(s->photons.p), s->photons.p = nullptr;
+        VRJ_CUDA(s->photons.alloc(capacity * sizeof(double2)));
+        s->capacity = capacity;
+    }
+    if (s->npix < npix) {
+        DeviceBuffer *bufs[5] = {&s->acc_colour, &s->acc_sum, &s->acc_bias, &s->acc_weight, &s->acc_wbias};
+        size_t per[5] = {3, 3, 3, 1, 1};
+        for (int i = 0; i < 5; i++) {
+            if (bufs[i]->p) cudaFree(bufs[i]->p), bufs[i]->p = nullptr;
+            VRJ_CUDA(bufs[i]->alloc(npix * per[i] * sizeof(double)));
+        }
+        s->npix = npix;
+    }
+    if (s->steps < steps) {
+        if (s->counters.p) cudaFree(s->counters.p), s->counters.p = nullptr;
+        VRJ_CUDA(s->counters.alloc((size_t)steps * 2 * sizeof(uint32_t)));
+        s->steps = steps;
+    }
+    if (!s->stats.p) VRJ_CUDA(s->stats.alloc(ST_COUNT * sizeof(unsigned long long)));
+    if (!s->lights.p || s->lights.bytes < (size_t)(n_lights + 1) * sizeof(LightDev)) {
+        if (s->lights.p) cudaFree(s->lights.p), s->lights.p = nullptr;
+        VRJ_CUDA(s->lights.alloc((size_t)(n_lights + 1) * sizeof(LightDev)));
+    }
+    if (!s->light_samples.p || s->light_samples.bytes < n_light_samples * sizeof(double)) {
+        if (s->light_samples.p) cudaFree(s->light_samples.p), s->light_samples.p = nullptr;
+        VRJ_CUDA(s->light_samples.alloc(std::max<size_t>(2, n_light_samples) * sizeof(double)));
+    }
+    return VRJ_OK;
+}
+
+template <typename K>
+int persistent_grid(const VrjScene *sc, K kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return sc->sm_count * per_sm;
+}
+
+template <typename NT, bool COUNT>
+VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, uint64_t *launches) {
+    const uint32_t steps = rc.max_depth + 2;
+    uint32_t *counts = s->counters.as<uint32_t>();    // queue length produced by step k
+    uint32_t *work = counts + steps;                  // work-fetch counter of step k
+    VRJ_CUDA(cudaMemsetAsync(counts, 0, (size_t)steps * 2 * sizeof(uint32_t), s->stream));
+    unsigned long long *stats = s->stats.as<unsigned long long>();
+    double2 *photons = s->photons.as<double2>();
+    VRJ_CUDA(s->mark(-1));
+    {
+        auto k = k_primary<NT, COUNT>;
+        int grid = persistent_grid(sc, k);
+        k<<<grid, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), counts + 0, work + 0, photons, stats, whitted ? 0 : 1);
+        (*launches)++;
+        VRJ_CUDA(s->mark(0));
+    }
+    // SimpleRandom needs at most max_depth levels, Whitted max_depth + 1 (limit 0 still shades)
+    const uint32_t levels = whitted ? rc.max_depth + 1 : rc.max_depth;
+    int grid_b = whitted ? persistent_grid(sc, k_bounce<NT, COUNT, true>) : persistent_grid(sc, k_bounce<NT, COUNT, false>);
+    for (uint32_t k = 0; k < levels; k++) {
+        PathQueue in = s->queue(k & 1), out = s->queue((k + 1) & 1);
+        if (whitted)
+            k_bounce<NT, COUNT, true><<<grid_b, 128, 0, s->stream>>>(sc->dev, rc, in, counts + k, out, counts + k + 1, work + k + 1, photons, stats);
+        else
+            k_bounce<NT, COUNT, false><<<grid_b, 128, 0, s->stream>>>(sc->dev, rc, in, counts + k, out, counts + k + 1, work + k + 1, photons, stats);
+        (*launches)++;
+        VRJ_CUDA(s->mark(1));
+        // long recursion limits: stop launching once the queue has drained
+        if (levels > 12 && (k + 1) % 8 == 0 && k + 1 < levels) {
+            VRJ_CUDA(cudaMemcpyAsync(s->host_count, counts + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+            VRJ_CUDA(cudaStreamSynchronize(s->stream));
+            if (*s->host_count == 0) break;
+        }
+    }
+    AccumDev acc;
+    acc.colour = s->acc_colour.as<double>(), acc.sum = s->acc_sum.as<double>(), acc.bias = s->acc_bias.as<double>();
+    acc.weight = s->acc_weight.as<double>(), acc.weight_bias = s->acc_wbias.as<double>();
+    k_resolve<<<(rc.npix + 255) / 256, 256, 0, s->stream>>>(acc, photons, rc.npix, rc.batch_samples);
+    (*launches)++;
+    VRJ_CUDA(s->mark(2));
+    VRJ_CUDA(cudaGetLastError());
+    return VRJ_OK;
+}
+
+void fill_stats(VrjStats *st, const unsigned long long *h, uint64_t launches, float ms) {
+    st->primary_rays = h[ST_PRIMARY], st->bounce_rays = h[ST_BOUNCE], st->shadow_rays = h[ST_SHADOW];
+    st->paths_missed = h[ST_MISSED], st->paths_escaped = h[ST_ESCAPED], st->paths_depth_limited = h[ST_LIMITED];
+    st->node_visits = h[ST_NODES], st->triangle_tests = h[ST_TRIS];
+    st->kernel_launches = launches;
+    st->device_ms = ms;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *vrj_last_error(void) { return g_error.c_str(); }
+int32_t vrj_abi_version(void) { return VRJ_ABI_VERSION; }
+int32_t vrj_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out) {
+    if (!out) return fail(VRJ_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    VrjStatus st = validate(d);
+    if (st != VRJ_OK) return st;
+    VRJ_CUDA(cudaSetDevice(device));
+    VrjScene *sc = new VrjScene();
+    sc->device = device;
+    cudaDeviceProp prop;
+    cudaError_t pe = cudaGetDeviceProperties(&prop, device);
+    if (pe != cudaSuccess) {
+        delete sc;
+        return fail(VRJ_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(pe));
+    }
+    sc->sm_count = prop.multiProcessorCount;
+    sc->n_spectra = d->n_spectra;
+
+#define VRJ_TRY(expr)             \
+    do {                          \
+        VrjStatus s_ = (expr);    \
+        if (s_ != VRJ_OK) {       \
+            delete sc;            \
+            return s_;            \
+        }                         \
+    } while (0)
+
+    // spectra / materials / analytic primitives
+    std::vector<SpectrumDev> spectra(d->n_spectra);
+    for (uint32_t i = 0; i < d->n_spectra; i++)
+        spectra[i] = SpectrumDev{d->spectra[i].shortest_wavelength, d->spectra[i].longest_wavelength, d->spectra[i].first_sample, d->spectra[i].n_samples};
+    std::vector<double> samples(d->spectrum_samples, d->spectrum_samples + d->n_spectrum_samples);
+    std::vector<MaterialDev> materials(d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; i++)
+        materials[i] = MaterialDev{d->materials[i].kind, d->materials[i].spectrum, d->materials[i].p0, d->materials[i].p1, d->materials[i].p2};
+    std::vector<SphereDev> spheres(d->n_spheres);
+    for (uint32_t i = 0; i < d->n_spheres; i++)
+        spheres[i] = SphereDev{d->spheres[i].centre[0], d->spheres[i].centre[1], d->spheres[i].centre[2], d->spheres[i].radius, d->spheres[i].material, 0};
+    std::vector<PlaneDev> planes(d->n_planes);
+    for (uint32_t i = 0; i < d->n_planes; i++) {
+        PlaneDev &p = planes[i];
+        for (int k = 0; k < 3; k++) p.n[k] = d->planes[i].normal[k], p.t[k] = d->planes[i].tangent[k], p.c[k] = d->planes[i].cotangent[k];
+        p.distance = d->planes[i].distance_from_origin, p.material = d->planes[i].material, p.pad = 0;
+    }
+    // triangles: 80-byte position and normal records
+    std::vector<double> tri_pos((size_t)d->n_triangles * 10), tri_nrm((size_t)d->n_triangles * 10);
+    for (uint64_t t = 0; t < d->n_triangles; t++) {
+        const double *v[3] = {d->tri_v0 + 4 * t, d->tri_v1 + 4 * t, d->tri_v2 + 4 * t};
+        const double *n[3] = {d->tri_n0 + 4 * t, d->tri_n1 + 4 * t, d->tri_n2 + 4 * t};
+        for (int k = 0; k < 3; k++)
+            for (int c = 0; c < 3; c++) tri_pos[t * 10 + 3 * k + c] = v[k][c], tri_nrm[t * 10 + 3 * k + c] = n[k][c];
+        uint64_t bits = ((uint64_t)d->tri_prim_id[t] << 32) | d->tri_material[t];
+        std::memcpy(&tri_pos[t * 10 + 9], &bits, 8);
+        tri_nrm[t * 10 + 9] = 0.0;
+    }
+    // wide nodes per BVH
+    WideBuilder wb;
+    wb.d = d;
+    std::vector<uint32_t> bvh_root(d->n_bvhs, 0);
+    std::vector<bool> bvh_empty(d->n_bvhs, false);
+    for (uint32_t b = 0; b < d->n_bvhs; b++) {
+        const VrjBvh &bv = d->bvhs[b];
+        if (bv.n_nodes == 0 || bv.n_triangles == 0) {
+            bvh_empty[b] = true;
+            continue;
+        }
+        int64_t root = (int64_t)bv.first_node;
+        if (wb.is_leaf(root)) {
+            size_t w = wb.new_node();
+            bool e;
+            int32_t r = wb.child_ref(root, &e);
+            wb.put_child(w, 0, root, r, e);
+            wb.put_child(w, 1, root, -1, true);
+            bvh_root[b] = (uint32_t)w;
+        } else {
+            bvh_root[b] = (uint32_t)wb.build(root);
+        }
+    }
+    std::vector<ItemDev> items;
+    for (uint32_t i = 0; i < d->n_items; i++) {
+        const VrjItem &it = d->items[i];
+        if (it.kind == VRJ_ITEM_BVH && bvh_empty[it.index]) continue; // an empty BVH never reports a hit
+        ItemDev id{it.kind, it.index, it.object_id, it.prim_id, it.kind == VRJ_ITEM_BVH ? bvh_root[it.index] : 0u, 0u};
+        items.push_back(id);
+    }
+    std::vector<float4> n32(wb.n32.size() / 4);
+    std::memcpy(n32.data(), wb.n32.data(), wb.n32.size() * sizeof(float));
+    std::vector<double2> n64(wb.n64.size() / 2), tp(tri_pos.size() / 2), tn(tri_nrm.size() / 2);
+    std::memcpy(n64.data(), wb.n64.data(), wb.n64.size() * sizeof(double));
+    std::memcpy(tp.data(), tri_pos.data(), tri_pos.size() * sizeof(double));
+    std::memcpy(tn.data(), tri_nrm.data(), tri_nrm.size() * sizeof(double));
+
+    VRJ_TRY(upload(sc, n32, sc->dev.nodes32));
+    VRJ_TRY(upload(sc, n64, sc->dev.nodes64));
+    VRJ_TRY(upload(sc, tp, sc->dev.tri_pos));
+    VRJ_TRY(upload(sc, tn, sc->dev.tri_nrm));
+    VRJ_TRY(upload(sc, spheres, sc->dev.spheres));
+    VRJ_TRY(upload(sc, planes, sc->dev.planes));
+    VRJ_TRY(upload(sc, materials, sc->dev.materials));
+    VRJ_TRY(upload(sc, spectra, sc->dev.spectra));
+    VRJ_TRY(upload(sc, samples, sc->dev.spectrum_samples));
+    VRJ_TRY(upload(sc, items, sc->dev.items));
+    sc->dev.n_items = (uint32_t)items.size();
+    for (int k = 0; k < 3; k++) sc->dev.cam[k] = d->camera_location[k];
+    *out = sc;
+    return VRJ_OK;
+#undef VRJ_TRY
+}
+
+void vrj_scene_destroy(VrjScene *scene) {
+    if (!scene) return;
+    cudaSetDevice(scene->device);
+    delete scene;
+}
+
+uint64_t vrj_scene_device_bytes(const VrjScene *scene) { return scene ? scene->device_bytes : 0; }
+
+VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t height, uint64_t width,
+                          const VrjRenderParams *p, VrjAccumOut *out) {
+    VrjScene *scene = const_cast<VrjScene *>(scene_c);
+    if (!scene || !tile || !p || !out) return fail(VRJ_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (tile->end_column < tile->start_column || tile->end_row < tile->start_row || tile->end_column > width || tile->end_row > height)
+        return fail(VRJ_ERR_INVALID_ARGUMENT, "tile outside the image");
+    if (width * height > 0xffffffffull) return fail(VRJ_ERR_UNSUPPORTED, "image larger than 2^32 pixels");
+    if (p->integrator > VRJ_INTEGRATOR_WHITTED) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown integrator");
+    if (p->bvh_filter > VRJ_FILTER_F64) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
+    if (p->max_depth > 65535) return fail(VRJ_ERR_INVALID_ARGUMENT, "max_depth exceeds u16 (RECURSION_LIMIT is a u16)");
+    if (p->n_lights && !p->lights) return fail(VRJ_ERR_INVALID_ARGUMENT, "lights is NULL");
+    size_t n_light_samples = 0;
+    for (uint32_t i = 0; i < p->n_lights; i++) {
+        if (p->lights[i].spectrum.n_samples < 2 || !p->lights[i].spectrum.samples) return fail(VRJ_ERR_INVALID_ARGUMENT, "light spectrum needs >= 2 samples");
+        n_light_samples += p->lights[i].spectrum.n_samples;
+    }
+    if (p->ambient_light) {
+        if (p->ambient_light->n_samples < 2 || !p->ambient_light->samples) return fail(VRJ_ERR_INVALID_ARGUMENT, "ambient spectrum needs >= 2 samples");
+        n_light_samples += p->ambient_light->n_samples;
+    }
+    const uint64_t tw = tile->end_column - tile->start_column, th = tile->end_row - tile->start_row;
+    const uint64_t npix = tw * th;
+    if (out->stats) std::memset(out->stats, 0, sizeof(VrjStats));
+    if (npix == 0 || p->spp == 0) return VRJ_OK;
+    VRJ_CUDA(cudaSetDevice(scene->device));
+
+    // batch: as many samples of the whole tile in flight as fit the path budget
+    const uint64_t path_budget = 1ull << 24;
+    uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(p->spp, path_budget / npix));
+    if (npix * (uint64_t)batch > 0xfffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "tile too large");
+    const bool whitted = p->integrator == VRJ_INTEGRATOR_WHITTED;
+    Scratch *s = acquire_scratch(scene);
+    struct Releaser {
+        VrjScene *sc;
+        Scratch *s;
+        ~Releaser() { release_scratch(sc, s); }
+    } releaser{scene, s};
+    VrjStatus st = ensure_scratch(s, npix * batch, npix, p->max_depth + 2, p->n_lights, n_light_samples);
+    if (st != VRJ_OK) return st;
+
+    const cudaMemcpyKind in_kind = out->memory == VRJ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind out_kind = out->memory == VRJ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    struct Arr {
+        double *user;
+        DeviceBuffer *dev;
+        size_t per;
+    } arrs[5] = {{out->colour, &s->acc_colour, 3}, {out->colour_sum, &s->acc_sum, 3}, {out->colour_bias, &s->acc_bias, 3},
+                 {out->weight, &s->acc_weight, 1}, {out->weight_bias, &s->acc_wbias, 1}};
+    for (int i = 1; i < 5; i++) {
+        if (out->accumulate && arrs[i].user)
+            VRJ_CUDA(cudaMemcpyAsync(arrs[i].dev->p, arrs[i].user, npix * arrs[i].per * sizeof(double), in_kind, s->stream));
+        else
+            VRJ_CUDA(cudaMemsetAsync(arrs[i].dev->p, 0, npix * arrs[i].per * sizeof(double), s->stream));
+    }
+    VRJ_CUDA(cudaMemsetAsync(s->stats.p, 0, ST_COUNT * sizeof(unsigned long long), s->stream));
+    if (p->n_lights || p->ambient_light) {
+        std::vector<LightDev> lights(p->n_lights + 1);
+        std::vector<double> lsamples;
+        auto put = [&lsamples](const VrjSpectrumData &sd) {
+            SpectrumDev d{sd.shortest_wavelength, sd.longest_wavelength, (uint32_t)lsamples.size(), sd.n_samples};
+            lsamples.insert(lsamples.end(), sd.samples, sd.samples + sd.n_samples);
+            return d;
+        };
+        for (uint32_t i = 0; i < p->n_lights; i++) {
+            for (int k = 0; k < 3; k++) lights[i].dir[k] = p->lights[i].direction[k];
+            lights[i].spectrum = put(p->lights[i].spectrum);
+        }
+        lights[p->n_lights] = LightDev{};
+        if (p->ambient_light) lights[p->n_lights].spectrum = put(*p->ambient_light);
+        VRJ_CUDA(cudaMemcpyAsync(s->lights.p, lights.data(), lights.size() * sizeof(LightDev), cudaMemcpyHostToDevice, s->stream));
+        if (!lsamples.empty())
+            VRJ_CUDA(cudaMemcpyAsync(s->light_samples.p, lsamples.data(), lsamples.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        VRJ_CUDA(cudaStreamSynchronize(s->stream)); // the staging vectors are locals
+    }
+
+    RenderConst rc{};
+    rc.width = width, rc.height = height;
+    rc.start_column = tile->start_column, rc.start_row = tile->start_row;
+    rc.tile_w = (uint32_t)tw, rc.tile_h = (uint32_t)th, rc.npix = (uint32_t)npix;
+    rc.sample_stride = p->sample_stride ? p->sample_stride : 1;
+    rc.seed = p->seed;
+    rc.max_depth = p->max_depth, rc.n_lights = p->n_lights, rc.has_ambient = p->ambient_light ? 1u : 0u;
+    rc.bias = p->bias;
+    { // camera.rs:24-34
+        double w = (double)width, h = (double)height;
+        if (w > h) rc.film_w = w / h, rc.film_h = 1.0;
+        else rc.film_w = 1.0, rc.film_h = w / h;
+    }
+    rc.lights = s->lights.as<LightDev>();
+    rc.light_samples = s->light_samples.as<double>();
+
+    uint64_t launches = 0;
+    s->n_marks = 0;
+    VRJ_CUDA(cudaEventRecord(s->ev0, s->stream));
+    for (uint32_t done = 0; done < p->spp; done += batch) {
+        rc.batch_samples = std::min(batch, p->spp - done);
+        rc.first_sample = p->sample_offset + (uint64_t)done * rc.sample_stride;
+        if (p->count_traversal) {
+            st = p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, true>(scene, s, rc, whitted, &launches)
+                                                 : run_batch<float, true>(scene, s, rc, whitted, &launches);
+        } else {
+            st = p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, false>(scene, s, rc, whitted, &launches)
+                                                 : run_batch<float, false>(scene, s, rc, whitted, &launches);
+        }
+        if (st != VRJ_OK) return st;
+        if (out->photons) {
+            // debug output, batch-major: [(sample * npix + pixel) * 2]
+            VRJ_CUDA(cudaMemcpyAsync(out->photons + (size_t)done * npix * 2, s->photons.p,
+                                     (size_t)rc.batch_samples * npix * sizeof(double2), out_kind, s->stream));
+        }
+    }
+    VRJ_CUDA(cudaEventRecord(s->ev1, s->stream));
+    for (int i = 0; i < 5; i++)
+        if (arrs[i].user)
+            VRJ_CUDA(cudaMemcpyAsync(arrs[i].user, arrs[i].dev->p, npix * arrs[i].per * sizeof(double), out_kind, s->stream));
+    unsigned long long hstats[ST_COUNT];
+    VRJ_CUDA(cudaMemcpyAsync(hstats, s->stats.p, sizeof hstats, cudaMemcpyDeviceToHost, s->stream));
+    VRJ_CUDA(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    VRJ_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    if (out->stats) {
+        fill_stats(out->stats, hstats, launches, ms);
+        double cls_ms[3] = {0, 0, 0};
+        uint64_t cls_n[3] = {0, 0, 0};
+        for (size_t i = 1; i < s->n_marks; i++) {
+            int c = s->mark_class[i];
+            if (c < 0) continue;
+            float seg = 0.f;
+            if (cudaEventElapsedTime(&seg, s->marks[i - 1], s->marks[i]) == cudaSuccess) cls_ms[c] += seg, cls_n[c]++;
+        }
+        out->stats->primary_ms = cls_ms[0], out->stats->bounce_ms = cls_ms[1], out->stats->resolve_ms = cls_ms[2];
+        out->stats->primary_launches = cls_n[0], out->stats->bounce_launches = cls_n[1], out->stats->resolve_launches = cls_n[2];
+    }
+    return VRJ_OK;
+}
+
+VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *origins, const double *directions,
+                         uint32_t bvh_filter, int32_t *object_id, int32_t *prim_id, double *t, VrjStats *stats) {
+    VrjScene *scene = const_cast<VrjScene *>(scene_c);
+    if (!scene || (n && (!origins || !directions || !object_id || !prim_id || !t)))
+        return fail(VRJ_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (bvh_filter > VRJ_FILTER_F64) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
+    if (stats) std::memset(stats, 0, sizeof(VrjStats));
+    if (n == 0) return VRJ_OK;
+    VRJ_CUDA(cudaSetDevice(scene->device));
+    DeviceBuffer d_o, d_d, d_obj, d_prim, d_t, d_stats;
+    VRJ_CUDA(d_o.alloc(n * 24));
+    VRJ_CUDA(d_d.alloc(n * 24));
+    VRJ_CUDA(d_obj.alloc(n * 4));
+    VRJ_CUDA(d_prim.alloc(n * 4));
+    VRJ_CUDA(d_t.alloc(n * 8));
+    VRJ_CUDA(d_stats.alloc(ST_COUNT * sizeof(unsigned long long)));
+    cudaStream_t stream;
+    VRJ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    struct Cleanup {
+        cudaStream_t s;
+        cudaEvent_t a, b;
+        ~Cleanup() { cudaStreamDestroy(s), cudaEventDestroy(a), cudaEventDestroy(b); }
+    } cleanup{stream, e0, e1};
+    VRJ_CUDA(cudaMemcpyAsync(d_o.p, origins, n * 24, cudaMemcpyHostToDevice, stream));
+    VRJ_CUDA(cudaMemcpyAsync(d_d.p, directions, n * 24, cudaMemcpyHostToDevice, stream));
+    VRJ_CUDA(cudaMemsetAsync(d_stats.p, 0, ST_COUNT * sizeof(unsigned long long), stream));
+    int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)scene->sm_count * 16);
+    VRJ_CUDA(cudaEventRecord(e0, stream));
+    if (bvh_filter == VRJ_FILTER_F64)
+        k_trace_rays<double, true><<<grid, 128, 0, stream>>>(scene->dev, n, d_o.as<double>(), d_d.as<double>(), d_obj.as<int32_t>(),
+                                                             d_prim.as<int32_t>(), d_t.as<double>(), d_stats.as<unsigned long long>());
+    else
+        k_trace_rays<float, true><<<grid, 128, 0, stream>>>(scene->dev, n, d_o.as<double>(), d_d.as<double>(), d_obj.as<int32_t>(),
+                                                            d_prim.as<int32_t>(), d_t.as<double>(), d_stats.as<unsigned long long>());
+    VRJ_CUDA(cudaGetLastError());
+    VRJ_CUDA(cudaEventRecord(e1, stream));
+    VRJ_CUDA(cudaMemcpyAsync(object_id, d_obj.p, n * 4, cudaMemcpyDeviceToHost, stream));
+    VRJ_CUDA(cudaMemcpyAsync(prim_id, d_prim.p, n * 4, cudaMemcpyDeviceToHost, stream));
+    VRJ_CUDA(cudaMemcpyAsync(t, d_t.p, n * 8, cudaMemcpyDeviceToHost, stream));
+    unsigned long long hstats[ST_COUNT];
+    VRJ_CUDA(cudaMemcpyAsync(hstats, d_stats.p, sizeof hstats, cudaMemcpyDeviceToHost, stream));
+    VRJ_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    VRJ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (stats) fill_stats(stats, hstats, 1, ms);
+    return VRJ_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,357 @@
+// vrj_kernels.cuh -- the wavefront: persistent-thread kernels for one batch of samples.
+//
+//   k_primary : camera ray (camera.rs:45-66) -> closest hit -> miss: black sample
+//               (camera.rs:110-113); hit: draw the wavelength (photon.rs:18-24), enqueue.
+//   k_bounce  : one level of Integrator::integrate for every queued path: rebuild the hit,
+//               sample the material, trace the bounce ray (and, for Whitted, the shadow rays),
+//               finish the path (sky / depth limit) or enqueue it, warp-ballot compacted.
+//   k_resolve : per pixel, apply the batch's samples IN SAMPLE ORDER to the Kahan accumulator
+//               (AccumulationBuffer::update_pixel, accumulation_buffer.rs:44-60).
+//
+// The recursion of simple_random_integrator.rs:12-55 is unrolled with an affine accumulator:
+// every bsdf in the crate maps incoming intensity x to a*x + b, so after bounce k
+//   B += A * b_k ;  A *= a_k * (pdf_k * |W_k . n_k|)      and the sample is A * L_leaf + B.
+#pragma once
+#include "vrj_traverse.cuh"
+
+namespace vrj {
+
+struct LightDev {
+    double dir[3];
+    SpectrumDev spectrum; // samples live in RenderConst::light_samples
+};
+
+// Double-buffered path queue, structure of 16-byte arrays (every access is coalesced).
+struct PathQueue {
+    double2 *q0; // origin.x, origin.y      of the ray that produced the hit
+    double2 *q1; // origin.z, direction.x
+    double2 *q2; // direction.y, direction.z
+    double2 *q3; // wavelength, A
+    double2 *q4; // B, bits{item, triangle}
+    uint4 *q5;   // result slot, rng draw ordinal, recursion limit left, unused
+};
+
+struct RenderConst {
+    uint64_t width, height;             // full image
+    uint64_t start_column, start_row;   // tile origin
+    uint32_t tile_w, tile_h, npix;      // tile
+    uint32_t batch_samples;             // samples in this batch
+    uint64_t first_sample;              // sample index of batch slot 0
+    uint64_t sample_stride;
+    uint64_t seed;
+    uint32_t max_depth, n_lights;
+    uint32_t has_ambient, pad;
+    double bias;
+    double film_w, film_h;
+    const LightDev *lights;      // n_lights entries, then (if has_ambient) the ambient light's spectrum in entry n_lights
+    const double *light_samples;
+};
+
+__device__ __forceinline__ double light_intensity(const RenderConst &rc, const SpectrumDev &s, double wavelength) {
+    const double *p = rc.light_samples + s.first;
+    return spectrum_lookup(s.shortest, s.longest, s.n, wavelength, [p](uint32_t i) { return __ldg(p + i); });
+}
+
+enum { ST_PRIMARY = 0, ST_BOUNCE, ST_SHADOW, ST_MISSED, ST_ESCAPED, ST_LIMITED, ST_NODES, ST_TRIS, ST_COUNT };
+
+struct LocalStats {
+    uint32_t v[ST_COUNT];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < ST_COUNT; i++) v[i] = 0;
+    }
+    __device__ __forceinline__ void flush(unsigned long long *g) {
+#pragma unroll
+        for (int i = 0; i < ST_COUNT; i++) {
+            uint32_t s = __reduce_add_sync(0xffffffffu, v[i]);
+            if ((threadIdx.x & 31) == 0 && s) atomicAdd(g + i, (unsigned long long)s);
+        }
+    }
+};
+
+// warp-ballot compaction: one atomic per warp reserves a contiguous run of the output queue
+__device__ __forceinline__ uint32_t queue_reserve(bool alive, uint32_t *count) {
+    uint32_t mask = __ballot_sync(0xffffffffu, alive);
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0 && mask) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void queue_store(const PathQueue &q, uint32_t idx, D3 o, D3 d, double wl, double A, double B,
+                                            int item, int tri, uint32_t slot, uint32_t ordinal, uint32_t limit) {
+    q.q0[idx] = make_double2(o.x, o.y);
+    q.q1[idx] = make_double2(o.z, d.x);
+    q.q2[idx] = make_double2(d.y, d.z);
+    q.q3[idx] = make_double2(wl, A);
+    long long bits = (long long)(((unsigned long long)(uint32_t)tri << 32) | (unsigned long long)(uint32_t)item);
+    q.q4[idx] = make_double2(B, __longlong_as_double(bits));
+    q.q5[idx] = make_uint4(slot, ordinal, limit, 0u);
+}
+
+// Ray::new (raycasting/mod.rs:41-46) then .bias(amount) (raycasting/mod.rs:58-60): normalise, offset, normalise again
+__device__ __forceinline__ void biased_ray(D3 origin, D3 direction, double amount, D3 &o, D3 &d) {
+    D3 d1 = normalize(direction);
+    o = origin + d1 * amount;
+    d = normalize(d1);
+}
+
+__device__ __forceinline__ void slot_to_pixel(const RenderConst &rc, uint32_t slot, uint32_t &pixel_global,
+                                              uint64_t &sample, uint64_t &grow, uint64_t &gcol) {
+    uint32_t s = slot / rc.npix, p = slot - s * rc.npix;
+    uint32_t row = p / rc.tile_w, col = p - row * rc.tile_w;
+    grow = rc.start_row + row, gcol = rc.start_column + col;
+    pixel_global = (uint32_t)(grow * rc.width + gcol);
+    sample = rc.first_sample + (uint64_t)s * rc.sample_stride;
+}
+
+template <typename NT, bool COUNT>
+__global__ void __launch_bounds__(128) k_primary(DevScene sc, RenderConst rc, PathQueue out, uint32_t *out_count,
+                                                 uint32_t *work, double2 *photons, unsigned long long *stats,
+                                                 int simple_random) {
+    const uint32_t n = rc.npix * rc.batch_samples;
+    const uint32_t lane = threadIdx.x & 31;
+    LocalStats ls;
+    ls.clear();
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t slot = base + lane;
+        bool active = slot < n;
+        bool alive = false;
+        D3 o = d3(0, 0, 0), d = d3(0, 0, 1);
+        double wl = 0.0;
+        Hit hit;
+        hit.item = -1, hit.tri = -1, hit.t = 0.0;
+        uint32_t ordinal = 0;
+        if (active) {
+            uint32_t pixel;
+            uint64_t sample, grow, gcol;
+            slot_to_pixel(rc, slot, pixel, sample, grow, gcol);
+            Rng rng;
+            rng.init(rc.seed, pixel, sample, 0);
+            double ux = rng.f64(), uy = rng.f64();
+            // camera.rs:45-66
+            double px = ((double)gcol + ux) * (rc.film_w * (1.0 / (double)rc.width)) - rc.film_w * 0.5;
+            double py = ((double)(rc.height - (grow + 1)) + uy) * (rc.film_h * (1.0 / (double)rc.height)) - rc.film_h * 0.5;
+            o = d3(sc.cam[0], sc.cam[1], sc.cam[2]);
+            d = normalize(d3(px, py, 1.0));
+            TraceCounters tc = {0, 0};
+            hit = trace_closest<NT, COUNT, false>(sc, o, d, tc);
+            ls.v[ST_PRIMARY]++;
+            if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
+            if (hit.item < 0) {
+                photons[slot] = make_double2(0.0, 0.0); // camera.rs:110-113
+                ls.v[ST_MISSED]++;
+            } else if (simple_random && rc.max_depth == 0) {
+                rng.f64();                              // Photon::random_wavelength() is still drawn
+                photons[slot] = make_double2(0.0, 0.0); // simple_random_integrator.rs:20-25
+                ls.v[ST_LIMITED]++;
+            } else {
+                wl = 380.0 + (740.0 - 380.0) * rng.f64(); // photon.rs:18-24
+                ordinal = rng.ordinal;
+                alive = true;
+            }
+        }
+        uint32_t idx = queue_reserve(alive, out_count);
+        if (alive) queue_store(out, idx, o, d, wl, 1.0, 0.0, hit.item, hit.tri, slot, ordinal, rc.max_depth);
+    }
+    ls.flush(stats);
+}
+
+template <typename NT, bool COUNT, bool WHITTED>
+__global__ void __launch_bounds__(128) k_bounce(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
+                                                PathQueue out, uint32_t *out_count, uint32_t *work, double2 *photons,
+                                                unsigned long long *stats) {
+    const uint32_t n = *in_count;
+    const uint32_t lane = threadIdx.x & 31;
+    LocalStats ls;
+    ls.clear();
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t j = base + lane;
+        bool active = j < n;
+        bool alive = false;
+        D3 no = d3(0, 0, 0), nd = d3(0, 0, 1);
+        double wl = 0.0, A = 0.0, B = 0.0;
+        Hit nh;
+        nh.item = -1, nh.tri = -1, nh.t = 0.0;
+        uint32_t slot = 0, ordinal = 0, limit = 0;
+        if (active) {
+            double2 a0 = in.q0[j], a1 = in.q1[j], a2 = in.q2[j], a3 = in.q3[j], a4 = in.q4[j];
+            uint4 a5 = in.q5[j];
+            D3 o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
+            wl = a3.x, A = a3.y, B = a4.x;
+            long long bits = __double_as_longlong(a4.y);
+            int item = (int)(uint32_t)(bits & 0xffffffffll), tri = (int)(uint32_t)((unsigned long long)bits >> 32);
+            slot = a5.x, ordinal = a5.y, limit = a5.z;
+
+            HitFrame h;
+            bool ok = rebuild_hit(sc, o, d, item, tri, h);
+            // algebra_utils.rs:3-5, mat3.rs:111-118
+            M3 w2b = from_rows(h.tangent, h.cotangent, h.normal), b2w;
+            ok = try_inverse(w2b, b2w) && ok;
+            if (!ok) {
+                // the reference panics here (simple_random_integrator.rs:28,31); report a NaN sample
+                photons[slot] = make_double2(wl, CUDART_NAN);
+            } else {
+                MaterialDev m = sc.materials[h.material];
+                double s = spectrum_intensity(sc.spectra, sc.spectrum_samples, m.spectrum, wl);
+                D3 w_retro = mul(w2b, h.retro);
+                TraceCounters tc = {0, 0};
+                if (WHITTED) {
+                    // whitted_integrator.rs:33-50: one shadow ray per light
+                    double direct = 0.0; // fold starts from photon.intensity == 0
+                    for (uint32_t li = 0; li < rc.n_lights; li++) {
+                        LightDev L = rc.lights[li];
+                        D3 ldir = d3(L.dir[0], L.dir[1], L.dir[2]);
+                        D3 so, sd;
+                        biased_ray(h.location, ldir, rc.bias, so, sd);
+                        Hit sh = trace_closest<NT, COUNT, true>(sc, so, sd, tc);
+                        ls.v[ST_SHADOW]++;
+                        double term;
+                        if (sh.item >= 0) {
+                            term = rc.has_ambient ? light_intensity(rc, rc.lights[rc.n_lights].spectrum, wl) : 0.0;
+                        } else {
+                            double emitted = light_intensity(rc, L.spectrum, wl);
+                            emitted = emitted * fabs(dot(ldir, h.normal));
+                            double la, lb;
+                            material_bsdf_affine(m, s, w_retro, mul(w2b, ldir), la, lb); // (retro, incoming) order
+                            term = la * emitted + lb;
+                        }
+                        direct += term;
+                    }
+                    B += A * direct;
+                }
+                Rng rng;
+                uint32_t pixel;
+                uint64_t sample, grow, gcol;
+                slot_to_pixel(rc, slot, pixel, sample, grow, gcol);
+                rng.init(rc.seed, pixel, sample, ordinal);
+                D3 w_s;
+                double pdf;
+                material_sample(m, s, w_retro, rng, w_s, pdf);
+                ordinal = rng.ordinal;
+                D3 W = mul(b2w, w_s);
+                biased_ray(h.location, W, rc.bias, no, nd);
+                nh = trace_closest<NT, COUNT, false>(sc, no, nd, tc);
+                ls.v[ST_BOUNCE]++;
+                if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
+                double cosine = fabs(dot(W, h.normal));
+                if (WHITTED) {
+                    // whitted_integrator.rs:52-79: bsdf(retro, sampled, L_in) * |W.n|, pdf unused
+                    if (nh.item >= 0 && limit > 0) {
+                        double ba, bb;
+                        material_bsdf_affine(m, s, w_retro, w_s, ba, bb);
+                        B += A * (bb * cosine);
+                        A *= ba * cosine;
+                        limit -= 1;
+                        alive = true;
+                    } else {
+                        photons[slot] = make_double2(wl, B * (740.0 - 380.0));
+                        if (nh.item < 0) ls.v[ST_ESCAPED]++;
+                        else ls.v[ST_LIMITED]++;
+                    }
+                } else {
+                    // simple_random_integrator.rs:39-53: bsdf(sampled, retro, L_in * pdf * |W.n|)
+                    double ba, bb;
+                    material_bsdf_affine(m, s, w_s, w_retro, ba, bb);
+                    B += A * bb;
+                    A *= ba * (pdf * cosine);
+                    if (nh.item < 0) {
+                        double L = sky(W, wl); // :43-46 (W un-normalised, as written)
+                        photons[slot] = make_double2(wl, (A * L + B) * (740.0 - 380.0));
+                        ls.v[ST_ESCAPED]++;
+                    } else if (limit - 1 == 0) {
+                        // the recursion returns Photon{0,0} (:20-25): wavelength 0 makes the sample's XYZ ~0
+                        photons[slot] = make_double2(0.0, 0.0);
+                        ls.v[ST_LIMITED]++;
+                    } else {
+                        limit -= 1;
+                        alive = true;
+                    }
+                }
+            }
+        }
+        uint32_t idx = queue_reserve(alive, out_count);
+        if (alive) queue_store(out, idx, no, nd, wl, A, B, nh.item, nh.tri, slot, ordinal, limit);
+    }
+    ls.flush(stats);
+}
+
+struct AccumDev {
+    double *colour, *sum, *bias; // 3 per pixel
+    double *weight, *weight_bias;
+};
+
+// accumulation_buffer.rs:44-60 applied for the batch's samples in sample order
+__global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t npix, uint32_t batch_samples) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    double sx = acc.sum[3 * p], sy = acc.sum[3 * p + 1], sz = acc.sum[3 * p + 2];
+    double bx = acc.bias[3 * p], by = acc.bias[3 * p + 1], bz = acc.bias[3 * p + 2];
+    double w = acc.weight[p], wb = acc.weight_bias[p];
+    for (uint32_t s = 0; s < batch_samples; s++) {
+        double2 ph = photons[(size_t)s * npix + p];
+        D3 c = cmf(ph.x) * ph.y; // colour_xyz.rs:31-35
+        const double weight = 1.0;
+        double wy = weight - wb;
+        double wt = w + wy;
+        wb = (wt - w) - wy;
+        w = wt;
+        double yx = c.x * weight - bx, yy = c.y * weight - by, yz = c.z * weight - bz;
+        double tx = sx + yx, ty = sy + yy, tz = sz + yz;
+        bx = (tx - sx) - yx, by = (ty - sy) - yy, bz = (tz - sz) - yz;
+        sx = tx, sy = ty, sz = tz;
+    }
+    acc.sum[3 * p] = sx, acc.sum[3 * p + 1] = sy, acc.sum[3 * p + 2] = sz;
+    acc.bias[3 * p] = bx, acc.bias[3 * p + 1] = by, acc.bias[3 * p + 2] = bz;
+    acc.weight[p] = w, acc.weight_bias[p] = wb;
+    double inv = 1.0 / w;
+    acc.colour[3 * p] = sx * inv, acc.colour[3 * p + 1] = sy * inv, acc.colour[3 * p + 2] = sz * inv;
+}
+
+// Sampler::sample on a caller-supplied ray list (the bit-exact id gate)
+template <typename NT, bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_rays(DevScene sc, uint64_t n, const double *origins, const double *dirs,
+                                                    int32_t *object_id, int32_t *prim_id, double *t,
+                                                    unsigned long long *stats) {
+    LocalStats ls;
+    ls.clear();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ull);
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        if (i < n) {
+            D3 o = d3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+            D3 d = normalize(d3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2])); // Ray::new
+            TraceCounters tc = {0, 0};
+            Hit h = trace_closest<NT, COUNT, false>(sc, o, d, tc);
+            ls.v[ST_PRIMARY]++;
+            if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
+            if (h.item < 0) {
+                object_id[i] = -1, prim_id[i] = -1, t[i] = CUDART_INF;
+                ls.v[ST_MISSED]++;
+            } else {
+                ItemDev it = sc.items[h.item];
+                object_id[i] = (int32_t)it.object_id;
+                if (it.kind >= 2) {
+                    D3 v0, v1, v2;
+                    uint32_t mat, pid;
+                    load_tri_pos(sc, h.tri, v0, v1, v2, mat, pid);
+                    prim_id[i] = (int32_t)pid;
+                } else {
+                    prim_id[i] = (int32_t)it.prim_id;
+                }
+                t[i] = h.t;
+            }
+        }
+    }
+    ls.flush(stats);
+}
+
+} // namespace vrj

@@ -1,0 +1,278 @@
+// vrj_traverse.cuh -- closest-hit query (Sampler::sample, sampler.rs:9-20) over the flattened scene.
+//
+// The BVH keeps the reference's topology (median split, <= 1 triangle per leaf) but is walked
+// front-to-back with t_max pruning through a CONSERVATIVE box filter; every triangle that
+// survives the filter is decided by the exact binary64 Triangle::intersect arithmetic, and ties
+// follow the reference's rule (bounding_volume_hierarchy.rs:77-92: the later leaf in DFS order
+// wins; sampler.rs:14-19 / vec_aggregate.rs:13-21: the earlier object wins).  The filter may
+// only ever pass MORE boxes than the reference's slab test (axis_aligned_bounding_box.rs:9-27),
+// so it cannot change a result; its precision (f32 or f64 nodes) is a speed knob only.
+#pragma once
+#include "vrj_device.cuh"
+
+namespace vrj {
+
+struct ItemDev {
+    uint32_t kind, index, object_id, prim_id;
+    uint32_t root; // VRJ_ITEM_BVH: index of the root wide node
+    uint32_t pad;
+};
+
+struct DevScene {
+    const float4 *__restrict__ nodes32;  // 4 x float4 per wide node (64 B)
+    const double2 *__restrict__ nodes64; // 7 x double2 per wide node (112 B)
+    const double2 *__restrict__ tri_pos; // 5 x double2 per triangle (80 B): 9 coords + {material, prim_id}
+    const double2 *__restrict__ tri_nrm; // 5 x double2 per triangle (80 B): 9 coords + pad
+    const SphereDev *__restrict__ spheres;
+    const PlaneDev *__restrict__ planes;
+    const MaterialDev *__restrict__ materials;
+    const SpectrumDev *__restrict__ spectra;
+    const double *__restrict__ spectrum_samples;
+    const ItemDev *__restrict__ items;
+    uint32_t n_items;
+    double cam[3];
+};
+
+struct Hit {
+    double t;
+    int item; // -1 = miss
+    int tri;  // triangle index (absolute) for triangle hits
+};
+
+struct TraceCounters {
+    uint32_t node_visits, tri_tests;
+};
+
+#define VRJ_LEAF_DONE (-2147483647 - 1)
+
+template <typename T>
+struct FilterTraits;
+template <>
+struct FilterTraits<float> {
+    static __device__ __forceinline__ float rel() { return 9.5367431640625e-07f; }  // 2^-20
+    static __device__ __forceinline__ double abs_factor() { return 9.5367431640625e-07; }
+    static __device__ __forceinline__ double big() { return 1e18; }
+    static __device__ __forceinline__ float down(double v) { return __double2float_rd(v); }
+    static __device__ __forceinline__ float up(double v) { return __double2float_ru(v); }
+    static __device__ __forceinline__ float near(double v) { return __double2float_rn(v); }
+    static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float abs_(float a) { return fabsf(a); }
+};
+template <>
+struct FilterTraits<double> {
+    static __device__ __forceinline__ double rel() { return 9.094947017729282e-13; }  // 2^-40
+    static __device__ __forceinline__ double abs_factor() { return 9.094947017729282e-13; }
+    static __device__ __forceinline__ double big() { return 1e150; }
+    static __device__ __forceinline__ double down(double v) { return v; }
+    static __device__ __forceinline__ double up(double v) { return v; }
+    static __device__ __forceinline__ double near(double v) { return v; }
+    static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+    static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double abs_(double a) { return fabs(a); }
+};
+
+// Per-ray constants of the conservative slab filter: t = b * id - o * id with the o*id term
+// shifted by an absolute pad (rounding of o, 1/d and the box to NodeT) in the widening direction;
+// a relative pad is applied to the final enter / exit values.
+template <typename T>
+struct FilterRay {
+    T id[3], cn[3], cf[3];
+};
+template <typename T>
+__device__ __forceinline__ FilterRay<T> filter_ray(D3 o, D3 d) {
+    typedef FilterTraits<T> F;
+    FilterRay<T> f;
+    const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double id = 1.0 / dd[k];
+        if (!(fabs(id) <= F::big())) id = copysign(F::big(), dd[k]);
+        double ood = oo[k] * id;
+        double pad = fabs(ood) * F::abs_factor() + 1e-300;
+        f.id[k] = F::near(id);
+        f.cn[k] = F::down(-(ood + pad));
+        f.cf[k] = F::up(-(ood - pad));
+    }
+    return f;
+}
+template <typename T>
+__device__ __forceinline__ bool box_filter(const FilterRay<T> &f, T lox, T hix, T loy, T hiy, T loz, T hiz, T t_limit,
+                                           T &enter) {
+    typedef FilterTraits<T> F;
+    T nx = f.id[0] < (T)0 ? hix : lox, fx = f.id[0] < (T)0 ? lox : hix;
+    T ny = f.id[1] < (T)0 ? hiy : loy, fy = f.id[1] < (T)0 ? loy : hiy;
+    T nz = f.id[2] < (T)0 ? hiz : loz, fz = f.id[2] < (T)0 ? loz : hiz;
+    T tn = F::max_(F::max_(F::fma_(nx, f.id[0], f.cn[0]), F::fma_(ny, f.id[1], f.cn[1])), F::fma_(nz, f.id[2], f.cn[2]));
+    T tf = F::min_(F::min_(F::fma_(fx, f.id[0], f.cf[0]), F::fma_(fy, f.id[1], f.cf[1])), F::fma_(fz, f.id[2], f.cf[2]));
+    T ep = F::fma_(-F::rel(), F::abs_(tn), tn);
+    T xp = F::fma_(F::rel(), F::abs_(tf), tf);
+    enter = ep;
+    return (ep <= xp) && (xp >= (T)0) && (ep <= t_limit);
+}
+
+template <typename T>
+struct WideNode {
+    T c0[6], c1[6]; // lo.x, hi.x, lo.y, hi.y, lo.z, hi.z
+    int left, right;
+};
+__device__ __forceinline__ void load_node(const DevScene &sc, int i, WideNode<float> &n) {
+    const float4 *p = sc.nodes32 + (size_t)i * 4;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    int4 k = __ldg(reinterpret_cast<const int4 *>(p + 3));
+    n.c0[0] = a.x, n.c0[1] = a.y, n.c0[2] = a.z, n.c0[3] = a.w, n.c0[4] = c.x, n.c0[5] = c.y;
+    n.c1[0] = b.x, n.c1[1] = b.y, n.c1[2] = b.z, n.c1[3] = b.w, n.c1[4] = c.z, n.c1[5] = c.w;
+    n.left = k.x, n.right = k.y;
+}
+__device__ __forceinline__ void load_node(const DevScene &sc, int i, WideNode<double> &n) {
+    const double2 *p = sc.nodes64 + (size_t)i * 7;
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), g = __ldg(p + 5);
+    int4 k = __ldg(reinterpret_cast<const int4 *>(p + 6));
+    n.c0[0] = a.x, n.c0[1] = a.y, n.c0[2] = b.x, n.c0[3] = b.y, n.c0[4] = c.x, n.c0[5] = c.y;
+    n.c1[0] = d.x, n.c1[1] = d.y, n.c1[2] = e.x, n.c1[3] = e.y, n.c1[4] = g.x, n.c1[5] = g.y;
+    n.left = k.x, n.right = k.y;
+}
+
+__device__ __forceinline__ void load_tri_pos(const DevScene &sc, int tri, D3 &v0, D3 &v1, D3 &v2, uint32_t &material,
+                                             uint32_t &prim_id) {
+    const double2 *p = sc.tri_pos + (size_t)tri * 5;
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
+    v0 = d3(a.x, a.y, b.x), v1 = d3(b.y, c.x, c.y), v2 = d3(d.x, d.y, e.x);
+    long long bits = __double_as_longlong(e.y);
+    material = (uint32_t)(bits & 0xffffffffll), prim_id = (uint32_t)((unsigned long long)bits >> 32);
+}
+__device__ __forceinline__ void load_tri_nrm(const DevScene &sc, int tri, D3 &n0, D3 &n1, D3 &n2) {
+    const double2 *p = sc.tri_nrm + (size_t)tri * 5;
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
+    n0 = d3(a.x, a.y, b.x), n1 = d3(b.y, c.x, c.y), n2 = d3(d.x, d.y, e.x);
+}
+
+// One BoundingVolumeHierarchy::intersect: closest triangle with distance rule "later DFS leaf wins ties".
+// `t_limit` (distance of the best hit found in EARLIER objects) only prunes; the caller merges.
+template <typename NT, bool COUNT, bool ANY>
+__device__ __forceinline__ void bvh_closest(const DevScene &sc, int root, const TriRay &tr, const FilterRay<NT> &fr,
+                                            double t_limit, double &best_t, int &best_tri, TraceCounters &cnt) {
+    typedef FilterTraits<NT> F;
+    int stack[32];
+    int sp = 0;
+    int cur = root;
+    best_t = CUDART_INF, best_tri = -1;
+    // prune bound in NodeT, rounded up, with the relative slack of the filter
+    NT limit = F::up(t_limit * (1.0 + 4.0 * (double)F::rel()));
+    while (true) {
+        while (cur >= 0) {
+            WideNode<NT> n;
+            load_node(sc, cur, n);
+            if (COUNT) cnt.node_visits += 2;
+            NT e0, e1;
+            bool h0 = box_filter(fr, n.c0[0], n.c0[1], n.c0[2], n.c0[3], n.c0[4], n.c0[5], limit, e0);
+            bool h1 = box_filter(fr, n.c1[0], n.c1[1], n.c1[2], n.c1[3], n.c1[4], n.c1[5], limit, e1);
+            if (h0 && h1) {
+                bool swap = e1 < e0;
+                stack[sp++] = swap ? n.left : n.right;
+                cur = swap ? n.right : n.left;
+            } else if (h0 || h1) {
+                cur = h0 ? n.left : n.right;
+            } else {
+                cur = sp ? stack[--sp] : VRJ_LEAF_DONE;
+            }
+        }
+        if (cur == VRJ_LEAF_DONE) break;
+        {
+            int tri = ~cur;
+            D3 v0, v1, v2, loc;
+            uint32_t mat, pid;
+            load_tri_pos(sc, tri, v0, v1, v2, mat, pid);
+            if (COUNT) cnt.tri_tests += 1;
+            double dist, b0, b1, b2;
+            if (triangle_test(tr, v0, v1, v2, dist, b0, b1, b2, loc)) {
+                if (dist < best_t || (dist == best_t && tri > best_tri)) {
+                    best_t = dist, best_tri = tri;
+                    if (ANY) return;
+                    limit = F::up(fmin(best_t, t_limit) * (1.0 + 4.0 * (double)F::rel()));
+                }
+            }
+        }
+        cur = sp ? stack[--sp] : VRJ_LEAF_DONE;
+        if (cur == VRJ_LEAF_DONE) break;
+    }
+}
+
+// Sampler::sample.  ANY = true stops at the first hit found (shadow rays: only Some/None is used).
+template <typename NT, bool COUNT, bool ANY>
+__device__ __forceinline__ Hit trace_closest(const DevScene &sc, D3 o, D3 d, TraceCounters &cnt) {
+    Hit best;
+    best.t = CUDART_INF, best.item = -1, best.tri = -1;
+    bool have_tri_ray = false;
+    TriRay tr;
+    for (uint32_t i = 0; i < sc.n_items; i++) {
+        ItemDev it = sc.items[i];
+        double t;
+        int tri = -1;
+        bool hit = false;
+        if (it.kind == 0) {
+            hit = sphere_test(sc.spheres[it.index], o, d, t);
+        } else if (it.kind == 1) {
+            hit = plane_test(sc.planes[it.index], o, d, t);
+        } else {
+            if (!have_tri_ray) tr = tri_ray(o, d), have_tri_ray = true;
+            if (it.kind == 2) {
+                D3 v0, v1, v2, loc;
+                uint32_t mat, pid;
+                double b0, b1, b2;
+                load_tri_pos(sc, (int)it.index, v0, v1, v2, mat, pid);
+                if (COUNT) cnt.tri_tests += 1;
+                hit = triangle_test(tr, v0, v1, v2, t, b0, b1, b2, loc);
+                tri = (int)it.index;
+            } else {
+                FilterRay<NT> fr = filter_ray<NT>(o, d);
+                bvh_closest<NT, COUNT, ANY>(sc, (int)it.root, tr, fr, best.item < 0 ? CUDART_INF : best.t, t, tri, cnt);
+                hit = tri >= 0;
+            }
+        }
+        // Iterator::min_by: the kept element is replaced only when kept > candidate (NaN keeps)
+        if (hit && (best.item < 0 || best.t > t)) {
+            best.t = t, best.item = (int)i, best.tri = tri;
+            if (ANY) return best;
+        }
+    }
+    return best;
+}
+
+// Rebuild the IntersectionInfo (raycasting/mod.rs:67-97) of a known hit with the exact arithmetic
+// of the primitive's intersect(): the wavefront stores only (ray, item, triangle).
+__device__ __forceinline__ bool rebuild_hit(const DevScene &sc, D3 o, D3 d, int item, int tri, HitFrame &h) {
+    ItemDev it = sc.items[item];
+    if (it.kind == 0) {
+        SphereDev s = sc.spheres[it.index];
+        double t;
+        if (!sphere_test(s, o, d, t)) return false;
+        sphere_frame(s, o, d, t, h);
+        return true;
+    }
+    if (it.kind == 1) {
+        PlaneDev p = sc.planes[it.index];
+        double t;
+        if (!plane_test(p, o, d, t)) return false;
+        plane_frame(p, o, d, t, h);
+        return true;
+    }
+    TriRay tr = tri_ray(o, d);
+    D3 v0, v1, v2, n0, n1, n2;
+    uint32_t mat, pid;
+    double b0, b1, b2;
+    load_tri_pos(sc, tri, v0, v1, v2, mat, pid);
+    if (!triangle_test(tr, v0, v1, v2, h.distance, b0, b1, b2, h.location)) return false;
+    load_tri_nrm(sc, tri, n0, n1, n2);
+    // triangle.rs:73-83
+    h.normal = normalize(((d3(0.0, 0.0, 0.0) + n0 * b0) + n1 * b1) + n2 * b2);
+    h.cotangent = normalize(cross(v0 - v1, h.normal));
+    h.tangent = normalize(cross(h.cotangent, h.normal));
+    h.retro = normalize(o - h.location);
+    h.material = mat;
+    return true;
+}
+
+} // namespace vrj

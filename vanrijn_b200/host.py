@@ -1,0 +1,187 @@
+"""Script-level plumbing over the host library: build a scene from a scenes.SceneSpec through the
+C++ host mirror (load_obj, BoundingVolumeHierarchy::build, flatten), upload it, and call the
+C ABI.  Nothing here computes a ray, a hit or a colour; it only moves arrays across ctypes."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import dp
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(dp)
+
+
+class HostScene:
+    """A vanrijn::Scene built by the C++ host side, plus its flattened / uploaded forms."""
+
+    def __init__(self, spec):
+        H = capi.host()
+        self.H = H
+        self.h = C.c_void_p(H.vrjh_scene_new(*[float(x) for x in spec.camera]))
+        self.spec = spec
+        self._keep = []
+        for sp in spec.spectra:
+            if sp[0] == "rgb":
+                H.vrjh_add_spectrum_rgb(self.h, *[float(x) for x in sp[1]])
+            elif sp[0] == "grey":
+                H.vrjh_add_spectrum_grey(self.h, float(sp[1]))
+            elif sp[0] == "diamond":
+                H.vrjh_add_spectrum_diamond(self.h)
+            else:
+                arr, p = _d(sp[3])
+                H.vrjh_add_spectrum(self.h, float(sp[1]), float(sp[2]), len(arr), p)
+        for m in spec.materials:
+            H.vrjh_add_material(self.h, m.kind, m.spectrum, m.p0, m.p1, m.p2)
+        for obj in spec.objects:
+            if obj[0] == "list":
+                H.vrjh_begin_list(self.h)
+                for prim in obj[1]:
+                    if prim[0] == "sphere":
+                        H.vrjh_list_add_sphere(self.h, *[float(x) for x in prim[1]], float(prim[2]), prim[3])
+                    elif prim[0] == "plane":
+                        H.vrjh_list_add_plane(self.h, *[float(x) for x in prim[1]], float(prim[2]), prim[3])
+                    else:
+                        v, pv = _d(prim[1])
+                        n, pn = _d(prim[2])
+                        H.vrjh_list_add_triangle(self.h, pv, pn, prim[3])
+            elif obj[0] == "mesh":
+                v, pv = _d(obj[1])
+                n, pn = _d(obj[2])
+                r = H.vrjh_add_bvh(self.h, v.size // 9, pv, pn, obj[3])
+                if r < 0:
+                    raise capi.VrjError(H.vrjh_last_error().decode())
+            elif obj[0] == "obj":
+                r = H.vrjh_add_bvh_obj(self.h, obj[1].encode(), obj[2])
+                if r < 0:
+                    raise capi.VrjError(H.vrjh_last_error().decode())
+        self._dev = {}
+
+    def __del__(self):
+        try:
+            self.H.vrjh_scene_free(self.h)
+        except Exception:
+            pass
+
+    # ---- flattened description (host memory, owned by the C++ scene) ----
+    def desc(self):
+        d = self.H.vrjh_flatten(self.h)
+        if not d:
+            raise capi.VrjError(self.H.vrjh_last_error().decode())
+        return d.contents
+
+    def spectrum_data(self, spectrum_id):
+        """(SpectrumData, keepalive) for a spectrum of the spec, e.g. a light's."""
+        lo, hi = C.c_double(), C.c_double()
+        buf = np.zeros(64)
+        n = self.H.vrjh_get_spectrum(self.h, spectrum_id, C.byref(lo), C.byref(hi), buf.ctypes.data_as(dp), 64)
+        buf = buf[:n].copy()
+        return capi.SpectrumData(lo.value, hi.value, n, 0, buf.ctypes.data_as(dp)), buf
+
+    # ---- device ----
+    def device_scene(self, device=0):
+        if device not in self._dev:
+            s = self.H.vrjh_device_scene(self.h, device)
+            if not s:
+                raise capi.VrjError(self.H.vrjh_last_error().decode())
+            self._dev[device] = C.c_void_p(s)
+        return self._dev[device]
+
+    def device_bytes(self, device=0):
+        return int(capi.cuda().vrj_scene_device_bytes(self.device_scene(device)))
+
+    def trace(self, origins, dirs, bvh_filter=capi.FILTER_F32, device=0):
+        o, po = _d(origins)
+        d, pd = _d(dirs)
+        n = o.size // 3
+        obj = np.empty(n, np.int32)
+        prim = np.empty(n, np.int32)
+        t = np.empty(n, np.float64)
+        st = capi.Stats()
+        capi.check(capi.cuda().vrj_trace_rays(self.device_scene(device), n, po, pd, bvh_filter,
+                                              obj.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              prim.ctypes.data_as(C.POINTER(C.c_int32)), t.ctypes.data_as(dp), C.byref(st)))
+        return obj, prim, t, st
+
+    def make_params(self, spp=1, max_depth=128, sample_offset=0, seed=1, integrator=capi.INTEGRATOR_SIMPLE_RANDOM,
+                    bvh_filter=capi.FILTER_F32, bias=1e-7, lights=(), ambient=-1, sample_stride=1, count_traversal=False):
+        keep = []
+        larr = (capi.Light * max(1, len(lights)))()
+        for i, (direction, spectrum_id) in enumerate(lights):
+            larr[i].direction[:] = [float(x) for x in direction]
+            sd, buf = self.spectrum_data(spectrum_id)
+            larr[i].spectrum = sd
+            keep.append(buf)
+        amb = None
+        if ambient >= 0:
+            amb, buf = self.spectrum_data(ambient)
+            keep.append(buf)
+        p = capi.RenderParams(spp=spp, max_depth=max_depth, sample_offset=sample_offset, seed=seed, integrator=integrator,
+                              bvh_filter=bvh_filter, bias=bias, lights=larr,
+                              ambient_light=C.pointer(amb) if amb is not None else None, n_lights=len(lights),
+                              sample_stride=sample_stride, count_traversal=1 if count_traversal else 0)
+        keep.extend([larr, amb])
+        return p, keep
+
+    def render(self, tile, height, width, want=("colour", "colour_sum", "colour_bias", "weight", "weight_bias"),
+               want_photons=False, device=0, **kw):
+        """vrj_render_tile with host output buffers.  Returns a dict of numpy arrays + 'stats'."""
+        sc, ec, sr, er = tile
+        npix = (ec - sc) * (er - sr)
+        p, keep = self.make_params(**kw)
+        out = {}
+        ao = capi.AccumOut(memory=capi.MEM_HOST, accumulate=0)
+        for name in ("colour", "colour_sum", "colour_bias"):
+            if name in want:
+                out[name] = np.zeros(npix * 3)
+                setattr(ao, name, out[name].ctypes.data)
+        for name in ("weight", "weight_bias"):
+            if name in want:
+                out[name] = np.zeros(npix)
+                setattr(ao, name, out[name].ctypes.data)
+        if want_photons:
+            out["photons"] = np.zeros(p.spp * npix * 2)
+            ao.photons = out["photons"].ctypes.data
+        st = capi.Stats()
+        ao.stats = C.pointer(st)
+        t = capi.Tile(sc, ec, sr, er)
+        capi.check(capi.cuda().vrj_render_tile(self.device_scene(device), C.byref(t), height, width, C.byref(p), C.byref(ao)))
+        if want_photons:
+            out["photons"] = out["photons"].reshape(p.spp, npix, 2)
+        out["stats"] = st
+        return out
+
+    def render_device(self, tile, height, width, sum_ptr, weight_ptr, device=0, accumulate=False, colour_ptr=None, **kw):
+        """vrj_render_tile writing colour_sum / weight straight into caller-owned DEVICE memory
+        (e.g. torch tensors that torch.distributed then reduces).  Returns the stats."""
+        p, keep = self.make_params(**kw)
+        ao = capi.AccumOut(memory=capi.MEM_DEVICE, accumulate=1 if accumulate else 0)
+        ao.colour_sum = sum_ptr
+        ao.weight = weight_ptr
+        if colour_ptr:
+            ao.colour = colour_ptr
+        st = capi.Stats()
+        ao.stats = C.pointer(st)
+        t = capi.Tile(*tile)
+        capi.check(capi.cuda().vrj_render_tile(self.device_scene(device), C.byref(t), height, width, C.byref(p), C.byref(ao)))
+        return st
+
+    def partial_render_scene(self, tile, height, width, seed=1, sample_offset=0):
+        """The reference call: partial_render_scene(&scene, tile, height, width) -> AccumulationBuffer."""
+        sc, ec, sr, er = tile
+        npix = (ec - sc) * (er - sr)
+        out = {k: np.zeros(npix * 3) for k in ("colour", "colour_sum", "colour_bias")}
+        out["weight"] = np.zeros(npix)
+        out["weight_bias"] = np.zeros(npix)
+        t4 = (C.c_uint64 * 4)(sc, ec, sr, er)
+        r = self.H.vrjh_partial_render_scene(self.h, t4, height, width, seed, sample_offset, *[out[k].ctypes.data_as(dp) for k in
+                                             ("colour", "colour_sum", "colour_bias", "weight", "weight_bias")])
+        if r != 0:
+            raise capi.VrjError(self.H.vrjh_last_error().decode())
+        return out
+
+
+def build_scene(spec):
+    return HostScene(spec)
