@@ -75,15 +75,20 @@ def test_obj_loader_and_mesh_path_agree():
         assert np.array_equal(np.ctypeslib.as_array(getattr(da, name), (n * 4,)), np.ctypeslib.as_array(getattr(db, name), (n * 4,)))
 
 
-def photons_close(g, r, rtol):
+def photons_close(g, r, rtol, max_diverged=0):
     """g, r: (spp, npix, 2) = (wavelength, intensity*360).  Depth-limited paths carry wavelength 0 on
     both sides; there the oracle's intensity is the (physically nil) lambda=0 evaluation of the
-    bsdf chain, which the device zeroes -- compared through XYZ below, not here."""
-    assert np.array_equal(g[..., 0], r[..., 0])            # wavelengths bit-identical (same RNG stream)
-    live = r[..., 0] != 0.0
+    bsdf chain, which the device zeroes -- compared through XYZ, not here.
+    max_diverged: number of samples allowed to follow a different path.  Only non-zero where a
+    libm function (sin/cos of the Phong sampler) feeds the geometry: CUDA and glibc differ by an ulp
+    there, and an ulp can flip a near-critical total-internal-reflection decision bounces later."""
+    same = (g[..., 0] == r[..., 0])
+    assert (~same).sum() <= max_diverged, (~same).sum()   # wavelengths bit-identical (same RNG stream)
+    live = same & (r[..., 0] != 0.0)
     gi, ri = g[..., 1][live], r[..., 1][live]
-    scale = np.maximum(np.abs(ri), 1e-300)
-    assert np.max(np.abs(gi - ri) / scale) <= rtol, np.max(np.abs(gi - ri) / scale)
+    rel = np.abs(gi - ri) / np.maximum(np.abs(ri), 1e-300)
+    assert (rel > rtol).sum() <= max_diverged, (np.sort(rel)[-5:], rtol)
+    return int((~same).sum() + (rel > rtol).sum())
 
 
 @pytest.mark.parametrize("bvh_filter", [capi.FILTER_F32, capi.FILTER_F64])
@@ -104,10 +109,11 @@ def test_path_traced_samples_lambertian(bvh_filter):
 
 
 @pytest.mark.parametrize("variant,depth", [("mixed", 128), ("mixed", 3), ("lambertian", 2)])
-def test_path_traced_samples_all_materials(variant, depth):
-    """C5 materials (mirror sphere, diamond sphere, reflective mesh) and shallow recursion limits."""
+def test_path_traced_samples_mirror_and_glass(variant, depth):
+    """C5 materials (mirror sphere, diamond sphere, reflective mesh) and shallow recursion limits.
+    Geometry uses only + - * / sqrt here, so every path must follow the oracle's path exactly;
+    acos/exp (mirror lobe) enter the radiance only: 1e-9."""
     spec = scenes.scene_main(subdivisions=3, obj=False, variant=variant)
-    spec.objects[0][1].append(("sphere", (1.5, 0.0, 1.0), 0.8, spec.phong_rgb((0.9, 0.2, 0.2), 0.3, 0.5, 20.0)))
     hs, orc = both(spec)
     W, H, spp = 80, 45, 3
     g = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=depth, seed=5, want_photons=True)
@@ -116,6 +122,23 @@ def test_path_traced_samples_all_materials(variant, depth):
     for k in ("primary_rays", "bounce_rays", "paths_missed", "paths_escaped", "paths_depth_limited"):
         assert getattr(g["stats"], k) == getattr(r["stats"], k), k
     np.testing.assert_allclose(g["colour_sum"], r["colour_sum"], rtol=1e-8, atol=1e-20)
+
+
+@pytest.mark.parametrize("variant", ["lambertian", "mixed"])
+def test_path_traced_samples_phong(variant):
+    """Phong (trait-default cosine-hemisphere sampler: sin/cos; bsdf: powf).  The sampled direction
+    depends on libm, so a handful of long paths may legitimately diverge (see photons_close)."""
+    spec = scenes.scene_main(subdivisions=3, obj=False, variant=variant)
+    spec.objects[0][1].append(("sphere", (1.5, 0.0, 1.0), 0.8, spec.phong_rgb((0.9, 0.2, 0.2), 0.3, 0.5, 20.0)))
+    spec.objects[0][1].append(("sphere", (-1.0, -1.2, 0.5), 0.8, spec.phong_rgb((0.2, 0.9, 0.2), 0.5, 0.2, 5.0)))
+    hs, orc = both(spec)
+    W, H, spp = 80, 45, 3
+    g = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=5, want_photons=True)
+    r = orc.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=5, want_photons=True)
+    diverged = photons_close(g["photons"], r["photons"], 1e-9, max_diverged=5)
+    assert g["stats"].primary_rays == r["stats"].primary_rays and g["stats"].paths_missed == r["stats"].paths_missed
+    if diverged == 0:
+        np.testing.assert_allclose(g["colour_sum"], r["colour_sum"], rtol=1e-8, atol=1e-20)
 
 
 @pytest.mark.parametrize("reflective", [True, False])
