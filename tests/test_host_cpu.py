@@ -1,0 +1,221 @@
+"""CPU-only tests of the host side and of the C-ABI library's surface (no compute calls: there is no
+GPU here and the library has no CPU fallback).  The oracle is used as the checker for the host logic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oraclelib as O
+import vanrijn_b200 as V
+from vanrijn_b200 import capi, scenes, sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "vanrijn_cuda.h")).read()
+    declared = sorted(set(re.findall(r"VRJ_API[^;(]*?\b(vrj_\w+)\s*\(", header)))
+    assert declared == sorted(capi.CUDA_SYMBOLS)
+    lib = capi.cuda()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.vrj_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """ctypes mirrors of the POD structs have the sizes and field offsets the C compiler gives the header's."""
+    import subprocess
+    pairs = [("VrjSpectrum", capi.Spectrum), ("VrjMaterial", capi.Material), ("VrjSphere", capi.Sphere),
+             ("VrjPlane", capi.Plane), ("VrjBvh", capi.Bvh), ("VrjItem", capi.Item), ("VrjSceneDesc", capi.SceneDesc),
+             ("VrjTile", capi.Tile), ("VrjSpectrumData", capi.SpectrumData), ("VrjLight", capi.Light),
+             ("VrjRenderParams", capi.RenderParams), ("VrjStats", capi.Stats), ("VrjAccumOut", capi.AccumOut)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vanrijn_cuda.h"', 'int main(void){']
+    for cname, ct in pairs:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in pairs:
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
+
+
+@pytest.mark.skipif(capi.cuda().vrj_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback_without_a_device():
+    hs = V.build_scene(scenes.scene_main(subdivisions=1, obj=False))
+    with pytest.raises(capi.VrjError):
+        hs.render((0, 4, 0, 4), 4, 4, spp=1)
+    with pytest.raises(capi.VrjError):
+        hs.trace(np.zeros((1, 3)), np.array([[0.0, 0.0, 1.0]]))
+    with pytest.raises(capi.VrjError):
+        hs.partial_render_scene((0, 4, 0, 4), 4, 4)
+
+
+def test_scene_validation_rejects_bad_descriptions():
+    hs = V.build_scene(scenes.scene_main(subdivisions=1, obj=False))
+    d = hs.desc()
+    h = C.c_void_p()
+    bad = capi.SceneDesc.from_buffer_copy(d)
+    bad.abi_version = 99
+    assert capi.cuda().vrj_scene_create(C.byref(bad), 0, C.byref(h)) == 1
+    assert b"abi_version" in capi.cuda().vrj_last_error()
+    bad = capi.SceneDesc.from_buffer_copy(d)
+    bad.n_materials = 1          # triangle/sphere materials now out of range
+    assert capi.cuda().vrj_scene_create(C.byref(bad), 0, C.byref(h)) == 1
+    assert capi.cuda().vrj_scene_create(None, 0, C.byref(h)) == 1
+
+
+def _flat_arrays(d):
+    nt, nn = d.n_triangles, d.n_nodes
+    tri = [np.ctypeslib.as_array(getattr(d, k), (nt, 4)) for k in ("tri_v0", "tri_v1", "tri_v2", "tri_n0", "tri_n1", "tri_n2")]
+    return (tri, np.ctypeslib.as_array(d.tri_prim_id, (nt,)), np.ctypeslib.as_array(d.node_min, (nn, 4)),
+            np.ctypeslib.as_array(d.node_max, (nn, 4)), np.ctypeslib.as_array(d.node_child, (nn, 2)))
+
+
+@pytest.mark.parametrize("sub", [0, 2, 4])
+def test_flattened_bvh_matches_reference_topology(sub):
+    """bounding_volume_hierarchy.rs:49-75: 2N-1 nodes, <=1 triangle per leaf, leaves in DFS order, every node
+    box = union of its children's, depth = oracle's depth; 16-byte alignment of the SoA arrays."""
+    spec = scenes.scene_bench(subdivisions=sub, obj=False)
+    hs, orc = V.build_scene(spec), O.OracleScene(spec)
+    d = hs.desc()
+    tri, prim_id, nmin, nmax, child = _flat_arrays(d)
+    n = d.n_triangles
+    assert n == 20 * 4 ** sub and d.n_nodes == 2 * n - 1 and d.n_bvhs == 1 and d.n_items == 1
+    assert d.bvhs[0].depth == orc.L.orc_bvh_depth(orc.h, 0)
+    assert sorted(prim_id.tolist()) == list(range(n))
+    for k in ("tri_v0", "tri_n0", "node_min", "node_max"):
+        assert C.cast(getattr(d, k), C.c_void_p).value % 16 == 0
+    next_leaf = [0]
+
+    def walk(i):
+        l, r = child[i]
+        if l < 0:
+            assert r == 1 and ~l == next_leaf[0]          # leaves appear in DFS order
+            next_leaf[0] += 1
+            t = ~l
+            pts = np.stack([tri[0][t, :3], tri[1][t, :3], tri[2][t, :3]])
+            assert np.array_equal(nmin[i, :3], pts.min(0)) and np.array_equal(nmax[i, :3], pts.max(0))
+            return nmin[i, :3], nmax[i, :3]
+        lo_l, hi_l = walk(l)
+        lo_r, hi_r = walk(r)
+        assert np.array_equal(nmin[i, :3], np.minimum(lo_l, lo_r)) and np.array_equal(nmax[i, :3], np.maximum(hi_l, hi_r))
+        return nmin[i, :3], nmax[i, :3]
+
+    walk(0)
+    assert next_leaf[0] == n
+
+
+def test_median_split_on_largest_axis():
+    """heuristic_split (bounding_volume_hierarchy.rs:38-46): the root's children hold len/2 and len-len/2
+    triangles, separated by box-centre on the root's largest dimension."""
+    spec = scenes.scene_bench(subdivisions=2, obj=False)
+    hs = V.build_scene(spec)  # owns the description's arrays
+    d = hs.desc()
+    tri, prim_id, nmin, nmax, child = _flat_arrays(d)
+    n = d.n_triangles
+    axis = int(np.argmax(nmax[0, :3] - nmin[0, :3]))
+    pts = np.stack([tri[0][:, :3], tri[1][:, :3], tri[2][:, :3]], 1)
+    centre = (pts.min(1)[:, axis] + pts.max(1)[:, axis]) / 2.0
+    assert centre[: n // 2].max() <= centre[n // 2:].min()
+
+
+def test_obj_loader_matches_oracle_loader(tmp_path):
+    """mesh.rs:13-88 / obj 0.9: index forms a, a/b, a//c, a/b/c, negative indices, polygons (fan), f32 parse."""
+    p = tmp_path / "t.obj"
+    p.write_text("# test\nv 0 0 0\nv 1 0 0.1\nv 1 1 0\nv 0 1 0.333333343\nv 0.5 0.5 1e-3\nvn 0 0 1\nvn 0 1 0\nvt 0 0\n"
+                 "f 1//1 2//1 3//2\nf 1 2 3 4\nf 1/1/1 3/1/2 5/1/1\nf -1//-1 -2//-2 -3//-1 -4//-2 -5//1\nf 1/1 2/1 5/1\n")
+    verts = np.zeros((16, 9))
+    norms = np.zeros((16, 9))
+    n = capi.host().vrjh_load_obj(str(p).encode(), verts.ctypes.data_as(capi.dp), norms.ctypes.data_as(capi.dp), 16)
+    pv, pn = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+    m = O.lib().orc_load_obj(str(p).encode(), C.byref(pv), C.byref(pn))
+    assert n == m == 1 + 2 + 1 + 3 + 1
+    ov = np.ctypeslib.as_array(pv, (m, 9)).copy()
+    on = np.ctypeslib.as_array(pn, (m, 9)).copy()
+    assert np.array_equal(verts[:n], ov) and np.array_equal(norms[:n], on)
+    assert verts[1, 8] == 0.0 and verts[2, 8] == float(np.float32(0.333333343))    # fan: (v0,v1,v2),(v0,v2,v3); f32 widened
+    assert np.all(norms[1] == 0.0)                                                    # no normal index -> zero normal
+    assert capi.host().vrjh_load_obj(b"/nonexistent.obj", verts.ctypes.data_as(capi.dp), norms.ctypes.data_as(capi.dp), 16) == -1
+
+
+def test_proxy_obj_round_trips_through_the_loader():
+    path, name = scenes.bunny_obj_path(subdivisions=3)
+    pos, nrm, faces = scenes.bunny_proxy(3)
+    v, n = scenes.mesh_arrays(pos, nrm, faces)
+    verts = np.zeros((len(v), 9))
+    norms = np.zeros((len(v), 9))
+    cnt = capi.host().vrjh_load_obj(path.encode(), verts.ctypes.data_as(capi.dp), norms.ctypes.data_as(capi.dp), len(v))
+    assert cnt == len(v) == 1280
+    assert np.array_equal(verts, v) and np.array_equal(norms, n)
+
+
+def test_plane_and_items_flatten_like_the_reference_constructs_them():
+    spec = scenes.scene_main(subdivisions=1, obj=False)
+    hs = V.build_scene(spec)  # owns the description's arrays
+    d = hs.desc()
+    assert [d.items[i].kind for i in range(d.n_items)] == [1, 0, 0, 0, 3]      # plane, 3 spheres, bvh: Scene.objects order
+    assert [d.items[i].object_id for i in range(d.n_items)] == [0, 0, 0, 0, 1]
+    assert [d.items[i].prim_id for i in range(4)] == [0, 1, 2, 3]
+    p = d.planes[0]
+    # Plane::new (plane.rs:17-32) for normal (0,1,0): smallest coord -> z axis (x == z -> index 2)
+    out = O.hit16(O.lib().orc_plane_intersect, O.vec(0, 1, 0), -2.0, O.vec(0, 0, 0), O.vec(0, -1, 0))
+    assert np.array_equal(np.array(p.normal[:]), out["normal"])
+    assert np.array_equal(np.array(p.tangent[:]), out["tangent"]) and np.array_equal(np.array(p.cotangent[:]), out["cotangent"])
+    # spectra: reflection_from_linear_rgb on the host == oracle's
+    s = np.zeros(32)
+    O.lib().orc_rgb_to_spectrum(0.55, 0.27, 0.04, s.ctypes.data_as(O.dp))
+    sp = d.spectra[d.materials[0].spectrum]
+    got = np.ctypeslib.as_array(d.spectrum_samples, (d.n_spectrum_samples,))[sp.first_sample: sp.first_sample + sp.n_samples]
+    assert np.array_equal(got, s) and sp.shortest_wavelength == 380.0 and sp.longest_wavelength == 720.0
+
+
+def test_tile_iterator_and_merge_tile_match_the_oracle():
+    cap = 512
+    a, b = (C.c_uint64 * (4 * cap))(), (C.c_uint64 * (4 * cap))()
+    for w, h, ts in [(20, 15, 5), (21, 16, 5), (640, 480, 32), (7, 3, 2048)]:
+        n = capi.host().vrjh_tile_iterator(w, h, ts, a, cap)
+        assert n == O.lib().orc_tile_iterator(w, h, ts, b, cap)
+        assert list(a[:4 * n]) == list(b[:4 * n])
+    rng = np.random.default_rng(1)
+    W, H, tile = 16, 12, (3, 7, 4, 9)
+    dc, dw = rng.random((H, W, 3)), rng.random((H, W)) + 0.1
+    sc_, sw = rng.random((5, 4, 3)), rng.random((5, 4)) + 0.1
+    got_c, got_w = dc.copy(), dw.copy()
+    t4 = (C.c_uint64 * 4)(*tile)
+    assert capi.host().vrjh_merge_tile(got_c.ctypes.data_as(capi.dp), got_w.ctypes.data_as(capi.dp), W, H, t4,
+                                       np.ascontiguousarray(sc_).ctypes.data_as(capi.dp), np.ascontiguousarray(sw).ctypes.data_as(capi.dp)) == 0
+    for i in range(5):
+        for j in range(4):
+            out = np.zeros(3)
+            O.lib().orc_accum_blend(dc[4 + i, 3 + j].copy().ctypes.data_as(O.dp), dw[4 + i, 3 + j],
+                                    sc_[i, j].copy().ctypes.data_as(O.dp), sw[i, j], out.ctypes.data_as(O.dp))
+            assert np.array_equal(got_c[4 + i, 3 + j], out)
+            assert got_w[4 + i, 3 + j] == dw[4 + i, 3 + j] + sw[i, j]
+    mask = np.ones((H, W), bool)
+    mask[4:9, 3:7] = False
+    assert np.array_equal(got_c[mask], dc[mask]) and np.array_equal(got_w[mask], dw[mask])
+    # a tile that leaves the destination is an error (the reference panics on the Array2D index, array2d.rs:58-66)
+    t_bad = (C.c_uint64 * 4)(14, 18, 4, 9)
+    assert capi.host().vrjh_merge_tile(got_c.ctypes.data_as(capi.dp), got_w.ctypes.data_as(capi.dp), W, H, t_bad,
+                                       np.zeros(60).ctypes.data_as(capi.dp), np.zeros(20).ctypes.data_as(capi.dp)) == 1
+
+
+def test_shard_samples_partition_the_sample_indices():
+    for world in (1, 2, 4, 8):
+        for spp in (1, 3, 16):
+            seen = []
+            for step in range(3):
+                for rank in range(world):
+                    seen += sharding.shard_sample_indices(rank, world, step, spp)
+            assert sorted(seen) == list(range(3 * spp * world))
+    with pytest.raises(ValueError):
+        sharding.shard_samples(2, 2, 0, 1)
