@@ -186,8 +186,10 @@ typedef struct VrjStats {
     uint64_t kernel_launches;
     double device_ms; /* CUDA-event time of the kernels of this call (first launch .. last launch) */
     /* CUDA-event time per kernel class, summed over the call's launches (events on the launching stream) */
-    double primary_ms, bounce_ms, resolve_ms;
+    double primary_ms, bounce_ms, resolve_ms;   /* k_trace (camera rays), k_trace (bounce rays), k_resolve */
     uint64_t primary_launches, bounce_launches, resolve_launches;
+    double shade_ms;                            /* k_shade */
+    uint64_t shade_launches;
 } VrjStats;
 
 /* The five arrays of AccumulationBuffer (accumulation_buffer.rs:6-12), tile-local, row-major like

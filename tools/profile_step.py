@@ -1,0 +1,23 @@
+"""Small driver for ncu: the bench workload (C3, 1920x1080, depth 8), `--spp` samples, `--reps` calls."""
+import argparse, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import vanrijn_b200 as V
+from vanrijn_b200 import scenes, capi
+ap = argparse.ArgumentParser()
+ap.add_argument("--spp", type=int, default=8)
+ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--width", type=int, default=1920)
+ap.add_argument("--height", type=int, default=1080)
+ap.add_argument("--depth", type=int, default=8)
+ap.add_argument("--filter", default="f32")
+ap.add_argument("--variant", default="lambertian")
+a = ap.parse_args()
+hs = V.build_scene(scenes.scene_main(subdivisions=6, obj=True, variant=a.variant))
+f = capi.FILTER_F64 if a.filter == "f64" else capi.FILTER_F32
+for i in range(a.reps):
+    r = hs.render((0, a.width, 0, a.height), a.height, a.width, spp=a.spp, max_depth=a.depth, seed=1, sample_offset=i * a.spp,
+                  bvh_filter=f, want=("colour_sum", "weight"))
+    st = r["stats"]
+    print("rep %d: %.1f Mrays/s device (%.2f ms; primary %.2f bounce %.2f resolve %.2f), rays %d" % (
+        i, st.rays / st.device_ms / 1e3, st.device_ms, st.primary_ms, st.bounce_ms, st.resolve_ms, st.rays), flush=True)

@@ -50,7 +50,7 @@ struct Scratch {
     size_t npix = 0;
     uint32_t steps = 0;
     DeviceBuffer queues[2][6];
-    DeviceBuffer photons, counters, stats;
+    DeviceBuffer photons, hits, counters, stats;
     DeviceBuffer acc_colour, acc_sum, acc_bias, acc_weight, acc_wbias;
     DeviceBuffer lights, light_samples;
     cudaStream_t stream = nullptr;
@@ -260,6 +260,8 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
             }
         if (s->photons.p) cudaFree(s->photons.p), s->photons.p = nullptr;
         VRJ_CUDA(s->photons.alloc(capacity * sizeof(double2)));
+        if (s->hits.p) cudaFree(s->hits.p), s->hits.p = nullptr;
+        VRJ_CUDA(s->hits.alloc(capacity * sizeof(int2)));
         s->capacity = capacity;
     }
     if (s->npix < npix) {
@@ -273,7 +275,7 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
     }
     if (s->steps < steps) {
         if (s->counters.p) cudaFree(s->counters.p), s->counters.p = nullptr;
-        VRJ_CUDA(s->counters.alloc((size_t)steps * 2 * sizeof(uint32_t)));
+        VRJ_CUDA(s->counters.alloc((size_t)steps * 3 * sizeof(uint32_t)));
         s->steps = steps;
     }
     if (!s->stats.p) VRJ_CUDA(s->stats.alloc(ST_COUNT * sizeof(unsigned long long)));
@@ -297,33 +299,41 @@ int persistent_grid(const VrjScene *sc, K kernel) {
 
 template <typename NT, bool COUNT>
 VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, uint64_t *launches) {
-    const uint32_t steps = rc.max_depth + 2;
-    uint32_t *counts = s->counters.as<uint32_t>();    // queue length produced by step k
-    uint32_t *work = counts + steps;                  // work-fetch counter of step k
-    VRJ_CUDA(cudaMemsetAsync(counts, 0, (size_t)steps * 2 * sizeof(uint32_t), s->stream));
+    // launch sequence: T_p S_0 [T_k S_k]*, k = 1..levels; SimpleRandom needs max_depth levels, Whitted one more
+    // (its limit-0 level still shades and traces); the final S only finishes paths.
+    const uint32_t levels = whitted ? rc.max_depth + 1 : rc.max_depth;
+    uint32_t *counts = s->counters.as<uint32_t>();     // counts[k]: queue length written by S_{k-1} (k >= 1)
+    uint32_t *work = counts + (rc.max_depth + 3);      // work[2k] for T_k, work[2k+1] for S_k
+    VRJ_CUDA(cudaMemsetAsync(counts, 0, (size_t)(rc.max_depth + 3) * 3 * sizeof(uint32_t), s->stream));
     unsigned long long *stats = s->stats.as<unsigned long long>();
     double2 *photons = s->photons.as<double2>();
+    int2 *hits = s->hits.as<int2>();
+    const int g_tp = persistent_grid(sc, k_trace<NT, COUNT, true>), g_t = persistent_grid(sc, k_trace<NT, COUNT, false>);
+    const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, COUNT, false, true>);
+    const int g_s = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, COUNT, false, false>);
     VRJ_CUDA(s->mark(-1));
-    {
-        auto k = k_primary<NT, COUNT>;
-        int grid = persistent_grid(sc, k);
-        k<<<grid, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), counts + 0, work + 0, photons, stats, whitted ? 0 : 1);
-        (*launches)++;
-        VRJ_CUDA(s->mark(0));
-    }
-    // SimpleRandom needs at most max_depth levels, Whitted max_depth + 1 (limit 0 still shades)
-    const uint32_t levels = whitted ? rc.max_depth + 1 : rc.max_depth;
-    int grid_b = whitted ? persistent_grid(sc, k_bounce<NT, COUNT, true>) : persistent_grid(sc, k_bounce<NT, COUNT, false>);
-    for (uint32_t k = 0; k < levels; k++) {
-        PathQueue in = s->queue(k & 1), out = s->queue((k + 1) & 1);
-        if (whitted)
-            k_bounce<NT, COUNT, true><<<grid_b, 128, 0, s->stream>>>(sc->dev, rc, in, counts + k, out, counts + k + 1, work + k + 1, photons, stats);
-        else
-            k_bounce<NT, COUNT, false><<<grid_b, 128, 0, s->stream>>>(sc->dev, rc, in, counts + k, out, counts + k + 1, work + k + 1, photons, stats);
+    k_trace<NT, COUNT, true><<<g_tp, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, hits, work + 0, stats);
+    (*launches)++;
+    VRJ_CUDA(s->mark(0));
+    if (whitted)
+        k_shade<NT, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, hits, s->queue(1), counts + 1, work + 1, photons, stats);
+    else
+        k_shade<NT, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, hits, s->queue(1), counts + 1, work + 1, photons, stats);
+    (*launches)++;
+    VRJ_CUDA(s->mark(3));
+    for (uint32_t k = 1; k <= levels; k++) {
+        PathQueue cur = s->queue(k & 1), nxt = s->queue((k + 1) & 1);
+        k_trace<NT, COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, cur, counts + k, hits, work + 2 * k, stats);
         (*launches)++;
         VRJ_CUDA(s->mark(1));
+        if (whitted)
+            k_shade<NT, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, cur, counts + k, hits, nxt, counts + k + 1, work + 2 * k + 1, photons, stats);
+        else
+            k_shade<NT, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, cur, counts + k, hits, nxt, counts + k + 1, work + 2 * k + 1, photons, stats);
+        (*launches)++;
+        VRJ_CUDA(s->mark(3));
         // long recursion limits: stop launching once the queue has drained
-        if (levels > 12 && (k + 1) % 8 == 0 && k + 1 < levels) {
+        if (levels > 12 && k % 8 == 0 && k < levels) {
             VRJ_CUDA(cudaMemcpyAsync(s->host_count, counts + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
             VRJ_CUDA(cudaStreamSynchronize(s->stream));
             if (*s->host_count == 0) break;
@@ -515,7 +525,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         Scratch *s;
         ~Releaser() { release_scratch(sc, s); }
     } releaser{scene, s};
-    VrjStatus st = ensure_scratch(s, npix * batch, npix, p->max_depth + 2, p->n_lights, n_light_samples);
+    VrjStatus st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples);
     if (st != VRJ_OK) return st;
 
     const cudaMemcpyKind in_kind = out->memory == VRJ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -600,8 +610,8 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     VRJ_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     if (out->stats) {
         fill_stats(out->stats, hstats, launches, ms);
-        double cls_ms[3] = {0, 0, 0};
-        uint64_t cls_n[3] = {0, 0, 0};
+        double cls_ms[4] = {0, 0, 0, 0};
+        uint64_t cls_n[4] = {0, 0, 0, 0};
         for (size_t i = 1; i < s->n_marks; i++) {
             int c = s->mark_class[i];
             if (c < 0) continue;
@@ -610,6 +620,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         }
         out->stats->primary_ms = cls_ms[0], out->stats->bounce_ms = cls_ms[1], out->stats->resolve_ms = cls_ms[2];
         out->stats->primary_launches = cls_n[0], out->stats->bounce_launches = cls_n[1], out->stats->resolve_launches = cls_n[2];
+        out->stats->shade_ms = cls_ms[3], out->stats->shade_launches = cls_n[3];
     }
     return VRJ_OK;
 }

@@ -1,10 +1,12 @@
 // vrj_kernels.cuh -- the wavefront: persistent-thread kernels for one batch of samples.
 //
-//   k_primary : camera ray (camera.rs:45-66) -> closest hit -> miss: black sample
-//               (camera.rs:110-113); hit: draw the wavelength (photon.rs:18-24), enqueue.
-//   k_bounce  : one level of Integrator::integrate for every queued path: rebuild the hit,
-//               sample the material, trace the bounce ray (and, for Whitted, the shadow rays),
-//               finish the path (sky / depth limit) or enqueue it, warp-ballot compacted.
+//   k_trace   : Sampler::sample for every ray of the queue (the first launch generates the camera
+//               rays, camera.rs:45-66): a pure map ray -> (item, triangle); carries no shading state,
+//               so its register budget is the traversal's alone.
+//   k_shade   : consumes those hits: finishes paths (miss: black / sky; depth limit) or runs one level
+//               of Integrator::integrate -- rebuild the hit, sample the material (Whitted: trace the
+//               shadow rays), update the affine accumulator -- and enqueues the bounce ray,
+//               warp-ballot compacted.
 //   k_resolve : per pixel, apply the batch's samples IN SAMPLE ORDER to the Kahan accumulator
 //               (AccumulationBuffer::update_pixel, accumulation_buffer.rs:44-60).
 //
@@ -21,14 +23,15 @@ struct LightDev {
     SpectrumDev spectrum; // samples live in RenderConst::light_samples
 };
 
-// Double-buffered path queue, structure of 16-byte arrays (every access is coalesced).
+// Path queue, structure of 16-byte arrays (every access is coalesced).  k_shade writes an entry
+// (compacted), k_trace reads its ray and fills hit[]; the next k_shade consumes both.
 struct PathQueue {
-    double2 *q0; // origin.x, origin.y      of the ray that produced the hit
+    double2 *q0; // origin.x, origin.y      of the ray to trace / that produced the hit
     double2 *q1; // origin.z, direction.x
     double2 *q2; // direction.y, direction.z
     double2 *q3; // wavelength, A
-    double2 *q4; // B, bits{item, triangle}
-    uint4 *q5;   // result slot, rng draw ordinal, recursion limit left, unused
+    double2 *q4; // B, aux (SimpleRandom: W.y of the un-normalised bounce direction; Whitted: B before the bounce term)
+    uint4 *q5;   // result slot, rng draw ordinal, recursion limit of the NEXT integrate level, flags (1 = terminal)
 };
 
 struct RenderConst {
@@ -80,14 +83,13 @@ __device__ __forceinline__ uint32_t queue_reserve(bool alive, uint32_t *count) {
 }
 
 __device__ __forceinline__ void queue_store(const PathQueue &q, uint32_t idx, D3 o, D3 d, double wl, double A, double B,
-                                            int item, int tri, uint32_t slot, uint32_t ordinal, uint32_t limit) {
+                                            double aux, uint32_t slot, uint32_t ordinal, uint32_t limit, uint32_t flags) {
     q.q0[idx] = make_double2(o.x, o.y);
     q.q1[idx] = make_double2(o.z, d.x);
     q.q2[idx] = make_double2(d.y, d.z);
     q.q3[idx] = make_double2(wl, A);
-    long long bits = (long long)(((unsigned long long)(uint32_t)tri << 32) | (unsigned long long)(uint32_t)item);
-    q.q4[idx] = make_double2(B, __longlong_as_double(bits));
-    q.q5[idx] = make_uint4(slot, ordinal, limit, 0u);
+    q.q4[idx] = make_double2(B, aux);
+    q.q5[idx] = make_uint4(slot, ordinal, limit, flags);
 }
 
 // Ray::new (raycasting/mod.rs:41-46) then .bias(amount) (raycasting/mod.rs:58-60): normalise, offset, normalise again
@@ -106,67 +108,12 @@ __device__ __forceinline__ void slot_to_pixel(const RenderConst &rc, uint32_t sl
     sample = rc.first_sample + (uint64_t)s * rc.sample_stride;
 }
 
-template <typename NT, bool COUNT>
-__global__ void __launch_bounds__(128) k_primary(DevScene sc, RenderConst rc, PathQueue out, uint32_t *out_count,
-                                                 uint32_t *work, double2 *photons, unsigned long long *stats,
-                                                 int simple_random) {
-    const uint32_t n = rc.npix * rc.batch_samples;
-    const uint32_t lane = threadIdx.x & 31;
-    LocalStats ls;
-    ls.clear();
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t slot = base + lane;
-        bool active = slot < n;
-        bool alive = false;
-        D3 o = d3(0, 0, 0), d = d3(0, 0, 1);
-        double wl = 0.0;
-        Hit hit;
-        hit.item = -1, hit.tri = -1, hit.t = 0.0;
-        uint32_t ordinal = 0;
-        if (active) {
-            uint32_t pixel;
-            uint64_t sample, grow, gcol;
-            slot_to_pixel(rc, slot, pixel, sample, grow, gcol);
-            Rng rng;
-            rng.init(rc.seed, pixel, sample, 0);
-            double ux = rng.f64(), uy = rng.f64();
-            // camera.rs:45-66
-            double px = ((double)gcol + ux) * (rc.film_w * (1.0 / (double)rc.width)) - rc.film_w * 0.5;
-            double py = ((double)(rc.height - (grow + 1)) + uy) * (rc.film_h * (1.0 / (double)rc.height)) - rc.film_h * 0.5;
-            o = d3(sc.cam[0], sc.cam[1], sc.cam[2]);
-            d = normalize(d3(px, py, 1.0));
-            TraceCounters tc = {0, 0};
-            hit = trace_closest<NT, COUNT, false>(sc, o, d, tc);
-            ls.v[ST_PRIMARY]++;
-            if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
-            if (hit.item < 0) {
-                photons[slot] = make_double2(0.0, 0.0); // camera.rs:110-113
-                ls.v[ST_MISSED]++;
-            } else if (simple_random && rc.max_depth == 0) {
-                rng.f64();                              // Photon::random_wavelength() is still drawn
-                photons[slot] = make_double2(0.0, 0.0); // simple_random_integrator.rs:20-25
-                ls.v[ST_LIMITED]++;
-            } else {
-                wl = 380.0 + (740.0 - 380.0) * rng.f64(); // photon.rs:18-24
-                ordinal = rng.ordinal;
-                alive = true;
-            }
-        }
-        uint32_t idx = queue_reserve(alive, out_count);
-        if (alive) queue_store(out, idx, o, d, wl, 1.0, 0.0, hit.item, hit.tri, slot, ordinal, rc.max_depth);
-    }
-    ls.flush(stats);
-}
-
-template <typename NT, bool COUNT, bool WHITTED>
-__global__ void __launch_bounds__(128) k_bounce(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
-                                                PathQueue out, uint32_t *out_count, uint32_t *work, double2 *photons,
-                                                unsigned long long *stats) {
-    const uint32_t n = *in_count;
+// ---- k_trace: Sampler::sample for every ray of a queue; a pure map ray -> (item, triangle) ----
+// PRIMARY: the ray is generated from the camera (camera.rs:45-66) and stored for k_shade.
+template <typename NT, bool COUNT, bool PRIMARY>
+__global__ void __launch_bounds__(128) k_trace(DevScene sc, RenderConst rc, PathQueue q, const uint32_t *in_count, int2 *hits,
+                                               uint32_t *work, unsigned long long *stats) {
+    const uint32_t n = PRIMARY ? rc.npix * rc.batch_samples : *in_count;
     const uint32_t lane = threadIdx.x & 31;
     LocalStats ls;
     ls.clear();
@@ -176,111 +123,180 @@ __global__ void __launch_bounds__(128) k_bounce(DevScene sc, RenderConst rc, Pat
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         uint32_t j = base + lane;
-        bool active = j < n;
-        bool alive = false;
-        D3 no = d3(0, 0, 0), nd = d3(0, 0, 1);
-        double wl = 0.0, A = 0.0, B = 0.0;
-        Hit nh;
-        nh.item = -1, nh.tri = -1, nh.t = 0.0;
-        uint32_t slot = 0, ordinal = 0, limit = 0;
-        if (active) {
-            double2 a0 = in.q0[j], a1 = in.q1[j], a2 = in.q2[j], a3 = in.q3[j], a4 = in.q4[j];
-            uint4 a5 = in.q5[j];
-            D3 o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
-            wl = a3.x, A = a3.y, B = a4.x;
-            long long bits = __double_as_longlong(a4.y);
-            int item = (int)(uint32_t)(bits & 0xffffffffll), tri = (int)(uint32_t)((unsigned long long)bits >> 32);
-            slot = a5.x, ordinal = a5.y, limit = a5.z;
-
-            HitFrame h;
-            bool ok = rebuild_hit(sc, o, d, item, tri, h);
-            // algebra_utils.rs:3-5, mat3.rs:111-118
-            M3 w2b = from_rows(h.tangent, h.cotangent, h.normal), b2w;
-            ok = try_inverse(w2b, b2w) && ok;
-            if (!ok) {
-                // the reference panics here (simple_random_integrator.rs:28,31); report a NaN sample
-                photons[slot] = make_double2(wl, CUDART_NAN);
-            } else {
-                MaterialDev m = sc.materials[h.material];
-                double s = spectrum_intensity(sc.spectra, sc.spectrum_samples, m.spectrum, wl);
-                D3 w_retro = mul(w2b, h.retro);
-                TraceCounters tc = {0, 0};
-                if (WHITTED) {
-                    // whitted_integrator.rs:33-50: one shadow ray per light
-                    double direct = 0.0; // fold starts from photon.intensity == 0
-                    for (uint32_t li = 0; li < rc.n_lights; li++) {
-                        LightDev L = rc.lights[li];
-                        D3 ldir = d3(L.dir[0], L.dir[1], L.dir[2]);
-                        D3 so, sd;
-                        biased_ray(h.location, ldir, rc.bias, so, sd);
-                        Hit sh = trace_closest<NT, COUNT, true>(sc, so, sd, tc);
-                        ls.v[ST_SHADOW]++;
-                        double term;
-                        if (sh.item >= 0) {
-                            term = rc.has_ambient ? light_intensity(rc, rc.lights[rc.n_lights].spectrum, wl) : 0.0;
-                        } else {
-                            double emitted = light_intensity(rc, L.spectrum, wl);
-                            emitted = emitted * fabs(dot(ldir, h.normal));
-                            double la, lb;
-                            material_bsdf_affine(m, s, w_retro, mul(w2b, ldir), la, lb); // (retro, incoming) order
-                            term = la * emitted + lb;
-                        }
-                        direct += term;
-                    }
-                    B += A * direct;
-                }
-                Rng rng;
+        if (j < n) {
+            D3 o, d;
+            if (PRIMARY) {
                 uint32_t pixel;
                 uint64_t sample, grow, gcol;
-                slot_to_pixel(rc, slot, pixel, sample, grow, gcol);
-                rng.init(rc.seed, pixel, sample, ordinal);
-                D3 w_s;
-                double pdf;
-                material_sample(m, s, w_retro, rng, w_s, pdf);
-                ordinal = rng.ordinal;
-                D3 W = mul(b2w, w_s);
-                biased_ray(h.location, W, rc.bias, no, nd);
-                nh = trace_closest<NT, COUNT, false>(sc, no, nd, tc);
-                ls.v[ST_BOUNCE]++;
-                if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
-                double cosine = fabs(dot(W, h.normal));
+                slot_to_pixel(rc, j, pixel, sample, grow, gcol);
+                Rng rng;
+                rng.init(rc.seed, pixel, sample, 0);
+                double ux = rng.f64(), uy = rng.f64();
+                double px = ((double)gcol + ux) * (rc.film_w * (1.0 / (double)rc.width)) - rc.film_w * 0.5;
+                double py = ((double)(rc.height - (grow + 1)) + uy) * (rc.film_h * (1.0 / (double)rc.height)) - rc.film_h * 0.5;
+                o = d3(sc.cam[0], sc.cam[1], sc.cam[2]);
+                d = normalize(d3(px, py, 1.0));
+                q.q0[j] = make_double2(o.x, o.y);
+                q.q1[j] = make_double2(o.z, d.x);
+                q.q2[j] = make_double2(d.y, d.z);
+            } else {
+                double2 a0 = q.q0[j], a1 = q.q1[j], a2 = q.q2[j];
+                o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
+            }
+            TraceCounters tc = {0, 0};
+            Hit h = trace_closest<NT, COUNT, false>(sc, o, d, tc);
+            hits[j] = make_int2(h.item, h.tri);
+            ls.v[PRIMARY ? ST_PRIMARY : ST_BOUNCE]++;
+            if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
+        }
+    }
+    ls.flush(stats);
+}
+
+// ---- k_shade: consume the hits of the previous k_trace; finish paths (black / sky / depth limit) or run one
+// level of Integrator::integrate and enqueue the bounce ray, warp-ballot compacted ----
+template <typename NT, bool COUNT, bool WHITTED, bool FIRST>
+__global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
+                                               const int2 *hits, PathQueue out, uint32_t *out_count, uint32_t *work,
+                                               double2 *photons, unsigned long long *stats) {
+    const uint32_t n = FIRST ? rc.npix * rc.batch_samples : *in_count;
+    const uint32_t lane = threadIdx.x & 31;
+    LocalStats ls;
+    ls.clear();
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t j = base + lane;
+        bool alive = false;
+        D3 no = d3(0, 0, 0), nd = d3(0, 0, 1);
+        double wl = 0.0, A = 0.0, B = 0.0, aux = 0.0;
+        uint32_t slot = 0, ordinal = 0, limit = 0, flags = 0;
+        if (j < n) {
+            int2 hit = hits[j];
+            bool finished = false;
+            if (FIRST) {
+                slot = j;
+                if (hit.x < 0) {
+                    photons[slot] = make_double2(0.0, 0.0); // camera.rs:110-113
+                    ls.v[ST_MISSED]++;
+                    finished = true;
+                } else {
+                    uint32_t pixel;
+                    uint64_t sample, grow, gcol;
+                    slot_to_pixel(rc, slot, pixel, sample, grow, gcol);
+                    Rng rng;
+                    rng.init(rc.seed, pixel, sample, 2);
+                    wl = 380.0 + (740.0 - 380.0) * rng.f64(); // photon.rs:18-24
+                    ordinal = 3, A = 1.0, B = 0.0, limit = rc.max_depth;
+                    if (!WHITTED && limit == 0) {
+                        photons[slot] = make_double2(0.0, 0.0); // simple_random_integrator.rs:20-25
+                        ls.v[ST_LIMITED]++;
+                        finished = true;
+                    }
+                }
+            } else {
+                double2 a3 = in.q3[j], a4 = in.q4[j];
+                uint4 a5 = in.q5[j];
+                wl = a3.x, A = a3.y, B = a4.x, aux = a4.y;
+                slot = a5.x, ordinal = a5.y, limit = a5.z, flags = a5.w;
                 if (WHITTED) {
-                    // whitted_integrator.rs:52-79: bsdf(retro, sampled, L_in) * |W.n|, pdf unused
-                    if (nh.item >= 0 && limit > 0) {
-                        double ba, bb;
+                    // whitted_integrator.rs:52-79: the bounce term counts only if the ray hit and the level had limit > 0
+                    if (hit.x < 0 || (flags & 1u)) {
+                        photons[slot] = make_double2(wl, aux * (740.0 - 380.0));
+                        if (hit.x < 0) ls.v[ST_ESCAPED]++;
+                        else ls.v[ST_LIMITED]++;
+                        finished = true;
+                    }
+                } else if (hit.x < 0) {
+                    double L = rgb_reflection_intensity(aux, aux, 1.0, wl); // sky(W): simple_random_integrator.rs:43-46,57-65
+                    photons[slot] = make_double2(wl, (A * L + B) * (740.0 - 380.0));
+                    ls.v[ST_ESCAPED]++;
+                    finished = true;
+                } else if (limit == 0) {
+                    // the recursion returns Photon{0,0} (:20-25): wavelength 0 makes the sample's XYZ ~0
+                    photons[slot] = make_double2(0.0, 0.0);
+                    ls.v[ST_LIMITED]++;
+                    finished = true;
+                }
+            }
+            if (!finished) {
+                double2 a0 = in.q0[j], a1 = in.q1[j], a2 = in.q2[j];
+                D3 o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
+                HitFrame h;
+                bool ok = rebuild_hit(sc, o, d, hit.x, hit.y, h);
+                // algebra_utils.rs:3-5, mat3.rs:111-118
+                M3 w2b = from_rows(h.tangent, h.cotangent, h.normal), b2w;
+                ok = try_inverse(w2b, b2w) && ok;
+                if (!ok) {
+                    // the reference panics here (simple_random_integrator.rs:28,31); report a NaN sample
+                    photons[slot] = make_double2(wl, CUDART_NAN);
+                } else {
+                    MaterialDev m = sc.materials[h.material];
+                    double s = spectrum_intensity(sc.spectra, sc.spectrum_samples, m.spectrum, wl);
+                    D3 w_retro = mul(w2b, h.retro);
+                    if (WHITTED) {
+                        // whitted_integrator.rs:33-50: one shadow ray per light
+                        TraceCounters tc = {0, 0};
+                        double direct = 0.0; // fold starts from photon.intensity == 0
+                        for (uint32_t li = 0; li < rc.n_lights; li++) {
+                            LightDev Lt = rc.lights[li];
+                            D3 ldir = d3(Lt.dir[0], Lt.dir[1], Lt.dir[2]);
+                            D3 so, sd;
+                            biased_ray(h.location, ldir, rc.bias, so, sd);
+                            Hit sh = trace_closest<NT, COUNT, true>(sc, so, sd, tc);
+                            ls.v[ST_SHADOW]++;
+                            double term;
+                            if (sh.item >= 0) {
+                                term = rc.has_ambient ? light_intensity(rc, rc.lights[rc.n_lights].spectrum, wl) : 0.0;
+                            } else {
+                                double emitted = light_intensity(rc, Lt.spectrum, wl);
+                                emitted = emitted * fabs(dot(ldir, h.normal));
+                                double la, lb;
+                                material_bsdf_affine(m, s, w_retro, mul(w2b, ldir), la, lb); // (retro, incoming) order
+                                term = la * emitted + lb;
+                            }
+                            direct += term;
+                        }
+                        if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
+                        B += A * direct;
+                    }
+                    Rng rng;
+                    uint32_t pixel;
+                    uint64_t sample, grow, gcol;
+                    slot_to_pixel(rc, slot, pixel, sample, grow, gcol);
+                    rng.init(rc.seed, pixel, sample, ordinal);
+                    D3 w_s;
+                    double pdf;
+                    material_sample(m, s, w_retro, rng, w_s, pdf);
+                    ordinal = rng.ordinal;
+                    D3 W = mul(b2w, w_s);
+                    biased_ray(h.location, W, rc.bias, no, nd);
+                    double cosine = fabs(dot(W, h.normal));
+                    double ba, bb;
+                    if (WHITTED) {
+                        // bsdf(retro, sampled, L_in) * |W.n|, pdf unused; B before the bounce term is kept in aux
                         material_bsdf_affine(m, s, w_retro, w_s, ba, bb);
+                        aux = B;
                         B += A * (bb * cosine);
                         A *= ba * cosine;
-                        limit -= 1;
-                        alive = true;
+                        flags = limit == 0 ? 1u : 0u; // the ray is still traced at limit 0, its result unused
+                        limit = limit ? limit - 1 : 0;
                     } else {
-                        photons[slot] = make_double2(wl, B * (740.0 - 380.0));
-                        if (nh.item < 0) ls.v[ST_ESCAPED]++;
-                        else ls.v[ST_LIMITED]++;
-                    }
-                } else {
-                    // simple_random_integrator.rs:39-53: bsdf(sampled, retro, L_in * pdf * |W.n|)
-                    double ba, bb;
-                    material_bsdf_affine(m, s, w_s, w_retro, ba, bb);
-                    B += A * bb;
-                    A *= ba * (pdf * cosine);
-                    if (nh.item < 0) {
-                        double L = sky(W, wl); // :43-46 (W un-normalised, as written)
-                        photons[slot] = make_double2(wl, (A * L + B) * (740.0 - 380.0));
-                        ls.v[ST_ESCAPED]++;
-                    } else if (limit - 1 == 0) {
-                        // the recursion returns Photon{0,0} (:20-25): wavelength 0 makes the sample's XYZ ~0
-                        photons[slot] = make_double2(0.0, 0.0);
-                        ls.v[ST_LIMITED]++;
-                    } else {
+                        // simple_random_integrator.rs:39-53: bsdf(sampled, retro, L_in * pdf * |W.n|)
+                        material_bsdf_affine(m, s, w_s, w_retro, ba, bb);
+                        B += A * bb;
+                        A *= ba * (pdf * cosine);
+                        aux = W.y; // the sky uses the un-normalised W
                         limit -= 1;
-                        alive = true;
                     }
+                    alive = true;
                 }
             }
         }
         uint32_t idx = queue_reserve(alive, out_count);
-        if (alive) queue_store(out, idx, no, nd, wl, A, B, nh.item, nh.tri, slot, ordinal, limit);
+        if (alive) queue_store(out, idx, no, nd, wl, A, B, aux, slot, ordinal, limit, flags);
     }
     ls.flush(stats);
 }
