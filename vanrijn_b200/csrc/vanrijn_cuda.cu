@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -50,7 +51,7 @@ struct Scratch {
     size_t npix = 0;
     uint32_t steps = 0;
     DeviceBuffer queues[2][6];
-    DeviceBuffer photons, hits, counters, stats;
+    DeviceBuffer photons, hits[2], tbest[2], list, counters, stats;
     DeviceBuffer acc_colour, acc_sum, acc_bias, acc_weight, acc_wbias;
     DeviceBuffer lights, light_samples;
     cudaStream_t stream = nullptr;
@@ -76,6 +77,11 @@ struct Scratch {
         }
         mark_class[n_marks] = cls;
         return cudaEventRecord(marks[n_marks++], stream);
+    }
+    TraceBuffers trace_buffers(int i) const {
+        TraceBuffers t;
+        t.hits = hits[i].as<int2>(), t.tbest = tbest[i].as<double>(), t.list = list.as<uint32_t>();
+        return t;
     }
     PathQueue queue(int i) const {
         PathQueue q;
@@ -260,8 +266,14 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
             }
         if (s->photons.p) cudaFree(s->photons.p), s->photons.p = nullptr;
         VRJ_CUDA(s->photons.alloc(capacity * sizeof(double2)));
-        if (s->hits.p) cudaFree(s->hits.p), s->hits.p = nullptr;
-        VRJ_CUDA(s->hits.alloc(capacity * sizeof(int2)));
+        for (int i = 0; i < 2; i++) {
+            if (s->hits[i].p) cudaFree(s->hits[i].p), s->hits[i].p = nullptr;
+            VRJ_CUDA(s->hits[i].alloc(capacity * sizeof(int2)));
+            if (s->tbest[i].p) cudaFree(s->tbest[i].p), s->tbest[i].p = nullptr;
+            VRJ_CUDA(s->tbest[i].alloc(capacity * sizeof(double)));
+        }
+        if (s->list.p) cudaFree(s->list.p), s->list.p = nullptr;
+        VRJ_CUDA(s->list.alloc(capacity * sizeof(uint32_t)));
         s->capacity = capacity;
     }
     if (s->npix < npix) {
@@ -275,7 +287,7 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
     }
     if (s->steps < steps) {
         if (s->counters.p) cudaFree(s->counters.p), s->counters.p = nullptr;
-        VRJ_CUDA(s->counters.alloc((size_t)steps * 3 * sizeof(uint32_t)));
+        VRJ_CUDA(s->counters.alloc((size_t)steps * 4 * sizeof(uint32_t)));
         s->steps = steps;
     }
     if (!s->stats.p) VRJ_CUDA(s->stats.alloc(ST_COUNT * sizeof(unsigned long long)));
@@ -299,42 +311,54 @@ int persistent_grid(const VrjScene *sc, K kernel) {
 
 template <typename NT, bool COUNT>
 VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, uint64_t *launches) {
-    // launch sequence: T_p S_0 [T_k S_k]*, k = 1..levels; SimpleRandom needs max_depth levels, Whitted one more
+    // launch sequence: G T S_0 [T S_k]*, k = 1..levels; SimpleRandom needs max_depth levels, Whitted one more
     // (its limit-0 level still shades and traces); the final S only finishes paths.
     const uint32_t levels = whitted ? rc.max_depth + 1 : rc.max_depth;
-    uint32_t *counts = s->counters.as<uint32_t>();     // counts[k]: queue length written by S_{k-1} (k >= 1)
-    uint32_t *work = counts + (rc.max_depth + 3);      // work[2k] for T_k, work[2k+1] for S_k
-    VRJ_CUDA(cudaMemsetAsync(counts, 0, (size_t)(rc.max_depth + 3) * 3 * sizeof(uint32_t), s->stream));
+    const uint32_t stride = rc.max_depth + 3;
+    uint32_t *qcount = s->counters.as<uint32_t>(); // qcount[k]: length of the queue S_{k-1} wrote (k >= 1)
+    uint32_t *lcount = qcount + stride;             // lcount[k]: rays of queue k staged for BVH traversal
+    uint32_t *work_t = lcount + stride;             // work-fetch counters of T_k
+    uint32_t *work_s = work_t + stride;             // ... of G (k = 0 only) / S_k
+    VRJ_CUDA(cudaMemsetAsync(qcount, 0, (size_t)stride * 4 * sizeof(uint32_t), s->stream));
     unsigned long long *stats = s->stats.as<unsigned long long>();
     double2 *photons = s->photons.as<double2>();
-    int2 *hits = s->hits.as<int2>();
-    const int g_tp = persistent_grid(sc, k_trace<NT, COUNT, true>), g_t = persistent_grid(sc, k_trace<NT, COUNT, false>);
+    const int g_gen = persistent_grid(sc, k_raygen<COUNT>), g_t = persistent_grid(sc, k_trace<NT, COUNT>);
     const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, COUNT, false, true>);
     const int g_s = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, COUNT, false, false>);
+    const bool has_bvh = sc->dev.n_bvh_items > 0;
     VRJ_CUDA(s->mark(-1));
-    k_trace<NT, COUNT, true><<<g_tp, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, hits, work + 0, stats);
+    // the raygen kernel shares work_s[0] with nobody: S_0 uses work_t[stride-1] (never used by a T)
+    k_raygen<COUNT><<<g_gen, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_s + 0, stats);
     (*launches)++;
-    VRJ_CUDA(s->mark(0));
+    VRJ_CUDA(s->mark(4));
+    if (has_bvh) {
+        k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats);
+        (*launches)++;
+        VRJ_CUDA(s->mark(0));
+    }
+    uint32_t *work_s0 = work_t + (stride - 1);
     if (whitted)
-        k_shade<NT, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, hits, s->queue(1), counts + 1, work + 1, photons, stats);
+        k_shade<NT, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats);
     else
-        k_shade<NT, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, hits, s->queue(1), counts + 1, work + 1, photons, stats);
+        k_shade<NT, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats);
     (*launches)++;
     VRJ_CUDA(s->mark(3));
     for (uint32_t k = 1; k <= levels; k++) {
-        PathQueue cur = s->queue(k & 1), nxt = s->queue((k + 1) & 1);
-        k_trace<NT, COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, cur, counts + k, hits, work + 2 * k, stats);
-        (*launches)++;
-        VRJ_CUDA(s->mark(1));
+        const int ci = k & 1, ni = (k + 1) & 1;
+        if (has_bvh) {
+            k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats);
+            (*launches)++;
+            VRJ_CUDA(s->mark(1));
+        }
         if (whitted)
-            k_shade<NT, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, cur, counts + k, hits, nxt, counts + k + 1, work + 2 * k + 1, photons, stats);
+            k_shade<NT, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats);
         else
-            k_shade<NT, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, cur, counts + k, hits, nxt, counts + k + 1, work + 2 * k + 1, photons, stats);
+            k_shade<NT, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats);
         (*launches)++;
         VRJ_CUDA(s->mark(3));
         // long recursion limits: stop launching once the queue has drained
         if (levels > 12 && k % 8 == 0 && k < levels) {
-            VRJ_CUDA(cudaMemcpyAsync(s->host_count, counts + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+            VRJ_CUDA(cudaMemcpyAsync(s->host_count, qcount + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
             VRJ_CUDA(cudaStreamSynchronize(s->stream));
             if (*s->host_count == 0) break;
         }
@@ -450,10 +474,18 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         }
     }
     std::vector<ItemDev> items;
+    std::vector<uint32_t> analytic_items, bvh_items;
     for (uint32_t i = 0; i < d->n_items; i++) {
         const VrjItem &it = d->items[i];
         if (it.kind == VRJ_ITEM_BVH && bvh_empty[it.index]) continue; // an empty BVH never reports a hit
-        ItemDev id{it.kind, it.index, it.object_id, it.prim_id, it.kind == VRJ_ITEM_BVH ? bvh_root[it.index] : 0u, 0u};
+        ItemDev id{};
+        id.kind = it.kind, id.index = it.index, id.object_id = it.object_id, id.prim_id = it.prim_id;
+        id.root = it.kind == VRJ_ITEM_BVH ? bvh_root[it.index] : 0u;
+        if (it.kind == VRJ_ITEM_BVH) {
+            const uint64_t rn = d->bvhs[it.index].first_node;
+            for (int k = 0; k < 3; k++) id.lo[k] = round_down_f32(d->node_min[rn * 4 + k]), id.hi[k] = round_up_f32(d->node_max[rn * 4 + k]);
+        }
+        (it.kind == VRJ_ITEM_BVH ? bvh_items : analytic_items).push_back((uint32_t)items.size());
         items.push_back(id);
     }
     std::vector<float4> n32(wb.n32.size() / 4);
@@ -473,8 +505,14 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     VRJ_TRY(upload(sc, spectra, sc->dev.spectra));
     VRJ_TRY(upload(sc, samples, sc->dev.spectrum_samples));
     VRJ_TRY(upload(sc, items, sc->dev.items));
+    VRJ_TRY(upload(sc, analytic_items, sc->dev.analytic_items));
+    VRJ_TRY(upload(sc, bvh_items, sc->dev.bvh_items));
     sc->dev.n_items = (uint32_t)items.size();
+    sc->dev.n_analytic = (uint32_t)analytic_items.size(), sc->dev.n_bvh_items = (uint32_t)bvh_items.size();
     for (int k = 0; k < 3; k++) sc->dev.cam[k] = d->camera_location[k];
+    sc->dev.refill_threshold = 16, sc->dev.leaf_threshold = 2, sc->dev.node_batch = 4, sc->dev.max_iters = 64;
+    if (const char *tune = std::getenv("VRJ_TUNE")) // experiments only: "refill,leaf,node_batch,max_iters"
+        std::sscanf(tune, "%d,%d,%d,%d", &sc->dev.refill_threshold, &sc->dev.leaf_threshold, &sc->dev.node_batch, &sc->dev.max_iters);
     *out = sc;
     return VRJ_OK;
 #undef VRJ_TRY
@@ -610,8 +648,8 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     VRJ_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     if (out->stats) {
         fill_stats(out->stats, hstats, launches, ms);
-        double cls_ms[4] = {0, 0, 0, 0};
-        uint64_t cls_n[4] = {0, 0, 0, 0};
+        double cls_ms[5] = {0, 0, 0, 0, 0}; // 0 T (camera rays), 1 T (bounce rays), 2 resolve, 3 shade, 4 raygen
+        uint64_t cls_n[5] = {0, 0, 0, 0, 0};
         for (size_t i = 1; i < s->n_marks; i++) {
             int c = s->mark_class[i];
             if (c < 0) continue;
@@ -620,7 +658,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         }
         out->stats->primary_ms = cls_ms[0], out->stats->bounce_ms = cls_ms[1], out->stats->resolve_ms = cls_ms[2];
         out->stats->primary_launches = cls_n[0], out->stats->bounce_launches = cls_n[1], out->stats->resolve_launches = cls_n[2];
-        out->stats->shade_ms = cls_ms[3], out->stats->shade_launches = cls_n[3];
+        out->stats->shade_ms = cls_ms[3] + cls_ms[4], out->stats->shade_launches = cls_n[3] + cls_n[4];
     }
     return VRJ_OK;
 }
@@ -633,14 +671,19 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     if (bvh_filter > VRJ_FILTER_F64) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
     if (stats) std::memset(stats, 0, sizeof(VrjStats));
     if (n == 0) return VRJ_OK;
+    if (n > 0xfffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "more than 2^32 rays in one call");
     VRJ_CUDA(cudaSetDevice(scene->device));
-    DeviceBuffer d_o, d_d, d_obj, d_prim, d_t, d_stats;
+    DeviceBuffer d_o, d_d, d_obj, d_prim, d_t, d_stats, d_q[3], d_hits, d_tbest, d_list;
     VRJ_CUDA(d_o.alloc(n * 24));
     VRJ_CUDA(d_d.alloc(n * 24));
     VRJ_CUDA(d_obj.alloc(n * 4));
     VRJ_CUDA(d_prim.alloc(n * 4));
     VRJ_CUDA(d_t.alloc(n * 8));
-    VRJ_CUDA(d_stats.alloc(ST_COUNT * sizeof(unsigned long long)));
+    for (int i = 0; i < 3; i++) VRJ_CUDA(d_q[i].alloc(n * 16));
+    VRJ_CUDA(d_hits.alloc(n * 8));
+    VRJ_CUDA(d_tbest.alloc(n * 8));
+    VRJ_CUDA(d_list.alloc(n * 4));
+    VRJ_CUDA(d_stats.alloc((ST_COUNT + 1) * sizeof(unsigned long long)));
     cudaStream_t stream;
     VRJ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     cudaEvent_t e0, e1;
@@ -652,15 +695,25 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     } cleanup{stream, e0, e1};
     VRJ_CUDA(cudaMemcpyAsync(d_o.p, origins, n * 24, cudaMemcpyHostToDevice, stream));
     VRJ_CUDA(cudaMemcpyAsync(d_d.p, directions, n * 24, cudaMemcpyHostToDevice, stream));
-    VRJ_CUDA(cudaMemsetAsync(d_stats.p, 0, ST_COUNT * sizeof(unsigned long long), stream));
-    int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)scene->sm_count * 16);
+    VRJ_CUDA(cudaMemsetAsync(d_stats.p, 0, (ST_COUNT + 1) * sizeof(unsigned long long), stream));
+    unsigned long long *dstats = d_stats.as<unsigned long long>();
+    uint32_t *d_lcount = reinterpret_cast<uint32_t *>(dstats + ST_COUNT), *d_work = d_lcount + 1;
+    PathQueue q{};
+    q.q0 = d_q[0].as<double2>(), q.q1 = d_q[1].as<double2>(), q.q2 = d_q[2].as<double2>();
+    TraceBuffers tb{d_hits.as<int2>(), d_tbest.as<double>(), d_list.as<uint32_t>()};
+    const uint32_t n32 = (uint32_t)n;
+    int grid_a = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)scene->sm_count * 16);
     VRJ_CUDA(cudaEventRecord(e0, stream));
-    if (bvh_filter == VRJ_FILTER_F64)
-        k_trace_rays<double, true><<<grid, 128, 0, stream>>>(scene->dev, n, d_o.as<double>(), d_d.as<double>(), d_obj.as<int32_t>(),
-                                                             d_prim.as<int32_t>(), d_t.as<double>(), d_stats.as<unsigned long long>());
-    else
-        k_trace_rays<float, true><<<grid, 128, 0, stream>>>(scene->dev, n, d_o.as<double>(), d_d.as<double>(), d_obj.as<int32_t>(),
-                                                            d_prim.as<int32_t>(), d_t.as<double>(), d_stats.as<unsigned long long>());
+    k_stage_ray_list<true><<<grid_a, 128, 0, stream>>>(scene->dev, n32, d_o.as<double>(), d_d.as<double>(), q, tb, d_lcount, dstats);
+    uint64_t launches = 2;
+    if (scene->dev.n_bvh_items) {
+        launches++;
+        if (bvh_filter == VRJ_FILTER_F64)
+            k_trace<double, true><<<persistent_grid(scene, k_trace<double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats);
+        else
+            k_trace<float, true><<<persistent_grid(scene, k_trace<float, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats);
+    }
+    k_hit_ids<<<(n32 + 255) / 256, 256, 0, stream>>>(scene->dev, n32, tb, d_obj.as<int32_t>(), d_prim.as<int32_t>(), d_t.as<double>(), dstats);
     VRJ_CUDA(cudaGetLastError());
     VRJ_CUDA(cudaEventRecord(e1, stream));
     VRJ_CUDA(cudaMemcpyAsync(object_id, d_obj.p, n * 4, cudaMemcpyDeviceToHost, stream));
@@ -671,7 +724,7 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     VRJ_CUDA(cudaStreamSynchronize(stream));
     float ms = 0.f;
     VRJ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    if (stats) fill_stats(stats, hstats, 1, ms);
+    if (stats) fill_stats(stats, hstats, launches, ms);
     return VRJ_OK;
 }
 

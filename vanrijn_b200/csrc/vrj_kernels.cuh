@@ -108,12 +108,35 @@ __device__ __forceinline__ void slot_to_pixel(const RenderConst &rc, uint32_t sl
     sample = rc.first_sample + (uint64_t)s * rc.sample_stride;
 }
 
-// ---- k_trace: Sampler::sample for every ray of a queue; a pure map ray -> (item, triangle) ----
-// PRIMARY: the ray is generated from the camera (camera.rs:45-66) and stored for k_shade.
-template <typename NT, bool COUNT, bool PRIMARY>
-__global__ void __launch_bounds__(128) k_trace(DevScene sc, RenderConst rc, PathQueue q, const uint32_t *in_count, int2 *hits,
-                                               uint32_t *work, unsigned long long *stats) {
-    const uint32_t n = PRIMARY ? rc.npix * rc.batch_samples : *in_count;
+// Stage-1 results of one ray + the list of rays that still need BVH traversal
+struct TraceBuffers {
+    int2 *hits;            // per queue entry: (item, triangle), -1 = miss
+    double *tbest;         // per queue entry: distance of that hit (+inf on a miss)
+    uint32_t *list;        // queue entries whose ray passed a BVH root pre-test
+};
+
+// analytic objects + BVH root pre-test for the ray just written to queue entry `idx`; all 32 lanes call
+template <bool COUNT>
+__device__ __forceinline__ void stage_ray(const DevScene &sc, bool have_ray, uint32_t idx, D3 o, D3 d, const TraceBuffers &tb,
+                                          uint32_t *list_count, LocalStats &ls) {
+    bool need = false;
+    if (have_ray) {
+        Hit best;
+        TraceCounters tc = {0, 0};
+        need = pretrace<COUNT>(sc, o, d, best, tc);
+        tb.hits[idx] = make_int2(best.item, best.tri);
+        tb.tbest[idx] = best.t;
+        if (COUNT) ls.v[ST_TRIS] += tc.tri_tests;
+    }
+    uint32_t pos = queue_reserve(need, list_count);
+    if (need) tb.list[pos] = idx;
+}
+
+// ---- k_raygen: camera rays (camera.rs:45-66) into queue 0, staged for traversal ----
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_raygen(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, uint32_t *list_count,
+                                                uint32_t *work, unsigned long long *stats) {
+    const uint32_t n = rc.npix * rc.batch_samples;
     const uint32_t lane = threadIdx.x & 31;
     LocalStats ls;
     ls.clear();
@@ -123,42 +146,73 @@ __global__ void __launch_bounds__(128) k_trace(DevScene sc, RenderConst rc, Path
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         uint32_t j = base + lane;
+        D3 o = d3(0, 0, 0), d = d3(0, 0, 1);
         if (j < n) {
-            D3 o, d;
-            if (PRIMARY) {
-                uint32_t pixel;
-                uint64_t sample, grow, gcol;
-                slot_to_pixel(rc, j, pixel, sample, grow, gcol);
-                Rng rng;
-                rng.init(rc.seed, pixel, sample, 0);
-                double ux = rng.f64(), uy = rng.f64();
-                double px = ((double)gcol + ux) * (rc.film_w * (1.0 / (double)rc.width)) - rc.film_w * 0.5;
-                double py = ((double)(rc.height - (grow + 1)) + uy) * (rc.film_h * (1.0 / (double)rc.height)) - rc.film_h * 0.5;
-                o = d3(sc.cam[0], sc.cam[1], sc.cam[2]);
-                d = normalize(d3(px, py, 1.0));
-                q.q0[j] = make_double2(o.x, o.y);
-                q.q1[j] = make_double2(o.z, d.x);
-                q.q2[j] = make_double2(d.y, d.z);
-            } else {
-                double2 a0 = q.q0[j], a1 = q.q1[j], a2 = q.q2[j];
-                o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
-            }
-            TraceCounters tc = {0, 0};
-            Hit h = trace_closest<NT, COUNT, false>(sc, o, d, tc);
-            hits[j] = make_int2(h.item, h.tri);
-            ls.v[PRIMARY ? ST_PRIMARY : ST_BOUNCE]++;
-            if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
+            uint32_t pixel;
+            uint64_t sample, grow, gcol;
+            slot_to_pixel(rc, j, pixel, sample, grow, gcol);
+            Rng rng;
+            rng.init(rc.seed, pixel, sample, 0);
+            double ux = rng.f64(), uy = rng.f64();
+            double px = ((double)gcol + ux) * (rc.film_w * (1.0 / (double)rc.width)) - rc.film_w * 0.5;
+            double py = ((double)(rc.height - (grow + 1)) + uy) * (rc.film_h * (1.0 / (double)rc.height)) - rc.film_h * 0.5;
+            o = d3(sc.cam[0], sc.cam[1], sc.cam[2]);
+            d = normalize(d3(px, py, 1.0));
+            q.q0[j] = make_double2(o.x, o.y);
+            q.q1[j] = make_double2(o.z, d.x);
+            q.q2[j] = make_double2(d.y, d.z);
+            ls.v[ST_PRIMARY]++;
         }
+        stage_ray<COUNT>(sc, j < n, j, o, d, tb, list_count, ls);
     }
     ls.flush(stats);
+}
+
+// ---- k_trace: BVH traversal for the staged rays; updates hits / tbest where a triangle is closer ----
+struct ListRaySource {
+    const PathQueue &q;
+    const TraceBuffers &tb;
+    __device__ __forceinline__ void load(uint32_t r, D3 &o, D3 &d, Hit &best) {
+        uint32_t j = tb.list[r];
+        double2 a0 = q.q0[j], a1 = q.q1[j], a2 = q.q2[j];
+        o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
+        int2 h = tb.hits[j];
+        best.item = h.x, best.tri = h.y, best.t = tb.tbest[j];
+    }
+};
+struct ListHitSink {
+    const TraceBuffers &tb;
+    __device__ __forceinline__ void store(uint32_t r, const Hit &best, bool improved) {
+        if (!improved) return;
+        uint32_t j = tb.list[r];
+        tb.hits[j] = make_int2(best.item, best.tri);
+        tb.tbest[j] = best.t;
+    }
+};
+
+template <typename NT, bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
+                                               uint32_t *work, unsigned long long *stats) {
+    const uint32_t n = *list_count;
+    ListRaySource source{q, tb};
+    ListHitSink sink{tb};
+    TraceCounters tc = {0, 0};
+    trace_persistent<NT, COUNT>(sc, n, work, source, sink, tc);
+    if (COUNT) {
+        LocalStats ls;
+        ls.clear();
+        ls.v[ST_NODES] = tc.node_visits, ls.v[ST_TRIS] = tc.tri_tests;
+        ls.flush(stats);
+    }
 }
 
 // ---- k_shade: consume the hits of the previous k_trace; finish paths (black / sky / depth limit) or run one
 // level of Integrator::integrate and enqueue the bounce ray, warp-ballot compacted ----
 template <typename NT, bool COUNT, bool WHITTED, bool FIRST>
 __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
-                                               const int2 *hits, PathQueue out, uint32_t *out_count, uint32_t *work,
-                                               double2 *photons, unsigned long long *stats) {
+                                               TraceBuffers tb_in, PathQueue out, uint32_t *out_count, TraceBuffers tb_out,
+                                               uint32_t *list_count, uint32_t *work, double2 *photons,
+                                               unsigned long long *stats) {
     const uint32_t n = FIRST ? rc.npix * rc.batch_samples : *in_count;
     const uint32_t lane = threadIdx.x & 31;
     LocalStats ls;
@@ -174,7 +228,7 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderConst rc, Path
         double wl = 0.0, A = 0.0, B = 0.0, aux = 0.0;
         uint32_t slot = 0, ordinal = 0, limit = 0, flags = 0;
         if (j < n) {
-            int2 hit = hits[j];
+            int2 hit = tb_in.hits[j];
             bool finished = false;
             if (FIRST) {
                 slot = j;
@@ -296,7 +350,11 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderConst rc, Path
             }
         }
         uint32_t idx = queue_reserve(alive, out_count);
-        if (alive) queue_store(out, idx, no, nd, wl, A, B, aux, slot, ordinal, limit, flags);
+        if (alive) {
+            queue_store(out, idx, no, nd, wl, A, B, aux, slot, ordinal, limit, flags);
+            ls.v[ST_BOUNCE]++;
+        }
+        stage_ray<COUNT>(sc, alive, idx, no, nd, tb_out, list_count, ls);
     }
     ls.flush(stats);
 }
@@ -333,41 +391,50 @@ __global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t npix, u
     acc.colour[3 * p] = sx * inv, acc.colour[3 * p + 1] = sy * inv, acc.colour[3 * p + 2] = sz * inv;
 }
 
-// Sampler::sample on a caller-supplied ray list (the bit-exact id gate)
-template <typename NT, bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_rays(DevScene sc, uint64_t n, const double *origins, const double *dirs,
-                                                    int32_t *object_id, int32_t *prim_id, double *t,
-                                                    unsigned long long *stats) {
+// Sampler::sample on a caller-supplied ray list (the bit-exact id gate): same stages as the render path
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_stage_ray_list(DevScene sc, uint32_t n, const double *origins, const double *dirs,
+                                                        PathQueue q, TraceBuffers tb, uint32_t *list_count,
+                                                        unsigned long long *stats) {
     LocalStats ls;
     ls.clear();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ull);
-         i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t padded = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += gridDim.x * blockDim.x) {
+        D3 o = d3(0, 0, 0), d = d3(0, 0, 1);
         if (i < n) {
-            D3 o = d3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
-            D3 d = normalize(d3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2])); // Ray::new
-            TraceCounters tc = {0, 0};
-            Hit h = trace_closest<NT, COUNT, false>(sc, o, d, tc);
+            o = d3(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2]);
+            d = normalize(d3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2])); // Ray::new
+            q.q0[i] = make_double2(o.x, o.y);
+            q.q1[i] = make_double2(o.z, d.x);
+            q.q2[i] = make_double2(d.y, d.z);
             ls.v[ST_PRIMARY]++;
-            if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
-            if (h.item < 0) {
-                object_id[i] = -1, prim_id[i] = -1, t[i] = CUDART_INF;
-                ls.v[ST_MISSED]++;
-            } else {
-                ItemDev it = sc.items[h.item];
-                object_id[i] = (int32_t)it.object_id;
-                if (it.kind >= 2) {
-                    D3 v0, v1, v2;
-                    uint32_t mat, pid;
-                    load_tri_pos(sc, h.tri, v0, v1, v2, mat, pid);
-                    prim_id[i] = (int32_t)pid;
-                } else {
-                    prim_id[i] = (int32_t)it.prim_id;
-                }
-                t[i] = h.t;
-            }
         }
+        stage_ray<COUNT>(sc, i < n, i, o, d, tb, list_count, ls);
     }
     ls.flush(stats);
+}
+
+__global__ void k_hit_ids(DevScene sc, uint32_t n, TraceBuffers tb, int32_t *object_id, int32_t *prim_id, double *t,
+                          unsigned long long *stats) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int2 h = tb.hits[i];
+    if (h.x < 0) {
+        object_id[i] = -1, prim_id[i] = -1, t[i] = CUDART_INF;
+        atomicAdd(stats + ST_MISSED, 1ull);
+        return;
+    }
+    ItemDev it = sc.items[h.x];
+    object_id[i] = (int32_t)it.object_id;
+    if (it.kind >= 2) {
+        D3 v0, v1, v2;
+        uint32_t mat, pid;
+        load_tri_pos(sc, h.y, v0, v1, v2, mat, pid);
+        prim_id[i] = (int32_t)pid;
+    } else {
+        prim_id[i] = (int32_t)it.prim_id;
+    }
+    t[i] = tb.tbest[i];
 }
 
 } // namespace vrj

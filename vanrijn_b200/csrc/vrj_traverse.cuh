@@ -16,6 +16,7 @@ struct ItemDev {
     uint32_t kind, index, object_id, prim_id;
     uint32_t root; // VRJ_ITEM_BVH: index of the root wide node
     uint32_t pad;
+    float lo[3], hi[3]; // VRJ_ITEM_BVH: the root's box, rounded outward (pre-test before a ray is queued for traversal)
 };
 
 struct DevScene {
@@ -30,6 +31,12 @@ struct DevScene {
     const double *__restrict__ spectrum_samples;
     const ItemDev *__restrict__ items;
     uint32_t n_items;
+    // the same items split by kind for the persistent traversal: indices into items[]
+    const uint32_t *__restrict__ analytic_items; // spheres, planes, flat-list triangles
+    const uint32_t *__restrict__ bvh_items;
+    uint32_t n_analytic, n_bvh_items;
+    // persistent-traversal tuning (lanes): refill when this many lanes are idle; run postponed leaf tests when this many are parked
+    int refill_threshold, leaf_threshold, node_batch, max_iters;
     double cam[3];
 };
 
@@ -239,6 +246,184 @@ __device__ __forceinline__ Hit trace_closest(const DevScene &sc, D3 o, D3 d, Tra
         }
     }
     return best;
+}
+
+// ------------------------------------------------------------------------------------------
+// Closest hit, stage 1 (runs inside the fully-SIMD ray-producing kernels): the analytic objects
+// (spheres, planes, flat-list triangles) and a conservative pre-test of every BVH's root box.
+// Returns the best analytic hit and whether the ray has to be queued for BVH traversal.
+template <bool COUNT>
+__device__ __forceinline__ bool pretrace(const DevScene &sc, D3 o, D3 d, Hit &best, TraceCounters &cnt) {
+    best.t = CUDART_INF, best.item = -1, best.tri = -1;
+    for (uint32_t a = 0; a < sc.n_analytic; a++) {
+        uint32_t i = sc.analytic_items[a];
+        ItemDev it = sc.items[i];
+        double t;
+        int tri = -1;
+        bool hit;
+        if (it.kind == 0) hit = sphere_test(sc.spheres[it.index], o, d, t);
+        else if (it.kind == 1) hit = plane_test(sc.planes[it.index], o, d, t);
+        else {
+            TriRay tr = tri_ray(o, d);
+            D3 v0, v1, v2, loc;
+            uint32_t mat, pid;
+            double b0, b1, b2;
+            load_tri_pos(sc, (int)it.index, v0, v1, v2, mat, pid);
+            if (COUNT) cnt.tri_tests += 1;
+            hit = triangle_test(tr, v0, v1, v2, t, b0, b1, b2, loc);
+            tri = (int)it.index;
+        }
+        // sampler.rs:14-19 (min_by keeps the earlier object on ties); items are visited in object order here
+        if (hit && (best.item < 0 || t < best.t)) best.t = t, best.item = (int)i, best.tri = tri;
+    }
+    bool need = false;
+    if (sc.n_bvh_items) {
+        FilterRay<float> fr = filter_ray<float>(o, d);
+        float limit = FilterTraits<float>::up(best.t * (1.0 + 4.0 * (double)FilterTraits<float>::rel()));
+        for (uint32_t b = 0; b < sc.n_bvh_items; b++) {
+            ItemDev it = sc.items[sc.bvh_items[b]];
+            float e;
+            need = need || box_filter(fr, it.lo[0], it.hi[0], it.lo[1], it.hi[1], it.lo[2], it.hi[2], limit, e);
+        }
+    }
+    return need;
+}
+
+// ------------------------------------------------------------------------------------------
+// Closest hit, stage 2: the persistent-thread BVH engine.  Every lane owns one ray at a time; when
+// enough lanes of the warp have run dry they write their results and fetch new rays with ONE
+// warp-aggregated atomic, so short traversals do not hold the warp hostage to the longest one.  Box
+// steps run in small batches between warp votes; exact triangle tests are postponed until several lanes
+// are parked at a leaf (or nobody has box work left), so the expensive binary64 test runs with many lanes.
+//
+// Semantics: objects compete with "smaller distance wins, earlier object wins ties" (sampler.rs:14-19),
+// triangles inside one BVH with "later DFS leaf wins ties" (bounding_volume_hierarchy.rs:77-92).
+//
+// Source:  void load(uint32_t r, D3 &o, D3 &d, Hit &best)   -- ray r of the list and its best analytic hit
+// Sink:    void store(uint32_t r, const Hit &best, bool improved)
+template <typename NT, bool COUNT, typename Source, typename Sink>
+__device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n, uint32_t *work, Source &source, Sink &sink,
+                                                 TraceCounters &cnt) {
+    typedef FilterTraits<NT> F;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t NONE = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const int refill_threshold = sc.refill_threshold, leaf_threshold = sc.leaf_threshold;
+    const int node_batch = sc.node_batch, max_iters = sc.max_iters;
+    int stack[32];
+    int sp = 0, cur = VRJ_LEAF_DONE;
+    uint32_t r = NONE, bcur = 0;
+    bool improved = false;
+    TriRay tr;
+    FilterRay<NT> fr;
+    Hit best;
+    double loc_t = CUDART_INF;
+    int loc_tri = -1;
+    NT limit = (NT)0;
+    bool exhausted = false;
+    tr.o = d3(0, 0, 0), tr.sx = tr.sy = tr.pdz = 0.0, tr.perm = 0;
+    best.t = CUDART_INF, best.item = -1, best.tri = -1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) fr.id[k] = fr.cn[k] = fr.cf[k] = (NT)0;
+
+    // the current BVH's closest triangle competes with the best of the other objects, then the next BVH starts
+    auto finish_bvh = [&]() {
+        uint32_t item = sc.bvh_items[bcur];
+        if (loc_tri >= 0 && (best.item < 0 || loc_t < best.t || (loc_t == best.t && (int)item < best.item)))
+            best.t = loc_t, best.item = (int)item, best.tri = loc_tri, improved = true;
+        bcur++;
+        if (bcur < sc.n_bvh_items) {
+            cur = (int)sc.items[sc.bvh_items[bcur]].root;
+            sp = 0, loc_t = CUDART_INF, loc_tri = -1;
+            limit = F::up(best.t * (1.0 + 4.0 * (double)F::rel()));
+        } else {
+            cur = VRJ_LEAF_DONE;
+        }
+    };
+    auto node_step = [&]() {
+        WideNode<NT> nd;
+        load_node(sc, cur, nd);
+        if (COUNT) cnt.node_visits += 2;
+        NT e0, e1;
+        bool h0 = box_filter(fr, nd.c0[0], nd.c0[1], nd.c0[2], nd.c0[3], nd.c0[4], nd.c0[5], limit, e0);
+        bool h1 = box_filter(fr, nd.c1[0], nd.c1[1], nd.c1[2], nd.c1[3], nd.c1[4], nd.c1[5], limit, e1);
+        if (h0 && h1) {
+            bool swap = e1 < e0;
+            stack[sp++] = swap ? nd.left : nd.right;
+            cur = swap ? nd.right : nd.left;
+        } else if (h0 || h1) {
+            cur = h0 ? nd.left : nd.right;
+        } else if (sp) {
+            cur = stack[--sp];
+        } else {
+            finish_bvh();
+        }
+    };
+
+    while (true) {
+        // ---- results out, new rays in ----
+        bool idle = cur == VRJ_LEAF_DONE;
+        unsigned idle_mask = __ballot_sync(FULL, idle);
+        if (idle_mask) {
+            if (idle && r != NONE) {
+                sink.store(r, best, improved);
+                r = NONE;
+            }
+            if (exhausted) {
+                if (idle_mask == FULL) break;
+            } else if (idle_mask == FULL || __popc(idle_mask) >= refill_threshold) {
+                uint32_t want = (uint32_t)__popc(idle_mask), base = 0;
+                int leader = __ffs(idle_mask) - 1;
+                if ((int)lane == leader) base = atomicAdd(work, want);
+                base = __shfl_sync(FULL, base, leader);
+                if (base + want >= n) exhausted = true;
+                if (idle) {
+                    uint32_t my = base + (uint32_t)__popc(idle_mask & ((1u << lane) - 1u));
+                    if (my < n) {
+                        D3 o, d;
+                        source.load(my, o, d, best);
+                        r = my, improved = false;
+                        tr = tri_ray(o, d);
+                        fr = filter_ray<NT>(o, d);
+                        bcur = 0;
+                        cur = (int)sc.items[sc.bvh_items[0]].root;
+                        sp = 0, loc_t = CUDART_INF, loc_tri = -1;
+                        limit = F::up(best.t * (1.0 + 4.0 * (double)F::rel()));
+                    }
+                }
+            }
+        }
+        // ---- traverse until enough lanes have run dry ----
+#pragma unroll 1
+        for (int it = 0; it < max_iters; it++) {
+#pragma unroll 1
+            for (int u = 0; u < node_batch; u++)
+                if (cur >= 0) node_step();
+            bool at_leaf = cur < 0 && cur != VRJ_LEAF_DONE;
+            unsigned leaf_mask = __ballot_sync(FULL, at_leaf);
+            unsigned node_mask = __ballot_sync(FULL, cur >= 0);
+            if (leaf_mask && (node_mask == 0 || __popc(leaf_mask) >= leaf_threshold)) {
+                if (at_leaf) {
+                    int tri = ~cur;
+                    D3 v0, v1, v2, loc;
+                    uint32_t mat, pid;
+                    load_tri_pos(sc, tri, v0, v1, v2, mat, pid);
+                    if (COUNT) cnt.tri_tests += 1;
+                    double dist, b0, b1, b2;
+                    if (triangle_test(tr, v0, v1, v2, dist, b0, b1, b2, loc)) {
+                        if (dist < loc_t || (dist == loc_t && tri > loc_tri)) {
+                            loc_t = dist, loc_tri = tri;
+                            limit = F::up(fmin(loc_t, best.t) * (1.0 + 4.0 * (double)F::rel()));
+                        }
+                    }
+                    if (sp) cur = stack[--sp];
+                    else finish_bvh();
+                }
+            }
+            unsigned done_mask = __ballot_sync(FULL, cur == VRJ_LEAF_DONE);
+            if (done_mask == FULL || (!exhausted && __popc(done_mask) >= refill_threshold)) break;
+        }
+    }
 }
 
 // Rebuild the IntersectionInfo (raycasting/mod.rs:67-97) of a known hit with the exact arithmetic
