@@ -8,7 +8,8 @@ NVCC ?= nvcc
 HOSTCXX = g++
 NVFLAGS = -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 --extended-lambda \
           -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
-LIBDIR = vanrijn_b200/lib
+LIBDIR ?= vanrijn_b200/lib
+EXTRA ?=
 CSRC = vanrijn_b200/csrc
 CUDA_DEPS = $(CSRC)/vanrijn_cuda.cu $(CSRC)/vrj_kernels.cuh $(CSRC)/vrj_traverse.cuh $(CSRC)/vrj_device.cuh \
             $(CSRC)/rgb_basis_tables.inc include/vanrijn_cuda.h
@@ -18,7 +19,7 @@ all: $(LIBDIR)/libvanrijn_cuda.so $(LIBDIR)/libvanrijn_host.so oracle
 
 $(LIBDIR)/libvanrijn_cuda.so: $(CUDA_DEPS)
 	mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/vanrijn_cuda.cu
+	$(NVCC) $(NVFLAGS) $(EXTRA) -shared -o $@ $(CSRC)/vanrijn_cuda.cu
 
 $(LIBDIR)/libvanrijn_host.so: $(HOST_DEPS) $(LIBDIR)/libvanrijn_cuda.so
 	$(HOSTCXX) -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -Wextra -shared -o $@ \

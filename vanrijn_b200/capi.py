@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.environ.get("VRJ_LIBDIR") or os.path.join(HERE, "lib")  # VRJ_LIBDIR: kernel-variant experiments only
 
 dp = C.POINTER(C.c_double)
 u64p = C.POINTER(C.c_uint64)

@@ -553,7 +553,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     VRJ_CUDA(cudaSetDevice(scene->device));
 
     // batch: as many samples of the whole tile in flight as fit the path budget
-    const uint64_t path_budget = 1ull << 24;
+    const uint64_t path_budget = 1ull << 26; // 64 Mi paths in flight (~14 GB of queue state: sized for 180 GB of HBM)
     uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(p->spp, path_budget / npix));
     if (npix * (uint64_t)batch > 0xfffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "tile too large");
     const bool whitted = p->integrator == VRJ_INTEGRATOR_WHITTED;

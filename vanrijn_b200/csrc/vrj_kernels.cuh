@@ -16,7 +16,20 @@
 #pragma once
 #include "vrj_traverse.cuh"
 
+// minimum resident CTAs (of 128 threads) per SM the register allocator must allow
+#ifndef VRJ_SHADE_MINB
+#define VRJ_SHADE_MINB 5
+#endif
+#ifndef VRJ_SHADE_CHUNK
+#define VRJ_SHADE_CHUNK 1024
+#endif
+#ifndef VRJ_TRACE_MINB
+#define VRJ_TRACE_MINB 6
+#endif
+
 namespace vrj {
+
+constexpr int SHADE_CHUNK = VRJ_SHADE_CHUNK;
 
 struct LightDev {
     double dir[3];
@@ -134,7 +147,7 @@ __device__ __forceinline__ void stage_ray(const DevScene &sc, bool have_ray, uin
 
 // ---- k_raygen: camera rays (camera.rs:45-66) into queue 0, staged for traversal ----
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_raygen(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, uint32_t *list_count,
+__global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_raygen(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, uint32_t *list_count,
                                                 uint32_t *work, unsigned long long *stats) {
     const uint32_t n = rc.npix * rc.batch_samples;
     const uint32_t lane = threadIdx.x & 31;
@@ -191,7 +204,7 @@ struct ListHitSink {
 };
 
 template <typename NT, bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
+__global__ void __launch_bounds__(128, VRJ_TRACE_MINB) k_trace(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
                                                uint32_t *work, unsigned long long *stats) {
     const uint32_t n = *list_count;
     ListRaySource source{q, tb};
@@ -209,20 +222,44 @@ __global__ void __launch_bounds__(128) k_trace(DevScene sc, PathQueue q, TraceBu
 // ---- k_shade: consume the hits of the previous k_trace; finish paths (black / sky / depth limit) or run one
 // level of Integrator::integrate and enqueue the bounce ray, warp-ballot compacted ----
 template <typename NT, bool COUNT, bool WHITTED, bool FIRST>
-__global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
+__global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_shade(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
                                                TraceBuffers tb_in, PathQueue out, uint32_t *out_count, TraceBuffers tb_out,
                                                uint32_t *list_count, uint32_t *work, double2 *photons,
                                                unsigned long long *stats) {
     const uint32_t n = FIRST ? rc.npix * rc.batch_samples : *in_count;
-    const uint32_t lane = threadIdx.x & 31;
+    // A CTA takes SHADE_CHUNK queue entries at a time and orders them by hit class (miss / sphere / plane /
+    // triangle) in shared memory before shading, so the lanes of a warp run the same rebuild_hit branch.
+    __shared__ uint32_t s_sorted[SHADE_CHUNK];
+    __shared__ uint32_t s_count[4], s_base;
     LocalStats ls;
     ls.clear();
     while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        if (threadIdx.x == 0) s_base = atomicAdd(work, (uint32_t)SHADE_CHUNK);
+        if (threadIdx.x < 4) s_count[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t base = s_base;
         if (base >= n) break;
-        uint32_t j = base + lane;
+        const uint32_t total = min((uint32_t)SHADE_CHUNK, n - base);
+        uint32_t cls[SHADE_CHUNK / 128], pos[SHADE_CHUNK / 128];
+#pragma unroll
+        for (int e = 0; e < SHADE_CHUNK / 128; e++) {
+            uint32_t k = threadIdx.x + e * 128;
+            cls[e] = 4;
+            if (k < total) {
+                int item = tb_in.hits[base + k].x;
+                cls[e] = item < 0 ? 0u : 1u + min(sc.items[item].kind, 2u);
+                pos[e] = atomicAdd(&s_count[cls[e]], 1u);
+            }
+        }
+        __syncthreads();
+        const uint32_t c0 = s_count[0], c1 = c0 + s_count[1], c2 = c1 + s_count[2];
+#pragma unroll
+        for (int e = 0; e < SHADE_CHUNK / 128; e++)
+            if (cls[e] < 4) s_sorted[(cls[e] == 0 ? 0u : cls[e] == 1 ? c0 : cls[e] == 2 ? c1 : c2) + pos[e]] = base + threadIdx.x + e * 128;
+        __syncthreads();
+#pragma unroll 1
+      for (uint32_t k = threadIdx.x; k < ((total + 31u) & ~31u); k += 128) {
+        const uint32_t j = k < total ? s_sorted[k] : n;
         bool alive = false;
         D3 no = d3(0, 0, 0), nd = d3(0, 0, 1);
         double wl = 0.0, A = 0.0, B = 0.0, aux = 0.0;
@@ -355,6 +392,8 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderConst rc, Path
             ls.v[ST_BOUNCE]++;
         }
         stage_ray<COUNT>(sc, alive, idx, no, nd, tb_out, list_count, ls);
+      }
+        __syncthreads(); // s_sorted / s_count are reused by the next chunk
     }
     ls.flush(stats);
 }
