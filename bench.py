@@ -160,7 +160,7 @@ def main():
     import torch
     import torch.distributed as dist
     import vanrijn_b200 as V
-    from vanrijn_b200 import capi
+    from vanrijn_b200 import capi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -187,16 +187,16 @@ def main():
     red_w = torch.zeros_like(acc_w)
 
     def step(k, accumulate=True):
-        # sample indices: rank + world * (k*spp + j), j = 0..spp-1  (sharded by sample index)
+        # sharded by sample index: this rank renders samples offset, offset+world, ... (vanrijn_b200/sharding.py)
+        offset, stride = sharding.shard_samples(rank, world, k, spp)
         st = hs.render_device(tile, H, W, acc_sum.data_ptr(), acc_w.data_ptr(), device=local, accumulate=accumulate,
-                              spp=spp, max_depth=MAX_DEPTH, seed=SEED, sample_offset=rank + world * k * spp,
-                              sample_stride=world, bvh_filter=bvh_filter)
+                              spp=spp, max_depth=MAX_DEPTH, seed=SEED, sample_offset=offset, sample_stride=stride,
+                              bvh_filter=bvh_filter)
         if world > 1:
             # the one exchange step: combine the per-GPU accumulation buffers into rank 0's (NCCL over NVLink)
             red_sum.copy_(acc_sum)
             red_w.copy_(acc_w)
-            dist.reduce(red_sum, dst=0, op=dist.ReduceOp.SUM)
-            dist.reduce(red_w, dst=0, op=dist.ReduceOp.SUM)
+            sharding.reduce_accumulation(red_sum, red_w, dst=0)
         return st
 
     def fence():
@@ -211,8 +211,8 @@ def main():
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"rays": 0, "launches": 0, "device_ms": 0.0, "bounce_ms": 0.0, "bounce_rays": 0, "bounce_launches": 0,
-           "primary_ms": 0.0, "resolve_ms": 0.0}
+    agg = {"rays": 0, "launches": 0, "device_ms": 0.0, "trace_ms": 0.0, "trace_launches": 0, "staged": 0,
+           "shade_ms": 0.0, "resolve_ms": 0.0}
     fence()
     ev0.record()
     t0 = time.perf_counter()
@@ -221,11 +221,11 @@ def main():
         agg["rays"] += st.rays
         agg["launches"] += int(st.kernel_launches) + (4 if world > 1 else 0)
         agg["device_ms"] += st.device_ms
-        agg["bounce_ms"] += st.bounce_ms
-        agg["primary_ms"] += st.primary_ms
+        agg["trace_ms"] += st.primary_ms + st.bounce_ms
+        agg["trace_launches"] += int(st.primary_launches + st.bounce_launches)
+        agg["staged"] += int(st.staged_rays)
+        agg["shade_ms"] += st.shade_ms
         agg["resolve_ms"] += st.resolve_ms
-        agg["bounce_rays"] += int(st.bounce_rays)
-        agg["bounce_launches"] += int(st.bounce_launches)
     ev1.record()
     fence()
     wall = time.perf_counter() - t0
@@ -244,7 +244,7 @@ def main():
         capi.check(capi.cuda().vrj_scene_create(C.byref(desc), local, C.byref(h)))
         hs._dev["e2e"] = h
         r = hs.render(tile, H, W, device="e2e", spp=spp, max_depth=MAX_DEPTH, seed=SEED,
-                      sample_offset=rank + world * k * spp, sample_stride=world, bvh_filter=bvh_filter)
+                      sample_offset=sharding.shard_samples(rank, world, k, spp)[0], sample_stride=world, bvh_filter=bvh_filter)
         capi.cuda().vrj_scene_destroy(h)
         del hs._dev["e2e"]
         dt = time.perf_counter() - t1
@@ -275,21 +275,30 @@ def main():
     V_ = st_ord.node_visits / st_ord.rays
     T_ = st_ord.tri_tests / st_ord.rays
     bytes_per_ray = 32.0 * V_ + 48.0 * T_ + 144.0
-    bounce_s = agg["bounce_ms"] / 1e3
-    achieved = bytes_per_ray * agg["bounce_rays"] / bounce_s / 1e9 if bounce_s > 0 else 0.0
+    # dominant kernel: k_trace (BVH traversal).  Its algorithmic bytes per launch are the node and triangle
+    # records of ALL ray queries of that level (V and T are per-query means, zeros included) plus the ray read
+    # and hit write of the rays it was handed; the rest of the 144 B/ray state allowance moves in k_shade.
+    trace_s = agg["trace_ms"] / 1e3
+    trace_bytes = (32.0 * V_ + 48.0 * T_) * agg["rays"] + 64.0 * agg["staged"]
+    achieved = trace_bytes / trace_s / 1e9 if trace_s > 0 else 0.0
+    step_achieved = bytes_per_ray * agg["rays"] / (agg["device_ms"] / 1e3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_bounce_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("k_trace_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_bounce", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_ray": bytes_per_ray, "V_nodes_per_ray": V_, "T_tris_per_ray": T_,
-                "avg_launch_ms": agg["bounce_ms"] / max(1, agg["bounce_launches"]),
-                "kernel_share_of_step": agg["bounce_ms"] / max(1e-9, agg["device_ms"]),
-                "note": "scene (BVH+triangles) is L2-resident by design; the HBM roofline is the conservative yard-stick (SURVEY 8d)"}
+                "algorithmic_bytes_per_launch": trace_bytes / max(1, agg["trace_launches"]),
+                "avg_launch_ms": agg["trace_ms"] / max(1, agg["trace_launches"]),
+                "kernel_share_of_step": agg["trace_ms"] / max(1e-9, agg["device_ms"]),
+                "whole_step": {"achieved": step_achieved, "frac": step_achieved / peak,
+                               "what": "bytes_per_ray x all ray queries / CUDA-event time of all kernels of the step"},
+                "note": "the scene (BVH + triangles) is L2-resident by design, so the traversal kernel can exceed the HBM "
+                        "figure; the HBM roofline is SURVEY 8d's conservative yard-stick"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -309,12 +318,12 @@ def main():
                        "integrator": "SimpleRandom", "spp_per_step_per_gpu": spp, "bvh_filter": args.filter,
                        "sharding": "sample index mod n_gpus; NCCL reduce of (sumXYZ, weight) to rank 0 each step",
                        "l2": "inputs larger than L2: %.1f GB of path state per step; the %.0f MB scene is L2-resident by design"
-                             % (min(spp, (1 << 24) // npix) * npix * 208 / 1e9, scene_bytes / 1e6)},
+                             % (min(spp, (1 << 26) // npix) * npix * 240 / 1e9, scene_bytes / 1e6)},
             "e2e": {"value": e2e_rays_all / e2e_max / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene_bytes),
                     "d2h_bytes_per_step": int(out_bytes), "steps": e2e_steps,
                     "what": "vrj_scene_create + vrj_render_tile(host AccumulationBuffer arrays) + vrj_scene_destroy per step"},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_ms": {"primary": agg["primary_ms"], "bounce": agg["bounce_ms"], "resolve": agg["resolve_ms"]}}
+            "kernel_ms": {"k_trace": agg["trace_ms"], "k_raygen+k_shade": agg["shade_ms"], "k_resolve": agg["resolve_ms"]}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

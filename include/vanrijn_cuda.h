@@ -188,8 +188,9 @@ typedef struct VrjStats {
     /* CUDA-event time per kernel class, summed over the call's launches (events on the launching stream) */
     double primary_ms, bounce_ms, resolve_ms;   /* k_trace (camera rays), k_trace (bounce rays), k_resolve */
     uint64_t primary_launches, bounce_launches, resolve_launches;
-    double shade_ms;                            /* k_shade */
+    double shade_ms;                            /* k_raygen + k_shade */
     uint64_t shade_launches;
+    uint64_t staged_rays;                       /* rays that passed a BVH root pre-test and went through k_trace */
 } VrjStats;
 
 /* The five arrays of AccumulationBuffer (accumulation_buffer.rs:6-12), tile-local, row-major like

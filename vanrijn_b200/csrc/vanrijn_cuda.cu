@@ -377,6 +377,7 @@ void fill_stats(VrjStats *st, const unsigned long long *h, uint64_t launches, fl
     st->primary_rays = h[ST_PRIMARY], st->bounce_rays = h[ST_BOUNCE], st->shadow_rays = h[ST_SHADOW];
     st->paths_missed = h[ST_MISSED], st->paths_escaped = h[ST_ESCAPED], st->paths_depth_limited = h[ST_LIMITED];
     st->node_visits = h[ST_NODES], st->triangle_tests = h[ST_TRIS];
+    st->staged_rays = h[ST_STAGED];
     st->kernel_launches = launches;
     st->device_ms = ms;
 }

@@ -68,7 +68,7 @@ __device__ __forceinline__ double light_intensity(const RenderConst &rc, const S
     return spectrum_lookup(s.shortest, s.longest, s.n, wavelength, [p](uint32_t i) { return __ldg(p + i); });
 }
 
-enum { ST_PRIMARY = 0, ST_BOUNCE, ST_SHADOW, ST_MISSED, ST_ESCAPED, ST_LIMITED, ST_NODES, ST_TRIS, ST_COUNT };
+enum { ST_PRIMARY = 0, ST_BOUNCE, ST_SHADOW, ST_MISSED, ST_ESCAPED, ST_LIMITED, ST_NODES, ST_TRIS, ST_STAGED, ST_COUNT };
 
 struct LocalStats {
     uint32_t v[ST_COUNT];
@@ -142,7 +142,7 @@ __device__ __forceinline__ void stage_ray(const DevScene &sc, bool have_ray, uin
         if (COUNT) ls.v[ST_TRIS] += tc.tri_tests;
     }
     uint32_t pos = queue_reserve(need, list_count);
-    if (need) tb.list[pos] = idx;
+    if (need) tb.list[pos] = idx, ls.v[ST_STAGED]++;
 }
 
 // ---- k_raygen: camera rays (camera.rs:45-66) into queue 0, staged for traversal ----
