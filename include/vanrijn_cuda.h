@@ -220,6 +220,12 @@ VRJ_API void vrj_scene_destroy(VrjScene *scene);
 /* bytes copied host->device by vrj_scene_create */
 VRJ_API uint64_t vrj_scene_device_bytes(const VrjScene *scene);
 
+/* Free the per-device scratch blocks (path queues etc.) the library keeps between calls. */
+VRJ_API void vrj_release_scratch(void);
+/* Page-locked host memory for output arrays (optional: any host pointer works, pinned ones copy faster). */
+VRJ_API void *vrj_alloc_host(uint64_t bytes);
+VRJ_API void vrj_free_host(void *p);
+
 /* partial_render_scene: render `tile` of a width x height image, params->spp samples per pixel. */
 VRJ_API VrjStatus vrj_render_tile(const VrjScene *scene, const VrjTile *tile, uint64_t height, uint64_t width,
                           const VrjRenderParams *params, VrjAccumOut *out);

@@ -23,7 +23,8 @@ OK = 0
 
 # every symbol include/vanrijn_cuda.h declares
 CUDA_SYMBOLS = ["vrj_last_error", "vrj_abi_version", "vrj_device_count", "vrj_scene_create", "vrj_scene_destroy",
-                "vrj_scene_device_bytes", "vrj_render_tile", "vrj_trace_rays"]
+                "vrj_scene_device_bytes", "vrj_render_tile", "vrj_trace_rays", "vrj_release_scratch", "vrj_alloc_host",
+                "vrj_free_host"]
 
 
 class VrjError(RuntimeError):
@@ -138,6 +139,9 @@ def cuda():
         L.vrj_scene_destroy.argtypes = [C.c_void_p]
         L.vrj_scene_device_bytes.restype = C.c_uint64
         L.vrj_scene_device_bytes.argtypes = [C.c_void_p]
+        L.vrj_alloc_host.restype = C.c_void_p
+        L.vrj_alloc_host.argtypes = [C.c_uint64]
+        L.vrj_free_host.argtypes = [C.c_void_p]
         L.vrj_render_tile.restype = C.c_int32
         L.vrj_render_tile.argtypes = [C.c_void_p, C.POINTER(Tile), C.c_uint64, C.c_uint64, C.POINTER(RenderParams),
                                       C.POINTER(AccumOut)]

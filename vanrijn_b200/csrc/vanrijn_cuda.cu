@@ -5,6 +5,7 @@
 #include "vrj_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -99,11 +100,8 @@ struct VrjScene {
     uint64_t device_bytes = 0;
     DevScene dev{};
     std::vector<DeviceBuffer *> owned;
-    std::mutex pool_mutex;
-    std::vector<Scratch *> pool;
     uint32_t n_spectra = 0;
     ~VrjScene() {
-        for (auto *s : pool) delete s;
         for (auto *b : owned) delete b;
     }
 };
@@ -121,23 +119,33 @@ VrjStatus upload(VrjScene *sc, const std::vector<T> &host, P &dev_ptr) {
     return VRJ_OK;
 }
 
-float round_down_f32(double v) {
-    float f = (float)v;
-    if ((double)f > v) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+// next representable float above / below (bit arithmetic: this runs 12x per BVH node at scene upload)
+inline float float_up(float f) {
+    if (!(f == f) || f == std::numeric_limits<float>::infinity()) return f;
+    if (f == 0.0f) return std::numeric_limits<float>::denorm_min();
+    int32_t b;
+    std::memcpy(&b, &f, 4);
+    b += b >= 0 ? 1 : -1;
+    std::memcpy(&f, &b, 4);
     return f;
 }
-float round_up_f32(double v) {
+inline float float_down(float f) { return -float_up(-f); }
+inline float round_down_f32(double v) {
     float f = (float)v;
-    if ((double)f < v) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
-    return f;
+    return (double)f > v ? float_down(f) : f;
+}
+inline float round_up_f32(double v) {
+    float f = (float)v;
+    return (double)f < v ? float_up(f) : f;
 }
 
 // Re-express one reference-topology BVH (a box per node) as "wide" nodes that carry the boxes of
 // both children, so one fetch decides both; leaves (<= 1 triangle) live in the child references.
 struct WideBuilder {
     const VrjSceneDesc *d;
-    std::vector<float> n32;   // 16 floats per wide node
-    std::vector<double> n64;  // 14 doubles per wide node
+    float *n32 = nullptr;   // 16 floats per wide node (caller-provided, zero-filled)
+    double *n64 = nullptr;  // 14 doubles per wide node
+    size_t count = 0, capacity = 0;
     void box_of(int64_t node, double lo[3], double hi[3]) const {
         for (int k = 0; k < 3; k++) lo[k] = d->node_min[node * 4 + k], hi[k] = d->node_max[node * 4 + k];
     }
@@ -165,12 +173,7 @@ struct WideBuilder {
         pair[which] = ref;
         std::memcpy(&g[12], pair, 8);
     }
-    size_t new_node() {
-        size_t w = n32.size() / 16;
-        n32.resize(n32.size() + 16, 0.0f);
-        n64.resize(n64.size() + 14, 0.0);
-        return w;
-    }
+    size_t new_node() { return count < capacity ? count++ : (count++, capacity - 1); } // overflow is checked by the caller
     // returns the reference to use for `node` from its parent
     int32_t child_ref(int64_t node, bool *empty) {
         *empty = false;
@@ -238,16 +241,29 @@ VrjStatus validate(const VrjSceneDesc *d) {
     return VRJ_OK;
 }
 
+// Scratch blocks are pooled per device for the life of the process (not per scene): a caller that creates a
+// scene per frame does not pay multi-GB cudaMalloc/cudaFree each time.  vrj_release_scratch() empties the pool.
+std::mutex g_staging_mutex;
+void *g_staging = nullptr;
+size_t g_staging_bytes = 0;
+std::mutex g_pool_mutex;
+std::vector<std::pair<int, Scratch *>> g_pool;
+
 Scratch *acquire_scratch(VrjScene *sc) {
-    std::lock_guard<std::mutex> g(sc->pool_mutex);
-    if (sc->pool.empty()) return new Scratch();
-    Scratch *s = sc->pool.back();
-    sc->pool.pop_back();
-    return s;
+    std::lock_guard<std::mutex> g(g_pool_mutex);
+    for (size_t i = 0; i < g_pool.size(); i++)
+        if (g_pool[i].first == sc->device) {
+            Scratch *s = g_pool[i].second;
+            g_pool.erase(g_pool.begin() + i);
+            return s;
+        }
+    return new Scratch();
 }
 void release_scratch(VrjScene *sc, Scratch *s) {
-    std::lock_guard<std::mutex> g(sc->pool_mutex);
-    if (sc->pool.size() < 4) sc->pool.push_back(s);
+    std::lock_guard<std::mutex> g(g_pool_mutex);
+    size_t same = 0;
+    for (auto &e : g_pool) same += e.first == sc->device;
+    if (same < 2) g_pool.push_back({sc->device, s});
     else delete s;
 }
 
@@ -400,8 +416,10 @@ int32_t vrj_device_count(void) {
 VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out) {
     if (!out) return fail(VRJ_ERR_INVALID_ARGUMENT, "out is NULL");
     *out = nullptr;
+    auto t_start = std::chrono::steady_clock::now();
     VrjStatus st = validate(d);
     if (st != VRJ_OK) return st;
+    auto t_valid = std::chrono::steady_clock::now();
     VRJ_CUDA(cudaSetDevice(device));
     VrjScene *sc = new VrjScene();
     sc->device = device;
@@ -423,37 +441,79 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         }                         \
     } while (0)
 
-    // spectra / materials / analytic primitives
-    std::vector<SpectrumDev> spectra(d->n_spectra);
+    // ---- one staging block (page-locked, reused across calls) -> one device arena -> one copy ----
+    uint64_t n_wide = 0;
+    for (uint32_t b = 0; b < d->n_bvhs; b++) {
+        const VrjBvh &bv = d->bvhs[b];
+        if (bv.n_nodes == 0 || bv.n_triangles == 0) continue;
+        uint64_t internal = 0;
+        for (uint64_t n = bv.first_node; n < bv.first_node + bv.n_nodes; n++) internal += d->node_child[2 * n] >= 0;
+        n_wide += std::max<uint64_t>(1, internal);
+    }
+    struct Section {
+        size_t offset, bytes;
+    };
+    size_t cursor = 0;
+    auto reserve_section = [&cursor](size_t bytes) {
+        Section sct{cursor, bytes};
+        cursor += (bytes + 255) & ~size_t(255);
+        return sct;
+    };
+    const Section s_n32 = reserve_section(n_wide * 64), s_n64 = reserve_section(n_wide * 112);
+    const Section s_tp = reserve_section((size_t)d->n_triangles * 80), s_tn = reserve_section((size_t)d->n_triangles * 80);
+    const Section s_sph = reserve_section(d->n_spheres * sizeof(SphereDev)), s_pl = reserve_section(d->n_planes * sizeof(PlaneDev));
+    const Section s_mat = reserve_section(d->n_materials * sizeof(MaterialDev)), s_spc = reserve_section(d->n_spectra * sizeof(SpectrumDev));
+    const Section s_smp = reserve_section(d->n_spectrum_samples * sizeof(double));
+    const Section s_it = reserve_section(d->n_items * sizeof(ItemDev)), s_an = reserve_section(d->n_items * 4), s_bv = reserve_section(d->n_items * 4);
+    const size_t arena_bytes = std::max<size_t>(cursor, 256);
+
+    std::lock_guard<std::mutex> staging_guard(g_staging_mutex);
+    if (g_staging_bytes < arena_bytes) {
+        if (g_staging) cudaFreeHost(g_staging), g_staging = nullptr, g_staging_bytes = 0;
+        cudaError_t he = cudaMallocHost(&g_staging, arena_bytes);
+        if (he != cudaSuccess) {
+            delete sc;
+            return fail(VRJ_ERR_OUT_OF_MEMORY, std::string("cudaMallocHost: ") + cudaGetErrorString(he));
+        }
+        g_staging_bytes = arena_bytes;
+    }
+    char *stage = static_cast<char *>(g_staging);
+
+    SpectrumDev *spectra = reinterpret_cast<SpectrumDev *>(stage + s_spc.offset);
     for (uint32_t i = 0; i < d->n_spectra; i++)
         spectra[i] = SpectrumDev{d->spectra[i].shortest_wavelength, d->spectra[i].longest_wavelength, d->spectra[i].first_sample, d->spectra[i].n_samples};
-    std::vector<double> samples(d->spectrum_samples, d->spectrum_samples + d->n_spectrum_samples);
-    std::vector<MaterialDev> materials(d->n_materials);
+    if (d->n_spectrum_samples) std::memcpy(stage + s_smp.offset, d->spectrum_samples, d->n_spectrum_samples * sizeof(double));
+    MaterialDev *materials = reinterpret_cast<MaterialDev *>(stage + s_mat.offset);
     for (uint32_t i = 0; i < d->n_materials; i++)
         materials[i] = MaterialDev{d->materials[i].kind, d->materials[i].spectrum, d->materials[i].p0, d->materials[i].p1, d->materials[i].p2};
-    std::vector<SphereDev> spheres(d->n_spheres);
+    SphereDev *spheres = reinterpret_cast<SphereDev *>(stage + s_sph.offset);
     for (uint32_t i = 0; i < d->n_spheres; i++)
         spheres[i] = SphereDev{d->spheres[i].centre[0], d->spheres[i].centre[1], d->spheres[i].centre[2], d->spheres[i].radius, d->spheres[i].material, 0};
-    std::vector<PlaneDev> planes(d->n_planes);
+    PlaneDev *planes = reinterpret_cast<PlaneDev *>(stage + s_pl.offset);
     for (uint32_t i = 0; i < d->n_planes; i++) {
         PlaneDev &p = planes[i];
         for (int k = 0; k < 3; k++) p.n[k] = d->planes[i].normal[k], p.t[k] = d->planes[i].tangent[k], p.c[k] = d->planes[i].cotangent[k];
         p.distance = d->planes[i].distance_from_origin, p.material = d->planes[i].material, p.pad = 0;
     }
     // triangles: 80-byte position and normal records
-    std::vector<double> tri_pos((size_t)d->n_triangles * 10), tri_nrm((size_t)d->n_triangles * 10);
+    double *tri_pos = reinterpret_cast<double *>(stage + s_tp.offset), *tri_nrm = reinterpret_cast<double *>(stage + s_tn.offset);
     for (uint64_t t = 0; t < d->n_triangles; t++) {
         const double *v[3] = {d->tri_v0 + 4 * t, d->tri_v1 + 4 * t, d->tri_v2 + 4 * t};
         const double *n[3] = {d->tri_n0 + 4 * t, d->tri_n1 + 4 * t, d->tri_n2 + 4 * t};
+        double *tp = tri_pos + t * 10, *tn = tri_nrm + t * 10;
         for (int k = 0; k < 3; k++)
-            for (int c = 0; c < 3; c++) tri_pos[t * 10 + 3 * k + c] = v[k][c], tri_nrm[t * 10 + 3 * k + c] = n[k][c];
+            for (int c = 0; c < 3; c++) tp[3 * k + c] = v[k][c], tn[3 * k + c] = n[k][c];
         uint64_t bits = ((uint64_t)d->tri_prim_id[t] << 32) | d->tri_material[t];
-        std::memcpy(&tri_pos[t * 10 + 9], &bits, 8);
-        tri_nrm[t * 10 + 9] = 0.0;
+        std::memcpy(&tp[9], &bits, 8);
+        tn[9] = 0.0;
     }
     // wide nodes per BVH
     WideBuilder wb;
     wb.d = d;
+    wb.n32 = reinterpret_cast<float *>(stage + s_n32.offset), wb.n64 = reinterpret_cast<double *>(stage + s_n64.offset);
+    wb.capacity = (size_t)n_wide;
+    std::memset(stage + s_n32.offset, 0, s_n32.bytes);
+    std::memset(stage + s_n64.offset, 0, s_n64.bytes);
     std::vector<uint32_t> bvh_root(d->n_bvhs, 0);
     std::vector<bool> bvh_empty(d->n_bvhs, false);
     for (uint32_t b = 0; b < d->n_bvhs; b++) {
@@ -474,8 +534,13 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
             bvh_root[b] = (uint32_t)wb.build(root);
         }
     }
-    std::vector<ItemDev> items;
-    std::vector<uint32_t> analytic_items, bvh_items;
+    if (wb.count != n_wide) {
+        delete sc;
+        return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh nodes do not form the trees their VrjBvh ranges describe");
+    }
+    ItemDev *items = reinterpret_cast<ItemDev *>(stage + s_it.offset);
+    uint32_t *analytic_items = reinterpret_cast<uint32_t *>(stage + s_an.offset), *bvh_items = reinterpret_cast<uint32_t *>(stage + s_bv.offset);
+    uint32_t n_items = 0, n_analytic = 0, n_bvh_items = 0;
     for (uint32_t i = 0; i < d->n_items; i++) {
         const VrjItem &it = d->items[i];
         if (it.kind == VRJ_ITEM_BVH && bvh_empty[it.index]) continue; // an empty BVH never reports a hit
@@ -485,35 +550,50 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         if (it.kind == VRJ_ITEM_BVH) {
             const uint64_t rn = d->bvhs[it.index].first_node;
             for (int k = 0; k < 3; k++) id.lo[k] = round_down_f32(d->node_min[rn * 4 + k]), id.hi[k] = round_up_f32(d->node_max[rn * 4 + k]);
+            bvh_items[n_bvh_items++] = n_items;
+        } else {
+            analytic_items[n_analytic++] = n_items;
         }
-        (it.kind == VRJ_ITEM_BVH ? bvh_items : analytic_items).push_back((uint32_t)items.size());
-        items.push_back(id);
+        items[n_items++] = id;
     }
-    std::vector<float4> n32(wb.n32.size() / 4);
-    std::memcpy(n32.data(), wb.n32.data(), wb.n32.size() * sizeof(float));
-    std::vector<double2> n64(wb.n64.size() / 2), tp(tri_pos.size() / 2), tn(tri_nrm.size() / 2);
-    std::memcpy(n64.data(), wb.n64.data(), wb.n64.size() * sizeof(double));
-    std::memcpy(tp.data(), tri_pos.data(), tri_pos.size() * sizeof(double));
-    std::memcpy(tn.data(), tri_nrm.data(), tri_nrm.size() * sizeof(double));
-
-    VRJ_TRY(upload(sc, n32, sc->dev.nodes32));
-    VRJ_TRY(upload(sc, n64, sc->dev.nodes64));
-    VRJ_TRY(upload(sc, tp, sc->dev.tri_pos));
-    VRJ_TRY(upload(sc, tn, sc->dev.tri_nrm));
-    VRJ_TRY(upload(sc, spheres, sc->dev.spheres));
-    VRJ_TRY(upload(sc, planes, sc->dev.planes));
-    VRJ_TRY(upload(sc, materials, sc->dev.materials));
-    VRJ_TRY(upload(sc, spectra, sc->dev.spectra));
-    VRJ_TRY(upload(sc, samples, sc->dev.spectrum_samples));
-    VRJ_TRY(upload(sc, items, sc->dev.items));
-    VRJ_TRY(upload(sc, analytic_items, sc->dev.analytic_items));
-    VRJ_TRY(upload(sc, bvh_items, sc->dev.bvh_items));
-    sc->dev.n_items = (uint32_t)items.size();
-    sc->dev.n_analytic = (uint32_t)analytic_items.size(), sc->dev.n_bvh_items = (uint32_t)bvh_items.size();
+    auto t_prep = std::chrono::steady_clock::now();
+    DeviceBuffer *arena = new DeviceBuffer();
+    sc->owned.push_back(arena);
+    {
+        cudaError_t ae = arena->alloc(arena_bytes);
+        if (ae == cudaSuccess) ae = cudaMemcpy(arena->p, stage, arena_bytes, cudaMemcpyHostToDevice);
+        if (ae != cudaSuccess) {
+            delete sc;
+            return fail(ae == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(ae));
+        }
+    }
+    sc->device_bytes = arena_bytes;
+    char *base = arena->as<char>();
+    sc->dev.nodes32 = reinterpret_cast<const float4 *>(base + s_n32.offset);
+    sc->dev.nodes64 = reinterpret_cast<const double2 *>(base + s_n64.offset);
+    sc->dev.tri_pos = reinterpret_cast<const double2 *>(base + s_tp.offset);
+    sc->dev.tri_nrm = reinterpret_cast<const double2 *>(base + s_tn.offset);
+    sc->dev.spheres = reinterpret_cast<const SphereDev *>(base + s_sph.offset);
+    sc->dev.planes = reinterpret_cast<const PlaneDev *>(base + s_pl.offset);
+    sc->dev.materials = reinterpret_cast<const MaterialDev *>(base + s_mat.offset);
+    sc->dev.spectra = reinterpret_cast<const SpectrumDev *>(base + s_spc.offset);
+    sc->dev.spectrum_samples = reinterpret_cast<const double *>(base + s_smp.offset);
+    sc->dev.items = reinterpret_cast<const ItemDev *>(base + s_it.offset);
+    sc->dev.analytic_items = reinterpret_cast<const uint32_t *>(base + s_an.offset);
+    sc->dev.bvh_items = reinterpret_cast<const uint32_t *>(base + s_bv.offset);
+    sc->dev.n_items = n_items, sc->dev.n_analytic = n_analytic, sc->dev.n_bvh_items = n_bvh_items;
     for (int k = 0; k < 3; k++) sc->dev.cam[k] = d->camera_location[k];
     sc->dev.refill_threshold = 16, sc->dev.leaf_threshold = 2, sc->dev.node_batch = 4, sc->dev.max_iters = 64;
     if (const char *tune = std::getenv("VRJ_TUNE")) // experiments only: "refill,leaf,node_batch,max_iters"
         std::sscanf(tune, "%d,%d,%d,%d", &sc->dev.refill_threshold, &sc->dev.leaf_threshold, &sc->dev.node_batch, &sc->dev.max_iters);
+    if (std::getenv("VRJ_TIMING")) {
+        auto t_end = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        std::fprintf(stderr, "vrj_scene_create: validate %.2f ms, prepare %.2f ms, upload %.2f ms\n", ms(t_start, t_valid),
+                     ms(t_valid, t_prep), ms(t_prep, t_end));
+    }
     *out = sc;
     return VRJ_OK;
 #undef VRJ_TRY
@@ -526,6 +606,28 @@ void vrj_scene_destroy(VrjScene *scene) {
 }
 
 uint64_t vrj_scene_device_bytes(const VrjScene *scene) { return scene ? scene->device_bytes : 0; }
+
+void vrj_release_scratch(void) {
+    std::lock_guard<std::mutex> g(g_pool_mutex);
+    for (auto &e : g_pool) {
+        cudaSetDevice(e.first);
+        delete e.second;
+    }
+    g_pool.clear();
+}
+
+void *vrj_alloc_host(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        g_error = "cudaMallocHost failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void vrj_free_host(void *p) {
+    if (p) cudaFreeHost(p);
+}
 
 VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t height, uint64_t width,
                           const VrjRenderParams *p, VrjAccumOut *out) {

@@ -126,20 +126,18 @@ class HostScene:
         return p, keep
 
     def render(self, tile, height, width, want=("colour", "colour_sum", "colour_bias", "weight", "weight_bias"),
-               want_photons=False, device=0, **kw):
-        """vrj_render_tile with host output buffers.  Returns a dict of numpy arrays + 'stats'."""
+               want_photons=False, device=0, buffers=None, **kw):
+        """vrj_render_tile with host output buffers (`buffers`: optional dict of caller-owned, e.g. pinned,
+        float64 arrays to fill instead of fresh ones).  Returns a dict of numpy arrays + 'stats'."""
         sc, ec, sr, er = tile
         npix = (ec - sc) * (er - sr)
         p, keep = self.make_params(**kw)
         out = {}
         ao = capi.AccumOut(memory=capi.MEM_HOST, accumulate=0)
-        for name in ("colour", "colour_sum", "colour_bias"):
+        for name, per in (("colour", 3), ("colour_sum", 3), ("colour_bias", 3), ("weight", 1), ("weight_bias", 1)):
             if name in want:
-                out[name] = np.zeros(npix * 3)
-                setattr(ao, name, out[name].ctypes.data)
-        for name in ("weight", "weight_bias"):
-            if name in want:
-                out[name] = np.zeros(npix)
+                out[name] = buffers[name] if buffers is not None else np.zeros(npix * per)
+                assert out[name].size == npix * per and out[name].dtype == np.float64
                 setattr(ao, name, out[name].ctypes.data)
         if want_photons:
             out["photons"] = np.zeros(p.spp * npix * 2)
