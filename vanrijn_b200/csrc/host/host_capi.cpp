@@ -68,14 +68,22 @@ int vrjh_add_spectrum_diamond(void *p) {
 /* copies spectrum `id` out: returns n_samples, fills lo/hi and up to cap samples */
 int vrjh_get_spectrum(void *p, int id, double *lo, double *hi, double *samples, int cap) {
     HostScene *h = static_cast<HostScene *>(p);
-    const Spectrum &s = h->spectra.at(id);
+    if (id < 0 || id >= (int)h->spectra.size()) {
+        g_host_error = "spectrum id out of range";
+        return -1;
+    }
+    const Spectrum &s = h->spectra[id];
     *lo = s.shortest_wavelength, *hi = s.longest_wavelength;
     for (int i = 0; i < (int)s.samples.size() && i < cap; i++) samples[i] = s.samples[i];
     return (int)s.samples.size();
 }
 int vrjh_add_material(void *p, int kind, int spectrum, double p0, double p1, double p2) {
     HostScene *h = static_cast<HostScene *>(p);
-    const Spectrum &s = h->spectra.at(spectrum);
+    if (spectrum < 0 || spectrum >= (int)h->spectra.size()) {
+        g_host_error = "spectrum id out of range";
+        return -1;
+    }
+    const Spectrum &s = h->spectra[spectrum];
     std::shared_ptr<Material> m;
     switch (kind) {
     case VRJ_MAT_LAMBERTIAN: m = std::make_shared<LambertianMaterial>(s, p0); break;

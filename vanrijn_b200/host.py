@@ -77,6 +77,8 @@ class HostScene:
         lo, hi = C.c_double(), C.c_double()
         buf = np.zeros(64)
         n = self.H.vrjh_get_spectrum(self.h, spectrum_id, C.byref(lo), C.byref(hi), buf.ctypes.data_as(dp), 64)
+        if n < 0:
+            raise capi.VrjError(self.H.vrjh_last_error().decode())
         buf = buf[:n].copy()
         return capi.SpectrumData(lo.value, hi.value, n, 0, buf.ctypes.data_as(dp)), buf
 
