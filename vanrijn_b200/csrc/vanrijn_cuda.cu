@@ -460,7 +460,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         return sct;
     };
     const Section s_n32 = reserve_section(n_wide * 64), s_n64 = reserve_section(n_wide * 112);
-    const Section s_tp = reserve_section((size_t)d->n_triangles * 80), s_tn = reserve_section((size_t)d->n_triangles * 80);
+    const Section s_tp = reserve_section((size_t)d->n_triangles * 96), s_tn = reserve_section((size_t)d->n_triangles * 96);
     const Section s_sph = reserve_section(d->n_spheres * sizeof(SphereDev)), s_pl = reserve_section(d->n_planes * sizeof(PlaneDev));
     const Section s_mat = reserve_section(d->n_materials * sizeof(MaterialDev)), s_spc = reserve_section(d->n_spectra * sizeof(SpectrumDev));
     const Section s_smp = reserve_section(d->n_spectrum_samples * sizeof(double));
@@ -495,17 +495,17 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         for (int k = 0; k < 3; k++) p.n[k] = d->planes[i].normal[k], p.t[k] = d->planes[i].tangent[k], p.c[k] = d->planes[i].cotangent[k];
         p.distance = d->planes[i].distance_from_origin, p.material = d->planes[i].material, p.pad = 0;
     }
-    // triangles: 80-byte position and normal records
+    // triangles: 96-byte position and normal records (32-byte aligned for 256-bit loads)
     double *tri_pos = reinterpret_cast<double *>(stage + s_tp.offset), *tri_nrm = reinterpret_cast<double *>(stage + s_tn.offset);
     for (uint64_t t = 0; t < d->n_triangles; t++) {
         const double *v[3] = {d->tri_v0 + 4 * t, d->tri_v1 + 4 * t, d->tri_v2 + 4 * t};
         const double *n[3] = {d->tri_n0 + 4 * t, d->tri_n1 + 4 * t, d->tri_n2 + 4 * t};
-        double *tp = tri_pos + t * 10, *tn = tri_nrm + t * 10;
+        double *tp = tri_pos + t * 12, *tn = tri_nrm + t * 12;
         for (int k = 0; k < 3; k++)
             for (int c = 0; c < 3; c++) tp[3 * k + c] = v[k][c], tn[3 * k + c] = n[k][c];
         uint64_t bits = ((uint64_t)d->tri_prim_id[t] << 32) | d->tri_material[t];
         std::memcpy(&tp[9], &bits, 8);
-        tn[9] = 0.0;
+        tp[10] = tp[11] = 0.0, tn[9] = tn[10] = tn[11] = 0.0;
     }
     // wide nodes per BVH
     WideBuilder wb;

@@ -22,8 +22,8 @@ struct ItemDev {
 struct DevScene {
     const float4 *__restrict__ nodes32;  // 4 x float4 per wide node (64 B)
     const double2 *__restrict__ nodes64; // 7 x double2 per wide node (112 B)
-    const double2 *__restrict__ tri_pos; // 5 x double2 per triangle (80 B): 9 coords + {material, prim_id}
-    const double2 *__restrict__ tri_nrm; // 5 x double2 per triangle (80 B): 9 coords + pad
+    const double2 *__restrict__ tri_pos; // 96-byte records (3 x 256-bit loads): 9 coords + {material, prim_id} + pad
+    const double2 *__restrict__ tri_nrm; // 96-byte records: 9 coords + pad
     const SphereDev *__restrict__ spheres;
     const PlaneDev *__restrict__ planes;
     const MaterialDev *__restrict__ materials;
@@ -125,13 +125,24 @@ struct WideNode {
     T c0[6], c1[6]; // lo.x, hi.x, lo.y, hi.y, lo.z, hi.z
     int left, right;
 };
+// 256-bit read-only loads (sm_100: LDG.E.256): a 64-byte node is two L1 transactions per lane instead of four --
+// k_trace is bound by L1 wavefronts (every lane fetches a different node), not by bytes.
+__device__ __forceinline__ void ldg256(const void *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg256(const void *p, double2 &a, double2 &b) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
 __device__ __forceinline__ void load_node(const DevScene &sc, int i, WideNode<float> &n) {
     const float4 *p = sc.nodes32 + (size_t)i * 4;
-    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    int4 k = __ldg(reinterpret_cast<const int4 *>(p + 3));
+    float4 a, b, c, kf;
+    ldg256(p, a, b);
+    ldg256(p + 2, c, kf);
     n.c0[0] = a.x, n.c0[1] = a.y, n.c0[2] = a.z, n.c0[3] = a.w, n.c0[4] = c.x, n.c0[5] = c.y;
     n.c1[0] = b.x, n.c1[1] = b.y, n.c1[2] = b.z, n.c1[3] = b.w, n.c1[4] = c.z, n.c1[5] = c.w;
-    n.left = k.x, n.right = k.y;
+    n.left = __float_as_int(kf.x), n.right = __float_as_int(kf.y);
 }
 __device__ __forceinline__ void load_node(const DevScene &sc, int i, WideNode<double> &n) {
     const double2 *p = sc.nodes64 + (size_t)i * 7;
@@ -144,15 +155,21 @@ __device__ __forceinline__ void load_node(const DevScene &sc, int i, WideNode<do
 
 __device__ __forceinline__ void load_tri_pos(const DevScene &sc, int tri, D3 &v0, D3 &v1, D3 &v2, uint32_t &material,
                                              uint32_t &prim_id) {
-    const double2 *p = sc.tri_pos + (size_t)tri * 5;
-    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
+    const double2 *p = sc.tri_pos + (size_t)tri * 6;
+    double2 a, b, c, d, e, f;
+    ldg256(p, a, b);
+    ldg256(p + 2, c, d);
+    ldg256(p + 4, e, f);
     v0 = d3(a.x, a.y, b.x), v1 = d3(b.y, c.x, c.y), v2 = d3(d.x, d.y, e.x);
     long long bits = __double_as_longlong(e.y);
     material = (uint32_t)(bits & 0xffffffffll), prim_id = (uint32_t)((unsigned long long)bits >> 32);
 }
 __device__ __forceinline__ void load_tri_nrm(const DevScene &sc, int tri, D3 &n0, D3 &n1, D3 &n2) {
-    const double2 *p = sc.tri_nrm + (size_t)tri * 5;
-    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
+    const double2 *p = sc.tri_nrm + (size_t)tri * 6;
+    double2 a, b, c, d, e, f;
+    ldg256(p, a, b);
+    ldg256(p + 2, c, d);
+    ldg256(p + 4, e, f);
     n0 = d3(a.x, a.y, b.x), n1 = d3(b.y, c.x, c.y), n2 = d3(d.x, d.y, e.x);
 }
 
