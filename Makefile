@@ -23,7 +23,7 @@ $(LIBDIR)/libvanrijn_cuda.so: $(CUDA_DEPS)
 
 $(LIBDIR)/libvanrijn_host.so: $(HOST_DEPS) $(LIBDIR)/libvanrijn_cuda.so
 	$(HOSTCXX) -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -Wextra -shared -o $@ \
-	    $(CSRC)/host/vanrijn_host.cpp $(CSRC)/host/host_capi.cpp -L$(LIBDIR) -lvanrijn_cuda -Wl,-rpath,'$$ORIGIN'
+	    $(CSRC)/host/vanrijn_host.cpp $(CSRC)/host/host_capi.cpp -L$(LIBDIR) -lvanrijn_cuda -pthread -Wl,-rpath,'$$ORIGIN'
 
 oracle:
 	$(MAKE) -s -C oracle

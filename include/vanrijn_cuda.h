@@ -191,6 +191,8 @@ typedef struct VrjStats {
     double shade_ms;                            /* k_raygen + k_shade */
     uint64_t shade_launches;
     uint64_t staged_rays;                       /* rays that passed a BVH root pre-test and went through k_trace */
+    double tail_ms;                             /* k_tail (all launches, including the no-op ones) */
+    uint64_t tail_launches;
 } VrjStats;
 
 /* The five arrays of AccumulationBuffer (accumulation_buffer.rs:6-12), tile-local, row-major like

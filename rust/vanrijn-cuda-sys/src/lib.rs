@@ -81,6 +81,7 @@ pub struct VrjStats {
     pub device_ms: f64, pub primary_ms: f64, pub bounce_ms: f64, pub resolve_ms: f64,
     pub primary_launches: u64, pub bounce_launches: u64, pub resolve_launches: u64,
     pub shade_ms: f64, pub shade_launches: u64, pub staged_rays: u64,
+    pub tail_ms: f64, pub tail_launches: u64,
 }
 
 #[repr(C)]

@@ -12,12 +12,15 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--filter", default="f32")
 ap.add_argument("--variant", default="lambertian")
+ap.add_argument("--count", action="store_true")
 a = ap.parse_args()
 hs = V.build_scene(scenes.scene_main(subdivisions=6, obj=True, variant=a.variant))
 f = capi.FILTER_F64 if a.filter == "f64" else capi.FILTER_F32
 for i in range(a.reps):
     r = hs.render((0, a.width, 0, a.height), a.height, a.width, spp=a.spp, max_depth=a.depth, seed=1, sample_offset=i * a.spp,
-                  bvh_filter=f, want=("colour_sum", "weight"))
+                  bvh_filter=f, want=("colour_sum", "weight"), count_traversal=a.count)
     st = r["stats"]
     print("rep %d: %.1f Mrays/s device (%.2f ms; primary %.2f bounce %.2f resolve %.2f), rays %d" % (
         i, st.rays / st.device_ms / 1e3, st.device_ms, st.primary_ms, st.bounce_ms, st.resolve_ms, st.rays), flush=True)
+    if a.count:
+        print("   node visits/ray %.2f  triangle tests/ray %.3f  staged %.3f of rays" % (st.node_visits / st.rays, st.triangle_tests / st.rays, st.staged_rays / st.rays))

@@ -98,7 +98,8 @@ class Stats(C.Structure):
                                           "paths_depth_limited", "node_visits", "triangle_tests", "kernel_launches")] + \
                [("device_ms", C.c_double), ("primary_ms", C.c_double), ("bounce_ms", C.c_double), ("resolve_ms", C.c_double),
                 ("primary_launches", C.c_uint64), ("bounce_launches", C.c_uint64), ("resolve_launches", C.c_uint64),
-                ("shade_ms", C.c_double), ("shade_launches", C.c_uint64), ("staged_rays", C.c_uint64)]
+                ("shade_ms", C.c_double), ("shade_launches", C.c_uint64), ("staged_rays", C.c_uint64),
+                ("tail_ms", C.c_double), ("tail_launches", C.c_uint64)]
 
     @property
     def rays(self):

@@ -12,6 +12,7 @@
 #include <limits>
 #include <mutex>
 #include <numeric>
+#include <thread>
 
 namespace vanrijn {
 
@@ -134,7 +135,6 @@ struct BuildCtx {
     std::vector<uint32_t> order;
     std::vector<double> node_min, node_max;
     std::vector<int32_t> node_child;
-    uint32_t depth = 0;
 
     // util/axis_aligned_bounding_box.rs:76-99: first strictly-largest extent; degenerate extents count as -1
     static int largest_dimension(const double lo[3], const double hi[3]) {
@@ -146,14 +146,11 @@ struct BuildCtx {
         }
         return dim;
     }
-    // bounding_volume_hierarchy.rs:49-75.  Returns the node index.  Node boxes are unions of
-    // triangle boxes (min/max are exact, so bottom-up equals the reference's fold over the slice).
-    int32_t build(size_t begin, size_t end, uint32_t level) {
-        depth = std::max(depth, level + 1);
-        int32_t me = (int32_t)(node_child.size() / 2);
-        node_child.push_back(0), node_child.push_back(0);
-        node_min.insert(node_min.end(), 3, std::numeric_limits<double>::infinity());
-        node_max.insert(node_max.end(), 3, -std::numeric_limits<double>::infinity());
+    // bounding_volume_hierarchy.rs:49-75.  Node `me` covers order[begin, end).  A median-split tree over n
+    // primitives has exactly 2n-1 nodes, so DFS pre-order indices are known up front (left = me+1,
+    // right = me + 2*n_left) and the big subtrees can be built on separate threads.  Node boxes are unions of
+    // triangle boxes (min/max are exact, so this equals the reference's fold over the slice).
+    uint32_t build(size_t begin, size_t end, uint32_t level, size_t me) {
         double blo[3], bhi[3];
         for (int k = 0; k < 3; k++) blo[k] = std::numeric_limits<double>::infinity(), bhi[k] = -blo[k];
         for (size_t i = begin; i < end; i++) {
@@ -164,7 +161,7 @@ struct BuildCtx {
         if (end - begin <= 1) {
             node_child[2 * me] = ~(int32_t)begin; // leaf: ~first triangle (BVH-local, leaf order)
             node_child[2 * me + 1] = (int32_t)(end - begin);
-            return me;
+            return level + 1;
         }
         int axis = largest_dimension(blo, bhi);
         // bounding_volume_hierarchy.rs:38-46: sort by box centre on that axis.  The reference uses
@@ -172,10 +169,18 @@ struct BuildCtx {
         std::stable_sort(order.begin() + begin, order.begin() + end,
                          [this, axis](uint32_t a, uint32_t b) { return centre[3 * a + axis] < centre[3 * b + axis]; });
         size_t pivot = begin + (end - begin) / 2;
-        int32_t l = build(begin, pivot, level + 1);
-        int32_t r = build(pivot, end, level + 1);
-        node_child[2 * me] = l, node_child[2 * me + 1] = r;
-        return me;
+        size_t l = me + 1, r = me + 2 * (pivot - begin);
+        node_child[2 * me] = (int32_t)l, node_child[2 * me + 1] = (int32_t)r;
+        uint32_t dl, dr;
+        if (level < 4 && end - begin > 65536) {
+            std::thread left([&] { dl = build(begin, pivot, level + 1, l); });
+            dr = build(pivot, end, level + 1, r);
+            left.join();
+        } else {
+            dl = build(begin, pivot, level + 1, l);
+            dr = build(pivot, end, level + 1, r);
+        }
+        return std::max(dl, dr);
     }
 };
 } // namespace
@@ -204,9 +209,10 @@ std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vec
         }
     cx.order.resize(n);
     std::iota(cx.order.begin(), cx.order.end(), 0u);
-    cx.node_child.reserve(4 * n + 2);
-    cx.build(0, n, 0);
-    bvh->depth_ = cx.depth;
+    const size_t n_nodes = n ? 2 * n - 1 : 1;
+    cx.node_child.assign(2 * n_nodes, 0);
+    cx.node_min.assign(3 * n_nodes, 0.0), cx.node_max.assign(3 * n_nodes, 0.0);
+    bvh->depth_ = cx.build(0, n, 0, 0);
     bvh->node_min_ = std::move(cx.node_min), bvh->node_max_ = std::move(cx.node_max), bvh->node_child_ = std::move(cx.node_child);
     bvh->tri_v_.resize(n * 9), bvh->tri_n_.resize(n * 9), bvh->tri_prim_id_.resize(n), bvh->tri_material_.resize(n);
     std::vector<std::shared_ptr<Primitive>> reordered(n);

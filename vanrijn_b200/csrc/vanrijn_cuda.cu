@@ -101,6 +101,7 @@ struct VrjScene {
     DevScene dev{};
     std::vector<DeviceBuffer *> owned;
     uint32_t n_spectra = 0;
+    uint32_t tail_max = 1u << 17; // queue length at which k_tail finishes the batch in one launch (0 = never)
     ~VrjScene() {
         for (auto *b : owned) delete b;
     }
@@ -303,7 +304,7 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
     }
     if (s->steps < steps) {
         if (s->counters.p) cudaFree(s->counters.p), s->counters.p = nullptr;
-        VRJ_CUDA(s->counters.alloc((size_t)steps * 4 * sizeof(uint32_t)));
+        VRJ_CUDA(s->counters.alloc(((size_t)steps * 4 + 4) * sizeof(uint32_t)));
         s->steps = steps;
     }
     if (!s->stats.p) VRJ_CUDA(s->stats.alloc(ST_COUNT * sizeof(unsigned long long)));
@@ -327,56 +328,71 @@ int persistent_grid(const VrjScene *sc, K kernel) {
 
 template <typename NT, bool COUNT>
 VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, uint64_t *launches) {
-    // launch sequence: G T S_0 [T S_k]*, k = 1..levels; SimpleRandom needs max_depth levels, Whitted one more
-    // (its limit-0 level still shades and traces); the final S only finishes paths.
+    // launch sequence: G T S_0 [X_k T_k S_k]*, k = 1..levels (X = k_tail, a no-op until the queue is short);
+    // SimpleRandom needs max_depth levels, Whitted one more (its limit-0 level still shades and traces);
+    // the final S only finishes paths.
     const uint32_t levels = whitted ? rc.max_depth + 1 : rc.max_depth;
     const uint32_t stride = rc.max_depth + 3;
     uint32_t *qcount = s->counters.as<uint32_t>(); // qcount[k]: length of the queue S_{k-1} wrote (k >= 1)
     uint32_t *lcount = qcount + stride;             // lcount[k]: rays of queue k staged for BVH traversal
     uint32_t *work_t = lcount + stride;             // work-fetch counters of T_k
     uint32_t *work_s = work_t + stride;             // ... of G (k = 0 only) / S_k
-    VRJ_CUDA(cudaMemsetAsync(qcount, 0, (size_t)stride * 4 * sizeof(uint32_t), s->stream));
+    uint32_t *tail_done = work_s + stride;          // set by the k_tail launch that finished the batch
+    VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 4 + 1) * sizeof(uint32_t), s->stream));
     unsigned long long *stats = s->stats.as<unsigned long long>();
     double2 *photons = s->photons.as<double2>();
     const int g_gen = persistent_grid(sc, k_raygen<COUNT>), g_t = persistent_grid(sc, k_trace<NT, COUNT>);
     const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, COUNT, false, true>);
     const int g_s = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, COUNT, false, false>);
+    // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
+    // per-level latency it removes is smaller than what its one-thread-per-path traversal costs (measured)
+    const uint32_t tail_max = levels > 12 ? sc->tail_max : 0u;
+    const int g_x = (int)std::max<uint32_t>(1, (tail_max + 127) / 128);
     const bool has_bvh = sc->dev.n_bvh_items > 0;
     VRJ_CUDA(s->mark(-1));
-    // the raygen kernel shares work_s[0] with nobody: S_0 uses work_t[stride-1] (never used by a T)
+    // the raygen kernel uses work_s[0]; S_0 uses work_t[stride-1] (never used by a T)
     k_raygen<COUNT><<<g_gen, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_s + 0, stats);
     (*launches)++;
     VRJ_CUDA(s->mark(4));
     if (has_bvh) {
-        k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats);
+        k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
         (*launches)++;
         VRJ_CUDA(s->mark(0));
     }
     uint32_t *work_s0 = work_t + (stride - 1);
     if (whitted)
-        k_shade<NT, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats);
+        k_shade<NT, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
     else
-        k_shade<NT, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats);
+        k_shade<NT, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
     (*launches)++;
     VRJ_CUDA(s->mark(3));
     for (uint32_t k = 1; k <= levels; k++) {
         const int ci = k & 1, ni = (k + 1) & 1;
+        if (tail_max) {
+            if (whitted)
+                k_tail<NT, COUNT, true><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
+            else
+                k_tail<NT, COUNT, false><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
+            (*launches)++;
+            VRJ_CUDA(s->mark(5));
+        }
         if (has_bvh) {
-            k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats);
+            k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
             (*launches)++;
             VRJ_CUDA(s->mark(1));
         }
         if (whitted)
-            k_shade<NT, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats);
+            k_shade<NT, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
         else
-            k_shade<NT, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats);
+            k_shade<NT, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
         (*launches)++;
         VRJ_CUDA(s->mark(3));
-        // long recursion limits: stop launching once the queue has drained
-        if (levels > 12 && k % 8 == 0 && k < levels) {
+        // stop launching once the batch has drained (queue empty, or finished by k_tail)
+        if (levels > 12 && k % 4 == 0 && k < levels) {
             VRJ_CUDA(cudaMemcpyAsync(s->host_count, qcount + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+            VRJ_CUDA(cudaMemcpyAsync(s->host_count + 1, tail_done, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
             VRJ_CUDA(cudaStreamSynchronize(s->stream));
-            if (*s->host_count == 0) break;
+            if (s->host_count[0] == 0 || s->host_count[1] != 0) break;
         }
     }
     AccumDev acc;
@@ -584,8 +600,8 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     sc->dev.n_items = n_items, sc->dev.n_analytic = n_analytic, sc->dev.n_bvh_items = n_bvh_items;
     for (int k = 0; k < 3; k++) sc->dev.cam[k] = d->camera_location[k];
     sc->dev.refill_threshold = 16, sc->dev.leaf_threshold = 2, sc->dev.node_batch = 4, sc->dev.max_iters = 64;
-    if (const char *tune = std::getenv("VRJ_TUNE")) // experiments only: "refill,leaf,node_batch,max_iters"
-        std::sscanf(tune, "%d,%d,%d,%d", &sc->dev.refill_threshold, &sc->dev.leaf_threshold, &sc->dev.node_batch, &sc->dev.max_iters);
+    if (const char *tune = std::getenv("VRJ_TUNE")) // experiments only: "refill,leaf,node_batch,max_iters,tail_max"
+        std::sscanf(tune, "%d,%d,%d,%d,%u", &sc->dev.refill_threshold, &sc->dev.leaf_threshold, &sc->dev.node_batch, &sc->dev.max_iters, &sc->tail_max);
     if (std::getenv("VRJ_TIMING")) {
         auto t_end = std::chrono::steady_clock::now();
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -751,8 +767,8 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     VRJ_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     if (out->stats) {
         fill_stats(out->stats, hstats, launches, ms);
-        double cls_ms[5] = {0, 0, 0, 0, 0}; // 0 T (camera rays), 1 T (bounce rays), 2 resolve, 3 shade, 4 raygen
-        uint64_t cls_n[5] = {0, 0, 0, 0, 0};
+        double cls_ms[6] = {0, 0, 0, 0, 0, 0}; // 0 T (camera rays), 1 T (bounce rays), 2 resolve, 3 shade, 4 raygen, 5 tail
+        uint64_t cls_n[6] = {0, 0, 0, 0, 0, 0};
         for (size_t i = 1; i < s->n_marks; i++) {
             int c = s->mark_class[i];
             if (c < 0) continue;
@@ -762,6 +778,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         out->stats->primary_ms = cls_ms[0], out->stats->bounce_ms = cls_ms[1], out->stats->resolve_ms = cls_ms[2];
         out->stats->primary_launches = cls_n[0], out->stats->bounce_launches = cls_n[1], out->stats->resolve_launches = cls_n[2];
         out->stats->shade_ms = cls_ms[3] + cls_ms[4], out->stats->shade_launches = cls_n[3] + cls_n[4];
+        out->stats->tail_ms = cls_ms[5], out->stats->tail_launches = cls_n[5];
     }
     return VRJ_OK;
 }
@@ -812,9 +829,9 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     if (scene->dev.n_bvh_items) {
         launches++;
         if (bvh_filter == VRJ_FILTER_F64)
-            k_trace<double, true><<<persistent_grid(scene, k_trace<double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats);
+            k_trace<double, true><<<persistent_grid(scene, k_trace<double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
         else
-            k_trace<float, true><<<persistent_grid(scene, k_trace<float, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats);
+            k_trace<float, true><<<persistent_grid(scene, k_trace<float, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
     }
     k_hit_ids<<<(n32 + 255) / 256, 256, 0, stream>>>(scene->dev, n32, tb, d_obj.as<int32_t>(), d_prim.as<int32_t>(), d_t.as<double>(), dstats);
     VRJ_CUDA(cudaGetLastError());

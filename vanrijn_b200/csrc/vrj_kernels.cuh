@@ -205,7 +205,8 @@ struct ListHitSink {
 
 template <typename NT, bool COUNT>
 __global__ void __launch_bounds__(128, VRJ_TRACE_MINB) k_trace(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
-                                               uint32_t *work, unsigned long long *stats) {
+                                               uint32_t *work, unsigned long long *stats, const uint32_t *tail_done) {
+    if (tail_done && *tail_done) return;
     const uint32_t n = *list_count;
     ListRaySource source{q, tb};
     ListHitSink sink{tb};
@@ -219,13 +220,138 @@ __global__ void __launch_bounds__(128, VRJ_TRACE_MINB) k_trace(DevScene sc, Path
     }
 }
 
-// ---- k_shade: consume the hits of the previous k_trace; finish paths (black / sky / depth limit) or run one
-// level of Integrator::integrate and enqueue the bounce ray, warp-ballot compacted ----
+// ---- one level of the integrator for one path (shared by k_shade and k_tail) ----
+struct PathRegs {
+    D3 o, d;                 // in: the ray that produced `hit`; out: the bounce ray
+    double wl, A, B, aux;    // wavelength, affine accumulator, aux (SimpleRandom: W.y; Whitted: B before the bounce term)
+    uint32_t slot, ordinal, limit, flags;
+};
+
+// Consumes the closest hit of p's ray: finishes the path (miss: black / sky; depth limit) and returns false, or
+// runs one level of Integrator::integrate -- rebuild the IntersectionInfo, sample the material (Whitted: trace the
+// shadow rays), update the affine accumulator -- leaves the bounce ray and the new state in p and returns true.
+// `first`: p.slot is set, the rest of the state is initialised here (camera.rs:108-119).
+// `load_ray(o, d)` fetches the ray only when it is needed.
+template <typename NT, bool COUNT, bool WHITTED, typename RayLoader>
+__device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderConst &rc, PathRegs &p, int2 hit, bool first,
+                                            RayLoader load_ray, double2 *photons, LocalStats &ls) {
+    if (first) {
+        if (hit.x < 0) {
+            photons[p.slot] = make_double2(0.0, 0.0); // camera.rs:110-113
+            ls.v[ST_MISSED]++;
+            return false;
+        }
+        uint32_t pixel;
+        uint64_t sample, grow, gcol;
+        slot_to_pixel(rc, p.slot, pixel, sample, grow, gcol);
+        Rng rng;
+        rng.init(rc.seed, pixel, sample, 2);
+        p.wl = 380.0 + (740.0 - 380.0) * rng.f64(); // photon.rs:18-24
+        p.ordinal = 3, p.A = 1.0, p.B = 0.0, p.aux = 0.0, p.limit = rc.max_depth, p.flags = 0;
+        if (!WHITTED && p.limit == 0) {
+            photons[p.slot] = make_double2(0.0, 0.0); // simple_random_integrator.rs:20-25
+            ls.v[ST_LIMITED]++;
+            return false;
+        }
+    } else if (WHITTED) {
+        // whitted_integrator.rs:52-79: the bounce term counts only if the ray hit and the level had limit > 0
+        if (hit.x < 0 || (p.flags & 1u)) {
+            photons[p.slot] = make_double2(p.wl, p.aux * (740.0 - 380.0));
+            if (hit.x < 0) ls.v[ST_ESCAPED]++;
+            else ls.v[ST_LIMITED]++;
+            return false;
+        }
+    } else if (hit.x < 0) {
+        double L = rgb_reflection_intensity(p.aux, p.aux, 1.0, p.wl); // sky(W): simple_random_integrator.rs:43-46,57-65
+        photons[p.slot] = make_double2(p.wl, (p.A * L + p.B) * (740.0 - 380.0));
+        ls.v[ST_ESCAPED]++;
+        return false;
+    } else if (p.limit == 0) {
+        // the recursion returns Photon{0,0} (:20-25): wavelength 0 makes the sample's XYZ ~0
+        photons[p.slot] = make_double2(0.0, 0.0);
+        ls.v[ST_LIMITED]++;
+        return false;
+    }
+    load_ray(p.o, p.d);
+    HitFrame h;
+    bool ok = rebuild_hit(sc, p.o, p.d, hit.x, hit.y, h);
+    // algebra_utils.rs:3-5, mat3.rs:111-118
+    M3 w2b = from_rows(h.tangent, h.cotangent, h.normal), b2w;
+    ok = try_inverse(w2b, b2w) && ok;
+    if (!ok) {
+        // the reference panics here (simple_random_integrator.rs:28,31); report a NaN sample
+        photons[p.slot] = make_double2(p.wl, CUDART_NAN);
+        return false;
+    }
+    MaterialDev m = sc.materials[h.material];
+    double s = spectrum_intensity(sc.spectra, sc.spectrum_samples, m.spectrum, p.wl);
+    D3 w_retro = mul(w2b, h.retro);
+    if (WHITTED) {
+        // whitted_integrator.rs:33-50: one shadow ray per light
+        TraceCounters tc = {0, 0};
+        double direct = 0.0; // fold starts from photon.intensity == 0
+        for (uint32_t li = 0; li < rc.n_lights; li++) {
+            LightDev Lt = rc.lights[li];
+            D3 ldir = d3(Lt.dir[0], Lt.dir[1], Lt.dir[2]);
+            D3 so, sd;
+            biased_ray(h.location, ldir, rc.bias, so, sd);
+            Hit sh = trace_closest<NT, COUNT, true>(sc, so, sd, tc);
+            ls.v[ST_SHADOW]++;
+            double term;
+            if (sh.item >= 0) {
+                term = rc.has_ambient ? light_intensity(rc, rc.lights[rc.n_lights].spectrum, p.wl) : 0.0;
+            } else {
+                double emitted = light_intensity(rc, Lt.spectrum, p.wl);
+                emitted = emitted * fabs(dot(ldir, h.normal));
+                double la, lb;
+                material_bsdf_affine(m, s, w_retro, mul(w2b, ldir), la, lb); // (retro, incoming) order
+                term = la * emitted + lb;
+            }
+            direct += term;
+        }
+        if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
+        p.B += p.A * direct;
+    }
+    Rng rng;
+    uint32_t pixel;
+    uint64_t sample, grow, gcol;
+    slot_to_pixel(rc, p.slot, pixel, sample, grow, gcol);
+    rng.init(rc.seed, pixel, sample, p.ordinal);
+    D3 w_s;
+    double pdf;
+    material_sample(m, s, w_retro, rng, w_s, pdf);
+    p.ordinal = rng.ordinal;
+    D3 W = mul(b2w, w_s);
+    biased_ray(h.location, W, rc.bias, p.o, p.d);
+    double cosine = fabs(dot(W, h.normal));
+    double ba, bb;
+    if (WHITTED) {
+        // bsdf(retro, sampled, L_in) * |W.n|, pdf unused; B before the bounce term is kept in aux
+        material_bsdf_affine(m, s, w_retro, w_s, ba, bb);
+        p.aux = p.B;
+        p.B += p.A * (bb * cosine);
+        p.A *= ba * cosine;
+        p.flags = p.limit == 0 ? 1u : 0u; // the ray is still traced at limit 0, its result unused
+        p.limit = p.limit ? p.limit - 1 : 0;
+    } else {
+        // simple_random_integrator.rs:39-53: bsdf(sampled, retro, L_in * pdf * |W.n|)
+        material_bsdf_affine(m, s, w_s, w_retro, ba, bb);
+        p.B += p.A * bb;
+        p.A *= ba * (pdf * cosine);
+        p.aux = W.y; // the sky uses the un-normalised W
+        p.limit -= 1;
+    }
+    ls.v[ST_BOUNCE]++;
+    return true;
+}
+
+// ---- k_shade: consume the hits of a queue; survivors are enqueued warp-ballot compacted and staged ----
 template <typename NT, bool COUNT, bool WHITTED, bool FIRST>
 __global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_shade(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
                                                TraceBuffers tb_in, PathQueue out, uint32_t *out_count, TraceBuffers tb_out,
                                                uint32_t *list_count, uint32_t *work, double2 *photons,
-                                               unsigned long long *stats) {
+                                               unsigned long long *stats, const uint32_t *tail_done) {
+    if (*tail_done) return; // a k_tail launch has already finished every remaining path of this batch
     const uint32_t n = FIRST ? rc.npix * rc.batch_samples : *in_count;
     // A CTA takes SHADE_CHUNK queue entries at a time and orders them by hit class (miss / sphere / plane /
     // triangle) in shared memory before shading, so the lanes of a warp run the same rebuild_hit branch.
@@ -258,144 +384,74 @@ __global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_shade(DevScene sc, Rend
             if (cls[e] < 4) s_sorted[(cls[e] == 0 ? 0u : cls[e] == 1 ? c0 : cls[e] == 2 ? c1 : c2) + pos[e]] = base + threadIdx.x + e * 128;
         __syncthreads();
 #pragma unroll 1
-      for (uint32_t k = threadIdx.x; k < ((total + 31u) & ~31u); k += 128) {
-        const uint32_t j = k < total ? s_sorted[k] : n;
-        bool alive = false;
-        D3 no = d3(0, 0, 0), nd = d3(0, 0, 1);
-        double wl = 0.0, A = 0.0, B = 0.0, aux = 0.0;
-        uint32_t slot = 0, ordinal = 0, limit = 0, flags = 0;
-        if (j < n) {
-            int2 hit = tb_in.hits[j];
-            bool finished = false;
-            if (FIRST) {
-                slot = j;
-                if (hit.x < 0) {
-                    photons[slot] = make_double2(0.0, 0.0); // camera.rs:110-113
-                    ls.v[ST_MISSED]++;
-                    finished = true;
+        for (uint32_t k = threadIdx.x; k < ((total + 31u) & ~31u); k += 128) {
+            const uint32_t j = k < total ? s_sorted[k] : n;
+            bool alive = false;
+            PathRegs p;
+            p.o = d3(0, 0, 0), p.d = d3(0, 0, 1);
+            p.wl = p.A = p.B = p.aux = 0.0;
+            p.slot = p.ordinal = p.limit = p.flags = 0;
+            if (j < n) {
+                int2 hit = tb_in.hits[j];
+                if (FIRST) {
+                    p.slot = j;
                 } else {
-                    uint32_t pixel;
-                    uint64_t sample, grow, gcol;
-                    slot_to_pixel(rc, slot, pixel, sample, grow, gcol);
-                    Rng rng;
-                    rng.init(rc.seed, pixel, sample, 2);
-                    wl = 380.0 + (740.0 - 380.0) * rng.f64(); // photon.rs:18-24
-                    ordinal = 3, A = 1.0, B = 0.0, limit = rc.max_depth;
-                    if (!WHITTED && limit == 0) {
-                        photons[slot] = make_double2(0.0, 0.0); // simple_random_integrator.rs:20-25
-                        ls.v[ST_LIMITED]++;
-                        finished = true;
-                    }
+                    double2 a3 = in.q3[j], a4 = in.q4[j];
+                    uint4 a5 = in.q5[j];
+                    p.wl = a3.x, p.A = a3.y, p.B = a4.x, p.aux = a4.y;
+                    p.slot = a5.x, p.ordinal = a5.y, p.limit = a5.z, p.flags = a5.w;
                 }
-            } else {
-                double2 a3 = in.q3[j], a4 = in.q4[j];
-                uint4 a5 = in.q5[j];
-                wl = a3.x, A = a3.y, B = a4.x, aux = a4.y;
-                slot = a5.x, ordinal = a5.y, limit = a5.z, flags = a5.w;
-                if (WHITTED) {
-                    // whitted_integrator.rs:52-79: the bounce term counts only if the ray hit and the level had limit > 0
-                    if (hit.x < 0 || (flags & 1u)) {
-                        photons[slot] = make_double2(wl, aux * (740.0 - 380.0));
-                        if (hit.x < 0) ls.v[ST_ESCAPED]++;
-                        else ls.v[ST_LIMITED]++;
-                        finished = true;
-                    }
-                } else if (hit.x < 0) {
-                    double L = rgb_reflection_intensity(aux, aux, 1.0, wl); // sky(W): simple_random_integrator.rs:43-46,57-65
-                    photons[slot] = make_double2(wl, (A * L + B) * (740.0 - 380.0));
-                    ls.v[ST_ESCAPED]++;
-                    finished = true;
-                } else if (limit == 0) {
-                    // the recursion returns Photon{0,0} (:20-25): wavelength 0 makes the sample's XYZ ~0
-                    photons[slot] = make_double2(0.0, 0.0);
-                    ls.v[ST_LIMITED]++;
-                    finished = true;
-                }
+                alive = shade_entry<NT, COUNT, WHITTED>(
+                    sc, rc, p, hit, FIRST,
+                    [&in, j](D3 &o, D3 &d) {
+                        double2 a0 = in.q0[j], a1 = in.q1[j], a2 = in.q2[j];
+                        o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
+                    },
+                    photons, ls);
             }
-            if (!finished) {
-                double2 a0 = in.q0[j], a1 = in.q1[j], a2 = in.q2[j];
-                D3 o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
-                HitFrame h;
-                bool ok = rebuild_hit(sc, o, d, hit.x, hit.y, h);
-                // algebra_utils.rs:3-5, mat3.rs:111-118
-                M3 w2b = from_rows(h.tangent, h.cotangent, h.normal), b2w;
-                ok = try_inverse(w2b, b2w) && ok;
-                if (!ok) {
-                    // the reference panics here (simple_random_integrator.rs:28,31); report a NaN sample
-                    photons[slot] = make_double2(wl, CUDART_NAN);
-                } else {
-                    MaterialDev m = sc.materials[h.material];
-                    double s = spectrum_intensity(sc.spectra, sc.spectrum_samples, m.spectrum, wl);
-                    D3 w_retro = mul(w2b, h.retro);
-                    if (WHITTED) {
-                        // whitted_integrator.rs:33-50: one shadow ray per light
-                        TraceCounters tc = {0, 0};
-                        double direct = 0.0; // fold starts from photon.intensity == 0
-                        for (uint32_t li = 0; li < rc.n_lights; li++) {
-                            LightDev Lt = rc.lights[li];
-                            D3 ldir = d3(Lt.dir[0], Lt.dir[1], Lt.dir[2]);
-                            D3 so, sd;
-                            biased_ray(h.location, ldir, rc.bias, so, sd);
-                            Hit sh = trace_closest<NT, COUNT, true>(sc, so, sd, tc);
-                            ls.v[ST_SHADOW]++;
-                            double term;
-                            if (sh.item >= 0) {
-                                term = rc.has_ambient ? light_intensity(rc, rc.lights[rc.n_lights].spectrum, wl) : 0.0;
-                            } else {
-                                double emitted = light_intensity(rc, Lt.spectrum, wl);
-                                emitted = emitted * fabs(dot(ldir, h.normal));
-                                double la, lb;
-                                material_bsdf_affine(m, s, w_retro, mul(w2b, ldir), la, lb); // (retro, incoming) order
-                                term = la * emitted + lb;
-                            }
-                            direct += term;
-                        }
-                        if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
-                        B += A * direct;
-                    }
-                    Rng rng;
-                    uint32_t pixel;
-                    uint64_t sample, grow, gcol;
-                    slot_to_pixel(rc, slot, pixel, sample, grow, gcol);
-                    rng.init(rc.seed, pixel, sample, ordinal);
-                    D3 w_s;
-                    double pdf;
-                    material_sample(m, s, w_retro, rng, w_s, pdf);
-                    ordinal = rng.ordinal;
-                    D3 W = mul(b2w, w_s);
-                    biased_ray(h.location, W, rc.bias, no, nd);
-                    double cosine = fabs(dot(W, h.normal));
-                    double ba, bb;
-                    if (WHITTED) {
-                        // bsdf(retro, sampled, L_in) * |W.n|, pdf unused; B before the bounce term is kept in aux
-                        material_bsdf_affine(m, s, w_retro, w_s, ba, bb);
-                        aux = B;
-                        B += A * (bb * cosine);
-                        A *= ba * cosine;
-                        flags = limit == 0 ? 1u : 0u; // the ray is still traced at limit 0, its result unused
-                        limit = limit ? limit - 1 : 0;
-                    } else {
-                        // simple_random_integrator.rs:39-53: bsdf(sampled, retro, L_in * pdf * |W.n|)
-                        material_bsdf_affine(m, s, w_s, w_retro, ba, bb);
-                        B += A * bb;
-                        A *= ba * (pdf * cosine);
-                        aux = W.y; // the sky uses the un-normalised W
-                        limit -= 1;
-                    }
-                    alive = true;
-                }
-            }
+            uint32_t idx = queue_reserve(alive, out_count);
+            if (alive) queue_store(out, idx, p.o, p.d, p.wl, p.A, p.B, p.aux, p.slot, p.ordinal, p.limit, p.flags);
+            stage_ray<COUNT>(sc, alive, idx, p.o, p.d, tb_out, list_count, ls);
         }
-        uint32_t idx = queue_reserve(alive, out_count);
-        if (alive) {
-            queue_store(out, idx, no, nd, wl, A, B, aux, slot, ordinal, limit, flags);
-            ls.v[ST_BOUNCE]++;
-        }
-        stage_ray<COUNT>(sc, alive, idx, no, nd, tb_out, list_count, ls);
-      }
         __syncthreads(); // s_sorted / s_count are reused by the next chunk
     }
     ls.flush(stats);
+}
+
+// ---- k_tail: when few paths are left, finish ALL their remaining levels in one launch ----
+// A wavefront level costs at least the latency of its longest traversal (~100 us) however few rays it carries;
+// here every thread follows one path (trace -> shade -> trace ...) to its end, so the remaining levels overlap.
+// Runs before T_k on queue k; does nothing unless the queue is at most `tail_max` long; sets *tail_done so the
+// remaining T / S launches of the batch return immediately.
+template <typename NT, bool COUNT, bool WHITTED>
+__global__ void __launch_bounds__(128, 2) k_tail(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
+                                              uint32_t tail_max, double2 *photons, unsigned long long *stats,
+                                              uint32_t *tail_done) {
+    const uint32_t n = *in_count;
+    if (n > tail_max || *tail_done == 1u) return;
+    LocalStats ls;
+    ls.clear();
+    const uint32_t padded = (n + 31u) & ~31u;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < padded; j += gridDim.x * blockDim.x) {
+        if (j < n) {
+            PathRegs p;
+            double2 a0 = in.q0[j], a1 = in.q1[j], a2 = in.q2[j], a3 = in.q3[j], a4 = in.q4[j];
+            uint4 a5 = in.q5[j];
+            p.o = d3(a0.x, a0.y, a1.x), p.d = d3(a1.y, a2.x, a2.y);
+            p.wl = a3.x, p.A = a3.y, p.B = a4.x, p.aux = a4.y;
+            p.slot = a5.x, p.ordinal = a5.y, p.limit = a5.z, p.flags = a5.w;
+            bool alive = true;
+            while (alive) {
+                TraceCounters tc = {0, 0};
+                Hit h = trace_closest<NT, COUNT, false>(sc, p.o, p.d, tc);
+                if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
+                alive = shade_entry<NT, COUNT, WHITTED>(sc, rc, p, make_int2(h.item, h.tri), false, [](D3 &, D3 &) {}, photons, ls);
+            }
+        }
+    }
+    ls.flush(stats);
+    // every CTA read *in_count before any path could change it (k_tail never writes the queues); 2 = "done by this launch"
+    if (n && blockIdx.x == 0 && threadIdx.x == 0) *tail_done = 2u;
 }
 
 struct AccumDev {
