@@ -19,7 +19,7 @@ all: $(LIBDIR)/libvanrijn_cuda.so $(LIBDIR)/libvanrijn_host.so oracle
 
 $(LIBDIR)/libvanrijn_cuda.so: $(CUDA_DEPS)
 	mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) $(EXTRA) -shared -o $@ $(CSRC)/vanrijn_cuda.cu
+	$(NVCC) $(NVFLAGS) $(EXTRA) -shared -o $@ $(CSRC)/vanrijn_cuda.cu -ldl
 
 $(LIBDIR)/libvanrijn_host.so: $(HOST_DEPS) $(LIBDIR)/libvanrijn_cuda.so
 	$(HOSTCXX) -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -Wextra -shared -o $@ \

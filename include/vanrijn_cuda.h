@@ -234,6 +234,24 @@ VRJ_API VrjStatus vrj_render_tile(const VrjScene *scene, const VrjTile *tile, ui
 
 /* Sampler::sample on n rays (host arrays, 3 doubles each; directions are normalised like Ray::new).
  * object_id / prim_id are -1 and t is +inf on a miss. */
+/* ---- one box, several GPUs: shard by sample index, one NCCL reduce into the first device ----
+ * The reference parallelises whole-frame sample passes over workers and merges them (src/main.rs:199-217); here
+ * device g of G renders samples g, g+G, ... of the call into its own accumulation buffer, the (sum XYZ, weight)
+ * arrays are summed into devices[0] with ncclReduce over NVLink, and colour = sum * (1/weight) is formed there.
+ * Single process; NCCL is loaded at run time (libnccl.so.2) -- VRJ_ERR_UNSUPPORTED if it is missing. */
+typedef struct VrjComm VrjComm;
+typedef struct VrjMultiScene VrjMultiScene;
+VRJ_API VrjStatus vrj_comm_create(int32_t n_devices, const int32_t *devices, VrjComm **out);
+VRJ_API void vrj_comm_destroy(VrjComm *comm);
+/* the scene replicated on every device of the communicator */
+VRJ_API VrjStatus vrj_comm_scene_create(VrjComm *comm, const VrjSceneDesc *desc, VrjMultiScene **out);
+VRJ_API void vrj_comm_scene_destroy(VrjMultiScene *scene);
+/* same arguments and outputs as vrj_render_tile (out->memory = VRJ_MEM_DEVICE means memory of devices[0]);
+ * colour_bias / weight_bias are returned as zero (a reduced buffer has no compensation term), `accumulate` and
+ * `photons` are not supported; params->sample_stride must be 0 or 1. */
+VRJ_API VrjStatus vrj_render_sharded(VrjMultiScene *scene, const VrjTile *tile, uint64_t height, uint64_t width,
+                                     const VrjRenderParams *params, VrjAccumOut *out);
+
 VRJ_API VrjStatus vrj_trace_rays(const VrjScene *scene, uint64_t n, const double *origins, const double *directions,
                          uint32_t bvh_filter, int32_t *object_id, int32_t *prim_id, double *t, VrjStats *stats);
 

@@ -124,7 +124,7 @@ inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     for (int i = 0; i < 4; i++) out[i] = c[i];
 }
 /* One stream per (seed, pixel, sample); `ordinal` counts draws along the path:
- * 0 = camera x, 1 = camera y, 2 = wavelength, 3.. = material sampling in call order. */
+ * 0 = camera x, 1 = camera y, 2 = wavelength, (3 unused,) 4.. = material sampling in call order. */
 struct Rng {
     uint64_t seed;
     uint32_t pixel;
@@ -1127,6 +1127,7 @@ void orc_render_tile(const OrcScene *s, const uint64_t tile[4], uint64_t height,
                 photon = Photon{0.0, 0.0}; /* camera.rs:110-113 */
             } else {
                 Photon start{380.0 + (740.0 - 380.0) * rng.f64(), 0.0}; /* photon.rs:18-24 */
+                rng.ordinal = 4; /* ordinal 3 is left unused: material draws start on a Philox block boundary */
                 photon = p->integrator == ORC_INTEGRATOR_WHITTED ? integrate_whitted(cx, h, start, rng, p->max_depth)
                                                                   : integrate_simple(cx, h, start, rng, p->max_depth);
             }

@@ -22,6 +22,8 @@ pub const VRJ_MEM_HOST: u32 = 0;
 pub const VRJ_MEM_DEVICE: u32 = 1;
 
 #[repr(C)] pub struct VrjScene { _private: [u8; 0] }
+#[repr(C)] pub struct VrjComm { _private: [u8; 0] }
+#[repr(C)] pub struct VrjMultiScene { _private: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct VrjSpectrum { pub shortest_wavelength: f64, pub longest_wavelength: f64, pub first_sample: u32, pub n_samples: u32 }
@@ -105,6 +107,12 @@ extern "C" {
     pub fn vrj_free_host(p: *mut c_void);
     pub fn vrj_render_tile(scene: *const VrjScene, tile: *const VrjTile, height: u64, width: u64,
                            params: *const VrjRenderParams, out: *mut VrjAccumOut) -> i32;
+    pub fn vrj_comm_create(n_devices: i32, devices: *const i32, out: *mut *mut VrjComm) -> i32;
+    pub fn vrj_comm_destroy(comm: *mut VrjComm);
+    pub fn vrj_comm_scene_create(comm: *mut VrjComm, desc: *const VrjSceneDesc, out: *mut *mut VrjMultiScene) -> i32;
+    pub fn vrj_comm_scene_destroy(scene: *mut VrjMultiScene);
+    pub fn vrj_render_sharded(scene: *mut VrjMultiScene, tile: *const VrjTile, height: u64, width: u64,
+                              params: *const VrjRenderParams, out: *mut VrjAccumOut) -> i32;
     pub fn vrj_trace_rays(scene: *const VrjScene, n: u64, origins: *const f64, directions: *const f64, bvh_filter: u32,
                           object_id: *mut i32, prim_id: *mut i32, t: *mut f64, stats: *mut VrjStats) -> i32;
 }

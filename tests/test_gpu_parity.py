@@ -242,3 +242,58 @@ def test_errors_are_reported_not_swallowed():
         hs.render((0, 10, 0, 10), 5, 5, spp=1)          # tile outside the image
     with pytest.raises(capi.VrjError):
         hs.render((0, 4, 0, 4), 4, 4, spp=1, integrator=7)
+
+
+def test_concurrent_calls_on_one_scene():
+    """partial_render_scene is called from rayon workers on one shared &Scene (main.rs:197-209): concurrent
+    vrj_render_tile calls from several host threads must each return exactly the serial result."""
+    import threading
+    spec = scenes.scene_main(subdivisions=3, obj=False)
+    hs = V.build_scene(spec)
+    W, H = 160, 90
+    hs.device_scene(0)
+    serial = [hs.render((0, W, 0, H), H, W, spp=2, max_depth=8, seed=3, sample_offset=2 * i)["colour_sum"] for i in range(6)]
+    got = [None] * 6
+
+    def work(i):
+        got[i] = hs.render((0, W, 0, H), H, W, spp=2, max_depth=8, seed=3, sample_offset=2 * i)["colour_sum"]
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i in range(6):
+        assert np.array_equal(got[i], serial[i])
+
+
+def test_deep_recursion_tail_kernel_matches_oracle():
+    """Recursion limit 128 takes the k_tail path (remaining levels of a short queue finished in one launch):
+    same per-sample results as the oracle's recursion, and far fewer launches than 2 x 128."""
+    spec = scenes.scene_main(subdivisions=3, obj=False, variant="mixed")
+    hs, orc = both(spec)
+    W, H, spp = 96, 54, 4
+    g = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=21, want_photons=True)
+    r = orc.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=21, want_photons=True)
+    photons_close(g["photons"], r["photons"], 1e-9)
+    for k in ("primary_rays", "bounce_rays", "paths_missed", "paths_escaped", "paths_depth_limited"):
+        assert getattr(g["stats"], k) == getattr(r["stats"], k), k
+    assert g["stats"].kernel_launches < 60
+
+
+def test_single_process_sharded_render_matches_one_gpu():
+    """vrj_comm_* (SURVEY 8e): the scene replicated on G GPUs, samples g, g+G, ... on GPU g, one NCCL reduce.
+    The reduced sums equal the one-GPU sums up to summation order (1e-12), weights exactly."""
+    n = capi.cuda().vrj_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    spec = scenes.scene_main(subdivisions=3, obj=False)
+    hs = V.build_scene(spec)
+    W, H, spp = 128, 72, 7        # 7 samples over G devices: uneven shards
+    one = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=8, seed=5)
+    for G in sorted({2, min(n, 4), n}):
+        r = hs.render_sharded(list(range(G)), (0, W, 0, H), H, W, spp=spp, max_depth=8, seed=5)
+        assert np.array_equal(r["weight"], one["weight"])
+        np.testing.assert_allclose(r["colour_sum"], one["colour_sum"], rtol=1e-12, atol=1e-25)
+        np.testing.assert_allclose(r["colour"], one["colour"], rtol=1e-12, atol=1e-25)
+        assert r["stats"].rays == one["stats"].rays

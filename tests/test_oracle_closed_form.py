@@ -53,7 +53,7 @@ def test_one_bounce_lambertian_plane_under_the_sky():
             assert L.orc_mat3_inverse(M.ravel().copy().ctypes.data_as(dp), Minv.ctypes.data_as(dp)) == 1
             w_i = M @ hit["retro"]
             w_o, pdf, used = np.zeros(3), C.c_double(), C.c_uint32()
-            L.orc_material_sample(orc.h, 0, w_i.ctypes.data_as(dp), wl, seed, p, 0, 3, w_o.ctypes.data_as(dp), C.byref(pdf), C.byref(used))
+            L.orc_material_sample(orc.h, 0, w_i.ctypes.data_as(dp), wl, seed, p, 0, 4, w_o.ctypes.data_as(dp), C.byref(pdf), C.byref(used))
             assert used.value >= 2 and used.value % 2 == 0          # rejection sampling consumes pairs of draws
             assert abs(pdf.value - w_o[2] * np.sqrt(1 - w_o[2] ** 2) / np.pi) < 1e-12   # lambertian_material.rs:57
             Wd = Minv.reshape(3, 3) @ w_o

@@ -24,7 +24,8 @@ OK = 0
 # every symbol include/vanrijn_cuda.h declares
 CUDA_SYMBOLS = ["vrj_last_error", "vrj_abi_version", "vrj_device_count", "vrj_scene_create", "vrj_scene_destroy",
                 "vrj_scene_device_bytes", "vrj_render_tile", "vrj_trace_rays", "vrj_release_scratch", "vrj_alloc_host",
-                "vrj_free_host"]
+                "vrj_free_host", "vrj_comm_create", "vrj_comm_destroy", "vrj_comm_scene_create", "vrj_comm_scene_destroy",
+                "vrj_render_sharded"]
 
 
 class VrjError(RuntimeError):
@@ -146,6 +147,15 @@ def cuda():
         L.vrj_render_tile.restype = C.c_int32
         L.vrj_render_tile.argtypes = [C.c_void_p, C.POINTER(Tile), C.c_uint64, C.c_uint64, C.POINTER(RenderParams),
                                       C.POINTER(AccumOut)]
+        L.vrj_comm_create.restype = C.c_int32
+        L.vrj_comm_create.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
+        L.vrj_comm_destroy.argtypes = [C.c_void_p]
+        L.vrj_comm_scene_create.restype = C.c_int32
+        L.vrj_comm_scene_create.argtypes = [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
+        L.vrj_comm_scene_destroy.argtypes = [C.c_void_p]
+        L.vrj_render_sharded.restype = C.c_int32
+        L.vrj_render_sharded.argtypes = [C.c_void_p, C.POINTER(Tile), C.c_uint64, C.c_uint64, C.POINTER(RenderParams),
+                                         C.POINTER(AccumOut)]
         L.vrj_trace_rays.restype = C.c_int32
         L.vrj_trace_rays.argtypes = [C.c_void_p, C.c_uint64, dp, dp, C.c_uint32, C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), dp, C.POINTER(Stats)]

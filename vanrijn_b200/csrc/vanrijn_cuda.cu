@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <thread>
 #include <limits>
 #include <mutex>
 #include <string>
@@ -845,6 +847,235 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     float ms = 0.f;
     VRJ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     if (stats) fill_stats(stats, hstats, launches, ms);
+    return VRJ_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Single-process multi-GPU: sample-index sharding + one NCCL reduce
+} // extern "C"
+
+namespace {
+// the few NCCL entry points used, resolved from libnccl.so.2 at run time (ABI-stable across 2.x)
+typedef void *nccl_comm_t;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(nccl_comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(lib, "ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(lib, "ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+        Reduce = reinterpret_cast<decltype(Reduce)>(dlsym(lib, "ncclReduce"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        return CommInitAll && CommDestroy && GroupStart && GroupEnd && Reduce && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+const int kNcclDouble = 8, kNcclSum = 0; // nccl.h: ncclFloat64 = 8, ncclSum = 0
+
+__global__ void k_finalize(const double *sum, const double *weight, double *colour, uint32_t npix) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    double inv = 1.0 / weight[p]; // accumulation_buffer.rs:59
+    colour[3 * p] = sum[3 * p] * inv, colour[3 * p + 1] = sum[3 * p + 1] * inv, colour[3 * p + 2] = sum[3 * p + 2] * inv;
+}
+} // namespace
+
+struct VrjComm {
+    std::vector<int> devices;
+    std::vector<nccl_comm_t> comms;
+    std::vector<cudaStream_t> streams;
+};
+struct VrjMultiScene {
+    VrjComm *comm = nullptr;
+    std::vector<VrjScene *> scenes;
+    std::vector<DeviceBuffer *> sum, weight; // per device
+    DeviceBuffer colour;                      // on devices[0]
+    size_t npix = 0;
+};
+
+extern "C" {
+
+VrjStatus vrj_comm_create(int32_t n, const int32_t *devices, VrjComm **out) {
+    if (!out || n < 1 || !devices) return fail(VRJ_ERR_INVALID_ARGUMENT, "vrj_comm_create: bad arguments");
+    *out = nullptr;
+    if (!g_nccl.load()) return fail(VRJ_ERR_UNSUPPORTED, "NCCL (libnccl.so.2) could not be loaded");
+    VrjComm *c = new VrjComm();
+    c->devices.assign(devices, devices + n);
+    c->comms.assign(n, nullptr);
+    int rc = g_nccl.CommInitAll(c->comms.data(), n, c->devices.data());
+    if (rc != 0) {
+        std::string msg = std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(rc);
+        delete c;
+        return fail(VRJ_ERR_CUDA, msg);
+    }
+    for (int i = 0; i < n; i++) {
+        cudaStream_t st = nullptr;
+        if (cudaSetDevice(c->devices[i]) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+            vrj_comm_destroy(c);
+            return fail(VRJ_ERR_CUDA, "vrj_comm_create: cannot create a stream on every device");
+        }
+        c->streams.push_back(st);
+    }
+    *out = c;
+    return VRJ_OK;
+}
+
+void vrj_comm_destroy(VrjComm *c) {
+    if (!c) return;
+    for (size_t i = 0; i < c->streams.size(); i++) {
+        cudaSetDevice(c->devices[i]);
+        cudaStreamDestroy(c->streams[i]);
+    }
+    for (nccl_comm_t k : c->comms)
+        if (k) g_nccl.CommDestroy(k);
+    delete c;
+}
+
+void vrj_comm_scene_destroy(VrjMultiScene *m) {
+    if (!m) return;
+    for (size_t i = 0; i < m->scenes.size(); i++) {
+        cudaSetDevice(m->comm->devices[i]);
+        vrj_scene_destroy(m->scenes[i]);
+        if (i < m->sum.size()) delete m->sum[i];
+        if (i < m->weight.size()) delete m->weight[i];
+    }
+    cudaSetDevice(m->comm->devices[0]);
+    delete m;
+}
+
+VrjStatus vrj_comm_scene_create(VrjComm *c, const VrjSceneDesc *desc, VrjMultiScene **out) {
+    if (!c || !out) return fail(VRJ_ERR_INVALID_ARGUMENT, "vrj_comm_scene_create: NULL argument");
+    *out = nullptr;
+    VrjMultiScene *m = new VrjMultiScene();
+    m->comm = c;
+    for (int dev : c->devices) {
+        VrjScene *s = nullptr;
+        VrjStatus st = vrj_scene_create(desc, dev, &s);
+        if (st != VRJ_OK) {
+            std::string keep = g_error;
+            vrj_comm_scene_destroy(m);
+            return fail(st, keep);
+        }
+        m->scenes.push_back(s);
+        m->sum.push_back(new DeviceBuffer());
+        m->weight.push_back(new DeviceBuffer());
+    }
+    *out = m;
+    return VRJ_OK;
+}
+
+VrjStatus vrj_render_sharded(VrjMultiScene *m, const VrjTile *tile, uint64_t height, uint64_t width, const VrjRenderParams *p,
+                             VrjAccumOut *out) {
+    if (!m || !tile || !p || !out) return fail(VRJ_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (p->sample_stride > 1) return fail(VRJ_ERR_INVALID_ARGUMENT, "vrj_render_sharded shards the samples itself: sample_stride must be 0 or 1");
+    if (out->accumulate || out->photons) return fail(VRJ_ERR_UNSUPPORTED, "vrj_render_sharded: accumulate / photons are not supported");
+    if (tile->end_column < tile->start_column || tile->end_row < tile->start_row) return fail(VRJ_ERR_INVALID_ARGUMENT, "bad tile");
+    VrjComm *c = m->comm;
+    const int G = (int)c->devices.size();
+    const size_t npix = (size_t)(tile->end_column - tile->start_column) * (tile->end_row - tile->start_row);
+    if (out->stats) std::memset(out->stats, 0, sizeof(VrjStats));
+    if (npix == 0 || p->spp == 0) return VRJ_OK;
+    for (int g = 0; g < G; g++) {
+        VRJ_CUDA(cudaSetDevice(c->devices[g]));
+        if (m->sum[g]->bytes < npix * 24) {
+            if (m->sum[g]->p) cudaFree(m->sum[g]->p), m->sum[g]->p = nullptr;
+            if (m->weight[g]->p) cudaFree(m->weight[g]->p), m->weight[g]->p = nullptr;
+            VRJ_CUDA(m->sum[g]->alloc(npix * 24));
+            VRJ_CUDA(m->weight[g]->alloc(npix * 8));
+        }
+    }
+    VRJ_CUDA(cudaSetDevice(c->devices[0]));
+    if (m->colour.bytes < npix * 24) {
+        if (m->colour.p) cudaFree(m->colour.p), m->colour.p = nullptr;
+        VRJ_CUDA(m->colour.alloc(npix * 24));
+    }
+    // ---- every device renders its share of the sample indices into its own device buffers ----
+    std::vector<VrjStatus> status(G, VRJ_OK);
+    std::vector<std::string> messages(G);
+    std::vector<VrjStats> stats(G);
+    std::vector<std::thread> threads;
+    for (int g = 0; g < G; g++) {
+        threads.emplace_back([&, g]() {
+            VrjRenderParams q = *p;
+            q.spp = p->spp > (uint32_t)g ? (p->spp - (uint32_t)g + (uint32_t)G - 1) / (uint32_t)G : 0; // samples g, g+G, ...
+            q.sample_offset = p->sample_offset + (uint64_t)g;
+            q.sample_stride = (uint32_t)G;
+            VrjAccumOut o{};
+            o.memory = VRJ_MEM_DEVICE;
+            o.colour_sum = m->sum[g]->as<double>(), o.weight = m->weight[g]->as<double>();
+            o.stats = &stats[g];
+            std::memset(&stats[g], 0, sizeof(VrjStats));
+            if (q.spp == 0) {
+                cudaSetDevice(c->devices[g]);
+                cudaMemset(m->sum[g]->p, 0, npix * 24);
+                cudaMemset(m->weight[g]->p, 0, npix * 8);
+                return;
+            }
+            status[g] = vrj_render_tile(m->scenes[g], tile, height, width, &q, &o);
+            if (status[g] != VRJ_OK) messages[g] = vrj_last_error();
+        });
+    }
+    for (auto &t : threads) t.join();
+    for (int g = 0; g < G; g++)
+        if (status[g] != VRJ_OK) return fail(status[g], "device " + std::to_string(c->devices[g]) + ": " + messages[g]);
+    // ---- the one exchange step: ncclReduce(sum) of (sum XYZ, weight) into devices[0] ----
+    if (G > 1) {
+        int rc = g_nccl.GroupStart();
+        for (int g = 0; g < G && rc == 0; g++) {
+            cudaSetDevice(c->devices[g]);
+            rc = g_nccl.Reduce(m->sum[g]->p, m->sum[g]->p, npix * 3, kNcclDouble, kNcclSum, 0, c->comms[g], c->streams[g]);
+            if (rc == 0) rc = g_nccl.Reduce(m->weight[g]->p, m->weight[g]->p, npix, kNcclDouble, kNcclSum, 0, c->comms[g], c->streams[g]);
+        }
+        int rc2 = g_nccl.GroupEnd();
+        if (rc != 0 || rc2 != 0) return fail(VRJ_ERR_CUDA, std::string("ncclReduce: ") + g_nccl.GetErrorString(rc ? rc : rc2));
+        for (int g = 0; g < G; g++) {
+            VRJ_CUDA(cudaSetDevice(c->devices[g]));
+            VRJ_CUDA(cudaStreamSynchronize(c->streams[g]));
+        }
+    }
+    VRJ_CUDA(cudaSetDevice(c->devices[0]));
+    cudaStream_t s0 = c->streams[0];
+    k_finalize<<<(unsigned)((npix + 255) / 256), 256, 0, s0>>>(m->sum[0]->as<double>(), m->weight[0]->as<double>(), m->colour.as<double>(), (uint32_t)npix);
+    VRJ_CUDA(cudaGetLastError());
+    const cudaMemcpyKind kind = out->memory == VRJ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (out->colour) VRJ_CUDA(cudaMemcpyAsync(out->colour, m->colour.p, npix * 24, kind, s0));
+    if (out->colour_sum) VRJ_CUDA(cudaMemcpyAsync(out->colour_sum, m->sum[0]->p, npix * 24, kind, s0));
+    if (out->weight) VRJ_CUDA(cudaMemcpyAsync(out->weight, m->weight[0]->p, npix * 8, kind, s0));
+    if (out->memory == VRJ_MEM_DEVICE) {
+        if (out->colour_bias) VRJ_CUDA(cudaMemsetAsync(out->colour_bias, 0, npix * 24, s0));
+        if (out->weight_bias) VRJ_CUDA(cudaMemsetAsync(out->weight_bias, 0, npix * 8, s0));
+    } else {
+        if (out->colour_bias) std::memset(out->colour_bias, 0, npix * 24);
+        if (out->weight_bias) std::memset(out->weight_bias, 0, npix * 8);
+    }
+    VRJ_CUDA(cudaStreamSynchronize(s0));
+    if (out->stats) {
+        VrjStats &t = *out->stats;
+        for (int g = 0; g < G; g++) {
+            const VrjStats &a = stats[g];
+            t.primary_rays += a.primary_rays, t.bounce_rays += a.bounce_rays, t.shadow_rays += a.shadow_rays;
+            t.paths_missed += a.paths_missed, t.paths_escaped += a.paths_escaped, t.paths_depth_limited += a.paths_depth_limited;
+            t.node_visits += a.node_visits, t.triangle_tests += a.triangle_tests, t.kernel_launches += a.kernel_launches;
+            t.staged_rays += a.staged_rays;
+            t.device_ms = std::max(t.device_ms, a.device_ms); // devices run concurrently
+            t.primary_ms = std::max(t.primary_ms, a.primary_ms), t.bounce_ms = std::max(t.bounce_ms, a.bounce_ms);
+            t.shade_ms = std::max(t.shade_ms, a.shade_ms), t.resolve_ms = std::max(t.resolve_ms, a.resolve_ms);
+        }
+        t.kernel_launches += 1;
+    }
     return VRJ_OK;
 }
 

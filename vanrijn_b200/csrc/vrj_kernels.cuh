@@ -247,7 +247,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
         Rng rng;
         rng.init(rc.seed, pixel, sample, 2);
         p.wl = 380.0 + (740.0 - 380.0) * rng.f64(); // photon.rs:18-24
-        p.ordinal = 3, p.A = 1.0, p.B = 0.0, p.aux = 0.0, p.limit = rc.max_depth, p.flags = 0;
+        p.ordinal = 4, p.A = 1.0, p.B = 0.0, p.aux = 0.0, p.limit = rc.max_depth, p.flags = 0; // ordinal 3 unused: draws pair up per Philox block
         if (!WHITTED && p.limit == 0) {
             photons[p.slot] = make_double2(0.0, 0.0); // simple_random_integrator.rs:20-25
             ls.v[ST_LIMITED]++;

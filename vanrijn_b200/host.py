@@ -61,6 +61,9 @@ class HostScene:
 
     def __del__(self):
         try:
+            for comm, ms in getattr(self, "_comm", {}).values():
+                capi.cuda().vrj_comm_scene_destroy(ms)
+                capi.cuda().vrj_comm_destroy(comm)
             self.H.vrjh_scene_free(self.h)
         except Exception:
             pass
@@ -167,6 +170,37 @@ class HostScene:
         t = capi.Tile(*tile)
         capi.check(capi.cuda().vrj_render_tile(self.device_scene(device), C.byref(t), height, width, C.byref(p), C.byref(ao)))
         return st
+
+    def render_sharded(self, devices, tile, height, width, want=("colour", "colour_sum", "weight"), **kw):
+        """vrj_comm_* path: one process, the scene replicated on `devices`, samples sharded by index, one NCCL
+        reduce into devices[0].  Host outputs.  The communicator and replicas are cached on this object."""
+        L = capi.cuda()
+        key = tuple(devices)
+        if not hasattr(self, "_comm"):
+            self._comm = {}
+        if key not in self._comm:
+            comm, ms = C.c_void_p(), C.c_void_p()
+            arr = (C.c_int32 * len(devices))(*devices)
+            capi.check(L.vrj_comm_create(len(devices), arr, C.byref(comm)))
+            d = self.desc()
+            capi.check(L.vrj_comm_scene_create(comm, C.byref(d), C.byref(ms)))
+            self._comm[key] = (comm, ms)
+        comm, ms = self._comm[key]
+        sc, ec, sr, er = tile
+        npix = (ec - sc) * (er - sr)
+        p, keep = self.make_params(**kw)
+        out = {}
+        ao = capi.AccumOut(memory=capi.MEM_HOST, accumulate=0)
+        for name, per in (("colour", 3), ("colour_sum", 3), ("colour_bias", 3), ("weight", 1), ("weight_bias", 1)):
+            if name in want:
+                out[name] = np.zeros(npix * per)
+                setattr(ao, name, out[name].ctypes.data)
+        st = capi.Stats()
+        ao.stats = C.pointer(st)
+        t = capi.Tile(sc, ec, sr, er)
+        capi.check(L.vrj_render_sharded(ms, C.byref(t), height, width, C.byref(p), C.byref(ao)))
+        out["stats"] = st
+        return out
 
     def partial_render_scene(self, tile, height, width, seed=1, sample_offset=0):
         """The reference call: partial_render_scene(&scene, tile, height, width) -> AccumulationBuffer."""
