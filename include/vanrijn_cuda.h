@@ -209,6 +209,9 @@ typedef struct VrjAccumOut {
     double *weight_bias; /* 1 per pixel */
     double *photons;     /* optional debug output: spp * npix * 2 = (wavelength, intensity*360) per sample */
     VrjStats *stats;     /* host memory */
+    uint8_t *srgb8;      /* optional: 3 bytes per pixel, ClampingToneMapper applied to `colour` on the device
+                            (AccumulationBuffer::to_image_rgb_u8, accumulation_buffer.rs:38-42) -- a preview needs
+                            6 MB back instead of the 66 MB of f64 XYZ at 1080p */
 } VrjAccumOut;
 
 VRJ_API const char *vrj_last_error(void);
@@ -251,6 +254,13 @@ VRJ_API void vrj_comm_scene_destroy(VrjMultiScene *scene);
  * `photons` are not supported; params->sample_stride must be 0 or 1. */
 VRJ_API VrjStatus vrj_render_sharded(VrjMultiScene *scene, const VrjTile *tile, uint64_t height, uint64_t width,
                                      const VrjRenderParams *params, VrjAccumOut *out);
+
+/* ClampingToneMapper (src/image.rs:130-187) on `n_pixels` colours (3 doubles each) -> 3 bytes each.
+ * source VRJ_TONEMAP_XYZ: ColourXyz::to_srgb (colour_xyz.rs:48-84, constants as written) then clamp + truncating byte
+ * conversion (image.rs:120-123, 0.5 -> 127); VRJ_TONEMAP_LINEAR_RGB: clamp + byte only.  `memory` describes both pointers. */
+enum { VRJ_TONEMAP_XYZ = 0, VRJ_TONEMAP_LINEAR_RGB = 1 };
+VRJ_API VrjStatus vrj_tone_map(int32_t device, uint32_t memory, uint32_t source, const double *colour, uint64_t n_pixels,
+                               uint8_t *rgb8);
 
 VRJ_API VrjStatus vrj_trace_rays(const VrjScene *scene, uint64_t n, const double *origins, const double *directions,
                          uint32_t bvh_filter, int32_t *object_id, int32_t *prim_id, double *t, VrjStats *stats);

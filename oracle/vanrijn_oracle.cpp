@@ -1212,6 +1212,24 @@ void orc_linear_rgb_to_xyz(const double *rgb, double *xyz) {
 /* colour_xyz.rs:78-84 (constants as written there) */
 double orc_srgb_gamma(double u) { return u <= 0.0031308 ? 12.98 * u : 1.005 * std::pow(u, 1.0 / 2.4) - 0.055; }
 
+/* image.rs:130-187 ClampingToneMapper; image.rs:120-123 normalized_to_byte (truncating, saturating cast; NaN -> 0).
+ * source 0: ColourXyz::to_srgb first (colour_xyz.rs:48-84); source 1: linear RGB as is. */
+void orc_tone_map(int source, const double *colour, int64_t n, uint8_t *rgb8) {
+    for (int64_t i = 0; i < n; i++) {
+        double c[3] = {colour[3 * i], colour[3 * i + 1], colour[3 * i + 2]};
+        if (source == 0) {
+            double lin[3];
+            orc_xyz_to_linear_rgb(c, lin);
+            for (int k = 0; k < 3; k++) c[k] = orc_srgb_gamma(lin[k]);
+        }
+        for (int k = 0; k < 3; k++) {
+            double v = c[k] < 0.0 ? 0.0 : (c[k] > 1.0 ? 1.0 : c[k]); /* f64::clamp keeps NaN */
+            double b = v * 255.0;
+            rgb8[3 * i + k] = b != b ? 0 : (uint8_t)(int)b;
+        }
+    }
+}
+
 void orc_accum_update(double *st, double wavelength, double intensity, double weight) {
     PixelAccum a;
     a.colour = ld3(st), a.sum = ld3(st + 3), a.bias = ld3(st + 6), a.weight = st[9], a.weight_bias = st[10];

@@ -120,6 +120,8 @@ void orc_cmf_xyz(double wavelength, double *xyz);
 void orc_xyz_to_linear_rgb(const double *xyz, double *rgb);
 void orc_linear_rgb_to_xyz(const double *rgb, double *xyz);
 double orc_srgb_gamma(double u);
+/* ClampingToneMapper (image.rs:130-187): source 0 = XYZ -> sRGB -> clamp -> u8, 1 = linear RGB -> clamp -> u8 */
+void orc_tone_map(int source, const double *colour, int64_t n, uint8_t *rgb8);
 /* AccumulationBuffer::update_pixel on one pixel: state = {colour[3], sum[3], bias[3], weight, weight_bias} */
 void orc_accum_update(double *state11, double wavelength, double intensity, double weight);
 void orc_accum_blend(const double *c1, double w1, const double *c2, double w2, double *out3);

@@ -93,6 +93,7 @@ pub struct VrjAccumOut {
     pub weight: *mut f64, pub weight_bias: *mut f64,
     pub photons: *mut f64,
     pub stats: *mut VrjStats,
+    pub srgb8: *mut u8,
 }
 
 extern "C" {
@@ -113,6 +114,7 @@ extern "C" {
     pub fn vrj_comm_scene_destroy(scene: *mut VrjMultiScene);
     pub fn vrj_render_sharded(scene: *mut VrjMultiScene, tile: *const VrjTile, height: u64, width: u64,
                               params: *const VrjRenderParams, out: *mut VrjAccumOut) -> i32;
+    pub fn vrj_tone_map(device: i32, memory: u32, source: u32, colour: *const f64, n_pixels: u64, rgb8: *mut u8) -> i32;
     pub fn vrj_trace_rays(scene: *const VrjScene, n: u64, origins: *const f64, directions: *const f64, bvh_filter: u32,
                           object_id: *mut i32, prim_id: *mut i32, t: *mut f64, stats: *mut VrjStats) -> i32;
 }

@@ -93,6 +93,7 @@ def lib():
     L.orc_linear_rgb_to_xyz.argtypes = [dp, dp]
     L.orc_srgb_gamma.restype = C.c_double
     L.orc_srgb_gamma.argtypes = [C.c_double]
+    L.orc_tone_map.argtypes = [C.c_int, dp, C.c_int64, C.c_void_p]
     L.orc_accum_update.argtypes = [dp, C.c_double, C.c_double, C.c_double]
     L.orc_accum_blend.argtypes = [dp, C.c_double, dp, C.c_double, dp]
     L.orc_camera_ray.argtypes = [C.c_uint64, C.c_uint64, dp, C.c_uint64, C.c_uint64, C.c_double, C.c_double, dp, dp]
@@ -141,6 +142,13 @@ def hit16(fn, *args):
         return None
     return {"distance": out[0], "location": out[1:4], "normal": out[4:7], "tangent": out[7:10],
             "cotangent": out[10:13], "retro": out[13:16]}
+
+
+def tone_map(colour, source=0):
+    c = np.ascontiguousarray(colour, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((c.shape[0], 3), np.uint8)
+    lib().orc_tone_map(source, c.ctypes.data_as(dp), c.shape[0], out.ctypes.data)
+    return out
 
 
 class OracleScene:

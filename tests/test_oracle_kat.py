@@ -381,3 +381,22 @@ def test_rng_ranges_and_stream_layout():
     # different pixel / sample / seed give different streams
     assert L.orc_rng_f64(1, 7, 3, 0) != L.orc_rng_f64(1, 8, 3, 0) != L.orc_rng_f64(2, 7, 3, 0)
     assert L.orc_rng_f64(1, 7, 3, 0) != L.orc_rng_f64(1, 7, 4, 0)
+
+
+# ---------------- image.rs:193-332 (ClampingToneMapper, normalized_to_byte) -- "next" row N2
+def test_tone_mapper_kats():
+    rgb = lambda *v: O.tone_map(np.array([v], float), source=1)[0].tolist()
+    assert rgb(0.0, 0.0, 0.0) == [0, 0, 0]
+    assert rgb(1.0, 1.0, 1.0) == [0xff, 0xff, 0xff]
+    assert rgb(2.0, 2.0, 2.0) == [0xff, 0xff, 0xff]              # supersaturated white clamps
+    assert rgb(0.0, 2.0, 0.0) == [0, 0xff, 0]
+    assert rgb(0.5, 0.0, 0.0) == [0x7f, 0, 0]                    # truncating conversion: 0.5 -> 127
+    assert rgb(-1.0, float("nan"), 0.25) == [0, 0, 63]
+    # XYZ path: D65 white (Y = 1) maps to ~white; gamma constants as written (12.98 / 1.005)
+    white = O.tone_map(np.array([[0.95047, 1.0, 1.08883]]), source=0)[0]
+    assert white.min() >= 0xf0
+    dark = O.tone_map(np.array([[0.0002, 0.0002, 0.0002]]), source=0)[0]
+    xyz = np.array([0.0002, 0.0002, 0.0002])
+    lin = np.zeros(3)
+    L.orc_xyz_to_linear_rgb(xyz.ctypes.data_as(dp), lin.ctypes.data_as(dp))
+    assert dark.tolist() == [int(12.98 * v * 255.0) for v in lin]

@@ -19,13 +19,14 @@ MAT_LAMBERTIAN, MAT_PHONG, MAT_REFLECTIVE, MAT_DIELECTRIC = 0, 1, 2, 3
 INTEGRATOR_SIMPLE_RANDOM, INTEGRATOR_WHITTED = 0, 1
 FILTER_F32, FILTER_F64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
+TONEMAP_XYZ, TONEMAP_LINEAR_RGB = 0, 1
 OK = 0
 
 # every symbol include/vanrijn_cuda.h declares
 CUDA_SYMBOLS = ["vrj_last_error", "vrj_abi_version", "vrj_device_count", "vrj_scene_create", "vrj_scene_destroy",
                 "vrj_scene_device_bytes", "vrj_render_tile", "vrj_trace_rays", "vrj_release_scratch", "vrj_alloc_host",
                 "vrj_free_host", "vrj_comm_create", "vrj_comm_destroy", "vrj_comm_scene_create", "vrj_comm_scene_destroy",
-                "vrj_render_sharded"]
+                "vrj_render_sharded", "vrj_tone_map"]
 
 
 class VrjError(RuntimeError):
@@ -113,7 +114,7 @@ class Stats(C.Structure):
 class AccumOut(C.Structure):
     _fields_ = [("memory", C.c_uint32), ("accumulate", C.c_uint32), ("colour", C.c_void_p), ("colour_sum", C.c_void_p),
                 ("colour_bias", C.c_void_p), ("weight", C.c_void_p), ("weight_bias", C.c_void_p), ("photons", C.c_void_p),
-                ("stats", C.POINTER(Stats))]
+                ("stats", C.POINTER(Stats)), ("srgb8", C.c_void_p)]
 
 
 _cuda = None
@@ -156,6 +157,8 @@ def cuda():
         L.vrj_render_sharded.restype = C.c_int32
         L.vrj_render_sharded.argtypes = [C.c_void_p, C.POINTER(Tile), C.c_uint64, C.c_uint64, C.POINTER(RenderParams),
                                          C.POINTER(AccumOut)]
+        L.vrj_tone_map.restype = C.c_int32
+        L.vrj_tone_map.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, dp, C.c_uint64, C.c_void_p]
         L.vrj_trace_rays.restype = C.c_int32
         L.vrj_trace_rays.argtypes = [C.c_void_p, C.c_uint64, dp, dp, C.c_uint32, C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), dp, C.POINTER(Stats)]

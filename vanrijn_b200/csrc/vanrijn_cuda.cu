@@ -56,7 +56,7 @@ struct Scratch {
     DeviceBuffer queues[2][6];
     DeviceBuffer photons, hits[2], tbest[2], list, counters, stats;
     DeviceBuffer acc_colour, acc_sum, acc_bias, acc_weight, acc_wbias;
-    DeviceBuffer lights, light_samples;
+    DeviceBuffer lights, light_samples, srgb8;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> marks; // per-launch boundaries, reused across calls
@@ -762,6 +762,15 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     for (int i = 0; i < 5; i++)
         if (arrs[i].user)
             VRJ_CUDA(cudaMemcpyAsync(arrs[i].user, arrs[i].dev->p, npix * arrs[i].per * sizeof(double), out_kind, s->stream));
+    if (out->srgb8) {
+        if (s->srgb8.bytes < npix * 3) {
+            if (s->srgb8.p) cudaFree(s->srgb8.p), s->srgb8.p = nullptr;
+            VRJ_CUDA(s->srgb8.alloc(npix * 3));
+        }
+        k_tone_map<<<(unsigned)((npix + 255) / 256), 256, 0, s->stream>>>(s->acc_colour.as<double>(), s->srgb8.as<unsigned char>(), npix, 0);
+        launches++;
+        VRJ_CUDA(cudaMemcpyAsync(out->srgb8, s->srgb8.p, npix * 3, out_kind, s->stream));
+    }
     unsigned long long hstats[ST_COUNT];
     VRJ_CUDA(cudaMemcpyAsync(hstats, s->stats.p, sizeof hstats, cudaMemcpyDeviceToHost, s->stream));
     VRJ_CUDA(cudaStreamSynchronize(s->stream));
@@ -782,6 +791,27 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         out->stats->shade_ms = cls_ms[3] + cls_ms[4], out->stats->shade_launches = cls_n[3] + cls_n[4];
         out->stats->tail_ms = cls_ms[5], out->stats->tail_launches = cls_n[5];
     }
+    return VRJ_OK;
+}
+
+VrjStatus vrj_tone_map(int32_t device, uint32_t memory, uint32_t source, const double *colour, uint64_t n, uint8_t *rgb8) {
+    if (n && (!colour || !rgb8)) return fail(VRJ_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (source > VRJ_TONEMAP_LINEAR_RGB || memory > VRJ_MEM_DEVICE) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown source / memory");
+    if (n == 0) return VRJ_OK;
+    VRJ_CUDA(cudaSetDevice(device));
+    DeviceBuffer d_in, d_out;
+    const double *src = colour;
+    unsigned char *dst = rgb8;
+    if (memory == VRJ_MEM_HOST) {
+        VRJ_CUDA(d_in.alloc(n * 24));
+        VRJ_CUDA(d_out.alloc(n * 3));
+        VRJ_CUDA(cudaMemcpy(d_in.p, colour, n * 24, cudaMemcpyHostToDevice));
+        src = d_in.as<double>(), dst = d_out.as<unsigned char>();
+    }
+    k_tone_map<<<(unsigned)((n + 255) / 256), 256>>>(src, dst, n, (int)source);
+    VRJ_CUDA(cudaGetLastError());
+    if (memory == VRJ_MEM_HOST) VRJ_CUDA(cudaMemcpy(rgb8, d_out.p, n * 3, cudaMemcpyDeviceToHost));
+    else VRJ_CUDA(cudaDeviceSynchronize());
     return VRJ_OK;
 }
 
@@ -1054,6 +1084,12 @@ VrjStatus vrj_render_sharded(VrjMultiScene *m, const VrjTile *tile, uint64_t hei
     if (out->colour) VRJ_CUDA(cudaMemcpyAsync(out->colour, m->colour.p, npix * 24, kind, s0));
     if (out->colour_sum) VRJ_CUDA(cudaMemcpyAsync(out->colour_sum, m->sum[0]->p, npix * 24, kind, s0));
     if (out->weight) VRJ_CUDA(cudaMemcpyAsync(out->weight, m->weight[0]->p, npix * 8, kind, s0));
+    DeviceBuffer srgb8;
+    if (out->srgb8) {
+        VRJ_CUDA(srgb8.alloc(npix * 3));
+        k_tone_map<<<(unsigned)((npix + 255) / 256), 256, 0, s0>>>(m->colour.as<double>(), srgb8.as<unsigned char>(), npix, 0);
+        VRJ_CUDA(cudaMemcpyAsync(out->srgb8, srgb8.p, npix * 3, kind, s0));
+    }
     if (out->memory == VRJ_MEM_DEVICE) {
         if (out->colour_bias) VRJ_CUDA(cudaMemsetAsync(out->colour_bias, 0, npix * 24, s0));
         if (out->weight_bias) VRJ_CUDA(cudaMemsetAsync(out->weight_bias, 0, npix * 8, s0));

@@ -486,6 +486,28 @@ __global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t npix, u
     acc.colour[3 * p] = sx * inv, acc.colour[3 * p + 1] = sy * inv, acc.colour[3 * p + 2] = sz * inv;
 }
 
+// ---- k_tone_map: ClampingToneMapper (image.rs:130-187) ----
+// colour_xyz.rs:78-84, constants as written there (12.98 / 1.005, not the sRGB standard's 12.92 / 1.055)
+__device__ __forceinline__ double srgb_gamma(double u) { return u <= 0.0031308 ? 12.98 * u : 1.005 * pow(u, 1.0 / 2.4) - 0.055; }
+// f64::clamp(0,1) then `(v * 255.0) as u8` (image.rs:120-123,136-138): truncation, saturating, NaN -> 0
+__device__ __forceinline__ unsigned char clamp_to_byte(double v) {
+    v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+    double b = v * 255.0;
+    return b != b ? (unsigned char)0 : (unsigned char)(int)b;
+}
+__global__ void k_tone_map(const double *colour, unsigned char *rgb8, uint64_t n, int source) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    D3 c = d3(colour[3 * p], colour[3 * p + 1], colour[3 * p + 2]);
+    if (source == 0) {
+        // ColourXyz::to_linear_rgb (colour_xyz.rs:48-56) as Mat3 * Vec3, then the gamma per channel (:69-75)
+        D3 lin = d3(dot(d3(3.24096994, -1.53738318, -0.49861076), c), dot(d3(-0.96924364, 1.87596750, 0.04155506), c),
+                    dot(d3(0.05563008, -0.20397696, 1.05697151), c));
+        c = d3(srgb_gamma(lin.x), srgb_gamma(lin.y), srgb_gamma(lin.z));
+    }
+    rgb8[3 * p] = clamp_to_byte(c.x), rgb8[3 * p + 1] = clamp_to_byte(c.y), rgb8[3 * p + 2] = clamp_to_byte(c.z);
+}
+
 // Sampler::sample on a caller-supplied ray list (the bit-exact id gate): same stages as the render path
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_stage_ray_list(DevScene sc, uint32_t n, const double *origins, const double *dirs,

@@ -147,6 +147,9 @@ class HostScene:
         if want_photons:
             out["photons"] = np.zeros(p.spp * npix * 2)
             ao.photons = out["photons"].ctypes.data
+        if "srgb8" in want:
+            out["srgb8"] = np.zeros(npix * 3, np.uint8)
+            ao.srgb8 = out["srgb8"].ctypes.data
         st = capi.Stats()
         ao.stats = C.pointer(st)
         t = capi.Tile(sc, ec, sr, er)
@@ -215,6 +218,14 @@ class HostScene:
         if r != 0:
             raise capi.VrjError(self.H.vrjh_last_error().decode())
         return out
+
+
+def tone_map(colour, source=capi.TONEMAP_XYZ, device=0):
+    """ClampingToneMapper on host arrays through the device (vrj_tone_map): (n,3) float64 -> (n,3) uint8."""
+    c = np.ascontiguousarray(colour, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((c.shape[0], 3), np.uint8)
+    capi.check(capi.cuda().vrj_tone_map(device, capi.MEM_HOST, source, c.ctypes.data_as(dp), c.shape[0], out.ctypes.data))
+    return out
 
 
 def build_scene(spec):
