@@ -17,9 +17,19 @@ HOST_DEPS = $(CSRC)/host/vanrijn_host.cpp $(CSRC)/host/host_capi.cpp include/van
 
 all: $(LIBDIR)/libvanrijn_cuda.so $(LIBDIR)/libvanrijn_host.so oracle
 
-$(LIBDIR)/libvanrijn_cuda.so: $(CUDA_DEPS)
+# two translation units (the render loop; the device BVH builder), compiled separately so a change to one
+# does not recompile the other
+OBJDIR ?= build/obj
+$(OBJDIR)/vanrijn_cuda.o: $(CUDA_DEPS)
+	mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(EXTRA) -c -o $@ $(CSRC)/vanrijn_cuda.cu
+$(OBJDIR)/vrj_bvh_build.o: $(CSRC)/vrj_bvh_build.cu include/vanrijn_cuda.h
+	mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(EXTRA) -c -o $@ $(CSRC)/vrj_bvh_build.cu
+
+$(LIBDIR)/libvanrijn_cuda.so: $(OBJDIR)/vanrijn_cuda.o $(OBJDIR)/vrj_bvh_build.o
 	mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) $(EXTRA) -shared -o $@ $(CSRC)/vanrijn_cuda.cu -ldl
+	$(NVCC) $(NVFLAGS) -shared -o $@ $^ -ldl
 
 $(LIBDIR)/libvanrijn_host.so: $(HOST_DEPS) $(LIBDIR)/libvanrijn_cuda.so
 	$(HOSTCXX) -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -Wextra -shared -o $@ \

@@ -129,8 +129,12 @@ struct PrimitiveList : Aggregate {
 // bounding_volume_hierarchy.rs:18-75.  Only triangles may be stored (what load_obj produces).
 class BoundingVolumeHierarchy : public Aggregate {
   public:
+    // Where the recursion of bounding_volume_hierarchy.rs:49-75 runs.  Both produce the same tree (same boxes,
+    // node numbering and leaf order); Device calls vrj_bvh_build and throws if there is no GPU.
+    enum class Builder { Host, Device };
     // reorders `primitives` in place, as the reference's build(&mut [Arc<dyn Primitive>]) does
-    static std::unique_ptr<BoundingVolumeHierarchy> build(std::vector<std::shared_ptr<Primitive>> &primitives);
+    static std::unique_ptr<BoundingVolumeHierarchy> build(std::vector<std::shared_ptr<Primitive>> &primitives,
+                                                          Builder builder = Builder::Host, int device = 0);
     void flatten(FlatSceneBuilder &out, uint32_t object_id) const override;
     uint32_t depth() const { return depth_; }
     size_t triangle_count() const { return tri_v_.size() / 9; }

@@ -262,6 +262,27 @@ enum { VRJ_TONEMAP_XYZ = 0, VRJ_TONEMAP_LINEAR_RGB = 1 };
 VRJ_API VrjStatus vrj_tone_map(int32_t device, uint32_t memory, uint32_t source, const double *colour, uint64_t n_pixels,
                                uint8_t *rgb8);
 
+/* ---- BoundingVolumeHierarchy::build on the device ----
+ * Replaces the host-side recursion of src/raycasting/bounding_volume_hierarchy.rs:38-75 (bounds -> largest_dimension
+ * -> sort by box centre -> split at len/2) for triangle sets, and returns EXACTLY the tree that recursion builds
+ * with a stable sort: same boxes, same DFS pre-order node numbering, same leaf order.  Inputs and outputs are host
+ * arrays in the layout VrjSceneDesc uses:
+ *   vertices   9 doubles per triangle (v0 xyz, v1 xyz, v2 xyz), in the caller's order
+ *   order      n entries: order[i] = input index of the triangle at leaf position i (= VrjSceneDesc.tri_prim_id)
+ *   node_min / node_max   4 doubles {x, y, z, 0} per node, 2n-1 nodes (1 node when n == 0)
+ *   node_child            2 per node, BVH-local: internal {left, right}; leaf {~leaf position, triangle count}
+ *   depth      levels of the tree (VrjBvh.depth); may be NULL.  stats may be NULL. */
+typedef struct VrjBvhBuildStats {
+    double device_ms;        /* CUDA-event time of the build kernels (copies excluded) */
+    uint32_t global_levels;  /* levels sorted with the segmented radix sort */
+    uint32_t radix_passes;   /* 8-bit digit passes actually run (constant digits are skipped) */
+    uint32_t small_subtrees; /* subtrees finished by one CTA each in shared memory */
+    uint32_t pad;
+} VrjBvhBuildStats;
+VRJ_API VrjStatus vrj_bvh_build(int32_t device, uint64_t n_triangles, const double *vertices, uint32_t *order,
+                                double *node_min, double *node_max, int32_t *node_child, uint32_t *depth,
+                                VrjBvhBuildStats *stats);
+
 VRJ_API VrjStatus vrj_trace_rays(const VrjScene *scene, uint64_t n, const double *origins, const double *directions,
                          uint32_t bvh_filter, int32_t *object_id, int32_t *prim_id, double *t, VrjStats *stats);
 

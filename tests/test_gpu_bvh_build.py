@@ -1,0 +1,137 @@
+"""GPU tests of vrj_bvh_build: the device builder must return EXACTLY the tree the host mirror of
+BoundingVolumeHierarchy::build (bounding_volume_hierarchy.rs:38-75, stable sort) returns -- same leaf order, same node
+numbering, same boxes -- so hit ids and tie-breaking cannot depend on where the tree was built."""
+import numpy as np
+import pytest
+
+import vanrijn_b200 as V
+from vanrijn_b200 import capi, host, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def host_tree(verts):
+    """The host builder's arrays for one mesh, read back from the flattened scene description."""
+    v = np.ascontiguousarray(verts, np.float64).reshape(-1, 9)
+    spec = scenes.SceneSpec(camera=(0.0, 0.0, -5.0))
+    m = spec.lambertian_rgb((1.0, 1.0, 0.0), 0.05)
+    spec.objects.append(("mesh", v, np.zeros_like(v), m))
+    hs = V.build_scene(spec)
+    d = hs.desc()
+    n_nodes, n = int(d.n_nodes), int(d.n_triangles)
+    take = lambda p, count, dt: np.ctypeslib.as_array(p, shape=(count,)).astype(dt).copy() if count else np.zeros(0, dt)
+    out = dict(order=take(d.tri_prim_id, n, np.uint32),
+               node_min=take(d.node_min, 4 * n_nodes, np.float64).reshape(-1, 4),
+               node_max=take(d.node_max, 4 * n_nodes, np.float64).reshape(-1, 4),
+               node_child=take(d.node_child, 2 * n_nodes, np.int32).reshape(-1, 2),
+               depth=int(d.bvhs[0].depth))
+    return out, hs
+
+
+def check_same(verts):
+    ref, _ = host_tree(verts)
+    got = host.bvh_build(verts)
+    assert got["depth"] == ref["depth"]
+    assert np.array_equal(got["order"], ref["order"]), "leaf order differs"
+    assert np.array_equal(got["node_child"], ref["node_child"]), "node numbering differs"
+    assert np.array_equal(got["node_min"], ref["node_min"]) and np.array_equal(got["node_max"], ref["node_max"]), "boxes differ"
+    return got
+
+
+def random_triangles(n, seed, extent=10.0, size=0.2):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-extent, extent, size=(n, 1, 3))
+    v = c + rng.normal(size=(n, 3, 3)) * size
+    return v.astype(np.float32).astype(np.float64).reshape(n, 9)  # f32-parsed like an OBJ (mesh.rs:21-26)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 17, 100, 1023, 1024, 1025, 2047, 2048, 2049, 4097, 5000, 70001])
+def test_device_tree_equals_host_tree_random(n):
+    got = check_same(random_triangles(n, seed=n))
+    if n > 1024:
+        assert got["stats"].global_levels >= 1 and got["stats"].radix_passes >= 1
+
+
+def test_device_tree_equals_host_tree_full_f64_keys():
+    """Vertices that are NOT f32-representable: all 64 key bits vary, every radix digit pass runs."""
+    rng = np.random.default_rng(7)
+    v = rng.normal(size=(30000, 9)) * np.exp(rng.uniform(-20, 20, size=(30000, 1)))
+    got = check_same(v)
+    assert got["stats"].radix_passes >= 8
+
+
+def test_device_tree_equals_host_tree_with_ties():
+    """Translated copies share centre coordinates exactly (C4's grid does): the sort must be stable, level after level."""
+    base = random_triangles(700, seed=3, extent=1.0)
+    copies = []
+    for ix in range(4):
+        for iz in range(5):
+            off = np.array([4.0 * ix, 0.0, 4.0 * iz] * 3)
+            copies.append(base + off)
+    check_same(np.concatenate(copies, 0))
+    # every triangle identical: every key equal at every level, the order must stay the input order
+    same = np.tile(random_triangles(1, seed=5), (3000, 1))
+    got = check_same(same)
+    assert np.array_equal(got["order"], np.arange(3000, dtype=np.uint32))
+    # signed zeros compare equal (operator< on the host, x + 0.0 on the device)
+    z = random_triangles(2500, seed=9, extent=0.0, size=1.0)
+    z[::2, 0::3] = 0.0
+    z[1::2, 0::3] = -0.0
+    check_same(z)
+
+
+def test_empty_and_error_paths():
+    got = host.bvh_build(np.zeros((0, 9)))
+    assert got["depth"] == 1 and got["node_child"].tolist() == [[-1, 0]]
+    assert np.all(got["node_min"][0, :3] == np.inf) and np.all(got["node_max"][0, :3] == -np.inf)
+    import ctypes as C
+    L = capi.cuda()
+    v = np.zeros(9)
+    assert L.vrj_bvh_build(0, 1, v.ctypes.data_as(capi.dp), None, None, None, None, None, None) != capi.OK
+    assert b"NULL" in L.vrj_last_error()
+
+
+def test_scene_built_on_the_device_is_the_same_scene():
+    """The bench mesh through the scene path: identical flattened arrays, identical hits and image."""
+    spec = scenes.scene_main(subdivisions=6, obj=False)
+    a, b = V.build_scene(spec), V.build_scene(spec, device_builder=True)
+    da, db = a.desc(), b.desc()
+    assert int(da.n_nodes) == int(db.n_nodes) and int(da.n_triangles) == int(db.n_triangles) == 81920
+    n_nodes, n = int(da.n_nodes), int(da.n_triangles)
+    arr = lambda p, count: np.ctypeslib.as_array(p, shape=(count,))
+    assert np.array_equal(arr(da.tri_prim_id, n), arr(db.tri_prim_id, n))
+    assert np.array_equal(arr(da.node_child, 2 * n_nodes), arr(db.node_child, 2 * n_nodes))
+    assert np.array_equal(arr(da.node_min, 4 * n_nodes), arr(db.node_min, 4 * n_nodes))
+    assert np.array_equal(arr(da.node_max, 4 * n_nodes), arr(db.node_max, 4 * n_nodes))
+    assert np.array_equal(arr(da.tri_v0, 4 * n), arr(db.tri_v0, 4 * n))
+    W, H = 160, 90
+    ra = a.render((0, W, 0, H), H, W, spp=2, max_depth=4, seed=1, want=("colour_sum",), want_photons=True)
+    rb = b.render((0, W, 0, H), H, W, spp=2, max_depth=4, seed=1, want=("colour_sum",), want_photons=True)
+    assert np.array_equal(ra["photons"], rb["photons"])
+
+
+def test_large_build_properties():
+    """C4-sized input (9.9 M triangles): the tree is too big to rebuild on the host inside a test, so check the
+    properties a correct build has: order is a permutation, every parent box is the union of its children's boxes,
+    leaves hold their triangle's box, and the left subtree's centres do not exceed the right subtree's on the split axis."""
+    spec = scenes.scene_grid(copies=11)
+    v = spec.objects[1][1]
+    n = v.shape[0]
+    got = host.bvh_build(v)
+    order, child, mn, mx = got["order"], got["node_child"], got["node_min"][:, :3], got["node_max"][:, :3]
+    assert np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))
+    internal = child[:, 0] >= 0
+    l, r = child[internal, 0], child[internal, 1]
+    assert np.array_equal(mn[internal], np.minimum(mn[l], mn[r])) and np.array_equal(mx[internal], np.maximum(mx[l], mx[r]))
+    leaf = ~internal
+    pos = ~child[leaf, 0]
+    tri = v[order[pos]].reshape(-1, 3, 3)
+    assert np.array_equal(mn[leaf], tri.min(1)) and np.array_equal(mx[leaf], tri.max(1))
+    # root split: sorted by box centre on the largest axis
+    ext = mx[0] - mn[0]
+    axis = int(np.argmax(ext))
+    c = (v.reshape(-1, 3, 3).min(1)[:, axis] + v.reshape(-1, 3, 3).max(1)[:, axis]) / 2.0
+    half = n // 2
+    assert c[order[:half]].max() <= c[order[half:]].min()
+    print("C4 build: %.1f ms on the device, %d global levels, %d radix passes, %d small subtrees" % (
+        got["stats"].device_ms, got["stats"].global_levels, got["stats"].radix_passes, got["stats"].small_subtrees))

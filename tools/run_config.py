@@ -15,6 +15,7 @@ ap.add_argument("config", choices=["C2", "C3", "C4", "C5"])
 ap.add_argument("--spp", type=int, default=None)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--filter", default="f32")
+ap.add_argument("--device-builder", action="store_true", help="BoundingVolumeHierarchy::build on the GPU (vrj_bvh_build)")
 a = ap.parse_args()
 kw = dict(seed=1, bvh_filter=capi.FILTER_F64 if a.filter == "f64" else capi.FILTER_F32)
 t0 = time.time()
@@ -34,7 +35,7 @@ else:
     spec = scenes.scene_main(subdivisions=6, obj=True, variant="mixed")
     W, H, spp = 1920, 1080, a.spp or 16
     kw.update(max_depth=128)
-hs = V.build_scene(spec)
+hs = V.build_scene(spec, device_builder=a.device_builder)
 t1 = time.time()
 hs.device_scene(0)
 t2 = time.time()

@@ -26,7 +26,7 @@ OK = 0
 CUDA_SYMBOLS = ["vrj_last_error", "vrj_abi_version", "vrj_device_count", "vrj_scene_create", "vrj_scene_destroy",
                 "vrj_scene_device_bytes", "vrj_render_tile", "vrj_trace_rays", "vrj_release_scratch", "vrj_alloc_host",
                 "vrj_free_host", "vrj_comm_create", "vrj_comm_destroy", "vrj_comm_scene_create", "vrj_comm_scene_destroy",
-                "vrj_render_sharded", "vrj_tone_map"]
+                "vrj_render_sharded", "vrj_tone_map", "vrj_bvh_build"]
 
 
 class VrjError(RuntimeError):
@@ -111,6 +111,11 @@ class Stats(C.Structure):
         return {n: (float(getattr(self, n)) if t is C.c_double else int(getattr(self, n))) for n, t in self._fields_}
 
 
+class BvhBuildStats(C.Structure):
+    _fields_ = [("device_ms", C.c_double), ("global_levels", C.c_uint32), ("radix_passes", C.c_uint32),
+                ("small_subtrees", C.c_uint32), ("pad", C.c_uint32)]
+
+
 class AccumOut(C.Structure):
     _fields_ = [("memory", C.c_uint32), ("accumulate", C.c_uint32), ("colour", C.c_void_p), ("colour_sum", C.c_void_p),
                 ("colour_bias", C.c_void_p), ("weight", C.c_void_p), ("weight_bias", C.c_void_p), ("photons", C.c_void_p),
@@ -159,6 +164,9 @@ def cuda():
                                          C.POINTER(AccumOut)]
         L.vrj_tone_map.restype = C.c_int32
         L.vrj_tone_map.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, dp, C.c_uint64, C.c_void_p]
+        L.vrj_bvh_build.restype = C.c_int32
+        L.vrj_bvh_build.argtypes = [C.c_int32, C.c_uint64, dp, C.POINTER(C.c_uint32), dp, dp, C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_uint32), C.POINTER(BvhBuildStats)]
         L.vrj_trace_rays.restype = C.c_int32
         L.vrj_trace_rays.argtypes = [C.c_void_p, C.c_uint64, dp, dp, C.c_uint32, C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), dp, C.POINTER(Stats)]
@@ -186,8 +194,8 @@ def host():
         L.vrjh_list_add_sphere.argtypes = [C.c_void_p] + [C.c_double] * 4 + [C.c_int]
         L.vrjh_list_add_plane.argtypes = [C.c_void_p] + [C.c_double] * 4 + [C.c_int]
         L.vrjh_list_add_triangle.argtypes = [C.c_void_p, dp, dp, C.c_int]
-        L.vrjh_add_bvh.argtypes = [C.c_void_p, C.c_int64, dp, dp, C.c_int]
-        L.vrjh_add_bvh_obj.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.vrjh_add_bvh.argtypes = [C.c_void_p, C.c_int64, dp, dp, C.c_int, C.c_int]
+        L.vrjh_add_bvh_obj.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         L.vrjh_load_obj.restype = C.c_int64
         L.vrjh_load_obj.argtypes = [C.c_char_p, dp, dp, C.c_int64]
         L.vrjh_flatten.restype = C.POINTER(SceneDesc)

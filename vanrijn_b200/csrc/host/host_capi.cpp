@@ -116,7 +116,7 @@ void vrjh_list_add_triangle(void *p, const double *v, const double *n, int mater
     h->open_list->primitives.push_back(std::make_shared<Triangle>(vs, ns, h->materials.at(material)));
 }
 /* BoundingVolumeHierarchy::build over ntri triangles; returns object id or -1 */
-int vrjh_add_bvh(void *p, int64_t ntri, const double *verts, const double *normals, int material) {
+int vrjh_add_bvh(void *p, int64_t ntri, const double *verts, const double *normals, int material, int device_builder) {
     HostScene *h = static_cast<HostScene *>(p);
     int id = -1;
     guarded([&] {
@@ -128,18 +128,20 @@ int vrjh_add_bvh(void *p, int64_t ntri, const double *verts, const double *norma
             std::array<Vec3, 3> ns{Vec3(n[0], n[1], n[2]), Vec3(n[3], n[4], n[5]), Vec3(n[6], n[7], n[8])};
             prims[i] = std::make_shared<Triangle>(vs, ns, m);
         }
-        h->scene.objects.push_back(BoundingVolumeHierarchy::build(prims));
+        h->scene.objects.push_back(BoundingVolumeHierarchy::build(
+            prims, device_builder ? BoundingVolumeHierarchy::Builder::Device : BoundingVolumeHierarchy::Builder::Host));
         id = (int)h->scene.objects.size() - 1;
     });
     return id;
 }
 /* load_obj + BoundingVolumeHierarchy::build; returns object id or -1 */
-int vrjh_add_bvh_obj(void *p, const char *path, int material) {
+int vrjh_add_bvh_obj(void *p, const char *path, int material, int device_builder) {
     HostScene *h = static_cast<HostScene *>(p);
     int id = -1;
     guarded([&] {
         auto prims = load_obj(path, h->materials.at(material));
-        h->scene.objects.push_back(BoundingVolumeHierarchy::build(prims));
+        h->scene.objects.push_back(BoundingVolumeHierarchy::build(
+            prims, device_builder ? BoundingVolumeHierarchy::Builder::Device : BoundingVolumeHierarchy::Builder::Host));
         id = (int)h->scene.objects.size() - 1;
     });
     return id;

@@ -185,7 +185,8 @@ struct BuildCtx {
 };
 } // namespace
 
-std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vector<std::shared_ptr<Primitive>> &primitives) {
+std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vector<std::shared_ptr<Primitive>> &primitives,
+                                                                        Builder builder, int device) {
     std::unique_ptr<BoundingVolumeHierarchy> bvh(new BoundingVolumeHierarchy());
     const size_t n = primitives.size();
     std::vector<double> v(n * 9), nr(n * 9);
@@ -197,27 +198,41 @@ std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vec
             nr[i * 9 + 3 * k] = t->normals[k].x, nr[i * 9 + 3 * k + 1] = t->normals[k].y, nr[i * 9 + 3 * k + 2] = t->normals[k].z;
         }
     }
-    BuildCtx cx;
-    cx.v = &v;
-    cx.lo.resize(3 * n), cx.hi.resize(3 * n), cx.centre.resize(3 * n);
-    for (size_t i = 0; i < n; i++)
-        for (int k = 0; k < 3; k++) {
-            double a = v[i * 9 + k], b = v[i * 9 + 3 + k], c = v[i * 9 + 6 + k];
-            double mn = std::fmin(std::fmin(a, b), c), mx = std::fmax(std::fmax(a, b), c);
-            cx.lo[3 * i + k] = mn, cx.hi[3 * i + k] = mx;
-            cx.centre[3 * i + k] = (mn + mx) / 2.0; // bounding_volume_hierarchy.rs:30-36
-        }
-    cx.order.resize(n);
-    std::iota(cx.order.begin(), cx.order.end(), 0u);
     const size_t n_nodes = n ? 2 * n - 1 : 1;
-    cx.node_child.assign(2 * n_nodes, 0);
-    cx.node_min.assign(3 * n_nodes, 0.0), cx.node_max.assign(3 * n_nodes, 0.0);
-    bvh->depth_ = cx.build(0, n, 0, 0);
-    bvh->node_min_ = std::move(cx.node_min), bvh->node_max_ = std::move(cx.node_max), bvh->node_child_ = std::move(cx.node_child);
+    std::vector<uint32_t> order;
+    if (builder == Builder::Device) {
+        // the same recursion on the GPU (csrc/vrj_bvh_build.cu); 4 doubles per node box there, 3 here
+        std::vector<double> mn(4 * n_nodes), mx(4 * n_nodes);
+        order.resize(n);
+        bvh->node_child_.assign(2 * n_nodes, 0);
+        if (vrj_bvh_build(device, n, v.data(), order.data(), mn.data(), mx.data(), bvh->node_child_.data(), &bvh->depth_, nullptr) != VRJ_OK)
+            throw std::runtime_error(std::string("vrj_bvh_build: ") + vrj_last_error());
+        bvh->node_min_.resize(3 * n_nodes), bvh->node_max_.resize(3 * n_nodes);
+        for (size_t i = 0; i < n_nodes; i++)
+            for (int k = 0; k < 3; k++) bvh->node_min_[3 * i + k] = mn[4 * i + k], bvh->node_max_[3 * i + k] = mx[4 * i + k];
+    } else {
+        BuildCtx cx;
+        cx.v = &v;
+        cx.lo.resize(3 * n), cx.hi.resize(3 * n), cx.centre.resize(3 * n);
+        for (size_t i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++) {
+                double a = v[i * 9 + k], b = v[i * 9 + 3 + k], c = v[i * 9 + 6 + k];
+                double mn = std::fmin(std::fmin(a, b), c), mx = std::fmax(std::fmax(a, b), c);
+                cx.lo[3 * i + k] = mn, cx.hi[3 * i + k] = mx;
+                cx.centre[3 * i + k] = (mn + mx) / 2.0; // bounding_volume_hierarchy.rs:30-36
+            }
+        cx.order.resize(n);
+        std::iota(cx.order.begin(), cx.order.end(), 0u);
+        cx.node_child.assign(2 * n_nodes, 0);
+        cx.node_min.assign(3 * n_nodes, 0.0), cx.node_max.assign(3 * n_nodes, 0.0);
+        bvh->depth_ = cx.build(0, n, 0, 0);
+        bvh->node_min_ = std::move(cx.node_min), bvh->node_max_ = std::move(cx.node_max), bvh->node_child_ = std::move(cx.node_child);
+        order = std::move(cx.order);
+    }
     bvh->tri_v_.resize(n * 9), bvh->tri_n_.resize(n * 9), bvh->tri_prim_id_.resize(n), bvh->tri_material_.resize(n);
     std::vector<std::shared_ptr<Primitive>> reordered(n);
     for (size_t i = 0; i < n; i++) {
-        uint32_t src = cx.order[i];
+        uint32_t src = order[i];
         std::memcpy(&bvh->tri_v_[i * 9], &v[(size_t)src * 9], 72);
         std::memcpy(&bvh->tri_n_[i * 9], &nr[(size_t)src * 9], 72);
         bvh->tri_prim_id_[i] = src;

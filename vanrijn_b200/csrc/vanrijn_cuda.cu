@@ -26,6 +26,10 @@ VrjStatus fail(VrjStatus code, const std::string &msg) {
     g_error = msg;
     return code;
 }
+} // namespace
+// other translation units of the library (vrj_bvh_build.cu) report through the same thread-local message
+void vrj_set_error(const std::string &msg) { g_error = msg; }
+namespace {
 #define VRJ_CUDA(expr)                                                                                      \
     do {                                                                                                    \
         cudaError_t e_ = (expr);                                                                            \

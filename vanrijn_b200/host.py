@@ -17,8 +17,11 @@ def _d(a):
 class HostScene:
     """A vanrijn::Scene built by the C++ host side, plus its flattened / uploaded forms."""
 
-    def __init__(self, spec):
+    def __init__(self, spec, device_builder=False):
+        """device_builder: run BoundingVolumeHierarchy::build on the GPU (vrj_bvh_build) instead of on the host;
+        the tree is the same either way."""
         H = capi.host()
+        self.device_builder = bool(device_builder)
         self.H = H
         self.h = C.c_void_p(H.vrjh_scene_new(*[float(x) for x in spec.camera]))
         self.spec = spec
@@ -50,11 +53,11 @@ class HostScene:
             elif obj[0] == "mesh":
                 v, pv = _d(obj[1])
                 n, pn = _d(obj[2])
-                r = H.vrjh_add_bvh(self.h, v.size // 9, pv, pn, obj[3])
+                r = H.vrjh_add_bvh(self.h, v.size // 9, pv, pn, obj[3], int(self.device_builder))
                 if r < 0:
                     raise capi.VrjError(H.vrjh_last_error().decode())
             elif obj[0] == "obj":
-                r = H.vrjh_add_bvh_obj(self.h, obj[1].encode(), obj[2])
+                r = H.vrjh_add_bvh_obj(self.h, obj[1].encode(), obj[2], int(self.device_builder))
                 if r < 0:
                     raise capi.VrjError(H.vrjh_last_error().decode())
         self._dev = {}
@@ -228,5 +231,20 @@ def tone_map(colour, source=capi.TONEMAP_XYZ, device=0):
     return out
 
 
-def build_scene(spec):
-    return HostScene(spec)
+def bvh_build(vertices, device=0):
+    """vrj_bvh_build on (n, 9) float64 vertices -> dict(order, node_min, node_max, node_child, depth, stats)."""
+    v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 9)
+    n = v.shape[0]
+    n_nodes = 2 * n - 1 if n else 1
+    order = np.zeros(max(n, 1), np.uint32)
+    node_min, node_max = np.zeros((n_nodes, 4)), np.zeros((n_nodes, 4))
+    child = np.zeros((n_nodes, 2), np.int32)
+    depth, stats = C.c_uint32(0), capi.BvhBuildStats()
+    capi.check(capi.cuda().vrj_bvh_build(device, n, v.ctypes.data_as(dp), order.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                         node_min.ctypes.data_as(dp), node_max.ctypes.data_as(dp),
+                                         child.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(depth), C.byref(stats)))
+    return dict(order=order[:n], node_min=node_min, node_max=node_max, node_child=child, depth=depth.value, stats=stats)
+
+
+def build_scene(spec, device_builder=False):
+    return HostScene(spec, device_builder=device_builder)
