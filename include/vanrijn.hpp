@@ -24,6 +24,7 @@
 
 #include <array>
 #include <cstdint>
+#include <cstdlib>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -129,9 +130,11 @@ struct PrimitiveList : Aggregate {
 // bounding_volume_hierarchy.rs:18-75.  Only triangles may be stored (what load_obj produces).
 class BoundingVolumeHierarchy : public Aggregate {
   public:
-    // Where the recursion of bounding_volume_hierarchy.rs:49-75 runs.  Both produce the same tree (same boxes,
-    // node numbering and leaf order); Device calls vrj_bvh_build and throws if there is no GPU.
-    enum class Builder { Host, Device };
+    // Where the recursion of bounding_volume_hierarchy.rs:49-75 runs.  All three produce the same tree (same boxes,
+    // node numbering and leaf order).  Device calls vrj_bvh_build and throws if there is no GPU.  AtUpload keeps only
+    // the triangles: the tree is built on the GPU when the scene is uploaded (vrj_scene_create, VrjBvh.n_nodes == 0)
+    // and never exists on the host, so -- unlike the reference's build(&mut [..]) -- `primitives` is NOT reordered.
+    enum class Builder { Host, Device, AtUpload };
     // reorders `primitives` in place, as the reference's build(&mut [Arc<dyn Primitive>]) does
     static std::unique_ptr<BoundingVolumeHierarchy> build(std::vector<std::shared_ptr<Primitive>> &primitives,
                                                           Builder builder = Builder::Host, int device = 0);
@@ -218,6 +221,36 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &options);
 
 // Collects the flattened SoA arrays and exposes them as a VrjSceneDesc.
+// Allocator of the builder's big arrays: page-locked host memory (vrj_alloc_host) when a CUDA device is present, so
+// that vrj_scene_create copies them to the device directly at PCIe speed; ordinary memory otherwise.
+template <typename T>
+struct UploadAllocator {
+    using value_type = T;
+    UploadAllocator() = default;
+    template <typename U>
+    UploadAllocator(const UploadAllocator<U> &) {}
+    T *allocate(size_t n) {
+        const size_t bytes = n * sizeof(T) + 64; // 64-byte prefix records which allocator owns the block
+        static const bool pageable_only = std::getenv("VRJ_PAGEABLE_ARRAYS") != nullptr; // experiments only
+        char *p = pageable_only ? nullptr : static_cast<char *>(vrj_alloc_host(bytes));
+        const bool pinned = p != nullptr;
+        if (!p) p = static_cast<char *>(::operator new(bytes));
+        p[0] = pinned ? 1 : 0;
+        return reinterpret_cast<T *>(p + 64);
+    }
+    void deallocate(T *q, size_t) {
+        char *p = reinterpret_cast<char *>(q) - 64;
+        if (p[0]) vrj_free_host(p);
+        else ::operator delete(p);
+    }
+    template <typename U>
+    bool operator==(const UploadAllocator<U> &) const { return true; }
+    template <typename U>
+    bool operator!=(const UploadAllocator<U> &) const { return false; }
+};
+template <typename T>
+using UploadVector = std::vector<T, UploadAllocator<T>>;
+
 class FlatSceneBuilder {
   public:
     uint32_t add_spectrum(const Spectrum &s);
@@ -238,10 +271,10 @@ class FlatSceneBuilder {
     std::vector<VrjPlane> planes_;
     std::vector<VrjBvh> bvhs_;
     std::vector<VrjItem> items_;
-    std::vector<double> tri_[6];
-    std::vector<uint32_t> tri_material_, tri_prim_id_;
-    std::vector<double> node_min_, node_max_;
-    std::vector<int32_t> node_child_;
+    UploadVector<double> tri_[6];
+    UploadVector<uint32_t> tri_material_, tri_prim_id_;
+    UploadVector<double> node_min_, node_max_;
+    UploadVector<int32_t> node_child_;
     VrjSceneDesc desc_{};
 };
 

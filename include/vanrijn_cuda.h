@@ -93,7 +93,10 @@ typedef struct VrjPlane {
 
 /* One BoundingVolumeHierarchy (bounding_volume_hierarchy.rs:18-28), flattened:
  * nodes [first_node, first_node+n_nodes) in DFS pre-order (root first),
- * triangles [first_triangle, first_triangle+n_triangles) in leaf (DFS) order. */
+ * triangles [first_triangle, first_triangle+n_triangles) in leaf (DFS) order.
+ * n_nodes == 0 with n_triangles > 0: the caller has not built the tree; vrj_scene_create builds it on the device
+ * (the algorithm of vrj_bvh_build: the reference's tree exactly) from the triangles in the order given, and
+ * first_node / depth are ignored. */
 typedef struct VrjBvh {
     uint64_t first_node, n_nodes;
     uint64_t first_triangle, n_triangles;
@@ -222,8 +225,10 @@ VRJ_API int32_t vrj_device_count(void);
 /* Upload the flattened scene to `device` (once per scene). */
 VRJ_API VrjStatus vrj_scene_create(const VrjSceneDesc *desc, int32_t device, VrjScene **out);
 VRJ_API void vrj_scene_destroy(VrjScene *scene);
-/* bytes copied host->device by vrj_scene_create */
+/* bytes the scene occupies on the device (the traversal layout), and bytes vrj_scene_create copied host->device
+ * (the caller's arrays as they are: the traversal layout is formed on the device) */
 VRJ_API uint64_t vrj_scene_device_bytes(const VrjScene *scene);
+VRJ_API uint64_t vrj_scene_upload_bytes(const VrjScene *scene);
 
 /* Free the per-device scratch blocks (path queues etc.) the library keeps between calls. */
 VRJ_API void vrj_release_scratch(void);

@@ -24,7 +24,7 @@ OK = 0
 
 # every symbol include/vanrijn_cuda.h declares
 CUDA_SYMBOLS = ["vrj_last_error", "vrj_abi_version", "vrj_device_count", "vrj_scene_create", "vrj_scene_destroy",
-                "vrj_scene_device_bytes", "vrj_render_tile", "vrj_trace_rays", "vrj_release_scratch", "vrj_alloc_host",
+                "vrj_scene_device_bytes", "vrj_scene_upload_bytes", "vrj_render_tile", "vrj_trace_rays", "vrj_release_scratch", "vrj_alloc_host",
                 "vrj_free_host", "vrj_comm_create", "vrj_comm_destroy", "vrj_comm_scene_create", "vrj_comm_scene_destroy",
                 "vrj_render_sharded", "vrj_tone_map", "vrj_bvh_build"]
 
@@ -147,6 +147,8 @@ def cuda():
         L.vrj_scene_destroy.argtypes = [C.c_void_p]
         L.vrj_scene_device_bytes.restype = C.c_uint64
         L.vrj_scene_device_bytes.argtypes = [C.c_void_p]
+        L.vrj_scene_upload_bytes.restype = C.c_uint64
+        L.vrj_scene_upload_bytes.argtypes = [C.c_void_p]
         L.vrj_alloc_host.restype = C.c_void_p
         L.vrj_alloc_host.argtypes = [C.c_uint64]
         L.vrj_free_host.argtypes = [C.c_void_p]

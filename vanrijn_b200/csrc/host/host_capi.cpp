@@ -129,7 +129,7 @@ int vrjh_add_bvh(void *p, int64_t ntri, const double *verts, const double *norma
             prims[i] = std::make_shared<Triangle>(vs, ns, m);
         }
         h->scene.objects.push_back(BoundingVolumeHierarchy::build(
-            prims, device_builder ? BoundingVolumeHierarchy::Builder::Device : BoundingVolumeHierarchy::Builder::Host));
+            prims, static_cast<BoundingVolumeHierarchy::Builder>(device_builder))); // 0 host, 1 device, 2 at upload
         id = (int)h->scene.objects.size() - 1;
     });
     return id;
@@ -141,7 +141,7 @@ int vrjh_add_bvh_obj(void *p, const char *path, int material, int device_builder
     guarded([&] {
         auto prims = load_obj(path, h->materials.at(material));
         h->scene.objects.push_back(BoundingVolumeHierarchy::build(
-            prims, device_builder ? BoundingVolumeHierarchy::Builder::Device : BoundingVolumeHierarchy::Builder::Host));
+            prims, static_cast<BoundingVolumeHierarchy::Builder>(device_builder))); // 0 host, 1 device, 2 at upload
         id = (int)h->scene.objects.size() - 1;
     });
     return id;

@@ -200,7 +200,13 @@ std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vec
     }
     const size_t n_nodes = n ? 2 * n - 1 : 1;
     std::vector<uint32_t> order;
-    if (builder == Builder::Device) {
+    if (builder == Builder::AtUpload) {
+        order.resize(n);
+        std::iota(order.begin(), order.end(), 0u);
+        uint32_t depth = 1;
+        for (size_t m = n; m > 1; m = m - m / 2) depth++;
+        bvh->depth_ = depth; // node arrays stay empty: flatten() emits VrjBvh.n_nodes == 0
+    } else if (builder == Builder::Device) {
         // the same recursion on the GPU (csrc/vrj_bvh_build.cu); 4 doubles per node box there, 3 here
         std::vector<double> mn(4 * n_nodes), mx(4 * n_nodes);
         order.resize(n);
@@ -239,7 +245,7 @@ std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vec
         bvh->tri_material_[i] = static_cast<const Triangle *>(primitives[src].get())->material;
         reordered[i] = primitives[src];
     }
-    primitives.swap(reordered); // the reference sorts the caller's slice in place
+    if (builder != Builder::AtUpload) primitives.swap(reordered); // the reference sorts the caller's slice in place
     return bvh;
 }
 void BoundingVolumeHierarchy::flatten(FlatSceneBuilder &out, uint32_t object_id) const { out.add_bvh(*this, object_id); }
@@ -294,6 +300,9 @@ void FlatSceneBuilder::add_bvh(const BoundingVolumeHierarchy &b, uint32_t object
     d.depth = b.depth_;
     const size_t nt = b.triangle_count();
     for (int k = 0; k < 6; k++) tri_[k].reserve(tri_[k].size() + 4 * nt);
+    tri_material_.reserve(tri_material_.size() + nt), tri_prim_id_.reserve(tri_prim_id_.size() + nt);
+    node_min_.reserve(node_min_.size() + 4 * d.n_nodes), node_max_.reserve(node_max_.size() + 4 * d.n_nodes);
+    node_child_.reserve(node_child_.size() + 2 * d.n_nodes);
     for (size_t i = 0; i < nt; i++) {
         for (int k = 0; k < 3; k++) {
             const double *v = &b.tri_v_[i * 9 + 3 * k], *n = &b.tri_n_[i * 9 + 3 * k];

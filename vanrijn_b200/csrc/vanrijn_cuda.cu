@@ -3,6 +3,8 @@
 // point that computes returns VRJ_ERR_CUDA.
 #include "../../include/vanrijn_cuda.h"
 #include "vrj_kernels.cuh"
+#include "vrj_scene_prep.cuh"
+#include "vrj_internal.h"
 
 #include <algorithm>
 #include <chrono>
@@ -12,6 +14,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <thread>
+#include <unordered_map>
 #include <limits>
 #include <mutex>
 #include <string>
@@ -29,6 +32,91 @@ VrjStatus fail(VrjStatus code, const std::string &msg) {
 } // namespace
 // other translation units of the library (vrj_bvh_build.cu) report through the same thread-local message
 void vrj_set_error(const std::string &msg) { g_error = msg; }
+
+// ---- device memory pool ----
+// cudaMalloc / cudaFree cost 4-60 ms per call on the B200 boxes (measured, and erratic), more than uploading and
+// preparing a whole bunny-class scene; freed blocks are therefore kept per device and handed out again to requests
+// they fit (at most 2x + 1 MiB larger than asked).  vrj_release_scratch() returns everything to the driver.
+namespace {
+struct PoolBlock {
+    int device;
+    void *p;
+    size_t bytes;
+};
+std::mutex g_dev_pool_mutex;
+std::vector<PoolBlock> g_dev_pool_free;
+std::unordered_map<void *, PoolBlock> g_dev_pool_live;
+const size_t kPoolCapBytes = size_t(32) << 30;
+const size_t kPoolCapBlocks = 48;
+} // namespace
+void vrj_pool_trim() {
+    std::vector<PoolBlock> victims;
+    {
+        std::lock_guard<std::mutex> g(g_dev_pool_mutex);
+        victims.swap(g_dev_pool_free);
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const PoolBlock &b : victims) {
+        cudaSetDevice(b.device);
+        cudaFree(b.p);
+    }
+    cudaSetDevice(cur);
+}
+cudaError_t vrj_pool_alloc(void **out, size_t bytes) {
+    *out = nullptr;
+    bytes = (std::max<size_t>(bytes, 256) + 255) & ~size_t(255);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> g(g_dev_pool_mutex);
+        size_t best = g_dev_pool_free.size();
+        for (size_t i = 0; i < g_dev_pool_free.size(); i++) {
+            const PoolBlock &b = g_dev_pool_free[i];
+            if (b.device == dev && b.bytes >= bytes && b.bytes <= 2 * bytes + (size_t(1) << 20) &&
+                (best == g_dev_pool_free.size() || b.bytes < g_dev_pool_free[best].bytes))
+                best = i;
+        }
+        if (best != g_dev_pool_free.size()) {
+            PoolBlock b = g_dev_pool_free[best];
+            g_dev_pool_free.erase(g_dev_pool_free.begin() + best);
+            g_dev_pool_live[b.p] = b;
+            *out = b.p;
+            return cudaSuccess;
+        }
+    }
+    void *p = nullptr;
+    e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) { // give the cached blocks back and try once more
+        cudaGetLastError();
+        vrj_pool_trim();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> g(g_dev_pool_mutex);
+    g_dev_pool_live[p] = PoolBlock{dev, p, bytes};
+    *out = p;
+    return cudaSuccess;
+}
+void vrj_pool_free(void *p) {
+    if (!p) return;
+    PoolBlock b{0, p, 0};
+    bool keep = false;
+    {
+        std::lock_guard<std::mutex> g(g_dev_pool_mutex);
+        auto it = g_dev_pool_live.find(p);
+        if (it != g_dev_pool_live.end()) {
+            b = it->second;
+            g_dev_pool_live.erase(it);
+            size_t cached = 0;
+            for (const PoolBlock &f : g_dev_pool_free) cached += f.bytes;
+            keep = cached + b.bytes <= kPoolCapBytes && g_dev_pool_free.size() < kPoolCapBlocks;
+            if (keep) g_dev_pool_free.push_back(b);
+        }
+    }
+    if (!keep) cudaFree(p);
+}
 namespace {
 #define VRJ_CUDA(expr)                                                                                      \
     do {                                                                                                    \
@@ -41,12 +129,13 @@ namespace {
 struct DeviceBuffer {
     void *p = nullptr;
     size_t bytes = 0;
-    ~DeviceBuffer() {
-        if (p) cudaFree(p);
+    ~DeviceBuffer() { release(); }
+    void release() {
+        if (p) vrj_pool_free(p), p = nullptr;
     }
     cudaError_t alloc(size_t n) {
         bytes = n;
-        return cudaMalloc(&p, std::max<size_t>(n, 16));
+        return vrj_pool_alloc(&p, n);
     }
     template <typename T>
     T *as() const { return static_cast<T *>(p); }
@@ -104,6 +193,7 @@ struct VrjScene {
     int device = 0;
     int sm_count = 0;
     uint64_t device_bytes = 0;
+    uint64_t upload_bytes = 0;
     DevScene dev{};
     std::vector<DeviceBuffer *> owned;
     uint32_t n_spectra = 0;
@@ -114,17 +204,6 @@ struct VrjScene {
 };
 
 namespace {
-
-template <typename T, typename P>
-VrjStatus upload(VrjScene *sc, const std::vector<T> &host, P &dev_ptr) {
-    DeviceBuffer *b = new DeviceBuffer();
-    sc->owned.push_back(b);
-    VRJ_CUDA(b->alloc(host.size() * sizeof(T)));
-    if (!host.empty()) VRJ_CUDA(cudaMemcpy(b->p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
-    sc->device_bytes += host.size() * sizeof(T);
-    dev_ptr = b->as<T>();
-    return VRJ_OK;
-}
 
 // next representable float above / below (bit arithmetic: this runs 12x per BVH node at scene upload)
 inline float float_up(float f) {
@@ -145,65 +224,6 @@ inline float round_up_f32(double v) {
     float f = (float)v;
     return (double)f < v ? float_up(f) : f;
 }
-
-// Re-express one reference-topology BVH (a box per node) as "wide" nodes that carry the boxes of
-// both children, so one fetch decides both; leaves (<= 1 triangle) live in the child references.
-struct WideBuilder {
-    const VrjSceneDesc *d;
-    float *n32 = nullptr;   // 16 floats per wide node (caller-provided, zero-filled)
-    double *n64 = nullptr;  // 14 doubles per wide node
-    size_t count = 0, capacity = 0;
-    void box_of(int64_t node, double lo[3], double hi[3]) const {
-        for (int k = 0; k < 3; k++) lo[k] = d->node_min[node * 4 + k], hi[k] = d->node_max[node * 4 + k];
-    }
-    bool is_leaf(int64_t node) const { return d->node_child[2 * node] < 0; }
-    // reference for a child: wide index if internal, ~triangle if a 1-triangle leaf; false if empty leaf
-    void put_child(size_t w, int which, int64_t node, int32_t ref, bool empty) {
-        double lo[3], hi[3];
-        if (empty) {
-            for (int k = 0; k < 3; k++) lo[k] = std::numeric_limits<double>::infinity(), hi[k] = -lo[k];
-        } else {
-            box_of(node, lo, hi);
-        }
-        // f32 layout: [c0.lox c0.hix c0.loy c0.hiy][c1.lox c1.hix c1.loy c1.hiy][c0.loz c0.hiz c1.loz c1.hiz][l r 0 0]
-        float *f = &n32[w * 16];
-        float flo[3], fhi[3];
-        for (int k = 0; k < 3; k++) flo[k] = empty ? (float)lo[k] : round_down_f32(lo[k]), fhi[k] = empty ? (float)hi[k] : round_up_f32(hi[k]);
-        f[which * 4 + 0] = flo[0], f[which * 4 + 1] = fhi[0], f[which * 4 + 2] = flo[1], f[which * 4 + 3] = fhi[1];
-        f[8 + which * 2 + 0] = flo[2], f[8 + which * 2 + 1] = fhi[2];
-        std::memcpy(&f[12 + which], &ref, 4);
-        // f64 layout: c0 {lox hix loy hiy loz hiz} c1 {...} {bits(l,r), 0}
-        double *g = &n64[w * 14];
-        for (int k = 0; k < 3; k++) g[which * 6 + 2 * k] = lo[k], g[which * 6 + 2 * k + 1] = hi[k];
-        int32_t pair[2];
-        std::memcpy(pair, &g[12], 8);
-        pair[which] = ref;
-        std::memcpy(&g[12], pair, 8);
-    }
-    size_t new_node() { return count < capacity ? count++ : (count++, capacity - 1); } // overflow is checked by the caller
-    // returns the reference to use for `node` from its parent
-    int32_t child_ref(int64_t node, bool *empty) {
-        *empty = false;
-        if (is_leaf(node)) {
-            if (d->node_child[2 * node + 1] == 0) {
-                *empty = true;
-                return -1;
-            }
-            return d->node_child[2 * node]; // ~first_triangle, already absolute
-        }
-        return (int32_t)build(node);
-    }
-    size_t build(int64_t node) { // node is internal
-        size_t w = new_node();
-        int64_t l = d->node_child[2 * node], r = d->node_child[2 * node + 1];
-        bool el, er;
-        int32_t rl = child_ref(l, &el);
-        put_child(w, 0, l, rl, el);
-        int32_t rr = child_ref(r, &er);
-        put_child(w, 1, r, rr, er);
-        return w;
-    }
-};
 
 VrjStatus validate(const VrjSceneDesc *d) {
     if (!d) return fail(VRJ_ERR_INVALID_ARGUMENT, "scene description is NULL");
@@ -234,7 +254,9 @@ VrjStatus validate(const VrjSceneDesc *d) {
         const VrjBvh &b = d->bvhs[i];
         if (b.first_node + b.n_nodes > d->n_nodes || b.first_triangle + b.n_triangles > d->n_triangles)
             return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh range out of bounds");
-        if (b.depth > 31) return fail(VRJ_ERR_UNSUPPORTED, "bvh deeper than the 32-entry traversal stack");
+        // n_nodes == 0 with triangles: the tree is built on the device at upload (median split: depth known from n)
+        const uint32_t depth = (b.n_nodes == 0 && b.n_triangles) ? vrj_build::tree_depth(b.n_triangles) : b.depth;
+        if (depth > 31) return fail(VRJ_ERR_UNSUPPORTED, "bvh deeper than the 32-entry traversal stack");
         for (uint64_t n = b.first_node; n < b.first_node + b.n_nodes; n++) {
             int32_t l = d->node_child[2 * n], r = d->node_child[2 * n + 1];
             if (l >= 0) {
@@ -250,9 +272,53 @@ VrjStatus validate(const VrjSceneDesc *d) {
 
 // Scratch blocks are pooled per device for the life of the process (not per scene): a caller that creates a
 // scene per frame does not pay multi-GB cudaMalloc/cudaFree each time.  vrj_release_scratch() empties the pool.
+// Host arrays reach the device through one page-locked staging block kept for the life of the process (a pageable
+// cudaMemcpy ran at 0.2-2 GB/s on the B200 boxes; memcpy into pinned memory + one async copy runs at PCIe speed).
+// Arrays that are already page-locked (vrj_alloc_host) skip the staging copy.
 std::mutex g_staging_mutex;
-void *g_staging = nullptr;
+char *g_staging = nullptr;
 size_t g_staging_bytes = 0;
+struct Stager {
+    size_t cursor = 0, copied = 0;
+    cudaStream_t stream = nullptr;
+    cudaError_t reserve(size_t bytes) {
+        if (g_staging_bytes >= bytes) return cudaSuccess;
+        if (g_staging) cudaFreeHost(g_staging), g_staging = nullptr, g_staging_bytes = 0;
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&g_staging), bytes);
+        if (e == cudaSuccess) g_staging_bytes = bytes;
+        return e;
+    }
+    static void parallel_memcpy(char *dst, const char *src, size_t bytes) {
+        const size_t min_per_thread = size_t(4) << 20;
+        unsigned hw = std::thread::hardware_concurrency();
+        size_t n_threads = std::min<size_t>(std::min<size_t>(hw ? hw : 4, 8), bytes / min_per_thread);
+        if (n_threads < 2) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        std::vector<std::thread> pool;
+        const size_t per = ((bytes + n_threads - 1) / n_threads + 4095) & ~size_t(4095);
+        for (size_t t = 0; t < n_threads; t++) {
+            const size_t lo = t * per, hi = std::min(bytes, lo + per);
+            if (lo >= hi) break;
+            pool.emplace_back([=] { std::memcpy(dst + lo, src + lo, hi - lo); });
+        }
+        for (auto &th : pool) th.join();
+    }
+    cudaError_t copy(void *dst, const void *src, size_t bytes) {
+        if (!bytes) return cudaSuccess;
+        copied += bytes;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+            return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+        cudaGetLastError();
+        char *st = g_staging + cursor;
+        cursor += (bytes + 255) & ~size_t(255);
+        parallel_memcpy(st, static_cast<const char *>(src), bytes);
+        return cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, stream);
+    }
+};
+
 std::mutex g_pool_mutex;
 std::vector<std::pair<int, Scratch *>> g_pool;
 
@@ -284,18 +350,18 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
     if (s->capacity < capacity) {
         for (int i = 0; i < 2; i++)
             for (int k = 0; k < 6; k++) {
-                if (s->queues[i][k].p) cudaFree(s->queues[i][k].p), s->queues[i][k].p = nullptr;
+                s->queues[i][k].release();
                 VRJ_CUDA(s->queues[i][k].alloc(capacity * 16));
             }
-        if (s->photons.p) cudaFree(s->photons.p), s->photons.p = nullptr;
+        s->photons.release();
         VRJ_CUDA(s->photons.alloc(capacity * sizeof(double2)));
         for (int i = 0; i < 2; i++) {
-            if (s->hits[i].p) cudaFree(s->hits[i].p), s->hits[i].p = nullptr;
+            s->hits[i].release();
             VRJ_CUDA(s->hits[i].alloc(capacity * sizeof(int2)));
-            if (s->tbest[i].p) cudaFree(s->tbest[i].p), s->tbest[i].p = nullptr;
+            s->tbest[i].release();
             VRJ_CUDA(s->tbest[i].alloc(capacity * sizeof(double)));
         }
-        if (s->list.p) cudaFree(s->list.p), s->list.p = nullptr;
+        s->list.release();
         VRJ_CUDA(s->list.alloc(capacity * sizeof(uint32_t)));
         s->capacity = capacity;
     }
@@ -303,23 +369,23 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
         DeviceBuffer *bufs[5] = {&s->acc_colour, &s->acc_sum, &s->acc_bias, &s->acc_weight, &s->acc_wbias};
         size_t per[5] = {3, 3, 3, 1, 1};
         for (int i = 0; i < 5; i++) {
-            if (bufs[i]->p) cudaFree(bufs[i]->p), bufs[i]->p = nullptr;
+            bufs[i]->release();
             VRJ_CUDA(bufs[i]->alloc(npix * per[i] * sizeof(double)));
         }
         s->npix = npix;
     }
     if (s->steps < steps) {
-        if (s->counters.p) cudaFree(s->counters.p), s->counters.p = nullptr;
+        s->counters.release();
         VRJ_CUDA(s->counters.alloc(((size_t)steps * 4 + 4) * sizeof(uint32_t)));
         s->steps = steps;
     }
     if (!s->stats.p) VRJ_CUDA(s->stats.alloc(ST_COUNT * sizeof(unsigned long long)));
     if (!s->lights.p || s->lights.bytes < (size_t)(n_lights + 1) * sizeof(LightDev)) {
-        if (s->lights.p) cudaFree(s->lights.p), s->lights.p = nullptr;
+        s->lights.release();
         VRJ_CUDA(s->lights.alloc((size_t)(n_lights + 1) * sizeof(LightDev)));
     }
     if (!s->light_samples.p || s->light_samples.bytes < n_light_samples * sizeof(double)) {
-        if (s->light_samples.p) cudaFree(s->light_samples.p), s->light_samples.p = nullptr;
+        s->light_samples.release();
         VRJ_CUDA(s->light_samples.alloc(std::max<size_t>(2, n_light_samples) * sizeof(double)));
     }
     return VRJ_OK;
@@ -445,13 +511,14 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     VRJ_CUDA(cudaSetDevice(device));
     VrjScene *sc = new VrjScene();
     sc->device = device;
-    cudaDeviceProp prop;
-    cudaError_t pe = cudaGetDeviceProperties(&prop, device);
+    // one attribute, not cudaGetDeviceProperties: that call took 4-115 ms per scene on the B200 boxes (measured)
+    int sm_count = 0;
+    cudaError_t pe = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
     if (pe != cudaSuccess) {
         delete sc;
-        return fail(VRJ_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(pe));
+        return fail(VRJ_ERR_CUDA, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(pe));
     }
-    sc->sm_count = prop.multiProcessorCount;
+    sc->sm_count = sm_count;
     sc->n_spectra = d->n_spectra;
 
 #define VRJ_TRY(expr)             \
@@ -463,14 +530,39 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         }                         \
     } while (0)
 
-    // ---- one staging block (page-locked, reused across calls) -> one device arena -> one copy ----
-    uint64_t n_wide = 0;
+    // ---- layout of the device arena: the small tables first (staged on the host, one copy), then the big sections,
+    // which kernels write on the device from the caller's arrays (vrj_scene_prep.cuh) ----
+    // A VrjBvh with n_nodes == 0 and n_triangles > 0 is built here, on the device (vrj_bvh_build.cu).
+    struct BvhPlan {
+        bool empty = false, build = false;
+        uint64_t first_node = 0, n_nodes = 0, n_wide = 0, wide_base = 0;
+    };
+    std::vector<BvhPlan> plan(d->n_bvhs);
+    uint64_t n_wide = 0, n_dev_nodes = d->n_nodes;
     for (uint32_t b = 0; b < d->n_bvhs; b++) {
         const VrjBvh &bv = d->bvhs[b];
-        if (bv.n_nodes == 0 || bv.n_triangles == 0) continue;
-        uint64_t internal = 0;
-        for (uint64_t n = bv.first_node; n < bv.first_node + bv.n_nodes; n++) internal += d->node_child[2 * n] >= 0;
-        n_wide += std::max<uint64_t>(1, internal);
+        BvhPlan &pl = plan[b];
+        if (bv.n_triangles == 0) {
+            pl.empty = true; // an empty BVH never reports a hit
+            continue;
+        }
+        if (bv.n_nodes == 0) {
+            pl.build = true;
+            pl.first_node = n_dev_nodes, pl.n_nodes = 2 * bv.n_triangles - 1;
+            n_dev_nodes += pl.n_nodes;
+            pl.n_wide = std::max<uint64_t>(1, bv.n_triangles - 1);
+        } else {
+            pl.first_node = bv.first_node, pl.n_nodes = bv.n_nodes;
+            uint64_t internal = 0;
+            for (uint64_t n = bv.first_node; n < bv.first_node + bv.n_nodes; n++) internal += d->node_child[2 * n] >= 0;
+            pl.n_wide = std::max<uint64_t>(1, internal);
+        }
+        pl.wide_base = n_wide;
+        n_wide += pl.n_wide;
+    }
+    if (n_dev_nodes > 0x7ffffff0ull) {
+        delete sc;
+        return fail(VRJ_ERR_UNSUPPORTED, "scene too large for 31-bit indices");
     }
     struct Section {
         size_t offset, bytes;
@@ -481,26 +573,132 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         cursor += (bytes + 255) & ~size_t(255);
         return sct;
     };
-    const Section s_n32 = reserve_section(n_wide * 64), s_n64 = reserve_section(n_wide * 112);
-    const Section s_tp = reserve_section((size_t)d->n_triangles * 96), s_tn = reserve_section((size_t)d->n_triangles * 96);
     const Section s_sph = reserve_section(d->n_spheres * sizeof(SphereDev)), s_pl = reserve_section(d->n_planes * sizeof(PlaneDev));
     const Section s_mat = reserve_section(d->n_materials * sizeof(MaterialDev)), s_spc = reserve_section(d->n_spectra * sizeof(SpectrumDev));
     const Section s_smp = reserve_section(d->n_spectrum_samples * sizeof(double));
     const Section s_it = reserve_section(d->n_items * sizeof(ItemDev)), s_an = reserve_section(d->n_items * 4), s_bv = reserve_section(d->n_items * 4);
+    const size_t small_bytes = std::max<size_t>(cursor, 256);
+    const Section s_n32 = reserve_section(n_wide * 64), s_n64 = reserve_section(n_wide * 112);
+    const Section s_tp = reserve_section((size_t)d->n_triangles * 96), s_tn = reserve_section((size_t)d->n_triangles * 96);
     const size_t arena_bytes = std::max<size_t>(cursor, 256);
 
-    std::lock_guard<std::mutex> staging_guard(g_staging_mutex);
-    if (g_staging_bytes < arena_bytes) {
-        if (g_staging) cudaFreeHost(g_staging), g_staging = nullptr, g_staging_bytes = 0;
-        cudaError_t he = cudaMallocHost(&g_staging, arena_bytes);
-        if (he != cudaSuccess) {
+    DeviceBuffer *arena = new DeviceBuffer();
+    sc->owned.push_back(arena);
+    {
+        cudaError_t ae = arena->alloc(arena_bytes);
+        if (ae != cudaSuccess) {
             delete sc;
-            return fail(VRJ_ERR_OUT_OF_MEMORY, std::string("cudaMallocHost: ") + cudaGetErrorString(he));
+            return fail(ae == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA, std::string("scene arena: ") + cudaGetErrorString(ae));
         }
-        g_staging_bytes = arena_bytes;
     }
-    char *stage = static_cast<char *>(g_staging);
+    char *base = arena->as<char>();
+#define VRJ_TRY_CUDA(expr)                                                                                                 \
+    do {                                                                                                                   \
+        cudaError_t e_ = (expr);                                                                                           \
+        if (e_ != cudaSuccess) {                                                                                           \
+            delete sc;                                                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA,                            \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                                               \
+        }                                                                                                                  \
+    } while (0)
 
+    // ---- the caller's big arrays go to the device as they are (one temporary block, freed when this function returns) ----
+    const size_t nt = (size_t)d->n_triangles, nn = (size_t)n_dev_nodes;
+    size_t rcur = 0;
+    auto reserve_raw = [&rcur](size_t bytes) {
+        size_t o = rcur;
+        rcur += (bytes + 255) & ~size_t(255);
+        return o;
+    };
+    const size_t r_v[6] = {reserve_raw(nt * 32), reserve_raw(nt * 32), reserve_raw(nt * 32), reserve_raw(nt * 32), reserve_raw(nt * 32), reserve_raw(nt * 32)};
+    const size_t r_mat = reserve_raw(nt * 4), r_pid = reserve_raw(nt * 4), r_perm = reserve_raw(nt * 4);
+    const size_t r_min = reserve_raw(nn * 32), r_max = reserve_raw(nn * 32), r_child = reserve_raw(nn * 8);
+    uint64_t largest_bvh_nodes = 0, largest_build = 0;
+    bool any_build = false;
+    for (uint32_t b = 0; b < d->n_bvhs; b++) {
+        largest_bvh_nodes = std::max(largest_bvh_nodes, plan[b].n_nodes);
+        if (plan[b].build) any_build = true, largest_build = std::max<uint64_t>(largest_build, d->bvhs[b].n_triangles);
+    }
+    const size_t r_flags = reserve_raw(largest_bvh_nodes * 4), r_scan = reserve_raw((largest_bvh_nodes / 2048 + 2) * 4);
+    const size_t r_bv = reserve_raw(largest_build * 72), r_bo = reserve_raw(largest_build * 4);
+    DeviceBuffer raw;
+    VRJ_TRY_CUDA(raw.alloc(std::max<size_t>(rcur, 256)));
+    char *rb = raw.as<char>();
+    cudaStream_t stream = nullptr; // the legacy default stream: scene creation is synchronous
+    auto t_alloc = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> staging_guard(g_staging_mutex);
+    Stager stager;
+    stager.stream = stream;
+    VRJ_TRY_CUDA(stager.reserve(nt * (6 * 32 + 8) + (size_t)d->n_nodes * 72 + small_bytes + 16 * 256));
+    if (nt) {
+        const double *src[6] = {d->tri_v0, d->tri_v1, d->tri_v2, d->tri_n0, d->tri_n1, d->tri_n2};
+        for (int k = 0; k < 6; k++) VRJ_TRY_CUDA(stager.copy(rb + r_v[k], src[k], nt * 32));
+        VRJ_TRY_CUDA(stager.copy(rb + r_mat, d->tri_material, nt * 4));
+        VRJ_TRY_CUDA(stager.copy(rb + r_pid, d->tri_prim_id, nt * 4));
+    }
+    if (d->n_nodes) {
+        VRJ_TRY_CUDA(stager.copy(rb + r_min, d->node_min, (size_t)d->n_nodes * 32));
+        VRJ_TRY_CUDA(stager.copy(rb + r_max, d->node_max, (size_t)d->n_nodes * 32));
+        VRJ_TRY_CUDA(stager.copy(rb + r_child, d->node_child, (size_t)d->n_nodes * 8));
+    }
+    auto t_raw = std::chrono::steady_clock::now();
+    RawTriangles rt;
+    rt.v0 = reinterpret_cast<const double *>(rb + r_v[0]), rt.v1 = reinterpret_cast<const double *>(rb + r_v[1]);
+    rt.v2 = reinterpret_cast<const double *>(rb + r_v[2]), rt.n0 = reinterpret_cast<const double *>(rb + r_v[3]);
+    rt.n1 = reinterpret_cast<const double *>(rb + r_v[4]), rt.n2 = reinterpret_cast<const double *>(rb + r_v[5]);
+    rt.material = reinterpret_cast<const uint32_t *>(rb + r_mat), rt.prim_id = reinterpret_cast<const uint32_t *>(rb + r_pid);
+    double *dn_min = reinterpret_cast<double *>(rb + r_min), *dn_max = reinterpret_cast<double *>(rb + r_max);
+    int32_t *dn_child = reinterpret_cast<int32_t *>(rb + r_child);
+    uint32_t *perm = nullptr;
+    std::vector<double> built_root(d->n_bvhs * 8, 0.0); // root boxes of the BVHs built here (for the items' pre-test)
+    if (any_build) {
+        perm = reinterpret_cast<uint32_t *>(rb + r_perm);
+        k_identity_perm<<<(unsigned)((nt + 255) / 256), 256, 0, stream>>>((uint32_t)nt, perm);
+        for (uint32_t b = 0; b < d->n_bvhs; b++) {
+            if (!plan[b].build) continue;
+            const VrjBvh &bv = d->bvhs[b];
+            const uint32_t n = (uint32_t)bv.n_triangles, first = (uint32_t)bv.first_triangle;
+            double *bvv = reinterpret_cast<double *>(rb + r_bv);
+            uint32_t *border = reinterpret_cast<uint32_t *>(rb + r_bo);
+            k_gather_vertices<<<(n + 255) / 256, 256, 0, stream>>>(n, rt.v0 + 4 * (size_t)first, rt.v1 + 4 * (size_t)first, rt.v2 + 4 * (size_t)first, bvv);
+            VrjStatus bs = vrj_build::build_device(n, bvv, border, dn_min + 4 * plan[b].first_node, dn_max + 4 * plan[b].first_node,
+                                                   dn_child + 2 * plan[b].first_node, stream, nullptr);
+            if (bs != VRJ_OK) {
+                delete sc;
+                return bs;
+            }
+            k_offset_perm<<<(n + 255) / 256, 256, 0, stream>>>(n, border, first, perm);
+            VRJ_TRY_CUDA(cudaMemcpyAsync(&built_root[b * 8], dn_min + 4 * plan[b].first_node, 32, cudaMemcpyDeviceToHost, stream));
+            VRJ_TRY_CUDA(cudaMemcpyAsync(&built_root[b * 8 + 4], dn_max + 4 * plan[b].first_node, 32, cudaMemcpyDeviceToHost, stream));
+        }
+    }
+    if (nt)
+        k_pack_triangles<<<(unsigned)((nt + 127) / 128), 128, 0, stream>>>((uint32_t)nt, rt, perm, reinterpret_cast<double *>(base + s_tp.offset),
+                                                                           reinterpret_cast<double *>(base + s_tn.offset));
+    for (uint32_t b = 0; b < d->n_bvhs; b++) {
+        if (plan[b].empty) continue;
+        BvhNodes bn;
+        bn.node_min = dn_min, bn.node_max = dn_max, bn.node_child = dn_child;
+        bn.first_node = (uint32_t)plan[b].first_node, bn.n_nodes = (uint32_t)plan[b].n_nodes;
+        bn.child_offset = plan[b].build ? (int32_t)plan[b].first_node : 0;
+        bn.triangle_offset = plan[b].build ? (int32_t)d->bvhs[b].first_triangle : 0;
+        bn.wide_base = (uint32_t)plan[b].wide_base;
+        uint32_t *flags = reinterpret_cast<uint32_t *>(rb + r_flags);
+        const unsigned grid = (bn.n_nodes + 255) / 256;
+        k_mark_internal<<<grid, 256, 0, stream>>>(bn, flags);
+        VrjStatus ss = vrj_build::exclusive_scan_u32(flags, bn.n_nodes, reinterpret_cast<uint32_t *>(rb + r_scan), stream);
+        if (ss != VRJ_OK) {
+            delete sc;
+            return ss;
+        }
+        k_wide_nodes<<<grid, 256, 0, stream>>>(bn, flags, reinterpret_cast<float *>(base + s_n32.offset), reinterpret_cast<double *>(base + s_n64.offset));
+    }
+    VRJ_TRY_CUDA(cudaGetLastError());
+    VRJ_TRY_CUDA(cudaStreamSynchronize(stream)); // built_root is read below
+
+    // ---- the small tables ----
+    char *stage = g_staging + stager.cursor; // the staged arrays before it were copied before the synchronize above
+    std::memset(stage, 0, small_bytes);
     SpectrumDev *spectra = reinterpret_cast<SpectrumDev *>(stage + s_spc.offset);
     for (uint32_t i = 0; i < d->n_spectra; i++)
         spectra[i] = SpectrumDev{d->spectra[i].shortest_wavelength, d->spectra[i].longest_wavelength, d->spectra[i].first_sample, d->spectra[i].n_samples};
@@ -517,61 +715,19 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         for (int k = 0; k < 3; k++) p.n[k] = d->planes[i].normal[k], p.t[k] = d->planes[i].tangent[k], p.c[k] = d->planes[i].cotangent[k];
         p.distance = d->planes[i].distance_from_origin, p.material = d->planes[i].material, p.pad = 0;
     }
-    // triangles: 96-byte position and normal records (32-byte aligned for 256-bit loads)
-    double *tri_pos = reinterpret_cast<double *>(stage + s_tp.offset), *tri_nrm = reinterpret_cast<double *>(stage + s_tn.offset);
-    for (uint64_t t = 0; t < d->n_triangles; t++) {
-        const double *v[3] = {d->tri_v0 + 4 * t, d->tri_v1 + 4 * t, d->tri_v2 + 4 * t};
-        const double *n[3] = {d->tri_n0 + 4 * t, d->tri_n1 + 4 * t, d->tri_n2 + 4 * t};
-        double *tp = tri_pos + t * 12, *tn = tri_nrm + t * 12;
-        for (int k = 0; k < 3; k++)
-            for (int c = 0; c < 3; c++) tp[3 * k + c] = v[k][c], tn[3 * k + c] = n[k][c];
-        uint64_t bits = ((uint64_t)d->tri_prim_id[t] << 32) | d->tri_material[t];
-        std::memcpy(&tp[9], &bits, 8);
-        tp[10] = tp[11] = 0.0, tn[9] = tn[10] = tn[11] = 0.0;
-    }
-    // wide nodes per BVH
-    WideBuilder wb;
-    wb.d = d;
-    wb.n32 = reinterpret_cast<float *>(stage + s_n32.offset), wb.n64 = reinterpret_cast<double *>(stage + s_n64.offset);
-    wb.capacity = (size_t)n_wide;
-    std::memset(stage + s_n32.offset, 0, s_n32.bytes);
-    std::memset(stage + s_n64.offset, 0, s_n64.bytes);
-    std::vector<uint32_t> bvh_root(d->n_bvhs, 0);
-    std::vector<bool> bvh_empty(d->n_bvhs, false);
-    for (uint32_t b = 0; b < d->n_bvhs; b++) {
-        const VrjBvh &bv = d->bvhs[b];
-        if (bv.n_nodes == 0 || bv.n_triangles == 0) {
-            bvh_empty[b] = true;
-            continue;
-        }
-        int64_t root = (int64_t)bv.first_node;
-        if (wb.is_leaf(root)) {
-            size_t w = wb.new_node();
-            bool e;
-            int32_t r = wb.child_ref(root, &e);
-            wb.put_child(w, 0, root, r, e);
-            wb.put_child(w, 1, root, -1, true);
-            bvh_root[b] = (uint32_t)w;
-        } else {
-            bvh_root[b] = (uint32_t)wb.build(root);
-        }
-    }
-    if (wb.count != n_wide) {
-        delete sc;
-        return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh nodes do not form the trees their VrjBvh ranges describe");
-    }
     ItemDev *items = reinterpret_cast<ItemDev *>(stage + s_it.offset);
     uint32_t *analytic_items = reinterpret_cast<uint32_t *>(stage + s_an.offset), *bvh_items = reinterpret_cast<uint32_t *>(stage + s_bv.offset);
     uint32_t n_items = 0, n_analytic = 0, n_bvh_items = 0;
     for (uint32_t i = 0; i < d->n_items; i++) {
         const VrjItem &it = d->items[i];
-        if (it.kind == VRJ_ITEM_BVH && bvh_empty[it.index]) continue; // an empty BVH never reports a hit
+        if (it.kind == VRJ_ITEM_BVH && plan[it.index].empty) continue; // an empty BVH never reports a hit
         ItemDev id{};
         id.kind = it.kind, id.index = it.index, id.object_id = it.object_id, id.prim_id = it.prim_id;
-        id.root = it.kind == VRJ_ITEM_BVH ? bvh_root[it.index] : 0u;
+        id.root = it.kind == VRJ_ITEM_BVH ? (uint32_t)plan[it.index].wide_base : 0u;
         if (it.kind == VRJ_ITEM_BVH) {
-            const uint64_t rn = d->bvhs[it.index].first_node;
-            for (int k = 0; k < 3; k++) id.lo[k] = round_down_f32(d->node_min[rn * 4 + k]), id.hi[k] = round_up_f32(d->node_max[rn * 4 + k]);
+            const double *rmin = plan[it.index].build ? &built_root[it.index * 8] : d->node_min + d->bvhs[it.index].first_node * 4;
+            const double *rmax = plan[it.index].build ? &built_root[it.index * 8 + 4] : d->node_max + d->bvhs[it.index].first_node * 4;
+            for (int k = 0; k < 3; k++) id.lo[k] = round_down_f32(rmin[k]), id.hi[k] = round_up_f32(rmax[k]);
             bvh_items[n_bvh_items++] = n_items;
         } else {
             analytic_items[n_analytic++] = n_items;
@@ -579,18 +735,11 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         items[n_items++] = id;
     }
     auto t_prep = std::chrono::steady_clock::now();
-    DeviceBuffer *arena = new DeviceBuffer();
-    sc->owned.push_back(arena);
-    {
-        cudaError_t ae = arena->alloc(arena_bytes);
-        if (ae == cudaSuccess) ae = cudaMemcpy(arena->p, stage, arena_bytes, cudaMemcpyHostToDevice);
-        if (ae != cudaSuccess) {
-            delete sc;
-            return fail(ae == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(ae));
-        }
-    }
+    VRJ_TRY_CUDA(cudaMemcpyAsync(base, stage, small_bytes, cudaMemcpyHostToDevice, stream));
+    VRJ_TRY_CUDA(cudaStreamSynchronize(stream));
+#undef VRJ_TRY_CUDA
     sc->device_bytes = arena_bytes;
-    char *base = arena->as<char>();
+    sc->upload_bytes = stager.copied + small_bytes; // what crossed PCIe: the caller's arrays + the small tables
     sc->dev.nodes32 = reinterpret_cast<const float4 *>(base + s_n32.offset);
     sc->dev.nodes64 = reinterpret_cast<const double2 *>(base + s_n64.offset);
     sc->dev.tri_pos = reinterpret_cast<const double2 *>(base + s_tp.offset);
@@ -613,8 +762,8 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
             return std::chrono::duration<double, std::milli>(b - a).count();
         };
-        std::fprintf(stderr, "vrj_scene_create: validate %.2f ms, prepare %.2f ms, upload %.2f ms\n", ms(t_start, t_valid),
-                     ms(t_valid, t_prep), ms(t_prep, t_end));
+        std::fprintf(stderr, "vrj_scene_create: validate %.2f ms, device alloc %.2f ms, copies queued %.2f ms, device build + pack %.2f ms, tables %.2f ms\n",
+                     ms(t_start, t_valid), ms(t_valid, t_alloc), ms(t_alloc, t_raw), ms(t_raw, t_prep), ms(t_prep, t_end));
     }
     *out = sc;
     return VRJ_OK;
@@ -628,14 +777,18 @@ void vrj_scene_destroy(VrjScene *scene) {
 }
 
 uint64_t vrj_scene_device_bytes(const VrjScene *scene) { return scene ? scene->device_bytes : 0; }
+uint64_t vrj_scene_upload_bytes(const VrjScene *scene) { return scene ? scene->upload_bytes : 0; }
 
 void vrj_release_scratch(void) {
-    std::lock_guard<std::mutex> g(g_pool_mutex);
-    for (auto &e : g_pool) {
-        cudaSetDevice(e.first);
-        delete e.second;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mutex);
+        for (auto &e : g_pool) {
+            cudaSetDevice(e.first);
+            delete e.second;
+        }
+        g_pool.clear();
     }
-    g_pool.clear();
+    vrj_pool_trim();
 }
 
 void *vrj_alloc_host(uint64_t bytes) {
@@ -768,7 +921,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
             VRJ_CUDA(cudaMemcpyAsync(arrs[i].user, arrs[i].dev->p, npix * arrs[i].per * sizeof(double), out_kind, s->stream));
     if (out->srgb8) {
         if (s->srgb8.bytes < npix * 3) {
-            if (s->srgb8.p) cudaFree(s->srgb8.p), s->srgb8.p = nullptr;
+            s->srgb8.release();
             VRJ_CUDA(s->srgb8.alloc(npix * 3));
         }
         k_tone_map<<<(unsigned)((npix + 255) / 256), 256, 0, s->stream>>>(s->acc_colour.as<double>(), s->srgb8.as<unsigned char>(), npix, 0);
@@ -1025,15 +1178,15 @@ VrjStatus vrj_render_sharded(VrjMultiScene *m, const VrjTile *tile, uint64_t hei
     for (int g = 0; g < G; g++) {
         VRJ_CUDA(cudaSetDevice(c->devices[g]));
         if (m->sum[g]->bytes < npix * 24) {
-            if (m->sum[g]->p) cudaFree(m->sum[g]->p), m->sum[g]->p = nullptr;
-            if (m->weight[g]->p) cudaFree(m->weight[g]->p), m->weight[g]->p = nullptr;
+            m->sum[g]->release();
+            m->weight[g]->release();
             VRJ_CUDA(m->sum[g]->alloc(npix * 24));
             VRJ_CUDA(m->weight[g]->alloc(npix * 8));
         }
     }
     VRJ_CUDA(cudaSetDevice(c->devices[0]));
     if (m->colour.bytes < npix * 24) {
-        if (m->colour.p) cudaFree(m->colour.p), m->colour.p = nullptr;
+        m->colour.release();
         VRJ_CUDA(m->colour.alloc(npix * 24));
     }
     // ---- every device renders its share of the sample indices into its own device buffers ----

@@ -18,7 +18,7 @@
 // All arithmetic that reaches the output is min / max / one add / one halving of binary64 values, in
 // the host builder's order, so the results are identical, not merely close.  (-0.0 and +0.0 compare
 // equal in the sort, as with the host's operator<; a box bound that is a zero may differ in sign.)
-#include "../../include/vanrijn_cuda.h"
+#include "vrj_internal.h"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -252,6 +252,11 @@ __global__ void __launch_bounds__(1024) k_scan_totals(uint32_t n, uint32_t *__re
     }
 }
 
+__global__ void k_scan_add(uint32_t n, uint32_t *__restrict__ data, const uint32_t *__restrict__ tile_prefix) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) data[i] += tile_prefix[i / SCAN_TILE];
+}
+
 // stable scatter of one digit: warp w of the CTA owns elements [w*256, w*256+256) of the chunk, eight rounds
 // of 32 consecutive elements; __match_any_sync ranks equal digits inside a round
 __global__ void __launch_bounds__(CHUNK_THREADS) k_scatter(const Chunk *__restrict__ chunks, const unsigned long long *__restrict__ keys_in,
@@ -427,17 +432,15 @@ constexpr size_t SMALL_SMEM = (size_t)SMALL * 6 * 8 + (size_t)SMALL * 8 + (size_
 } // namespace vrj_build
 
 // =====================================================================================================
-// defined in vanrijn_cuda.cu: the message vrj_last_error() returns on this thread
-void vrj_set_error(const std::string &msg);
 
 namespace vrj_build {
 
 struct DevBuf {
     void *p = nullptr;
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p) vrj_pool_free(p);
     }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    cudaError_t alloc(size_t bytes) { return vrj_pool_alloc(&p, bytes); }
     template <typename T>
     T *as() const { return static_cast<T *>(p); }
 };
@@ -451,21 +454,41 @@ struct DevBuf {
         }                                                                                            \
     } while (0)
 
+struct Slice { // a piece of one device block
+    size_t offset = 0;
+    void *p = nullptr;
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
 uint32_t tree_depth(uint64_t n) { // BuildCtx::build's return value: a leaf at level d reports d + 1
     uint32_t d = 1;
     while (n > 1) n = n - n / 2, d++;
     return d;
 }
 
+VrjStatus exclusive_scan_u32(uint32_t *d_data, uint32_t n, uint32_t *d_scratch, cudaStream_t stream) {
+    if (n == 0) return VRJ_OK;
+    const uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles<<<n_tiles, 256, 0, stream>>>(n, d_data, d_scratch);
+    k_scan_totals<<<1, 1024, 0, stream>>>(n_tiles, d_scratch);
+    k_scan_add<<<(n + 255) / 256, 256, 0, stream>>>(n, d_data, d_scratch);
+    VRJB(cudaGetLastError());
+    return VRJ_OK;
+}
+
 // Build on the current device.  d_vertices: 9 doubles per triangle (input order).  Outputs (device):
 // d_order[n], d_node_min / d_node_max [4 * (2n-1)], d_node_child [2 * (2n-1)].  n >= 1.
 VrjStatus build_device(uint32_t n, const double *d_vertices, uint32_t *d_order, double *d_node_min, double *d_node_max,
                        int32_t *d_node_child, cudaStream_t stream, VrjBvhBuildStats *stats) {
-    DevBuf lo, hi, centre, keys[2], vals[2], d_segs, d_chunks, bounds, seg_axis, hist, totals, varying;
-    VRJB(lo.alloc((size_t)n * 24));
-    VRJB(hi.alloc((size_t)n * 24));
-    VRJB(centre.alloc((size_t)n * 24));
-    k_tri_boxes<<<(n + 255) / 256, 256, 0, stream>>>(n, d_vertices, lo.as<double>(), hi.as<double>(), centre.as<double>(), d_order);
+    // every temporary lives in ONE device block (a dozen cudaMalloc / cudaFree pairs cost more than a small build)
+    Slice lo, hi, centre, keys[2], vals[2], d_segs, d_chunks, bounds, seg_axis, hist, totals, varying;
+    size_t block_bytes = 0;
+    auto carve = [&block_bytes](Slice &sl, size_t bytes) {
+        sl.offset = block_bytes;
+        block_bytes += (bytes + 255) & ~size_t(255);
+    };
+    carve(lo, (size_t)n * 24), carve(hi, (size_t)n * 24), carve(centre, (size_t)n * 24);
 
     // ---- the shape of the tree: segments of every global level, then the small-subtree roots ----
     std::vector<std::vector<Segment>> levels;
@@ -509,21 +532,22 @@ VrjStatus build_device(uint32_t n, const double *d_vertices, uint32_t *d_order, 
     }
     const size_t roots_off = all_segs.size();
     all_segs.insert(all_segs.end(), roots.begin(), roots.end());
-    VRJB(d_segs.alloc(all_segs.size() * sizeof(Segment)));
-    VRJB(cudaMemcpyAsync(d_segs.p, all_segs.data(), all_segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream));
+    carve(d_segs, all_segs.size() * sizeof(Segment));
     if (!all_chunks.empty()) {
-        VRJB(d_chunks.alloc(all_chunks.size() * sizeof(Chunk)));
-        VRJB(cudaMemcpyAsync(d_chunks.p, all_chunks.data(), all_chunks.size() * sizeof(Chunk), cudaMemcpyHostToDevice, stream));
-        for (int i = 0; i < 2; i++) {
-            VRJB(keys[i].alloc((size_t)n * 8));
-            VRJB(vals[i].alloc((size_t)n * 4));
-        }
-        VRJB(bounds.alloc(max_segs * 6 * 8));
-        VRJB(seg_axis.alloc(max_segs * 4));
-        VRJB(hist.alloc(max_chunks * 256 * 4));
-        VRJB(totals.alloc(((max_chunks * 256 + SCAN_TILE - 1) / SCAN_TILE + 1) * 4));
-        VRJB(varying.alloc(32));
+        carve(d_chunks, all_chunks.size() * sizeof(Chunk));
+        for (int i = 0; i < 2; i++) carve(keys[i], (size_t)n * 8), carve(vals[i], (size_t)n * 4);
+        carve(bounds, max_segs * 6 * 8), carve(seg_axis, max_segs * 4);
+        carve(hist, max_chunks * 256 * 4), carve(totals, ((max_chunks * 256 + SCAN_TILE - 1) / SCAN_TILE + 1) * 4);
+        carve(varying, 32);
     }
+    DevBuf block;
+    VRJB(block.alloc(block_bytes));
+    for (Slice *sl : {&lo, &hi, &centre, &keys[0], &keys[1], &vals[0], &vals[1], &d_segs, &d_chunks, &bounds, &seg_axis, &hist, &totals, &varying})
+        sl->p = block.as<char>() + sl->offset;
+    k_tri_boxes<<<(n + 255) / 256, 256, 0, stream>>>(n, d_vertices, lo.as<double>(), hi.as<double>(), centre.as<double>(), d_order);
+    VRJB(cudaMemcpyAsync(d_segs.p, all_segs.data(), all_segs.size() * sizeof(Segment), cudaMemcpyHostToDevice, stream));
+    if (!all_chunks.empty())
+        VRJB(cudaMemcpyAsync(d_chunks.p, all_chunks.data(), all_chunks.size() * sizeof(Chunk), cudaMemcpyHostToDevice, stream));
     uint32_t passes_run = 0;
     for (size_t L = 0; L < info.size(); L++) {
         const LevelInfo &li = info[L];

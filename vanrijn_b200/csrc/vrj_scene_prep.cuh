@@ -1,0 +1,132 @@
+// vrj_scene_prep.cuh -- scene upload, device side: the caller's flattened SoA arrays (VrjSceneDesc) are copied
+// to the device as they are and re-expressed there as the traversal layout of vrj_traverse.cuh:
+//   k_pack_triangles : 6 vertex/normal arrays + material + prim id  ->  96-byte position and normal records,
+//                      optionally through a permutation (triangles of a BVH built on the device move to leaf order)
+//   k_mark_internal / exclusive scan / k_wide_nodes : reference-topology nodes (a box per node)  ->  "wide" nodes that
+//                      carry the boxes of both children (f32 rounded outward, and f64), leaves folded into child refs
+// Nothing here decides a hit: boxes only feed the conservative filter (vrj_traverse.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace vrj {
+
+struct RawTriangles {
+    const double *v0, *v1, *v2, *n0, *n1, *n2; // 4 doubles per entry
+    const uint32_t *material, *prim_id;
+};
+
+__global__ void k_pack_triangles(uint32_t n, RawTriangles raw, const uint32_t *__restrict__ perm, double *__restrict__ tri_pos,
+                                 double *__restrict__ tri_nrm) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t src = perm ? perm[t] : t;
+    const double *v[3] = {raw.v0 + 4 * src, raw.v1 + 4 * src, raw.v2 + 4 * src};
+    const double *nr[3] = {raw.n0 + 4 * src, raw.n1 + 4 * src, raw.n2 + 4 * src};
+    double *tp = tri_pos + (size_t)t * 12, *tn = tri_nrm + (size_t)t * 12;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double2 a = *reinterpret_cast<const double2 *>(v[k]), b = *reinterpret_cast<const double2 *>(nr[k]);
+        tp[3 * k] = a.x, tp[3 * k + 1] = a.y, tp[3 * k + 2] = v[k][2];
+        tn[3 * k] = b.x, tn[3 * k + 1] = b.y, tn[3 * k + 2] = nr[k][2];
+    }
+    const unsigned long long bits = ((unsigned long long)raw.prim_id[src] << 32) | raw.material[src];
+    tp[9] = __longlong_as_double((long long)bits);
+    tp[10] = tp[11] = 0.0, tn[9] = tn[10] = tn[11] = 0.0;
+}
+
+// input-order triangle index of every leaf position of a BVH built on the device
+__global__ void k_offset_perm(uint32_t n, const uint32_t *__restrict__ order, uint32_t first, uint32_t *__restrict__ perm) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[first + i] = first + order[i];
+}
+__global__ void k_identity_perm(uint32_t n, uint32_t *__restrict__ perm) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = i;
+}
+// 3 x (4 doubles per vertex) -> 9 doubles per triangle, the builder's input
+__global__ void k_gather_vertices(uint32_t n, const double *__restrict__ v0, const double *__restrict__ v1, const double *__restrict__ v2,
+                                  double *__restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double *v[3] = {v0 + 4 * (size_t)t, v1 + 4 * (size_t)t, v2 + 4 * (size_t)t};
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) out[(size_t)t * 9 + 3 * k + c] = v[k][c];
+}
+
+// One BVH's nodes inside the device node arrays.  Built by the caller: children and leaf triangles are absolute indices
+// (VrjSceneDesc); built on the device: they are local to the BVH and get the offsets below.
+struct BvhNodes {
+    const double *node_min, *node_max; // 4 doubles per node, indexed by absolute node index
+    const int32_t *node_child;         // 2 per node
+    uint32_t first_node, n_nodes;
+    int32_t child_offset, triangle_offset;
+    uint32_t wide_base;                // index of this BVH's first wide node
+};
+
+__global__ void k_mark_internal(BvhNodes b, uint32_t *__restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b.n_nodes) flags[i] = b.node_child[2 * (size_t)(b.first_node + i)] >= 0 ? 1u : 0u;
+}
+
+__device__ __forceinline__ void put_child(const BvhNodes &b, const uint32_t *__restrict__ rank, float *__restrict__ f, double *__restrict__ g,
+                                          int which, int64_t node /* absolute, or -1 for "no child" */, int32_t &ref_out) {
+    double lo[3], hi[3];
+    int32_t ref = -1;
+    bool empty = node < 0;
+    if (!empty) {
+        const int32_t l = b.node_child[2 * node], r = b.node_child[2 * node + 1];
+        if (l >= 0) {
+            ref = (int32_t)(b.wide_base + rank[node - b.first_node]);
+        } else if (r == 0) {
+            empty = true; // an empty leaf never reports a hit
+        } else {
+            ref = ~((~l) + b.triangle_offset);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        lo[k] = empty ? CUDART_INF : b.node_min[4 * node + k];
+        hi[k] = empty ? -CUDART_INF : b.node_max[4 * node + k];
+    }
+    // f32 layout: [c0.lox c0.hix c0.loy c0.hiy][c1.lox c1.hix c1.loy c1.hiy][c0.loz c0.hiz c1.loz c1.hiz][l r 0 0]
+    f[which * 4 + 0] = __double2float_rd(lo[0]), f[which * 4 + 1] = __double2float_ru(hi[0]);
+    f[which * 4 + 2] = __double2float_rd(lo[1]), f[which * 4 + 3] = __double2float_ru(hi[1]);
+    f[8 + which * 2 + 0] = __double2float_rd(lo[2]), f[8 + which * 2 + 1] = __double2float_ru(hi[2]);
+    // f64 layout: c0 {lox hix loy hiy loz hiz} c1 {...} {bits(l, r), 0}
+#pragma unroll
+    for (int k = 0; k < 3; k++) g[which * 6 + 2 * k] = lo[k], g[which * 6 + 2 * k + 1] = hi[k];
+    ref_out = ref;
+}
+
+// one thread per node of the BVH; internal nodes write their wide node.  `rank` = exclusive scan of k_mark_internal.
+__global__ void k_wide_nodes(BvhNodes b, const uint32_t *__restrict__ rank, float *__restrict__ nodes32, double *__restrict__ nodes64) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_nodes) return;
+    const int64_t me = (int64_t)b.first_node + i;
+    const int32_t l = b.node_child[2 * me], r = b.node_child[2 * me + 1];
+    int64_t c0, c1;
+    uint32_t w;
+    if (l >= 0) {
+        w = b.wide_base + rank[i];
+        c0 = (int64_t)l + b.child_offset, c1 = (int64_t)r + b.child_offset;
+    } else if (i == 0) {
+        w = b.wide_base; // the root is a leaf: one wide node whose first child is that leaf
+        c0 = me, c1 = -1;
+    } else {
+        return;
+    }
+    float *f = nodes32 + (size_t)w * 16;
+    double *g = nodes64 + (size_t)w * 14;
+    int32_t r0, r1;
+    put_child(b, rank, f, g, 0, c0, r0);
+    put_child(b, rank, f, g, 1, c1, r1);
+    f[12] = __int_as_float(r0), f[13] = __int_as_float(r1), f[14] = 0.f, f[15] = 0.f;
+    g[12] = __longlong_as_double((long long)(((unsigned long long)(uint32_t)r1 << 32) | (uint32_t)r0));
+    g[13] = 0.0;
+}
+
+} // namespace vrj

@@ -18,10 +18,11 @@ class HostScene:
     """A vanrijn::Scene built by the C++ host side, plus its flattened / uploaded forms."""
 
     def __init__(self, spec, device_builder=False):
-        """device_builder: run BoundingVolumeHierarchy::build on the GPU (vrj_bvh_build) instead of on the host;
-        the tree is the same either way."""
+        """device_builder: False/0 = BoundingVolumeHierarchy::build on the host; True/1 = on the GPU (vrj_bvh_build);
+        "upload"/2 = only the triangles are kept and the tree is built on the GPU inside vrj_scene_create.
+        The tree is the same in all three cases."""
         H = capi.host()
-        self.device_builder = bool(device_builder)
+        self.device_builder = 2 if device_builder == "upload" else int(device_builder)
         self.H = H
         self.h = C.c_void_p(H.vrjh_scene_new(*[float(x) for x in spec.camera]))
         self.spec = spec
