@@ -127,6 +127,13 @@ struct PrimitiveList : Aggregate {
     std::vector<std::shared_ptr<Primitive>> primitives;
     void flatten(FlatSceneBuilder &out, uint32_t object_id) const override;
 };
+// The triangles of a mesh as plain arrays: 9 doubles per triangle (v0 xyz, v1 xyz, v2 xyz), normals likewise.
+// What mesh.rs:13-72 computes, before it is wrapped into one Arc<dyn Primitive> per triangle.
+struct TriangleMesh {
+    std::vector<double> vertices, normals;
+    size_t triangle_count() const { return vertices.size() / 9; }
+};
+
 // bounding_volume_hierarchy.rs:18-75.  Only triangles may be stored (what load_obj produces).
 class BoundingVolumeHierarchy : public Aggregate {
   public:
@@ -138,12 +145,17 @@ class BoundingVolumeHierarchy : public Aggregate {
     // reorders `primitives` in place, as the reference's build(&mut [Arc<dyn Primitive>]) does
     static std::unique_ptr<BoundingVolumeHierarchy> build(std::vector<std::shared_ptr<Primitive>> &primitives,
                                                           Builder builder = Builder::Host, int device = 0);
+    // the same tree straight from arrays (load_obj_mesh), without one heap object per triangle: a 10 M-triangle scene
+    // spends seconds in those allocations alone
+    static std::unique_ptr<BoundingVolumeHierarchy> build(const TriangleMesh &mesh, std::shared_ptr<Material> material,
+                                                          Builder builder = Builder::Host, int device = 0);
     void flatten(FlatSceneBuilder &out, uint32_t object_id) const override;
     uint32_t depth() const { return depth_; }
     size_t triangle_count() const { return tri_v_.size() / 9; }
 
   private:
     friend class FlatSceneBuilder;
+    std::vector<uint32_t> build_arrays(const std::vector<double> &v, const std::vector<double> &n, Builder builder, int device);
     std::vector<double> tri_v_, tri_n_;       // 9 doubles per triangle, leaf (DFS) order
     std::vector<uint32_t> tri_prim_id_;       // original index of each triangle
     std::vector<std::shared_ptr<Material>> tri_material_;
@@ -196,6 +208,8 @@ class AccumulationBuffer {
 
 // mesh.rs:74-88
 std::vector<std::shared_ptr<Primitive>> load_obj(const std::string &filename, std::shared_ptr<Material> material);
+// the same parse, as arrays (OBJ -> SoA without a Rust dependency); load_obj wraps its result
+TriangleMesh load_obj_mesh(const std::string &filename);
 
 // The parameters partial_render_scene hard-codes (camera.rs:69,103), made explicit.
 struct DirectionalLight {

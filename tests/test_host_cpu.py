@@ -219,3 +219,18 @@ def test_shard_samples_partition_the_sample_indices():
             assert sorted(seen) == list(range(3 * spp * world))
     with pytest.raises(ValueError):
         sharding.shard_samples(2, 2, 0, 1)
+
+
+def test_array_path_and_per_triangle_object_path_flatten_identically():
+    """BoundingVolumeHierarchy::build(TriangleMesh) (arrays) and build(Vec<Arc<dyn Primitive>>) (one object per triangle,
+    as mesh.rs:74-88 + bounding_volume_hierarchy.rs:49-51 do it) must flatten to the same scene, for a mesh given as
+    arrays and for one read from OBJ text."""
+    for spec in (scenes.tiny_mesh_scene(subdivisions=3), scenes.scene_main(subdivisions=2, obj=True)):
+        a, b = V.build_scene(spec).desc(), V.build_scene(spec, per_triangle_objects=True).desc()
+        assert int(a.n_triangles) == int(b.n_triangles) > 0 and int(a.n_nodes) == int(b.n_nodes) > 0
+        n, nn = int(a.n_triangles), int(a.n_nodes)
+        arr = lambda p, count: np.ctypeslib.as_array(p, shape=(count,))
+        for name, count in (("tri_v0", 4 * n), ("tri_v1", 4 * n), ("tri_v2", 4 * n), ("tri_n0", 4 * n), ("tri_n1", 4 * n),
+                            ("tri_n2", 4 * n), ("tri_material", n), ("tri_prim_id", n), ("node_min", 4 * nn),
+                            ("node_max", 4 * nn), ("node_child", 2 * nn)):
+            assert np.array_equal(arr(getattr(a, name), count), arr(getattr(b, name), count)), name

@@ -115,33 +115,45 @@ void vrjh_list_add_triangle(void *p, const double *v, const double *n, int mater
     std::array<Vec3, 3> ns{Vec3(n[0], n[1], n[2]), Vec3(n[3], n[4], n[5]), Vec3(n[6], n[7], n[8])};
     h->open_list->primitives.push_back(std::make_shared<Triangle>(vs, ns, h->materials.at(material)));
 }
-/* BoundingVolumeHierarchy::build over ntri triangles; returns object id or -1 */
-int vrjh_add_bvh(void *p, int64_t ntri, const double *verts, const double *normals, int material, int device_builder) {
+/* BoundingVolumeHierarchy::build over ntri triangles; returns object id or -1.
+ * builder: 0 host, 1 device (vrj_bvh_build), 2 at upload (inside vrj_scene_create);
+ * +4 = go through one Triangle object per triangle as the reference's Vec<Arc<dyn Primitive>> does (same result, slower) */
+int vrjh_add_bvh(void *p, int64_t ntri, const double *verts, const double *normals, int material, int builder) {
     HostScene *h = static_cast<HostScene *>(p);
     int id = -1;
     guarded([&] {
-        std::vector<std::shared_ptr<Primitive>> prims((size_t)ntri);
         std::shared_ptr<Material> m = h->materials.at(material);
-        for (int64_t i = 0; i < ntri; i++) {
-            const double *v = verts + 9 * i, *n = normals + 9 * i;
-            std::array<Vec3, 3> vs{Vec3(v[0], v[1], v[2]), Vec3(v[3], v[4], v[5]), Vec3(v[6], v[7], v[8])};
-            std::array<Vec3, 3> ns{Vec3(n[0], n[1], n[2]), Vec3(n[3], n[4], n[5]), Vec3(n[6], n[7], n[8])};
-            prims[i] = std::make_shared<Triangle>(vs, ns, m);
+        const auto b = static_cast<BoundingVolumeHierarchy::Builder>(builder & 3);
+        if (builder & 4) {
+            std::vector<std::shared_ptr<Primitive>> prims((size_t)ntri);
+            for (int64_t i = 0; i < ntri; i++) {
+                const double *v = verts + 9 * i, *n = normals + 9 * i;
+                std::array<Vec3, 3> vs{Vec3(v[0], v[1], v[2]), Vec3(v[3], v[4], v[5]), Vec3(v[6], v[7], v[8])};
+                std::array<Vec3, 3> ns{Vec3(n[0], n[1], n[2]), Vec3(n[3], n[4], n[5]), Vec3(n[6], n[7], n[8])};
+                prims[i] = std::make_shared<Triangle>(vs, ns, m);
+            }
+            h->scene.objects.push_back(BoundingVolumeHierarchy::build(prims, b));
+        } else {
+            TriangleMesh mesh;
+            mesh.vertices.assign(verts, verts + 9 * ntri), mesh.normals.assign(normals, normals + 9 * ntri);
+            h->scene.objects.push_back(BoundingVolumeHierarchy::build(mesh, m, b));
         }
-        h->scene.objects.push_back(BoundingVolumeHierarchy::build(
-            prims, static_cast<BoundingVolumeHierarchy::Builder>(device_builder))); // 0 host, 1 device, 2 at upload
         id = (int)h->scene.objects.size() - 1;
     });
     return id;
 }
-/* load_obj + BoundingVolumeHierarchy::build; returns object id or -1 */
-int vrjh_add_bvh_obj(void *p, const char *path, int material, int device_builder) {
+/* load_obj + BoundingVolumeHierarchy::build; returns object id or -1 (builder as above) */
+int vrjh_add_bvh_obj(void *p, const char *path, int material, int builder) {
     HostScene *h = static_cast<HostScene *>(p);
     int id = -1;
     guarded([&] {
-        auto prims = load_obj(path, h->materials.at(material));
-        h->scene.objects.push_back(BoundingVolumeHierarchy::build(
-            prims, static_cast<BoundingVolumeHierarchy::Builder>(device_builder))); // 0 host, 1 device, 2 at upload
+        const auto b = static_cast<BoundingVolumeHierarchy::Builder>(builder & 3);
+        if (builder & 4) {
+            auto prims = load_obj(path, h->materials.at(material));
+            h->scene.objects.push_back(BoundingVolumeHierarchy::build(prims, b));
+        } else {
+            h->scene.objects.push_back(BoundingVolumeHierarchy::build(load_obj_mesh(path), h->materials.at(material), b));
+        }
         id = (int)h->scene.objects.size() - 1;
     });
     return id;

@@ -185,19 +185,10 @@ struct BuildCtx {
 };
 } // namespace
 
-std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vector<std::shared_ptr<Primitive>> &primitives,
-                                                                        Builder builder, int device) {
-    std::unique_ptr<BoundingVolumeHierarchy> bvh(new BoundingVolumeHierarchy());
-    const size_t n = primitives.size();
-    std::vector<double> v(n * 9), nr(n * 9);
-    for (size_t i = 0; i < n; i++) {
-        const Triangle *t = dynamic_cast<const Triangle *>(primitives[i].get());
-        if (!t) throw std::runtime_error("BoundingVolumeHierarchy::build: only Triangle primitives can be stored on the device BVH");
-        for (int k = 0; k < 3; k++) {
-            v[i * 9 + 3 * k] = t->vertices[k].x, v[i * 9 + 3 * k + 1] = t->vertices[k].y, v[i * 9 + 3 * k + 2] = t->vertices[k].z;
-            nr[i * 9 + 3 * k] = t->normals[k].x, nr[i * 9 + 3 * k + 1] = t->normals[k].y, nr[i * 9 + 3 * k + 2] = t->normals[k].z;
-        }
-    }
+// the recursion (or its device twin) over triangle arrays; fills every member but tri_material_ and returns the leaf order
+std::vector<uint32_t> BoundingVolumeHierarchy::build_arrays(const std::vector<double> &v, const std::vector<double> &nr, Builder builder, int device) {
+    BoundingVolumeHierarchy *bvh = this;
+    const size_t n = v.size() / 9;
     const size_t n_nodes = n ? 2 * n - 1 : 1;
     std::vector<uint32_t> order;
     if (builder == Builder::AtUpload) {
@@ -235,17 +226,46 @@ std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vec
         bvh->node_min_ = std::move(cx.node_min), bvh->node_max_ = std::move(cx.node_max), bvh->node_child_ = std::move(cx.node_child);
         order = std::move(cx.order);
     }
-    bvh->tri_v_.resize(n * 9), bvh->tri_n_.resize(n * 9), bvh->tri_prim_id_.resize(n), bvh->tri_material_.resize(n);
-    std::vector<std::shared_ptr<Primitive>> reordered(n);
+    bvh->tri_v_.resize(n * 9), bvh->tri_n_.resize(n * 9), bvh->tri_prim_id_.resize(n);
     for (size_t i = 0; i < n; i++) {
         uint32_t src = order[i];
         std::memcpy(&bvh->tri_v_[i * 9], &v[(size_t)src * 9], 72);
         std::memcpy(&bvh->tri_n_[i * 9], &nr[(size_t)src * 9], 72);
         bvh->tri_prim_id_[i] = src;
-        bvh->tri_material_[i] = static_cast<const Triangle *>(primitives[src].get())->material;
-        reordered[i] = primitives[src];
+    }
+    return order;
+}
+
+std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(std::vector<std::shared_ptr<Primitive>> &primitives,
+                                                                        Builder builder, int device) {
+    std::unique_ptr<BoundingVolumeHierarchy> bvh(new BoundingVolumeHierarchy());
+    const size_t n = primitives.size();
+    std::vector<double> v(n * 9), nr(n * 9);
+    for (size_t i = 0; i < n; i++) {
+        const Triangle *t = dynamic_cast<const Triangle *>(primitives[i].get());
+        if (!t) throw std::runtime_error("BoundingVolumeHierarchy::build: only Triangle primitives can be stored on the device BVH");
+        for (int k = 0; k < 3; k++) {
+            v[i * 9 + 3 * k] = t->vertices[k].x, v[i * 9 + 3 * k + 1] = t->vertices[k].y, v[i * 9 + 3 * k + 2] = t->vertices[k].z;
+            nr[i * 9 + 3 * k] = t->normals[k].x, nr[i * 9 + 3 * k + 1] = t->normals[k].y, nr[i * 9 + 3 * k + 2] = t->normals[k].z;
+        }
+    }
+    std::vector<uint32_t> order = bvh->build_arrays(v, nr, builder, device);
+    bvh->tri_material_.resize(n);
+    std::vector<std::shared_ptr<Primitive>> reordered(n);
+    for (size_t i = 0; i < n; i++) {
+        bvh->tri_material_[i] = static_cast<const Triangle *>(primitives[order[i]].get())->material;
+        reordered[i] = primitives[order[i]];
     }
     if (builder != Builder::AtUpload) primitives.swap(reordered); // the reference sorts the caller's slice in place
+    return bvh;
+}
+
+std::unique_ptr<BoundingVolumeHierarchy> BoundingVolumeHierarchy::build(const TriangleMesh &mesh, std::shared_ptr<Material> material,
+                                                                        Builder builder, int device) {
+    if (mesh.vertices.size() != mesh.normals.size() || mesh.vertices.size() % 9) throw std::runtime_error("TriangleMesh: 9 doubles per triangle, vertices and normals");
+    std::unique_ptr<BoundingVolumeHierarchy> bvh(new BoundingVolumeHierarchy());
+    bvh->build_arrays(mesh.vertices, mesh.normals, builder, device);
+    bvh->tri_material_.assign(mesh.vertices.size() / 9, material);
     return bvh;
 }
 void BoundingVolumeHierarchy::flatten(FlatSceneBuilder &out, uint32_t object_id) const { out.add_bvh(*this, object_id); }
@@ -351,10 +371,21 @@ const VrjSceneDesc &FlatSceneBuilder::desc(const Vec3 &camera) {
 // (a, a/b, a//c, a/b/c; 1-based, negative = relative to the end), f32 parse then widen,
 // fan triangulation around the polygon's first vertex, zero normal when a vertex has none.
 std::vector<std::shared_ptr<Primitive>> load_obj(const std::string &filename, std::shared_ptr<Material> material) {
+    const TriangleMesh mesh = load_obj_mesh(filename);
+    const size_t n = mesh.triangle_count();
+    std::vector<std::shared_ptr<Primitive>> out(n);
+    for (size_t i = 0; i < n; i++) {
+        const double *v = &mesh.vertices[9 * i], *m = &mesh.normals[9 * i];
+        out[i] = std::make_shared<Triangle>(std::array<Vec3, 3>{Vec3(v[0], v[1], v[2]), Vec3(v[3], v[4], v[5]), Vec3(v[6], v[7], v[8])},
+                                            std::array<Vec3, 3>{Vec3(m[0], m[1], m[2]), Vec3(m[3], m[4], m[5]), Vec3(m[6], m[7], m[8])}, material);
+    }
+    return out;
+}
+TriangleMesh load_obj_mesh(const std::string &filename) {
     FILE *f = std::fopen(filename.c_str(), "r");
     if (!f) throw std::runtime_error("load_obj: cannot open " + filename);
     std::vector<float> positions, normals;
-    std::vector<std::shared_ptr<Primitive>> out;
+    TriangleMesh out;
     std::vector<long> vi, ni;
     char line[8192];
     auto is_space = [](char c) { return c == ' ' || c == '\t'; };
@@ -392,9 +423,13 @@ std::vector<std::shared_ptr<Primitive>> load_obj(const std::string &filename, st
             auto normal = [&](size_t k) {
                 return ni[k] < 0 ? Vec3() : Vec3(normals[3 * ni[k]], normals[3 * ni[k] + 1], normals[3 * ni[k] + 2]);
             };
-            for (size_t k = 1; k + 1 < vi.size(); k++)
-                out.push_back(std::make_shared<Triangle>(std::array<Vec3, 3>{vertex(0), vertex(k), vertex(k + 1)},
-                                                         std::array<Vec3, 3>{normal(0), normal(k), normal(k + 1)}, material));
+            for (size_t k = 1; k + 1 < vi.size(); k++) {
+                const Vec3 tv[3] = {vertex(0), vertex(k), vertex(k + 1)}, tn[3] = {normal(0), normal(k), normal(k + 1)};
+                for (int c = 0; c < 3; c++) {
+                    out.vertices.insert(out.vertices.end(), {tv[c].x, tv[c].y, tv[c].z});
+                    out.normals.insert(out.normals.end(), {tn[c].x, tn[c].y, tn[c].z});
+                }
+            }
         }
     }
     std::fclose(f);

@@ -17,12 +17,13 @@ def _d(a):
 class HostScene:
     """A vanrijn::Scene built by the C++ host side, plus its flattened / uploaded forms."""
 
-    def __init__(self, spec, device_builder=False):
+    def __init__(self, spec, device_builder=False, per_triangle_objects=False):
         """device_builder: False/0 = BoundingVolumeHierarchy::build on the host; True/1 = on the GPU (vrj_bvh_build);
         "upload"/2 = only the triangles are kept and the tree is built on the GPU inside vrj_scene_create.
-        The tree is the same in all three cases."""
+        The tree is the same in all three cases.  per_triangle_objects: build through one Triangle object per triangle,
+        like the reference's Vec<Arc<dyn Primitive>> (same result; the default goes through arrays)."""
         H = capi.host()
-        self.device_builder = 2 if device_builder == "upload" else int(device_builder)
+        self.device_builder = (2 if device_builder == "upload" else int(device_builder)) | (4 if per_triangle_objects else 0)
         self.H = H
         self.h = C.c_void_p(H.vrjh_scene_new(*[float(x) for x in spec.camera]))
         self.spec = spec
@@ -247,5 +248,5 @@ def bvh_build(vertices, device=0):
     return dict(order=order[:n], node_min=node_min, node_max=node_max, node_child=child, depth=depth.value, stats=stats)
 
 
-def build_scene(spec, device_builder=False):
-    return HostScene(spec, device_builder=device_builder)
+def build_scene(spec, device_builder=False, per_triangle_objects=False):
+    return HostScene(spec, device_builder=device_builder, per_triangle_objects=per_triangle_objects)
