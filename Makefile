@@ -15,7 +15,7 @@ CUDA_DEPS = $(CSRC)/vanrijn_cuda.cu $(CSRC)/vrj_kernels.cuh $(CSRC)/vrj_traverse
             $(CSRC)/rgb_basis_tables.inc include/vanrijn_cuda.h
 HOST_DEPS = $(CSRC)/host/vanrijn_host.cpp $(CSRC)/host/host_capi.cpp include/vanrijn.hpp include/vanrijn_cuda.h
 
-all: $(LIBDIR)/libvanrijn_cuda.so $(LIBDIR)/libvanrijn_host.so oracle
+all: $(LIBDIR)/libvanrijn_cuda.so $(LIBDIR)/libvanrijn_host.so oracle examples
 
 # two translation units (the render loop; the device BVH builder), compiled separately so a change to one
 # does not recompile the other
@@ -38,8 +38,14 @@ $(LIBDIR)/libvanrijn_host.so: $(HOST_DEPS) $(LIBDIR)/libvanrijn_cuda.so
 oracle:
 	$(MAKE) -s -C oracle
 
-examples: $(LIBDIR)/libvanrijn_host.so
-	$(HOSTCXX) -O2 -std=c++17 -Iinclude -o build/drop_in_example examples/drop_in_example.cpp -L$(LIBDIR) -lvanrijn_host -lvanrijn_cuda -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+# build/vanrijn: the reference's harness (src/main.rs) over the host mirror; build/drop_in_example: doc-test + bench scene
+examples: build/vanrijn build/drop_in_example
+build/%: examples/%.cpp $(LIBDIR)/libvanrijn_host.so include/vanrijn.hpp
+	mkdir -p build
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lvanrijn_host -lvanrijn_cuda -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+build/vanrijn: examples/vanrijn_main.cpp $(LIBDIR)/libvanrijn_host.so include/vanrijn.hpp
+	mkdir -p build
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lvanrijn_host -lvanrijn_cuda -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 
 clean:
 	rm -f $(LIBDIR)/*.so oracle/*.so

@@ -191,10 +191,31 @@ class TileIterator {
     size_t tile_size_, total_height_, total_width_, current_column_ = 0, current_row_ = 0;
 };
 
+// image.rs:7-66 -- 8-bit RGB image, row-major, 3 bytes per pixel
+class ImageRgbU8 {
+  public:
+    ImageRgbU8(size_t width, size_t height) : pixel_data_(3 * width * height, 0), width_(width), height_(height) {}
+    size_t get_width() const { return width_; }
+    size_t get_height() const { return height_; }
+    static size_t num_channels() { return 3; }
+    const std::vector<uint8_t> &get_pixel_data() const { return pixel_data_; }
+    std::vector<uint8_t> &pixel_data() { return pixel_data_; }
+    // image.rs:52-66: 8-bit RGB PNG.  Written with stored (uncompressed) deflate blocks: the pixels decode identically,
+    // the file is simply larger than the `png` crate's.  Throws std::runtime_error on I/O failure.
+    void write_png(const std::string &filename) const;
+
+  private:
+    std::vector<uint8_t> pixel_data_;
+    size_t width_, height_;
+};
+
 // accumulation_buffer.rs:6-85: five row-major arrays
 class AccumulationBuffer {
   public:
     AccumulationBuffer(size_t width, size_t height);
+    // accumulation_buffer.rs:38-42 with ClampingToneMapper (image.rs:130-187): XYZ -> sRGB (colour_xyz.rs:48-84) ->
+    // clamp -> truncating byte, evaluated on the device (vrj_tone_map)
+    ImageRgbU8 to_image_rgb_u8(int device = 0) const;
     size_t width() const { return width_; }
     size_t height() const { return height_; }
     // accumulation_buffer.rs:62-85 -- touches only colour and weight of the destination

@@ -27,3 +27,25 @@ def exclude_degenerate(dirs):
     """Rays whose signed-largest direction component is exactly 0 (triangle.rs:108-122 then divides by it)."""
     d = dirs / np.linalg.norm(dirs, axis=1, keepdims=True)
     return d.max(axis=1) > 0.0
+
+
+def read_png_rgb8(path):
+    """Minimal PNG reader for 8-bit RGB, non-interlaced files (what ImageRgbU8::write_png emits): returns (h, w, 3) uint8."""
+    import struct, zlib
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w = 8, b"", None
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        crc, = struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])
+        assert zlib.crc32(typ + body) == crc, "chunk CRC"
+        if typ == b"IHDR":
+            w, h, depth, ctype, comp, flt, inter = struct.unpack(">IIBBBBB", body)
+            assert (depth, ctype, comp, flt, inter) == (8, 2, 0, 0, 0)
+        elif typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 3 * w + 1)
+    assert np.all(raw[:, 0] == 0)  # filter type 0 on every scanline
+    return raw[:, 1:].reshape(h, w, 3).copy()

@@ -1,0 +1,50 @@
+"""GPU test of the harness (examples/vanrijn_main.cpp = src/main.rs:104-247 without the SDL window): the PNG it writes
+holds exactly the bytes ClampingToneMapper gives for the frame the library renders."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+import vanrijn_b200 as V
+from vanrijn_b200 import host, scenes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("size,builder", [((160, 90), "upload"), ((2100, 6), "host")])
+def test_harness_png_equals_library_frame(tmp_path, size, builder):
+    exe = os.path.join(ROOT, "build", "vanrijn")
+    assert os.path.exists(exe), "build/vanrijn is missing: run make (or __graft_entry__.build())"
+    W, H = size
+    obj, _ = scenes.bunny_obj_path(subdivisions=3)
+    out = str(tmp_path / "frame.png")
+    r = subprocess.run([exe, "--size", str(W), str(H), "--out", out, "--obj", obj, "--spp", "4", "--depth", "8",
+                        "--builder", builder, "--seed", "5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Mrays/s" in r.stdout and "wrote" in r.stdout
+    png = helpers.read_png_rgb8(out)
+    assert png.shape == (H, W, 3)
+    # the same frame through the library: one call, 4 spp (2100 px wide = two 2048-px tiles in the harness; samples are
+    # pure functions of (seed, pixel, sample), so tiling cannot change them); merging a 4-sample tile into an empty
+    # frame is exact (x*4/4)
+    hs = V.build_scene(scenes.scene_main(subdivisions=3, obj=True))
+    ref = hs.render((0, W, 0, H), H, W, spp=4, max_depth=8, seed=5, want=("colour",))
+    want = host.tone_map(ref["colour"]).reshape(H, W, 3)
+    assert np.array_equal(png, want)
+    assert png.max() > 0
+
+
+def test_harness_time_limit_and_usage_errors(tmp_path):
+    exe = os.path.join(ROOT, "build", "vanrijn")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "--size" in r.stderr
+    out = str(tmp_path / "t.png")
+    r = subprocess.run([exe, "--size", "64", "36", "--time", "0.2", "--spp", "2", "--depth", "4", "--out", out,
+                        "--preview-every", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    passes = int(r.stdout.split(" passes")[0].split()[-1])
+    assert passes >= 1
+    assert helpers.read_png_rgb8(out).shape == (36, 64, 3)

@@ -7,6 +7,7 @@ import re
 import numpy as np
 import pytest
 
+import helpers
 import oraclelib as O
 import vanrijn_b200 as V
 from vanrijn_b200 import capi, scenes, sharding
@@ -234,3 +235,14 @@ def test_array_path_and_per_triangle_object_path_flatten_identically():
                             ("tri_n2", 4 * n), ("tri_material", n), ("tri_prim_id", n), ("node_min", 4 * nn),
                             ("node_max", 4 * nn), ("node_child", 2 * nn)):
             assert np.array_equal(arr(getattr(a, name), count), arr(getattr(b, name), count)), name
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 5), (300, 240)])
+def test_write_png_round_trips(tmp_path, w, h):
+    """image.rs:52-66: the PNG decodes (zlib's inflate + CRC/Adler checks) to exactly the pixels written; 300x240x3 + filter
+    bytes > 65535 exercises several stored deflate blocks."""
+    rng = np.random.default_rng(w * 1000 + h)
+    rgb = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    path = str(tmp_path / "t.png")
+    assert capi.host().vrjh_write_png(path.encode(), w, h, rgb.ctypes.data) == 0
+    assert np.array_equal(helpers.read_png_rgb8(path), rgb)

@@ -228,6 +228,14 @@ int vrjh_merge_tile(double *dst_colour, double *dst_weight, uint64_t dst_w, uint
         std::memcpy(dst_weight, dst.weight.data(), dst_w * dst_h * sizeof(double));
     });
 }
+/* ImageRgbU8::write_png on a raw RGB array */
+int vrjh_write_png(const char *path, uint64_t width, uint64_t height, const uint8_t *rgb) {
+    return guarded([&] {
+        ImageRgbU8 image(width, height);
+        std::memcpy(image.pixel_data().data(), rgb, 3 * width * height);
+        image.write_png(path);
+    });
+}
 int64_t vrjh_tile_iterator(uint64_t width, uint64_t height, uint64_t tile_size, uint64_t *tiles, int64_t cap) {
     int64_t n = 0;
     guarded([&] {

@@ -454,6 +454,86 @@ AccumulationBuffer::AccumulationBuffer(size_t width, size_t height)
     : colour(3 * width * height, 0.0), colour_sum(3 * width * height, 0.0), colour_bias(3 * width * height, 0.0),
       weight(width * height, 0.0), weight_bias(width * height, 0.0), width_(width), height_(height) {}
 
+ImageRgbU8 AccumulationBuffer::to_image_rgb_u8(int device) const {
+    ImageRgbU8 image(width_, height_);
+    if (vrj_tone_map(device, VRJ_MEM_HOST, VRJ_TONEMAP_XYZ, colour.data(), width_ * height_, image.pixel_data().data()) != VRJ_OK)
+        throw std::runtime_error(std::string("vrj_tone_map: ") + vrj_last_error());
+    return image;
+}
+
+// ------------------------------------------------------------------------------ PNG (image.rs:52-66)
+namespace {
+struct Crc32 {
+    uint32_t table[256];
+    Crc32() {
+        for (uint32_t n = 0; n < 256; n++) {
+            uint32_t c = n;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[n] = c;
+        }
+    }
+    uint32_t update(uint32_t crc, const uint8_t *p, size_t n) const {
+        for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+        return crc;
+    }
+};
+void put_be32(std::vector<uint8_t> &v, uint32_t x) {
+    v.push_back((uint8_t)(x >> 24)), v.push_back((uint8_t)(x >> 16)), v.push_back((uint8_t)(x >> 8)), v.push_back((uint8_t)x);
+}
+void put_chunk(std::vector<uint8_t> &file, const char type[4], const std::vector<uint8_t> &data) {
+    static const Crc32 crc;
+    put_be32(file, (uint32_t)data.size());
+    const size_t start = file.size();
+    file.insert(file.end(), type, type + 4);
+    file.insert(file.end(), data.begin(), data.end());
+    put_be32(file, crc.update(0xffffffffu, file.data() + start, file.size() - start) ^ 0xffffffffu);
+}
+} // namespace
+
+void ImageRgbU8::write_png(const std::string &filename) const {
+    if (width_ == 0 || height_ == 0 || width_ > 0x7fffffff || height_ > 0x7fffffff) throw std::runtime_error("write_png: bad image size");
+    // raw scanlines: filter byte 0 + RGB bytes
+    const size_t stride = 3 * width_ + 1;
+    std::vector<uint8_t> raw(stride * height_);
+    for (size_t r = 0; r < height_; r++) {
+        raw[r * stride] = 0;
+        std::memcpy(&raw[r * stride + 1], &pixel_data_[r * 3 * width_], 3 * width_);
+    }
+    // zlib stream of stored blocks (RFC 1950 / 1951) + Adler-32
+    std::vector<uint8_t> z;
+    z.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+    z.push_back(0x78), z.push_back(0x01);
+    uint32_t a = 1, b = 0;
+    for (size_t off = 0; off < raw.size() || off == 0;) {
+        const size_t n = std::min<size_t>(65535, raw.size() - off);
+        const bool last = off + n >= raw.size();
+        z.push_back(last ? 1 : 0);
+        z.push_back((uint8_t)(n & 0xff)), z.push_back((uint8_t)(n >> 8));
+        z.push_back((uint8_t)(~n & 0xff)), z.push_back((uint8_t)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        for (size_t i = 0; i < n; i++) {
+            a += raw[off + i];
+            if (a >= 65521) a -= 65521;
+            b += a;
+            if (b >= 65521) b -= 65521;
+        }
+        off += n;
+        if (last) break;
+    }
+    put_be32(z, (b << 16) | a);
+    std::vector<uint8_t> file = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::vector<uint8_t> ihdr;
+    put_be32(ihdr, (uint32_t)width_), put_be32(ihdr, (uint32_t)height_);
+    ihdr.insert(ihdr.end(), {8, 2, 0, 0, 0}); // 8 bits, colour type 2 (RGB), deflate, adaptive filtering, no interlace
+    put_chunk(file, "IHDR", ihdr);
+    put_chunk(file, "IDAT", z);
+    put_chunk(file, "IEND", {});
+    FILE *f = std::fopen(filename.c_str(), "wb");
+    if (!f) throw std::runtime_error("write_png: cannot open " + filename);
+    const bool ok = std::fwrite(file.data(), 1, file.size(), f) == file.size();
+    if (std::fclose(f) != 0 || !ok) throw std::runtime_error("write_png: write failed: " + filename);
+}
+
 void AccumulationBuffer::merge_tile(const Tile &tile, const AccumulationBuffer &src) {
     if (tile.width() != src.width() || tile.height() != src.height()) throw std::runtime_error("merge_tile: tile and source sizes differ");
     if (tile.end_row > height_ || tile.end_column > width_) throw std::runtime_error("merge_tile: tile outside the buffer");
