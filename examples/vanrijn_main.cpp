@@ -104,7 +104,7 @@ int main(int argc, char **argv) {
 
         const uint32_t passes_wanted = parameters.passes ? parameters.passes : (parameters.time > 0.0 ? 0xffffffffu : 1u);
         uint64_t rays = 0;
-        double device_ms = 0.0;
+        double device_ms = 0.0, call_s = 0.0, merge_s = 0.0;
         uint32_t pass = 0;
         const auto t0 = std::chrono::steady_clock::now();
         for (; pass < passes_wanted; pass++) {
@@ -117,8 +117,12 @@ int main(int argc, char **argv) {
                 o.spp = parameters.spp, o.max_depth = parameters.depth, o.seed = parameters.seed;
                 o.sample_offset = (uint64_t)pass * parameters.spp;
                 o.stats = &stats;
+                const auto t_call = std::chrono::steady_clock::now();
                 AccumulationBuffer rendered_tile = partial_render_scene(scene, tile, image_height, image_width, o);
+                call_s += seconds_since(t_call);
+                const auto t_merge = std::chrono::steady_clock::now();
                 rendered_image.merge_tile(tile, rendered_tile); // main.rs:216
+                merge_s += seconds_since(t_merge);
                 rays += stats.primary_rays + stats.bounce_rays + stats.shadow_rays;
                 device_ms += stats.device_ms;
             }
@@ -129,6 +133,7 @@ int main(int argc, char **argv) {
         std::printf("%u passes x %u spp at %zux%zu in %.3f s: %.1f Mrays/s wall, %.1f Mrays/s on the device, %.2f spp/s\n", pass,
                     parameters.spp, image_width, image_height, wall, rays / wall / 1e6, device_ms > 0 ? rays / device_ms / 1e3 : 0.0,
                     pass * (double)parameters.spp / wall);
+        std::printf("host time: partial_render_scene %.3f s (device %.3f s), merge_tile %.3f s\n", call_s, device_ms / 1e3, merge_s);
         if (!parameters.output_file.empty()) {
             rendered_image.to_image_rgb_u8().write_png(parameters.output_file); // main.rs:222-225
             std::printf("wrote %s\n", parameters.output_file.c_str());

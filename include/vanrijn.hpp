@@ -27,7 +27,9 @@
 #include <cstdlib>
 #include <memory>
 #include <stdexcept>
+#include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "vanrijn_cuda.h"
@@ -191,6 +193,41 @@ class TileIterator {
     size_t tile_size_, total_height_, total_width_, current_column_ = 0, current_row_ = 0;
 };
 
+// Allocator of the big host arrays that cross PCIe (the flattened scene, AccumulationBuffer): page-locked memory from
+// the library's pool (vrj_alloc_host) when a CUDA device is present, so copies run at PCIe speed and are not staged;
+// ordinary memory otherwise.  Elements are default-initialised (no zero fill) unless a value is given.
+template <typename T>
+struct UploadAllocator {
+    using value_type = T;
+    UploadAllocator() = default;
+    template <typename U>
+    UploadAllocator(const UploadAllocator<U> &) {}
+    T *allocate(size_t n) {
+        const size_t bytes = n * sizeof(T) + 64; // 64-byte prefix records which allocator owns the block
+        static const bool pageable_only = std::getenv("VRJ_PAGEABLE_ARRAYS") != nullptr; // experiments only
+        char *p = pageable_only ? nullptr : static_cast<char *>(vrj_alloc_host(bytes));
+        const bool pinned = p != nullptr;
+        if (!p) p = static_cast<char *>(::operator new(bytes));
+        p[0] = pinned ? 1 : 0;
+        return reinterpret_cast<T *>(p + 64);
+    }
+    void deallocate(T *q, size_t) {
+        char *p = reinterpret_cast<char *>(q) - 64;
+        if (p[0]) vrj_free_host(p);
+        else ::operator delete(p);
+    }
+    template <typename U>
+    void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; } // vector(n): no zero fill
+    template <typename U, typename... Args>
+    void construct(U *p, Args &&...args) { ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...); }
+    template <typename U>
+    bool operator==(const UploadAllocator<U> &) const { return true; }
+    template <typename U>
+    bool operator!=(const UploadAllocator<U> &) const { return false; }
+};
+template <typename T>
+using UploadVector = std::vector<T, UploadAllocator<T>>;
+
 // image.rs:7-66 -- 8-bit RGB image, row-major, 3 bytes per pixel
 class ImageRgbU8 {
   public:
@@ -220,10 +257,13 @@ class AccumulationBuffer {
     size_t height() const { return height_; }
     // accumulation_buffer.rs:62-85 -- touches only colour and weight of the destination
     void merge_tile(const Tile &tile, const AccumulationBuffer &src);
-    std::vector<double> colour, colour_sum, colour_bias; // 3 per pixel (XYZ)
-    std::vector<double> weight, weight_bias;             // 1 per pixel
+    UploadVector<double> colour, colour_sum, colour_bias; // 3 per pixel (XYZ)
+    UploadVector<double> weight, weight_bias;             // 1 per pixel
 
   private:
+    friend AccumulationBuffer partial_render_scene(const Scene &, Tile, size_t, size_t, const struct RenderOptions &);
+    struct Uninitialized {};
+    AccumulationBuffer(size_t width, size_t height, Uninitialized); // arrays about to be overwritten by a render
     size_t width_, height_;
 };
 
@@ -256,36 +296,6 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &options);
 
 // Collects the flattened SoA arrays and exposes them as a VrjSceneDesc.
-// Allocator of the builder's big arrays: page-locked host memory (vrj_alloc_host) when a CUDA device is present, so
-// that vrj_scene_create copies them to the device directly at PCIe speed; ordinary memory otherwise.
-template <typename T>
-struct UploadAllocator {
-    using value_type = T;
-    UploadAllocator() = default;
-    template <typename U>
-    UploadAllocator(const UploadAllocator<U> &) {}
-    T *allocate(size_t n) {
-        const size_t bytes = n * sizeof(T) + 64; // 64-byte prefix records which allocator owns the block
-        static const bool pageable_only = std::getenv("VRJ_PAGEABLE_ARRAYS") != nullptr; // experiments only
-        char *p = pageable_only ? nullptr : static_cast<char *>(vrj_alloc_host(bytes));
-        const bool pinned = p != nullptr;
-        if (!p) p = static_cast<char *>(::operator new(bytes));
-        p[0] = pinned ? 1 : 0;
-        return reinterpret_cast<T *>(p + 64);
-    }
-    void deallocate(T *q, size_t) {
-        char *p = reinterpret_cast<char *>(q) - 64;
-        if (p[0]) vrj_free_host(p);
-        else ::operator delete(p);
-    }
-    template <typename U>
-    bool operator==(const UploadAllocator<U> &) const { return true; }
-    template <typename U>
-    bool operator!=(const UploadAllocator<U> &) const { return false; }
-};
-template <typename T>
-using UploadVector = std::vector<T, UploadAllocator<T>>;
-
 class FlatSceneBuilder {
   public:
     uint32_t add_spectrum(const Spectrum &s);

@@ -454,6 +454,10 @@ AccumulationBuffer::AccumulationBuffer(size_t width, size_t height)
     : colour(3 * width * height, 0.0), colour_sum(3 * width * height, 0.0), colour_bias(3 * width * height, 0.0),
       weight(width * height, 0.0), weight_bias(width * height, 0.0), width_(width), height_(height) {}
 
+AccumulationBuffer::AccumulationBuffer(size_t width, size_t height, Uninitialized)
+    : colour(3 * width * height), colour_sum(3 * width * height), colour_bias(3 * width * height), weight(width * height),
+      weight_bias(width * height), width_(width), height_(height) {}
+
 ImageRgbU8 AccumulationBuffer::to_image_rgb_u8(int device) const {
     ImageRgbU8 image(width_, height_);
     if (vrj_tone_map(device, VRJ_MEM_HOST, VRJ_TONEMAP_XYZ, colour.data(), width_ * height_, image.pixel_data().data()) != VRJ_OK)
@@ -580,7 +584,9 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
 }
 
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &o) {
-    AccumulationBuffer buffer(tile.width(), tile.height());
+    // every element is overwritten by the copies out of vrj_render_tile (which returns early, writing nothing, for 0 spp)
+    AccumulationBuffer buffer = o.spp ? AccumulationBuffer(tile.width(), tile.height(), AccumulationBuffer::Uninitialized{})
+                                      : AccumulationBuffer(tile.width(), tile.height());
     VrjRenderParams p{};
     p.spp = o.spp, p.max_depth = o.max_depth, p.sample_offset = o.sample_offset, p.seed = o.seed;
     p.integrator = o.integrator, p.bvh_filter = o.bvh_filter, p.bias = 0.0000001, p.sample_stride = o.sample_stride;

@@ -321,6 +321,13 @@ struct Stager {
 
 std::mutex g_pool_mutex;
 std::vector<std::pair<int, Scratch *>> g_pool;
+struct HostBlock {
+    void *p;
+    size_t bytes;
+};
+std::mutex g_host_pool_mutex;
+std::vector<HostBlock> g_host_pool_free;
+std::unordered_map<void *, size_t> g_host_pool_live;
 
 Scratch *acquire_scratch(VrjScene *sc) {
     std::lock_guard<std::mutex> g(g_pool_mutex);
@@ -789,19 +796,58 @@ void vrj_release_scratch(void) {
         g_pool.clear();
     }
     vrj_pool_trim();
+    std::vector<HostBlock> victims;
+    {
+        std::lock_guard<std::mutex> g(g_host_pool_mutex);
+        victims.swap(g_host_pool_free);
+    }
+    for (const HostBlock &b : victims) cudaFreeHost(b.p);
 }
 
+// Page-locked host memory is pooled like device memory: cudaMallocHost / cudaFreeHost of an AccumulationBuffer's
+// 182 MB cost tens of milliseconds, more than rendering into it.  vrj_release_scratch() empties the pool.
 void *vrj_alloc_host(uint64_t bytes) {
+    const size_t want = (std::max<size_t>(bytes, 1) + 4095) & ~size_t(4095);
+    {
+        std::lock_guard<std::mutex> g(g_host_pool_mutex);
+        size_t best = g_host_pool_free.size();
+        for (size_t i = 0; i < g_host_pool_free.size(); i++) {
+            const HostBlock &b = g_host_pool_free[i];
+            if (b.bytes >= want && b.bytes <= 2 * want + (size_t(1) << 20) && (best == g_host_pool_free.size() || b.bytes < g_host_pool_free[best].bytes))
+                best = i;
+        }
+        if (best != g_host_pool_free.size()) {
+            HostBlock b = g_host_pool_free[best];
+            g_host_pool_free.erase(g_host_pool_free.begin() + best);
+            g_host_pool_live[b.p] = b.bytes;
+            return b.p;
+        }
+    }
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    if (cudaMallocHost(&p, want) != cudaSuccess) {
         g_error = "cudaMallocHost failed";
         cudaGetLastError();
         return nullptr;
     }
+    std::lock_guard<std::mutex> g(g_host_pool_mutex);
+    g_host_pool_live[p] = want;
     return p;
 }
 void vrj_free_host(void *p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    bool keep = false;
+    {
+        std::lock_guard<std::mutex> g(g_host_pool_mutex);
+        auto it = g_host_pool_live.find(p);
+        if (it != g_host_pool_live.end()) {
+            size_t cached = 0;
+            for (const HostBlock &b : g_host_pool_free) cached += b.bytes;
+            keep = cached + it->second <= (size_t(8) << 30) && g_host_pool_free.size() < 64;
+            if (keep) g_host_pool_free.push_back(HostBlock{p, it->second});
+            g_host_pool_live.erase(it);
+        }
+    }
+    if (!keep) cudaFreeHost(p);
 }
 
 VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t height, uint64_t width,
