@@ -30,7 +30,7 @@
 
 namespace vrj_build {
 
-constexpr int SMALL = 1024;     // segments up to this long are finished inside one CTA
+constexpr int SMALL = 1024;     // segments up to this long are finished inside one CTA (rank sort: work grows with SMALL)
 constexpr int CHUNK = 2048;     // elements per CTA in the global passes
 constexpr int CHUNK_THREADS = 256;
 constexpr int SCAN_TILE = 2048; // histogram entries per CTA in the scan
@@ -314,7 +314,7 @@ struct SmallSeg {
     uint32_t me;         // node index; len == 0 marks a dead entry
 };
 
-__global__ void __launch_bounds__(SMALL) k_small_subtrees(const Segment *__restrict__ segs, uint32_t *__restrict__ order,
+__global__ void __launch_bounds__(SMALL, 2048 / SMALL) k_small_subtrees(const Segment *__restrict__ segs, uint32_t *__restrict__ order,
                                                            const double *__restrict__ lo, const double *__restrict__ hi,
                                                            const double *__restrict__ centre, double *__restrict__ node_min,
                                                            double *__restrict__ node_max, int32_t *__restrict__ node_child) {
