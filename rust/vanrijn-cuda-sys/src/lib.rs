@@ -96,6 +96,17 @@ pub struct VrjAccumOut {
     pub srgb8: *mut u8,
 }
 
+/// Timing / shape of a device BVH build (`vrj_bvh_build`).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct VrjBvhBuildStats {
+    pub device_ms: f64,
+    pub global_levels: u32,
+    pub radix_passes: u32,
+    pub small_subtrees: u32,
+    pub pad: u32,
+}
+
 extern "C" {
     pub fn vrj_last_error() -> *const c_char;
     pub fn vrj_abi_version() -> i32;
@@ -103,6 +114,7 @@ extern "C" {
     pub fn vrj_scene_create(desc: *const VrjSceneDesc, device: i32, out: *mut *mut VrjScene) -> i32;
     pub fn vrj_scene_destroy(scene: *mut VrjScene);
     pub fn vrj_scene_device_bytes(scene: *const VrjScene) -> u64;
+    pub fn vrj_scene_upload_bytes(scene: *const VrjScene) -> u64;
     pub fn vrj_release_scratch();
     pub fn vrj_alloc_host(bytes: u64) -> *mut c_void;
     pub fn vrj_free_host(p: *mut c_void);
@@ -115,6 +127,9 @@ extern "C" {
     pub fn vrj_render_sharded(scene: *mut VrjMultiScene, tile: *const VrjTile, height: u64, width: u64,
                               params: *const VrjRenderParams, out: *mut VrjAccumOut) -> i32;
     pub fn vrj_tone_map(device: i32, memory: u32, source: u32, colour: *const f64, n_pixels: u64, rgb8: *mut u8) -> i32;
+    /// `BoundingVolumeHierarchy::build` (src/raycasting/bounding_volume_hierarchy.rs:38-75) on the device: the same tree.
+    pub fn vrj_bvh_build(device: i32, n_triangles: u64, vertices: *const f64, order: *mut u32, node_min: *mut f64,
+                         node_max: *mut f64, node_child: *mut i32, depth: *mut u32, stats: *mut VrjBvhBuildStats) -> i32;
     pub fn vrj_trace_rays(scene: *const VrjScene, n: u64, origins: *const f64, directions: *const f64, bvh_filter: u32,
                           object_id: *mut i32, prim_id: *mut i32, t: *mut f64, stats: *mut VrjStats) -> i32;
 }
