@@ -31,7 +31,8 @@ def test_struct_layouts_match_the_header(tmp_path):
     pairs = [("VrjSpectrum", capi.Spectrum), ("VrjMaterial", capi.Material), ("VrjSphere", capi.Sphere),
              ("VrjPlane", capi.Plane), ("VrjBvh", capi.Bvh), ("VrjItem", capi.Item), ("VrjSceneDesc", capi.SceneDesc),
              ("VrjTile", capi.Tile), ("VrjSpectrumData", capi.SpectrumData), ("VrjLight", capi.Light),
-             ("VrjRenderParams", capi.RenderParams), ("VrjStats", capi.Stats), ("VrjAccumOut", capi.AccumOut)]
+             ("VrjRenderParams", capi.RenderParams), ("VrjStats", capi.Stats), ("VrjAccumOut", capi.AccumOut),
+             ("VrjBvhBuildStats", capi.BvhBuildStats)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vanrijn_cuda.h"', 'int main(void){']
     for cname, ct in pairs:
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
@@ -227,7 +228,8 @@ def test_array_path_and_per_triangle_object_path_flatten_identically():
     as mesh.rs:74-88 + bounding_volume_hierarchy.rs:49-51 do it) must flatten to the same scene, for a mesh given as
     arrays and for one read from OBJ text."""
     for spec in (scenes.tiny_mesh_scene(subdivisions=3), scenes.scene_main(subdivisions=2, obj=True)):
-        a, b = V.build_scene(spec).desc(), V.build_scene(spec, per_triangle_objects=True).desc()
+        sa, sb = V.build_scene(spec), V.build_scene(spec, per_triangle_objects=True)  # own the arrays desc() points into
+        a, b = sa.desc(), sb.desc()
         assert int(a.n_triangles) == int(b.n_triangles) > 0 and int(a.n_nodes) == int(b.n_nodes) > 0
         n, nn = int(a.n_triangles), int(a.n_nodes)
         arr = lambda p, count: np.ctypeslib.as_array(p, shape=(count,))
