@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--spp", type=int, default=32, help="samples per pixel per step per GPU (one wavefront batch up to 32 at 1080p)")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
-    ap.add_argument("--filter", default="f32", choices=["f32", "f64"], help="precision of the conservative BVH box filter")
+    ap.add_argument("--filter", default="f32", choices=["f32", "f64", "f32x4"],
+                    help="conservative BVH box filter: 2-wide f32, 2-wide f64, or 4-wide f32 nodes (results identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -175,7 +176,7 @@ def main():
 
     W, H, spp = args.width, args.height, args.spp
     npix = W * H
-    bvh_filter = capi.FILTER_F64 if args.filter == "f64" else capi.FILTER_F32
+    bvh_filter = {"f64": capi.FILTER_F64, "f32x4": capi.FILTER_F32X4}.get(args.filter, capi.FILTER_F32)
     hs = V.build_scene(spec)
     hs.device_scene(local)
     scene_bytes = hs.device_bytes(local)

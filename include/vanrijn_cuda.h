@@ -60,7 +60,9 @@ enum { VRJ_MAT_LAMBERTIAN = 0, VRJ_MAT_PHONG = 1, VRJ_MAT_REFLECTIVE = 2, VRJ_MA
 enum { VRJ_INTEGRATOR_SIMPLE_RANDOM = 0, VRJ_INTEGRATOR_WHITTED = 1 };
 /* top-level traversal items, in Scene.objects order (sampler.rs:12-19: first object wins ties) */
 enum { VRJ_ITEM_SPHERE = 0, VRJ_ITEM_PLANE = 1, VRJ_ITEM_TRIANGLE = 2, VRJ_ITEM_BVH = 3 };
-enum { VRJ_FILTER_F32 = 0, VRJ_FILTER_F64 = 1 };
+/* precision / shape of the conservative box culling in front of the exact triangle test; results are identical in all modes.
+ * F32: 2-wide nodes, f32 boxes; F64: 2-wide, f64 boxes (cross-check); F32X4: 4-wide nodes (two reference levels per fetch) */
+enum { VRJ_FILTER_F32 = 0, VRJ_FILTER_F64 = 1, VRJ_FILTER_F32X4 = 2 };
 enum { VRJ_MEM_HOST = 0, VRJ_MEM_DEVICE = 1 };
 
 /* colour/spectrum.rs:6-10 -- uniform samples over [shortest, longest] */

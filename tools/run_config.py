@@ -17,7 +17,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--filter", default="f32")
 ap.add_argument("--device-builder", action="store_true", help="BoundingVolumeHierarchy::build on the GPU (vrj_bvh_build)")
 a = ap.parse_args()
-kw = dict(seed=1, bvh_filter=capi.FILTER_F64 if a.filter == "f64" else capi.FILTER_F32)
+kw = dict(seed=1, bvh_filter={"f64": capi.FILTER_F64, "f32x4": capi.FILTER_F32X4}.get(a.filter, capi.FILTER_F32))
 t0 = time.time()
 if a.config == "C2":
     spec, lights, amb = scenes.scene_direct(subdivisions=6, obj=True)

@@ -406,7 +406,7 @@ int persistent_grid(const VrjScene *sc, K kernel) {
 }
 
 template <typename NT, bool COUNT>
-VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, uint64_t *launches) {
+VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, bool quad, uint64_t *launches) {
     // launch sequence: G T S_0 [X_k T_k S_k]*, k = 1..levels (X = k_tail, a no-op until the queue is short);
     // SimpleRandom needs max_depth levels, Whitted one more (its limit-0 level still shades and traces);
     // the final S only finishes paths.
@@ -420,7 +420,7 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 4 + 1) * sizeof(uint32_t), s->stream));
     unsigned long long *stats = s->stats.as<unsigned long long>();
     double2 *photons = s->photons.as<double2>();
-    const int g_gen = persistent_grid(sc, k_raygen<COUNT>), g_t = persistent_grid(sc, k_trace<NT, COUNT>);
+    const int g_gen = persistent_grid(sc, k_raygen<COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT>) : persistent_grid(sc, k_trace<NT, COUNT>);
     const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, COUNT, false, true>);
     const int g_s = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, COUNT, false, false>);
     // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
@@ -434,7 +434,8 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     (*launches)++;
     VRJ_CUDA(s->mark(4));
     if (has_bvh) {
-        k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
+        if (quad) k_trace4<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
+        else k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
         (*launches)++;
         VRJ_CUDA(s->mark(0));
     }
@@ -456,7 +457,8 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
             VRJ_CUDA(s->mark(5));
         }
         if (has_bvh) {
-            k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            if (quad) k_trace4<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            else k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
             (*launches)++;
             VRJ_CUDA(s->mark(1));
         }
@@ -586,6 +588,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     const Section s_it = reserve_section(d->n_items * sizeof(ItemDev)), s_an = reserve_section(d->n_items * 4), s_bv = reserve_section(d->n_items * 4);
     const size_t small_bytes = std::max<size_t>(cursor, 256);
     const Section s_n32 = reserve_section(n_wide * 64), s_n64 = reserve_section(n_wide * 112);
+    const Section s_n4 = reserve_section(n_wide * 128); // upper bound: at most every internal node becomes a 4-wide node
     const Section s_tp = reserve_section((size_t)d->n_triangles * 96), s_tn = reserve_section((size_t)d->n_triangles * 96);
     const size_t arena_bytes = std::max<size_t>(cursor, 256);
 
@@ -627,6 +630,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         if (plan[b].build) any_build = true, largest_build = std::max<uint64_t>(largest_build, d->bvhs[b].n_triangles);
     }
     const size_t r_flags = reserve_raw(largest_bvh_nodes * 4), r_scan = reserve_raw((largest_bvh_nodes / 2048 + 2) * 4);
+    const size_t r_parent = reserve_raw(largest_bvh_nodes * 4), r_isquad = reserve_raw(largest_bvh_nodes * 4);
     const size_t r_bv = reserve_raw(largest_build * 72), r_bo = reserve_raw(largest_build * 4);
     DeviceBuffer raw;
     VRJ_TRY_CUDA(raw.alloc(std::max<size_t>(rcur, 256)));
@@ -699,6 +703,17 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
             return ss;
         }
         k_wide_nodes<<<grid, 256, 0, stream>>>(bn, flags, reinterpret_cast<float *>(base + s_n32.offset), reinterpret_cast<double *>(base + s_n64.offset));
+        // the 4-wide form of the same tree (VRJ_FILTER_F32X4); its nodes are numbered from the same base (there are fewer of them)
+        uint32_t *parent = reinterpret_cast<uint32_t *>(rb + r_parent), *is_quad = reinterpret_cast<uint32_t *>(rb + r_isquad);
+        k_parents<<<grid, 256, 0, stream>>>(bn, parent);
+        k_quad_flags<<<grid, 256, 0, stream>>>(bn, parent, is_quad);
+        VRJ_TRY_CUDA(cudaMemcpyAsync(flags, is_quad, (size_t)bn.n_nodes * 4, cudaMemcpyDeviceToDevice, stream));
+        ss = vrj_build::exclusive_scan_u32(flags, bn.n_nodes, reinterpret_cast<uint32_t *>(rb + r_scan), stream);
+        if (ss != VRJ_OK) {
+            delete sc;
+            return ss;
+        }
+        k_quad_nodes<<<grid, 256, 0, stream>>>(bn, flags, is_quad, reinterpret_cast<float *>(base + s_n4.offset));
     }
     VRJ_TRY_CUDA(cudaGetLastError());
     VRJ_TRY_CUDA(cudaStreamSynchronize(stream)); // built_root is read below
@@ -749,6 +764,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     sc->upload_bytes = stager.copied + small_bytes; // what crossed PCIe: the caller's arrays + the small tables
     sc->dev.nodes32 = reinterpret_cast<const float4 *>(base + s_n32.offset);
     sc->dev.nodes64 = reinterpret_cast<const double2 *>(base + s_n64.offset);
+    sc->dev.nodes4 = reinterpret_cast<const float4 *>(base + s_n4.offset);
     sc->dev.tri_pos = reinterpret_cast<const double2 *>(base + s_tp.offset);
     sc->dev.tri_nrm = reinterpret_cast<const double2 *>(base + s_tn.offset);
     sc->dev.spheres = reinterpret_cast<const SphereDev *>(base + s_sph.offset);
@@ -761,9 +777,10 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     sc->dev.bvh_items = reinterpret_cast<const uint32_t *>(base + s_bv.offset);
     sc->dev.n_items = n_items, sc->dev.n_analytic = n_analytic, sc->dev.n_bvh_items = n_bvh_items;
     for (int k = 0; k < 3; k++) sc->dev.cam[k] = d->camera_location[k];
-    sc->dev.refill_threshold = 16, sc->dev.leaf_threshold = 2, sc->dev.node_batch = 4, sc->dev.max_iters = 64;
-    if (const char *tune = std::getenv("VRJ_TUNE")) // experiments only: "refill,leaf,node_batch,max_iters,tail_max"
-        std::sscanf(tune, "%d,%d,%d,%d,%u", &sc->dev.refill_threshold, &sc->dev.leaf_threshold, &sc->dev.node_batch, &sc->dev.max_iters, &sc->tail_max);
+    sc->dev.refill_threshold = 16, sc->dev.leaf_threshold = 2, sc->dev.node_batch = 4, sc->dev.max_iters = 64, sc->dev.node_batch4 = 2;
+    if (const char *tune = std::getenv("VRJ_TUNE")) // experiments only: "refill,leaf,node_batch,max_iters,tail_max,node_batch4"
+        std::sscanf(tune, "%d,%d,%d,%d,%u,%d", &sc->dev.refill_threshold, &sc->dev.leaf_threshold, &sc->dev.node_batch, &sc->dev.max_iters, &sc->tail_max,
+                    &sc->dev.node_batch4);
     if (std::getenv("VRJ_TIMING")) {
         auto t_end = std::chrono::steady_clock::now();
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -858,7 +875,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         return fail(VRJ_ERR_INVALID_ARGUMENT, "tile outside the image");
     if (width * height > 0xffffffffull) return fail(VRJ_ERR_UNSUPPORTED, "image larger than 2^32 pixels");
     if (p->integrator > VRJ_INTEGRATOR_WHITTED) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown integrator");
-    if (p->bvh_filter > VRJ_FILTER_F64) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
+    if (p->bvh_filter > VRJ_FILTER_F32X4) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
     if (p->max_depth > 65535) return fail(VRJ_ERR_INVALID_ARGUMENT, "max_depth exceeds u16 (RECURSION_LIMIT is a u16)");
     if (p->n_lights && !p->lights) return fail(VRJ_ERR_INVALID_ARGUMENT, "lights is NULL");
     size_t n_light_samples = 0;
@@ -941,6 +958,8 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     rc.lights = s->lights.as<LightDev>();
     rc.light_samples = s->light_samples.as<double>();
 
+    // F32X4: the staged rays walk the 4-wide tree; inline any-hit queries (Whitted shadow rays, k_tail) use the 2-wide f32 tree
+    const bool quad = p->bvh_filter == VRJ_FILTER_F32X4;
     uint64_t launches = 0;
     s->n_marks = 0;
     VRJ_CUDA(cudaEventRecord(s->ev0, s->stream));
@@ -948,11 +967,11 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         rc.batch_samples = std::min(batch, p->spp - done);
         rc.first_sample = p->sample_offset + (uint64_t)done * rc.sample_stride;
         if (p->count_traversal) {
-            st = p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, true>(scene, s, rc, whitted, &launches)
-                                                 : run_batch<float, true>(scene, s, rc, whitted, &launches);
+            st = p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, true>(scene, s, rc, whitted, false, &launches)
+                                                 : run_batch<float, true>(scene, s, rc, whitted, quad, &launches);
         } else {
-            st = p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, false>(scene, s, rc, whitted, &launches)
-                                                 : run_batch<float, false>(scene, s, rc, whitted, &launches);
+            st = p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, false>(scene, s, rc, whitted, false, &launches)
+                                                 : run_batch<float, false>(scene, s, rc, whitted, quad, &launches);
         }
         if (st != VRJ_OK) return st;
         if (out->photons) {
@@ -1023,7 +1042,7 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     VrjScene *scene = const_cast<VrjScene *>(scene_c);
     if (!scene || (n && (!origins || !directions || !object_id || !prim_id || !t)))
         return fail(VRJ_ERR_INVALID_ARGUMENT, "NULL argument");
-    if (bvh_filter > VRJ_FILTER_F64) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
+    if (bvh_filter > VRJ_FILTER_F32X4) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
     if (stats) std::memset(stats, 0, sizeof(VrjStats));
     if (n == 0) return VRJ_OK;
     if (n > 0xfffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "more than 2^32 rays in one call");
@@ -1065,6 +1084,8 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
         launches++;
         if (bvh_filter == VRJ_FILTER_F64)
             k_trace<double, true><<<persistent_grid(scene, k_trace<double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
+        else if (bvh_filter == VRJ_FILTER_F32X4)
+            k_trace4<true><<<persistent_grid(scene, k_trace4<true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
         else
             k_trace<float, true><<<persistent_grid(scene, k_trace<float, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
     }

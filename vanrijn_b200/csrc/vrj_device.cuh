@@ -6,6 +6,29 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+// Experiment knobs (code size vs call overhead): which helpers are real functions instead of inlined copies.
+#ifndef VRJ_OUTLINE
+#define VRJ_OUTLINE 1
+#endif
+#define VRJ_FN_NORM ((VRJ_OUTLINE) & 1)
+#define VRJ_FN_PHILOX ((VRJ_OUTLINE) & 2)
+#define VRJ_FN_PRIM ((VRJ_OUTLINE) & 4)
+#if VRJ_FN_NORM
+#define VRJ_INL_NORM __noinline__
+#else
+#define VRJ_INL_NORM __forceinline__
+#endif
+#if VRJ_FN_PHILOX
+#define VRJ_INL_PHILOX __noinline__
+#else
+#define VRJ_INL_PHILOX __forceinline__
+#endif
+#if VRJ_FN_PRIM
+#define VRJ_INL_PRIM __noinline__
+#else
+#define VRJ_INL_PRIM __forceinline__
+#endif
+
 namespace vrj {
 
 // ------------------------------------------------------------------------------------------
@@ -25,7 +48,7 @@ __device__ __forceinline__ D3 cross(D3 a, D3 b) {
 }
 __device__ __forceinline__ double norm(D3 a) { return sqrt(dot(a, a)); }
 // vec3.rs:103-110: multiply by 1/norm
-__device__ __forceinline__ D3 normalize(D3 a) {
+__device__ VRJ_INL_NORM D3 normalize(D3 a) {
     double inv = 1.0 / norm(a);
     return d3(a.x * inv, a.y * inv, a.z * inv);
 }
@@ -87,7 +110,7 @@ struct Rng {
         ordinal = first_ordinal;
         cached_block = 0xffffffffu;
     }
-    __device__ __forceinline__ void block(uint32_t b) {
+    __device__ VRJ_INL_PHILOX void block(uint32_t b) {
         uint32_t c0 = b, c1 = pixel, c2 = s0, c3 = s1, ka = k0, kb = k1;
 #pragma unroll
         for (int r = 0; r < 10; r++) {
@@ -213,7 +236,7 @@ __device__ __forceinline__ TriRay tri_ray(D3 o, D3 d) {
 __device__ __forceinline__ double edge_fn(D3 a, D3 b) { return a.x * b.y - b.x * a.y; }
 
 // triangle.rs:35-72: returns true and the barycentrics + distance when the ray hits
-__device__ __forceinline__ bool triangle_test(const TriRay &r, D3 v0, D3 v1, D3 v2, double &distance, double &b0,
+__device__ VRJ_INL_PRIM bool triangle_test(const TriRay &r, D3 v0, D3 v1, D3 v2, double &distance, double &b0,
                                               double &b1, double &b2, D3 &location) {
     D3 p0 = permute(v0 - r.o, r.perm), p1 = permute(v1 - r.o, r.perm), p2 = permute(v2 - r.o, r.perm);
     D3 t0 = d3(p0.x + r.sx * p0.z, p0.y + r.sy * p0.z, p0.z);
@@ -238,7 +261,7 @@ struct SphereDev {
     uint32_t material, pad;
 };
 // sphere.rs:39-75 (distance only)
-__device__ __forceinline__ bool sphere_test(const SphereDev &s, D3 o, D3 d, double &distance) {
+__device__ VRJ_INL_PRIM bool sphere_test(const SphereDev &s, D3 o, D3 d, double &distance) {
     D3 c = d3(s.cx, s.cy, s.cz);
     double a = ((0.0 + d.x * d.x) + d.y * d.y) + d.z * d.z;
     double b = ((0.0 + (o.x * d.x - c.x * d.x) * 2.0) + (o.y * d.y - c.y * d.y) * 2.0) + (o.z * d.z - c.z * d.z) * 2.0;

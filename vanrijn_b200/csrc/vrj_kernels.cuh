@@ -26,6 +26,9 @@
 #ifndef VRJ_TRACE_MINB
 #define VRJ_TRACE_MINB 6
 #endif
+#ifndef VRJ_TRACE4_MINB
+#define VRJ_TRACE4_MINB 5
+#endif
 
 namespace vrj {
 
@@ -212,6 +215,24 @@ __global__ void __launch_bounds__(128, VRJ_TRACE_MINB) k_trace(DevScene sc, Path
     ListHitSink sink{tb};
     TraceCounters tc = {0, 0};
     trace_persistent<NT, COUNT>(sc, n, work, source, sink, tc);
+    if (COUNT) {
+        LocalStats ls;
+        ls.clear();
+        ls.v[ST_NODES] = tc.node_visits, ls.v[ST_TRIS] = tc.tri_tests;
+        ls.flush(stats);
+    }
+}
+
+// the same launch over the 4-wide form of the tree (VRJ_FILTER_F32X4)
+template <bool COUNT>
+__global__ void __launch_bounds__(128, VRJ_TRACE4_MINB) k_trace4(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
+                                                                 uint32_t *work, unsigned long long *stats, const uint32_t *tail_done) {
+    if (tail_done && *tail_done) return;
+    const uint32_t n = *list_count;
+    ListRaySource source{q, tb};
+    ListHitSink sink{tb};
+    TraceCounters tc = {0, 0};
+    trace_persistent_quad<COUNT>(sc, n, work, source, sink, tc);
     if (COUNT) {
         LocalStats ls;
         ls.clear();

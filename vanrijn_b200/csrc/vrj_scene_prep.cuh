@@ -129,4 +129,80 @@ __global__ void k_wide_nodes(BvhNodes b, const uint32_t *__restrict__ rank, floa
     g[13] = 0.0;
 }
 
+// ---- 4-wide nodes (VRJ_FILTER_F32X4): every second level of the reference tree is folded away, so a node carries
+// the f32 boxes (rounded outward) of its up to four grandchildren and a ray makes half as many dependent fetches.
+// 128-byte records: 24 floats [child][lo.x hi.x lo.y hi.y lo.z hi.z], 4 child refs (>= 0: 4-wide node, < 0: ~triangle,
+// empty slots have an inverted box and are never entered), 16 bytes of padding.  Leaves stay <= 1 triangle; the
+// leaf order (= tie-breaking order) is the reference's.
+constexpr uint32_t kNoParent = 0xffffffffu;
+__global__ void k_parents(BvhNodes b, uint32_t *__restrict__ parent) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_nodes) return;
+    if (i == 0) parent[0] = kNoParent; // the root is the BVH's first node
+    const int64_t me = (int64_t)b.first_node + i;
+    const int32_t l = b.node_child[2 * me], r = b.node_child[2 * me + 1];
+    if (l >= 0) {
+        parent[(int64_t)l + b.child_offset - b.first_node] = i;
+        parent[(int64_t)r + b.child_offset - b.first_node] = i;
+    }
+}
+// flags[i] = 1 for internal nodes at even depth: they become 4-wide nodes
+__global__ void k_quad_flags(BvhNodes b, const uint32_t *__restrict__ parent, uint32_t *__restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_nodes) return;
+    uint32_t depth = 0;
+    for (uint32_t p = parent[i]; p != kNoParent && depth < 64; p = parent[p]) depth++;
+    const bool internal = b.node_child[2 * (size_t)(b.first_node + i)] >= 0;
+    flags[i] = (internal && (depth & 1u) == 0u) ? 1u : 0u;
+}
+__device__ __forceinline__ void put_quad_slot(const BvhNodes &b, const uint32_t *__restrict__ rank4, float *__restrict__ f, int slot,
+                                              int64_t node /* absolute, or -1 */) {
+    double lo[3], hi[3];
+    int32_t ref = -1;
+    bool empty = node < 0;
+    if (!empty) {
+        const int32_t l = b.node_child[2 * node], r = b.node_child[2 * node + 1];
+        if (l >= 0) ref = (int32_t)(b.wide_base + rank4[node - b.first_node]);
+        else if (r == 0) empty = true;
+        else ref = ~((~l) + b.triangle_offset);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        lo[k] = empty ? CUDART_INF : b.node_min[4 * node + k];
+        hi[k] = empty ? -CUDART_INF : b.node_max[4 * node + k];
+        f[slot * 6 + 2 * k] = __double2float_rd(lo[k]), f[slot * 6 + 2 * k + 1] = __double2float_ru(hi[k]);
+    }
+    f[24 + slot] = __int_as_float(ref);
+}
+// `b.wide_base` is the index of this BVH's first 4-wide node; rank4 = exclusive scan of k_quad_flags
+__global__ void k_quad_nodes(BvhNodes b, const uint32_t *__restrict__ flags_scanned, const uint32_t *__restrict__ is_quad,
+                             float *__restrict__ nodes4) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_nodes) return;
+    const int64_t me = (int64_t)b.first_node + i;
+    const int32_t l = b.node_child[2 * me], r = b.node_child[2 * me + 1];
+    int64_t slots[4] = {-1, -1, -1, -1};
+    uint32_t q;
+    if (l >= 0) {
+        if (!is_quad[i]) return;
+        q = b.wide_base + flags_scanned[i];
+        const int64_t c[2] = {(int64_t)l + b.child_offset, (int64_t)r + b.child_offset};
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int32_t cl = b.node_child[2 * c[k]], cr = b.node_child[2 * c[k] + 1];
+            if (cl >= 0) slots[2 * k] = (int64_t)cl + b.child_offset, slots[2 * k + 1] = (int64_t)cr + b.child_offset;
+            else slots[2 * k] = c[k]; // a leaf child keeps its own slot
+        }
+    } else if (i == 0) {
+        q = b.wide_base; // the root is a leaf
+        slots[0] = me;
+    } else {
+        return;
+    }
+    float *f = nodes4 + (size_t)q * 32;
+#pragma unroll
+    for (int s = 0; s < 4; s++) put_quad_slot(b, flags_scanned, f, s, slots[s]);
+    f[28] = f[29] = f[30] = f[31] = 0.f;
+}
+
 } // namespace vrj

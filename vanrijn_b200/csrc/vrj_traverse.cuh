@@ -22,6 +22,7 @@ struct ItemDev {
 struct DevScene {
     const float4 *__restrict__ nodes32;  // 4 x float4 per wide node (64 B)
     const double2 *__restrict__ nodes64; // 7 x double2 per wide node (112 B)
+    const float4 *__restrict__ nodes4;   // 8 x float4 per 4-wide node (128 B): 4 boxes, 4 refs (VRJ_FILTER_F32X4)
     const double2 *__restrict__ tri_pos; // 96-byte records (3 x 256-bit loads): 9 coords + {material, prim_id} + pad
     const double2 *__restrict__ tri_nrm; // 96-byte records: 9 coords + pad
     const SphereDev *__restrict__ spheres;
@@ -36,7 +37,7 @@ struct DevScene {
     const uint32_t *__restrict__ bvh_items;
     uint32_t n_analytic, n_bvh_items;
     // persistent-traversal tuning (lanes): refill when this many lanes are idle; run postponed leaf tests when this many are parked
-    int refill_threshold, leaf_threshold, node_batch, max_iters;
+    int refill_threshold, leaf_threshold, node_batch, max_iters, node_batch4;
     double cam[3];
 };
 
@@ -411,6 +412,149 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
             }
         }
         // ---- traverse until enough lanes have run dry ----
+#pragma unroll 1
+        for (int it = 0; it < max_iters; it++) {
+#pragma unroll 1
+            for (int u = 0; u < node_batch; u++)
+                if (cur >= 0) node_step();
+            bool at_leaf = cur < 0 && cur != VRJ_LEAF_DONE;
+            unsigned leaf_mask = __ballot_sync(FULL, at_leaf);
+            unsigned node_mask = __ballot_sync(FULL, cur >= 0);
+            if (leaf_mask && (node_mask == 0 || __popc(leaf_mask) >= leaf_threshold)) {
+                if (at_leaf) {
+                    int tri = ~cur;
+                    D3 v0, v1, v2, loc;
+                    uint32_t mat, pid;
+                    load_tri_pos(sc, tri, v0, v1, v2, mat, pid);
+                    if (COUNT) cnt.tri_tests += 1;
+                    double dist, b0, b1, b2;
+                    if (triangle_test(tr, v0, v1, v2, dist, b0, b1, b2, loc)) {
+                        if (dist < loc_t || (dist == loc_t && tri > loc_tri)) {
+                            loc_t = dist, loc_tri = tri;
+                            limit = F::up(fmin(loc_t, best.t) * (1.0 + 4.0 * (double)F::rel()));
+                        }
+                    }
+                    if (sp) cur = stack[--sp];
+                    else finish_bvh();
+                }
+            }
+            unsigned done_mask = __ballot_sync(FULL, cur == VRJ_LEAF_DONE);
+            if (done_mask == FULL || (!exhausted && __popc(done_mask) >= refill_threshold)) break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The same engine over the 4-wide form of the tree (vrj_scene_prep.cuh): one 128-byte fetch decides four boxes, the
+// hit children are ordered by entry distance with a 5-comparator network, the nearest is followed and the others are
+// pushed farthest first.  Same filter, same exact triangle test, same tie rules: results are identical to the 2-wide
+// walk; only the number of dependent fetches per ray (about half) differs.
+__device__ __forceinline__ void cswap(float &ka, int &ra, float &kb, int &rb) {
+    const bool sw = kb < ka;
+    const float k = sw ? kb : ka, K = sw ? ka : kb;
+    const int r = sw ? rb : ra, R = sw ? ra : rb;
+    ka = k, kb = K, ra = r, rb = R;
+}
+template <bool COUNT, typename Source, typename Sink>
+__device__ __forceinline__ void trace_persistent_quad(const DevScene &sc, uint32_t n, uint32_t *work, Source &source, Sink &sink,
+                                                      TraceCounters &cnt) {
+    typedef FilterTraits<float> F;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t NONE = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const int refill_threshold = sc.refill_threshold, leaf_threshold = sc.leaf_threshold;
+    const int node_batch = sc.node_batch4, max_iters = sc.max_iters;
+    int stack[48]; // up to three pushes per 4-wide level, 16 levels
+    int sp = 0, cur = VRJ_LEAF_DONE;
+    uint32_t r = NONE, bcur = 0;
+    bool improved = false;
+    TriRay tr;
+    FilterRay<float> fr;
+    Hit best;
+    double loc_t = CUDART_INF;
+    int loc_tri = -1;
+    float limit = 0.f;
+    bool exhausted = false;
+    tr.o = d3(0, 0, 0), tr.sx = tr.sy = tr.pdz = 0.0, tr.perm = 0;
+    best.t = CUDART_INF, best.item = -1, best.tri = -1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) fr.id[k] = fr.cn[k] = fr.cf[k] = 0.f;
+
+    auto finish_bvh = [&]() {
+        uint32_t item = sc.bvh_items[bcur];
+        if (loc_tri >= 0 && (best.item < 0 || loc_t < best.t || (loc_t == best.t && (int)item < best.item)))
+            best.t = loc_t, best.item = (int)item, best.tri = loc_tri, improved = true;
+        bcur++;
+        if (bcur < sc.n_bvh_items) {
+            cur = (int)sc.items[sc.bvh_items[bcur]].root;
+            sp = 0, loc_t = CUDART_INF, loc_tri = -1;
+            limit = F::up(best.t * (1.0 + 4.0 * (double)F::rel()));
+        } else {
+            cur = VRJ_LEAF_DONE;
+        }
+    };
+    auto node_step = [&]() {
+        const float4 *p = sc.nodes4 + (size_t)cur * 8;
+        float4 a, b, c, d, e, f, g, h;
+        ldg256(p, a, b);
+        ldg256(p + 2, c, d);
+        ldg256(p + 4, e, f);
+        ldg256(p + 6, g, h);
+        if (COUNT) cnt.node_visits += 4;
+        float k0, k1, k2, k3;
+        const bool h0 = box_filter(fr, a.x, a.y, a.z, a.w, b.x, b.y, limit, k0);
+        const bool h1 = box_filter(fr, b.z, b.w, c.x, c.y, c.z, c.w, limit, k1);
+        const bool h2 = box_filter(fr, d.x, d.y, d.z, d.w, e.x, e.y, limit, k2);
+        const bool h3 = box_filter(fr, e.z, e.w, f.x, f.y, f.z, f.w, limit, k3);
+        int r0 = __float_as_int(g.x), r1 = __float_as_int(g.y), r2 = __float_as_int(g.z), r3 = __float_as_int(g.w);
+        const float inf = CUDART_INF_F;
+        k0 = h0 ? k0 : inf, k1 = h1 ? k1 : inf, k2 = h2 ? k2 : inf, k3 = h3 ? k3 : inf;
+        const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+        // misses carry +inf and sink to the end; a hit's key is finite (its box test passed ep <= limit)
+        cswap(k0, r0, k1, r1), cswap(k2, r2, k3, r3), cswap(k0, r0, k2, r2), cswap(k1, r1, k3, r3), cswap(k1, r1, k2, r2);
+        if (nh == 0) {
+            if (sp) cur = stack[--sp];
+            else finish_bvh();
+        } else {
+            if (nh > 3) stack[sp++] = r3;
+            if (nh > 2) stack[sp++] = r2;
+            if (nh > 1) stack[sp++] = r1;
+            cur = r0;
+        }
+    };
+
+    while (true) {
+        bool idle = cur == VRJ_LEAF_DONE;
+        unsigned idle_mask = __ballot_sync(FULL, idle);
+        if (idle_mask) {
+            if (idle && r != NONE) {
+                sink.store(r, best, improved);
+                r = NONE;
+            }
+            if (exhausted) {
+                if (idle_mask == FULL) break;
+            } else if (idle_mask == FULL || __popc(idle_mask) >= refill_threshold) {
+                uint32_t want = (uint32_t)__popc(idle_mask), base = 0;
+                int leader = __ffs(idle_mask) - 1;
+                if ((int)lane == leader) base = atomicAdd(work, want);
+                base = __shfl_sync(FULL, base, leader);
+                if (base + want >= n) exhausted = true;
+                if (idle) {
+                    uint32_t my = base + (uint32_t)__popc(idle_mask & ((1u << lane) - 1u));
+                    if (my < n) {
+                        D3 o, d;
+                        source.load(my, o, d, best);
+                        r = my, improved = false;
+                        tr = tri_ray(o, d);
+                        fr = filter_ray<float>(o, d);
+                        bcur = 0;
+                        cur = (int)sc.items[sc.bvh_items[0]].root;
+                        sp = 0, loc_t = CUDART_INF, loc_tri = -1;
+                        limit = F::up(best.t * (1.0 + 4.0 * (double)F::rel()));
+                    }
+                }
+            }
+        }
 #pragma unroll 1
         for (int it = 0; it < max_iters; it++) {
 #pragma unroll 1
