@@ -8,7 +8,9 @@
 // loop ends after --time seconds (or --passes passes, default 1 when --time is 0) and then writes --out.
 // Additions: --obj FILE (default $VANRIJN_BUNNY_OBJ; the reference hard-codes test_data/stanford_bunny.obj),
 // --spp N samples per partial_render_scene call (the reference: 1), --passes N, --depth N (RECURSION_LIMIT, 128),
-// --builder host|device|upload, --seed N, --preview-every N (rewrite --out every N passes: the progressive view).
+// --builder host|device|upload, --seed N, --preview-every N (rewrite --out every N passes: the progressive view),
+// --resident: keep the frame's AccumulationBuffer on the GPU (DeviceAccumulationBuffer) instead of downloading a
+// buffer per tile and merging on the host; previews then move 3 bytes per pixel.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -27,12 +29,13 @@ struct CommandLineParameters {
     double time = 0.0;
     uint32_t spp = 1, passes = 0, depth = 128, preview_every = 0;
     uint64_t seed = 1;
+    bool resident = false;
     BoundingVolumeHierarchy::Builder builder = BoundingVolumeHierarchy::Builder::AtUpload;
 };
 
 [[noreturn]] void usage(const char *why) {
     std::fprintf(stderr, "error: %s\nUSAGE: vanrijn --size <WIDTH> <HEIGHT> [--out <FILENAME>] [--time <SECONDS>] [--obj <FILE>] [--spp N] "
-                         "[--passes N] [--depth N] [--builder host|device|upload] [--seed N] [--preview-every N]\n", why);
+                         "[--passes N] [--depth N] [--builder host|device|upload] [--seed N] [--preview-every N] [--resident]\n", why);
     std::exit(2);
 }
 
@@ -54,6 +57,7 @@ CommandLineParameters parse_args(int argc, char **argv) {
         else if (a == "--depth") p.depth = (uint32_t)std::strtoul(value(), nullptr, 10), i++;
         else if (a == "--seed") p.seed = std::strtoull(value(), nullptr, 10), i++;
         else if (a == "--preview-every") p.preview_every = (uint32_t)std::strtoul(value(), nullptr, 10), i++;
+        else if (a == "--resident") p.resident = true;
         else if (a == "--builder") {
             const std::string b = value();
             i++;
@@ -107,8 +111,23 @@ int main(int argc, char **argv) {
         double device_ms = 0.0, call_s = 0.0, merge_s = 0.0;
         uint32_t pass = 0;
         const auto t0 = std::chrono::steady_clock::now();
+        std::unique_ptr<DeviceAccumulationBuffer> resident;
+        if (parameters.resident) resident.reset(new DeviceAccumulationBuffer(image_width, image_height));
         for (; pass < passes_wanted; pass++) {
             if (parameters.time > 0.0 && pass > 0 && seconds_since(t0) >= parameters.time) break;
+            if (resident) {
+                RenderOptions o;
+                VrjStats stats{};
+                o.spp = parameters.spp, o.max_depth = parameters.depth, o.seed = parameters.seed, o.stats = &stats;
+                const auto t_call = std::chrono::steady_clock::now();
+                resident->render(scene, o);
+                call_s += seconds_since(t_call);
+                rays += stats.primary_rays + stats.bounce_rays + stats.shadow_rays;
+                device_ms += stats.device_ms;
+                if (parameters.preview_every && !parameters.output_file.empty() && (pass + 1) % parameters.preview_every == 0)
+                    resident->to_image_rgb_u8().write_png(parameters.output_file);
+                continue;
+            }
             TileIterator tiles(image_width, image_height, 2048); // main.rs:199
             Tile tile;
             while (tiles.next(tile)) {
@@ -135,7 +154,8 @@ int main(int argc, char **argv) {
                     pass * (double)parameters.spp / wall);
         std::printf("host time: partial_render_scene %.3f s (device %.3f s), merge_tile %.3f s\n", call_s, device_ms / 1e3, merge_s);
         if (!parameters.output_file.empty()) {
-            rendered_image.to_image_rgb_u8().write_png(parameters.output_file); // main.rs:222-225
+            if (resident) resident->to_image_rgb_u8().write_png(parameters.output_file);
+            else rendered_image.to_image_rgb_u8().write_png(parameters.output_file); // main.rs:222-225
             std::printf("wrote %s\n", parameters.output_file.c_str());
         }
     } catch (const std::exception &e) {

@@ -262,6 +262,7 @@ class AccumulationBuffer {
 
   private:
     friend AccumulationBuffer partial_render_scene(const Scene &, Tile, size_t, size_t, const struct RenderOptions &);
+    friend class DeviceAccumulationBuffer;
     struct Uninitialized {};
     AccumulationBuffer(size_t width, size_t height, Uninitialized); // arrays about to be overwritten by a render
     size_t width_, height_;
@@ -294,6 +295,32 @@ struct RenderOptions {
 // camera.rs:95-100.  Throws std::runtime_error where the reference would panic or when CUDA fails.
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width);
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &options);
+
+// The frame's AccumulationBuffer kept in GPU memory between passes ("progressive preview").
+// main.rs:199-225 merges a freshly downloaded 1-spp buffer per tile into the frame on the host (merge_tile's weighted
+// mean) and tone-maps on the host; here every pass continues the Kahan accumulators where the last one stopped
+// (= one long sequence of update_pixel calls, accumulation_buffer.rs:44-60) and a preview is 3 bytes per pixel.
+class DeviceAccumulationBuffer {
+  public:
+    DeviceAccumulationBuffer(size_t width, size_t height, int device = 0);
+    ~DeviceAccumulationBuffer();
+    DeviceAccumulationBuffer(const DeviceAccumulationBuffer &) = delete;
+    DeviceAccumulationBuffer &operator=(const DeviceAccumulationBuffer &) = delete;
+    size_t width() const { return width_; }
+    size_t height() const { return height_; }
+    uint64_t samples_per_pixel() const { return samples_; }
+    // options.spp more samples per pixel of the whole frame; sample indices continue from the last call
+    void render(const Scene &scene, RenderOptions options);
+    ImageRgbU8 to_image_rgb_u8() const; // ClampingToneMapper on the device
+    AccumulationBuffer download() const; // the five arrays, as partial_render_scene would have produced them in one call
+
+  private:
+    double *colour_ = nullptr, *sum_ = nullptr, *bias_ = nullptr, *weight_ = nullptr, *weight_bias_ = nullptr;
+    uint8_t *srgb8_ = nullptr;
+    size_t width_, height_;
+    int device_;
+    uint64_t samples_ = 0;
+};
 
 // Collects the flattened SoA arrays and exposes them as a VrjSceneDesc.
 class FlatSceneBuilder {

@@ -238,6 +238,13 @@ VRJ_API void vrj_release_scratch(void);
 VRJ_API void *vrj_alloc_host(uint64_t bytes);
 VRJ_API void vrj_free_host(void *p);
 
+/* Device memory for output arrays that stay on the GPU between calls (VrjAccumOut.memory = VRJ_MEM_DEVICE with
+ * `accumulate`): a progressive renderer then moves 6 MB (srgb8) per preview instead of 182 MB per pass at 1080p.
+ * vrj_alloc_device returns zero-filled memory from the library's pool, or NULL. */
+VRJ_API void *vrj_alloc_device(int32_t device, uint64_t bytes);
+VRJ_API void vrj_free_device(void *p);
+VRJ_API VrjStatus vrj_copy_to_host(int32_t device, void *host_dst, const void *device_src, uint64_t bytes);
+
 /* partial_render_scene: render `tile` of a width x height image, params->spp samples per pixel. */
 VRJ_API VrjStatus vrj_render_tile(const VrjScene *scene, const VrjTile *tile, uint64_t height, uint64_t width,
                           const VrjRenderParams *params, VrjAccumOut *out);

@@ -37,6 +37,21 @@ def test_harness_png_equals_library_frame(tmp_path, size, builder):
     assert png.max() > 0
 
 
+def test_harness_resident_frame_equals_one_long_accumulation(tmp_path):
+    """--resident: the frame stays on the GPU and every pass continues the Kahan accumulators, so 3 passes x 2 spp
+    give exactly the frame of one 6-spp call (update_pixel applied 6 times per pixel, accumulation_buffer.rs:44-60)."""
+    exe = os.path.join(ROOT, "build", "vanrijn")
+    W, H = 192, 108
+    obj, _ = scenes.bunny_obj_path(subdivisions=3)
+    out = str(tmp_path / "resident.png")
+    r = subprocess.run([exe, "--size", str(W), str(H), "--out", out, "--obj", obj, "--spp", "2", "--passes", "3", "--depth", "8",
+                        "--resident", "--preview-every", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    hs = V.build_scene(scenes.scene_main(subdivisions=3, obj=True))
+    ref = hs.render((0, W, 0, H), H, W, spp=6, max_depth=8, seed=1, want=("colour",))
+    assert np.array_equal(helpers.read_png_rgb8(out), host.tone_map(ref["colour"]).reshape(H, W, 3))
+
+
 def test_harness_time_limit_and_usage_errors(tmp_path):
     exe = os.path.join(ROOT, "build", "vanrijn")
     r = subprocess.run([exe], capture_output=True, text=True)

@@ -25,7 +25,7 @@ OK = 0
 # every symbol include/vanrijn_cuda.h declares
 CUDA_SYMBOLS = ["vrj_last_error", "vrj_abi_version", "vrj_device_count", "vrj_scene_create", "vrj_scene_destroy",
                 "vrj_scene_device_bytes", "vrj_scene_upload_bytes", "vrj_render_tile", "vrj_trace_rays", "vrj_release_scratch", "vrj_alloc_host",
-                "vrj_free_host", "vrj_comm_create", "vrj_comm_destroy", "vrj_comm_scene_create", "vrj_comm_scene_destroy",
+                "vrj_free_host", "vrj_alloc_device", "vrj_free_device", "vrj_copy_to_host", "vrj_comm_create", "vrj_comm_destroy", "vrj_comm_scene_create", "vrj_comm_scene_destroy",
                 "vrj_render_sharded", "vrj_tone_map", "vrj_bvh_build"]
 
 
@@ -152,6 +152,11 @@ def cuda():
         L.vrj_alloc_host.restype = C.c_void_p
         L.vrj_alloc_host.argtypes = [C.c_uint64]
         L.vrj_free_host.argtypes = [C.c_void_p]
+        L.vrj_alloc_device.restype = C.c_void_p
+        L.vrj_alloc_device.argtypes = [C.c_int32, C.c_uint64]
+        L.vrj_free_device.argtypes = [C.c_void_p]
+        L.vrj_copy_to_host.restype = C.c_int32
+        L.vrj_copy_to_host.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64]
         L.vrj_render_tile.restype = C.c_int32
         L.vrj_render_tile.argtypes = [C.c_void_p, C.POINTER(Tile), C.c_uint64, C.c_uint64, C.POINTER(RenderParams),
                                       C.POINTER(AccumOut)]

@@ -615,4 +615,69 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
     return buffer;
 }
 
+// ------------------------------------------------------------------------------ device-resident frame
+DeviceAccumulationBuffer::DeviceAccumulationBuffer(size_t width, size_t height, int device) : width_(width), height_(height), device_(device) {
+    const size_t n = width * height;
+    colour_ = static_cast<double *>(vrj_alloc_device(device, 3 * n * 8)), sum_ = static_cast<double *>(vrj_alloc_device(device, 3 * n * 8));
+    bias_ = static_cast<double *>(vrj_alloc_device(device, 3 * n * 8)), weight_ = static_cast<double *>(vrj_alloc_device(device, n * 8));
+    weight_bias_ = static_cast<double *>(vrj_alloc_device(device, n * 8)), srgb8_ = static_cast<uint8_t *>(vrj_alloc_device(device, 3 * n));
+    if (!colour_ || !sum_ || !bias_ || !weight_ || !weight_bias_ || !srgb8_) {
+        const std::string why = vrj_last_error();
+        this->~DeviceAccumulationBuffer();
+        throw std::runtime_error("DeviceAccumulationBuffer: " + why);
+    }
+}
+DeviceAccumulationBuffer::~DeviceAccumulationBuffer() {
+    for (void *p : {(void *)colour_, (void *)sum_, (void *)bias_, (void *)weight_, (void *)weight_bias_, (void *)srgb8_}) vrj_free_device(p);
+    colour_ = sum_ = bias_ = weight_ = weight_bias_ = nullptr, srgb8_ = nullptr;
+}
+void DeviceAccumulationBuffer::render(const Scene &scene, RenderOptions o) {
+    VrjRenderParams p{};
+    p.spp = o.spp, p.max_depth = o.max_depth, p.sample_offset = o.sample_offset + samples_ * o.sample_stride, p.seed = o.seed;
+    p.integrator = o.integrator, p.bvh_filter = o.bvh_filter, p.bias = 0.0000001, p.sample_stride = o.sample_stride;
+    auto as_data = [](const Spectrum &s) {
+        return VrjSpectrumData{s.shortest_wavelength, s.longest_wavelength, (uint32_t)s.samples.size(), 0u, s.samples.data()};
+    };
+    std::vector<VrjLight> lights;
+    VrjSpectrumData ambient = as_data(o.ambient_light);
+    if (o.integrator == VRJ_INTEGRATOR_WHITTED) {
+        for (const DirectionalLight &l : o.lights) {
+            VrjLight d{};
+            d.direction[0] = l.direction.x, d.direction[1] = l.direction.y, d.direction[2] = l.direction.z;
+            d.spectrum = as_data(l.spectrum);
+            lights.push_back(d);
+        }
+        p.lights = lights.data(), p.n_lights = (uint32_t)lights.size(), p.ambient_light = &ambient;
+    }
+    VrjTile t{0, width_, 0, height_};
+    VrjAccumOut out{};
+    out.memory = VRJ_MEM_DEVICE, out.accumulate = 1; // continue the Kahan state left by the previous pass (zero at first)
+    out.colour = colour_, out.colour_sum = sum_, out.colour_bias = bias_, out.weight = weight_, out.weight_bias = weight_bias_;
+    out.stats = o.stats;
+    if (vrj_render_tile(device_scene(scene, device_), &t, height_, width_, &p, &out) != VRJ_OK)
+        throw std::runtime_error(std::string("vrj_render_tile: ") + vrj_last_error());
+    samples_ += o.spp;
+}
+ImageRgbU8 DeviceAccumulationBuffer::to_image_rgb_u8() const {
+    ImageRgbU8 image(width_, height_);
+    const size_t n = width_ * height_;
+    if (vrj_tone_map(device_, VRJ_MEM_DEVICE, VRJ_TONEMAP_XYZ, colour_, n, srgb8_) != VRJ_OK ||
+        vrj_copy_to_host(device_, image.pixel_data().data(), srgb8_, 3 * n) != VRJ_OK)
+        throw std::runtime_error(std::string("DeviceAccumulationBuffer::to_image_rgb_u8: ") + vrj_last_error());
+    return image;
+}
+AccumulationBuffer DeviceAccumulationBuffer::download() const {
+    AccumulationBuffer b(width_, height_, AccumulationBuffer::Uninitialized{});
+    const size_t n = width_ * height_;
+    const struct {
+        double *dst;
+        const double *src;
+        size_t count;
+    } copies[5] = {{b.colour.data(), colour_, 3 * n}, {b.colour_sum.data(), sum_, 3 * n}, {b.colour_bias.data(), bias_, 3 * n},
+                   {b.weight.data(), weight_, n}, {b.weight_bias.data(), weight_bias_, n}};
+    for (const auto &c : copies)
+        if (vrj_copy_to_host(device_, c.dst, c.src, c.count * 8) != VRJ_OK) throw std::runtime_error(std::string("vrj_copy_to_host: ") + vrj_last_error());
+    return b;
+}
+
 } // namespace vanrijn

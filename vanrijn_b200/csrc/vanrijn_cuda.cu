@@ -867,6 +867,23 @@ void vrj_free_host(void *p) {
     if (!keep) cudaFreeHost(p);
 }
 
+void *vrj_alloc_device(int32_t device, uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || vrj_pool_alloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess) {
+        g_error = std::string("vrj_alloc_device: ") + cudaGetErrorString(cudaGetLastError());
+        if (p) vrj_pool_free(p);
+        return nullptr;
+    }
+    return p;
+}
+void vrj_free_device(void *p) { vrj_pool_free(p); }
+VrjStatus vrj_copy_to_host(int32_t device, void *host_dst, const void *device_src, uint64_t bytes) {
+    if (bytes && (!host_dst || !device_src)) return fail(VRJ_ERR_INVALID_ARGUMENT, "NULL argument");
+    VRJ_CUDA(cudaSetDevice(device));
+    VRJ_CUDA(cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
+    return VRJ_OK;
+}
+
 VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t height, uint64_t width,
                           const VrjRenderParams *p, VrjAccumOut *out) {
     VrjScene *scene = const_cast<VrjScene *>(scene_c);
