@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--filter", default="f32", choices=["f32", "f64", "f32x4"],
                     help="conservative BVH box filter: 2-wide f32, 2-wide f64, or 4-wide f32 nodes (results identical)")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="f64 = the reference's type (parity path, the headline); f32 = VRJ_PRECISION_F32_FAST, reported separately")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -177,6 +179,7 @@ def main():
     W, H, spp = args.width, args.height, args.spp
     npix = W * H
     bvh_filter = {"f64": capi.FILTER_F64, "f32x4": capi.FILTER_F32X4}.get(args.filter, capi.FILTER_F32)
+    precision = capi.PRECISION_F32_FAST if args.precision == "f32" else capi.PRECISION_F64
     hs = V.build_scene(spec)
     hs.device_scene(local)
     scene_bytes = hs.device_bytes(local)
@@ -192,7 +195,7 @@ def main():
         offset, stride = sharding.shard_samples(rank, world, k, spp)
         st = hs.render_device(tile, H, W, acc_sum.data_ptr(), acc_w.data_ptr(), device=local, accumulate=accumulate,
                               spp=spp, max_depth=MAX_DEPTH, seed=SEED, sample_offset=offset, sample_stride=stride,
-                              bvh_filter=bvh_filter)
+                              bvh_filter=bvh_filter, precision=precision)
         if world > 1:
             # the one exchange step: combine the per-GPU accumulation buffers into rank 0's (NCCL over NVLink)
             red_sum.copy_(acc_sum)
@@ -258,7 +261,7 @@ def main():
         hs._dev["e2e"] = h
         r = hs.render(tile, H, W, device="e2e", buffers=pinned, spp=spp, max_depth=MAX_DEPTH, seed=SEED,
                       sample_offset=sharding.shard_samples(rank, world, k, spp)[0], sample_stride=world,
-                      bvh_filter=bvh_filter)                                              # D2H: the five arrays
+                      bvh_filter=bvh_filter, precision=precision)                                              # D2H: the five arrays
         capi.cuda().vrj_scene_destroy(h)
         del hs._dev["e2e"]
         dt = time.perf_counter() - t1
@@ -326,11 +329,12 @@ def main():
     value = rays_all / wall_max / 1e6
     line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "f32" else "f64", "data": "synthetic",
             "spp_per_s": args.steps * spp * world / wall_max,
             "device_ms_per_step": devms_max / args.steps,
             "config": {"workload": "C3 main.rs scene path trace %dx%d depth %d" % (W, H, MAX_DEPTH), "mesh": mesh_name,
                        "integrator": "SimpleRandom", "spp_per_step_per_gpu": spp, "bvh_filter": args.filter,
+                       "precision": "f32-fast (no parity claim)" if args.precision == "f32" else "f64 (the reference's type)",
                        "sharding": "sample index mod n_gpus; NCCL reduce of (sumXYZ, weight) to rank 0 each step",
                        "l2": "inputs larger than L2: %.1f GB of path state per step; the %.0f MB scene is L2-resident by design"
                              % (min(spp, (1 << 26) // npix) * npix * 240 / 1e9, scene_bytes / 1e6)},

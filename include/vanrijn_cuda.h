@@ -64,6 +64,11 @@ enum { VRJ_ITEM_SPHERE = 0, VRJ_ITEM_PLANE = 1, VRJ_ITEM_TRIANGLE = 2, VRJ_ITEM_
  * F32: 2-wide nodes, f32 boxes; F64: 2-wide, f64 boxes (cross-check); F32X4: 4-wide nodes (two reference levels per fetch) */
 enum { VRJ_FILTER_F32 = 0, VRJ_FILTER_F64 = 1, VRJ_FILTER_F32X4 = 2 };
 enum { VRJ_MEM_HOST = 0, VRJ_MEM_DEVICE = 1 };
+/* VRJ_PRECISION_F64: every hit, shading and accumulation operation in binary64, the reference's type and operation order.
+ * VRJ_PRECISION_F32_FAST: the same formulas in binary32 (accumulators stay binary64).  The reference has no binary32 build
+ * (realtype.rs is f64 everywhere), so this mode has no parity claim: hit ids can differ next to edges and images agree to
+ * about 1e-3; it is reported separately (SURVEY 8d "f32 fast"). */
+enum { VRJ_PRECISION_F64 = 0, VRJ_PRECISION_F32_FAST = 1 };
 
 /* colour/spectrum.rs:6-10 -- uniform samples over [shortest, longest] */
 typedef struct VrjSpectrum {
@@ -181,7 +186,7 @@ typedef struct VrjRenderParams {
     uint32_t n_lights;
     uint32_t sample_stride;   /* 0 or 1: consecutive samples; G: this call takes samples offset, offset+G, ... (sharding) */
     uint32_t count_traversal; /* non-zero: also count BVH node visits / triangle tests (slower kernel variant) */
-    uint32_t pad;
+    uint32_t precision;       /* VRJ_PRECISION_*; 0 = the reference's binary64 (the parity path) */
 } VrjRenderParams;
 
 typedef struct VrjStats {

@@ -72,7 +72,7 @@ pub struct VrjRenderParams {
     pub integrator: u32, pub bvh_filter: u32,
     pub bias: f64,
     pub lights: *const VrjLight, pub ambient_light: *const VrjSpectrumData,
-    pub n_lights: u32, pub sample_stride: u32, pub count_traversal: u32, pub pad: u32,
+    pub n_lights: u32, pub sample_stride: u32, pub count_traversal: u32, pub precision: u32,
 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]

@@ -335,3 +335,23 @@ def test_tone_map_on_device_matches_oracle():
     ref = O.tone_map(out["colour"], source=0).reshape(-1)
     d = np.abs(out["srgb8"].astype(int) - ref.astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 1e-3 and out["srgb8"].max() > 0
+
+
+def test_f32_fast_mode_tracks_the_parity_path():
+    """VRJ_PRECISION_F32_FAST has no counterpart in the reference (binary64 everywhere), so this is NOT a parity test: it
+    pins how far the binary32 path may drift from the binary64 one on the same samples (same Philox draws): a converged
+    image within 5e-3 relative RMSE, the same number of rays to 0.1 %, finite and correctly weighted accumulators --
+    for the Lambertian bench scene and for the mirror + glass scene."""
+    for variant, depth, tol in (("lambertian", 8, 5e-3), ("mixed", 32, 5e-2)):
+        hs = V.build_scene(scenes.scene_main(subdivisions=5, obj=False, variant=variant))
+        W, H, spp = 320, 180, 64
+        a = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=depth, seed=1, want=("colour", "weight"))
+        b = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=depth, seed=1, want=("colour", "weight"),
+                      precision=capi.PRECISION_F32_FAST)
+        ca, cb = a["colour"], b["colour"]
+        assert np.all(np.isfinite(cb)) and np.all(b["weight"] == spp)
+        rmse = np.sqrt(np.mean((ca - cb) ** 2))
+        assert rmse / ca.mean() < tol, (variant, rmse / ca.mean())
+        assert abs(b["stats"].rays - a["stats"].rays) <= 1e-3 * a["stats"].rays
+    with pytest.raises(capi.VrjError):
+        hs.render((0, 8, 0, 8), 8, 8, spp=1, precision=7)

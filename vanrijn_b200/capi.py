@@ -19,6 +19,7 @@ MAT_LAMBERTIAN, MAT_PHONG, MAT_REFLECTIVE, MAT_DIELECTRIC = 0, 1, 2, 3
 INTEGRATOR_SIMPLE_RANDOM, INTEGRATOR_WHITTED = 0, 1
 FILTER_F32, FILTER_F64, FILTER_F32X4 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
+PRECISION_F64, PRECISION_F32_FAST = 0, 1
 TONEMAP_XYZ, TONEMAP_LINEAR_RGB = 0, 1
 OK = 0
 
@@ -92,7 +93,7 @@ class RenderParams(C.Structure):
     _fields_ = [("spp", C.c_uint32), ("max_depth", C.c_uint32), ("sample_offset", C.c_uint64), ("seed", C.c_uint64),
                 ("integrator", C.c_uint32), ("bvh_filter", C.c_uint32), ("bias", C.c_double),
                 ("lights", C.POINTER(Light)), ("ambient_light", C.POINTER(SpectrumData)), ("n_lights", C.c_uint32),
-                ("sample_stride", C.c_uint32), ("count_traversal", C.c_uint32), ("pad", C.c_uint32)]
+                ("sample_stride", C.c_uint32), ("count_traversal", C.c_uint32), ("precision", C.c_uint32)]
 
 
 class Stats(C.Structure):

@@ -405,7 +405,7 @@ int persistent_grid(const VrjScene *sc, K kernel) {
     return sc->sm_count * per_sm;
 }
 
-template <typename NT, bool COUNT>
+template <typename NT, typename R, bool COUNT>
 VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, bool quad, uint64_t *launches) {
     // launch sequence: G T S_0 [X_k T_k S_k]*, k = 1..levels (X = k_tail, a no-op until the queue is short);
     // SimpleRandom needs max_depth levels, Whitted one more (its limit-0 level still shades and traces);
@@ -420,9 +420,9 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 4 + 1) * sizeof(uint32_t), s->stream));
     unsigned long long *stats = s->stats.as<unsigned long long>();
     double2 *photons = s->photons.as<double2>();
-    const int g_gen = persistent_grid(sc, k_raygen<COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT>) : persistent_grid(sc, k_trace<NT, COUNT>);
-    const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, COUNT, false, true>);
-    const int g_s = whitted ? persistent_grid(sc, k_shade<NT, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, COUNT, false, false>);
+    const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
+    const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, true>);
+    const int g_s = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, false>);
     // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
     // per-level latency it removes is smaller than what its one-thread-per-path traversal costs (measured)
     const uint32_t tail_max = levels > 12 ? sc->tail_max : 0u;
@@ -430,42 +430,42 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     const bool has_bvh = sc->dev.n_bvh_items > 0;
     VRJ_CUDA(s->mark(-1));
     // the raygen kernel uses work_s[0]; S_0 uses work_t[stride-1] (never used by a T)
-    k_raygen<COUNT><<<g_gen, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_s + 0, stats);
+    k_raygen<R, COUNT><<<g_gen, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_s + 0, stats);
     (*launches)++;
     VRJ_CUDA(s->mark(4));
     if (has_bvh) {
         if (quad) k_trace4<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
-        else k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
+        else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
         (*launches)++;
         VRJ_CUDA(s->mark(0));
     }
     uint32_t *work_s0 = work_t + (stride - 1);
     if (whitted)
-        k_shade<NT, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
+        k_shade<NT, R, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
     else
-        k_shade<NT, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
+        k_shade<NT, R, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
     (*launches)++;
     VRJ_CUDA(s->mark(3));
     for (uint32_t k = 1; k <= levels; k++) {
         const int ci = k & 1, ni = (k + 1) & 1;
         if (tail_max) {
             if (whitted)
-                k_tail<NT, COUNT, true><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
+                k_tail<NT, R, COUNT, true><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
             else
-                k_tail<NT, COUNT, false><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
+                k_tail<NT, R, COUNT, false><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
             (*launches)++;
             VRJ_CUDA(s->mark(5));
         }
         if (has_bvh) {
             if (quad) k_trace4<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
-            else k_trace<NT, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
             (*launches)++;
             VRJ_CUDA(s->mark(1));
         }
         if (whitted)
-            k_shade<NT, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
+            k_shade<NT, R, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
         else
-            k_shade<NT, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
+            k_shade<NT, R, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
         (*launches)++;
         VRJ_CUDA(s->mark(3));
         // stop launching once the batch has drained (queue empty, or finished by k_tail)
@@ -479,7 +479,7 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     AccumDev acc;
     acc.colour = s->acc_colour.as<double>(), acc.sum = s->acc_sum.as<double>(), acc.bias = s->acc_bias.as<double>();
     acc.weight = s->acc_weight.as<double>(), acc.weight_bias = s->acc_wbias.as<double>();
-    k_resolve<<<(rc.npix + 255) / 256, 256, 0, s->stream>>>(acc, photons, rc.npix, rc.batch_samples);
+    k_resolve<R><<<(rc.npix + 255) / 256, 256, 0, s->stream>>>(acc, photons, rc.npix, rc.batch_samples);
     (*launches)++;
     VRJ_CUDA(s->mark(2));
     VRJ_CUDA(cudaGetLastError());
@@ -590,6 +590,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     const Section s_n32 = reserve_section(n_wide * 64), s_n64 = reserve_section(n_wide * 112);
     const Section s_n4 = reserve_section(n_wide * 128); // upper bound: at most every internal node becomes a 4-wide node
     const Section s_tp = reserve_section((size_t)d->n_triangles * 96), s_tn = reserve_section((size_t)d->n_triangles * 96);
+    const Section s_tp32 = reserve_section((size_t)d->n_triangles * 48), s_tn32 = reserve_section((size_t)d->n_triangles * 48);
     const size_t arena_bytes = std::max<size_t>(cursor, 256);
 
     DeviceBuffer *arena = new DeviceBuffer();
@@ -685,7 +686,9 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     }
     if (nt)
         k_pack_triangles<<<(unsigned)((nt + 127) / 128), 128, 0, stream>>>((uint32_t)nt, rt, perm, reinterpret_cast<double *>(base + s_tp.offset),
-                                                                           reinterpret_cast<double *>(base + s_tn.offset));
+                                                                           reinterpret_cast<double *>(base + s_tn.offset),
+                                                                           reinterpret_cast<float *>(base + s_tp32.offset),
+                                                                           reinterpret_cast<float *>(base + s_tn32.offset));
     for (uint32_t b = 0; b < d->n_bvhs; b++) {
         if (plan[b].empty) continue;
         BvhNodes bn;
@@ -767,6 +770,8 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     sc->dev.nodes4 = reinterpret_cast<const float4 *>(base + s_n4.offset);
     sc->dev.tri_pos = reinterpret_cast<const double2 *>(base + s_tp.offset);
     sc->dev.tri_nrm = reinterpret_cast<const double2 *>(base + s_tn.offset);
+    sc->dev.tri_pos32 = reinterpret_cast<const float4 *>(base + s_tp32.offset);
+    sc->dev.tri_nrm32 = reinterpret_cast<const float4 *>(base + s_tn32.offset);
     sc->dev.spheres = reinterpret_cast<const SphereDev *>(base + s_sph.offset);
     sc->dev.planes = reinterpret_cast<const PlaneDev *>(base + s_pl.offset);
     sc->dev.materials = reinterpret_cast<const MaterialDev *>(base + s_mat.offset);
@@ -893,6 +898,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     if (width * height > 0xffffffffull) return fail(VRJ_ERR_UNSUPPORTED, "image larger than 2^32 pixels");
     if (p->integrator > VRJ_INTEGRATOR_WHITTED) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown integrator");
     if (p->bvh_filter > VRJ_FILTER_F32X4) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
+    if (p->precision > VRJ_PRECISION_F32_FAST) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown precision");
     if (p->max_depth > 65535) return fail(VRJ_ERR_INVALID_ARGUMENT, "max_depth exceeds u16 (RECURSION_LIMIT is a u16)");
     if (p->n_lights && !p->lights) return fail(VRJ_ERR_INVALID_ARGUMENT, "lights is NULL");
     size_t n_light_samples = 0;
@@ -966,7 +972,9 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     rc.sample_stride = p->sample_stride ? p->sample_stride : 1;
     rc.seed = p->seed;
     rc.max_depth = p->max_depth, rc.n_lights = p->n_lights, rc.has_ambient = p->ambient_light ? 1u : 0u;
-    rc.bias = p->bias;
+    // binary32 cannot represent origin + 1e-7 * direction at scene scale (ulp(5) = 4.8e-7): the fast mode needs a bias of a
+    // few hundred ulps or every bounce ray re-hits the surface it leaves
+    rc.bias = p->precision == VRJ_PRECISION_F32_FAST ? std::max(p->bias, 1e-4) : p->bias;
     { // camera.rs:24-34
         double w = (double)width, h = (double)height;
         if (w > h) rc.film_w = w / h, rc.film_h = 1.0;
@@ -977,6 +985,8 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
 
     // F32X4: the staged rays walk the 4-wide tree; inline any-hit queries (Whitted shadow rays, k_tail) use the 2-wide f32 tree
     const bool quad = p->bvh_filter == VRJ_FILTER_F32X4;
+    // VRJ_PRECISION_F32_FAST: the whole sample in binary32 over the 2-wide f32 tree (no reference counterpart; not a parity mode)
+    const bool fast = p->precision == VRJ_PRECISION_F32_FAST;
     uint64_t launches = 0;
     s->n_marks = 0;
     VRJ_CUDA(cudaEventRecord(s->ev0, s->stream));
@@ -984,11 +994,13 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         rc.batch_samples = std::min(batch, p->spp - done);
         rc.first_sample = p->sample_offset + (uint64_t)done * rc.sample_stride;
         if (p->count_traversal) {
-            st = p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, true>(scene, s, rc, whitted, false, &launches)
-                                                 : run_batch<float, true>(scene, s, rc, whitted, quad, &launches);
+            st = fast ? run_batch<float, float, true>(scene, s, rc, whitted, false, &launches)
+                 : p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, double, true>(scene, s, rc, whitted, false, &launches)
+                                                   : run_batch<float, double, true>(scene, s, rc, whitted, quad, &launches);
         } else {
-            st = p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, false>(scene, s, rc, whitted, false, &launches)
-                                                 : run_batch<float, false>(scene, s, rc, whitted, quad, &launches);
+            st = fast ? run_batch<float, float, false>(scene, s, rc, whitted, false, &launches)
+                 : p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, double, false>(scene, s, rc, whitted, false, &launches)
+                                                   : run_batch<float, double, false>(scene, s, rc, whitted, quad, &launches);
         }
         if (st != VRJ_OK) return st;
         if (out->photons) {
@@ -1100,11 +1112,11 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     if (scene->dev.n_bvh_items) {
         launches++;
         if (bvh_filter == VRJ_FILTER_F64)
-            k_trace<double, true><<<persistent_grid(scene, k_trace<double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
+            k_trace<double, double, true><<<persistent_grid(scene, k_trace<double, double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
         else if (bvh_filter == VRJ_FILTER_F32X4)
             k_trace4<true><<<persistent_grid(scene, k_trace4<true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
         else
-            k_trace<float, true><<<persistent_grid(scene, k_trace<float, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
+            k_trace<float, double, true><<<persistent_grid(scene, k_trace<float, double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
     }
     k_hit_ids<<<(n32 + 255) / 256, 256, 0, stream>>>(scene->dev, n32, tb, d_obj.as<int32_t>(), d_prim.as<int32_t>(), d_t.as<double>(), dstats);
     VRJ_CUDA(cudaGetLastError());

@@ -1,5 +1,8 @@
-// vrj_device.cuh -- device-side arithmetic of the render loop, binary64, in the reference's
-// operation order (compile with -fmad=false: rustc never contracts a*b+c).
+// vrj_device.cuh -- device-side arithmetic of the render loop in the reference's operation order (compile with
+// -fmad=false: rustc never contracts a*b+c).  Everything is a template over the real type R:
+//   R = double : the reference's type (realtype.rs is binary64 everywhere) -- the parity path, bit-faithful;
+//   R = float  : VRJ_PRECISION_F32_FAST, the same formulas in binary32 (SURVEY 8b/8d "f32 fast"); it has no
+//                counterpart in the reference and is reported separately, never as a parity result.
 // Reference paths are relative to /root/reference/src/.
 #pragma once
 #include <cuda_runtime.h>
@@ -33,47 +36,69 @@ namespace vrj {
 
 // ------------------------------------------------------------------------------------------
 // math/vec3.rs, math/mat3.rs, math/mat2.rs
-struct D3 {
-    double x, y, z;
+template <typename R>
+struct V3 {
+    R x, y, z;
 };
+typedef V3<double> D3;
+typedef V3<float> F3;
 __device__ __forceinline__ D3 d3(double x, double y, double z) { return D3{x, y, z}; }
-__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ D3 operator-(D3 a) { return d3(-a.x, -a.y, -a.z); }
-__device__ __forceinline__ D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
+template <typename R>
+__device__ __forceinline__ V3<R> v3(R x, R y, R z) { return V3<R>{x, y, z}; }
+template <typename R, typename S>
+__device__ __forceinline__ V3<R> convert(V3<S> a) { return V3<R>{(R)a.x, (R)a.y, (R)a.z}; }
+template <typename R>
+__device__ __forceinline__ V3<R> operator+(V3<R> a, V3<R> b) { return V3<R>{a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename R>
+__device__ __forceinline__ V3<R> operator-(V3<R> a, V3<R> b) { return V3<R>{a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename R>
+__device__ __forceinline__ V3<R> operator-(V3<R> a) { return V3<R>{-a.x, -a.y, -a.z}; }
+template <typename R>
+__device__ __forceinline__ V3<R> operator*(V3<R> a, R s) { return V3<R>{a.x * s, a.y * s, a.z * s}; }
 // vec3.rs:76-82: products summed from 0.0 in x, y, z order
-__device__ __forceinline__ double dot(D3 a, D3 b) { return ((0.0 + a.x * b.x) + a.y * b.y) + a.z * b.z; }
-__device__ __forceinline__ D3 cross(D3 a, D3 b) {
-    return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+template <typename R>
+__device__ __forceinline__ R dot(V3<R> a, V3<R> b) { return ((R(0) + a.x * b.x) + a.y * b.y) + a.z * b.z; }
+template <typename R>
+__device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b) {
+    return V3<R>{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
-__device__ __forceinline__ double norm(D3 a) { return sqrt(dot(a, a)); }
+template <typename R>
+__device__ __forceinline__ R norm(V3<R> a) { return sqrt(dot(a, a)); }
 // vec3.rs:103-110: multiply by 1/norm
-__device__ VRJ_INL_NORM D3 normalize(D3 a) {
-    double inv = 1.0 / norm(a);
-    return d3(a.x * inv, a.y * inv, a.z * inv);
+template <typename R>
+__device__ VRJ_INL_NORM V3<R> normalize(V3<R> a) {
+    R inv = R(1) / norm(a);
+    return V3<R>{a.x * inv, a.y * inv, a.z * inv};
 }
 
-struct M3 {
-    double e[3][3];
+template <typename R>
+struct M3T {
+    R e[3][3];
 };
+typedef M3T<double> M3;
 // mat3.rs:72-94 (first_minor with mat2.rs:13-15, cofactor sign), written out per element
-__device__ __forceinline__ double minor2(double a, double b, double c, double d) { return a * d - b * c; }
-__device__ __forceinline__ double first_minor(const M3 &m, int r, int c) {
+template <typename R>
+__device__ __forceinline__ R minor2(R a, R b, R c, R d) { return a * d - b * c; }
+template <typename R>
+__device__ __forceinline__ R first_minor(const M3T<R> &m, int r, int c) {
     const int r0 = r == 0 ? 1 : 0, r1 = r == 2 ? 1 : 2;
     const int c0 = c == 0 ? 1 : 0, c1 = c == 2 ? 1 : 2;
     return minor2(m.e[r0][c0], m.e[r0][c1], m.e[r1][c0], m.e[r1][c1]);
 }
-__device__ __forceinline__ double cofactor(const M3 &m, int r, int c) {
-    return (((r + c) & 1) ? -1.0 : 1.0) * first_minor(m, r, c);
+template <typename R>
+__device__ __forceinline__ R cofactor(const M3T<R> &m, int r, int c) {
+    return (((r + c) & 1) ? R(-1) : R(1)) * first_minor(m, r, c);
 }
 // mat3.rs:106-109
-__device__ __forceinline__ double determinant(const M3 &m) {
+template <typename R>
+__device__ __forceinline__ R determinant(const M3T<R> &m) {
     return m.e[0][0] * first_minor(m, 0, 0) - m.e[0][1] * first_minor(m, 0, 1) + m.e[0][2] * first_minor(m, 0, 2);
 }
 // mat3.rs:111-118: transpose(cofactor matrix) * determinant (sic)
-__device__ __forceinline__ bool try_inverse(const M3 &m, M3 &out) {
-    double det = determinant(m);
-    if (det == 0.0) return false;
+template <typename R>
+__device__ __forceinline__ bool try_inverse(const M3T<R> &m, M3T<R> &out) {
+    R det = determinant(m);
+    if (det == R(0)) return false;
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -81,13 +106,15 @@ __device__ __forceinline__ bool try_inverse(const M3 &m, M3 &out) {
     return true;
 }
 // mat3.rs:147-157
-__device__ __forceinline__ D3 mul(const M3 &m, D3 v) {
-    return d3(dot(d3(m.e[0][0], m.e[0][1], m.e[0][2]), v), dot(d3(m.e[1][0], m.e[1][1], m.e[1][2]), v),
-              dot(d3(m.e[2][0], m.e[2][1], m.e[2][2]), v));
+template <typename R>
+__device__ __forceinline__ V3<R> mul(const M3T<R> &m, V3<R> v) {
+    return V3<R>{dot(V3<R>{m.e[0][0], m.e[0][1], m.e[0][2]}, v), dot(V3<R>{m.e[1][0], m.e[1][1], m.e[1][2]}, v),
+                 dot(V3<R>{m.e[2][0], m.e[2][1], m.e[2][2]}, v)};
 }
 // util/algebra_utils.rs:3-5 + mat3.rs:34-42
-__device__ __forceinline__ M3 from_rows(D3 a, D3 b, D3 c) {
-    M3 m;
+template <typename R>
+__device__ __forceinline__ M3T<R> from_rows(V3<R> a, V3<R> b, V3<R> c) {
+    M3T<R> m;
     m.e[0][0] = a.x, m.e[0][1] = a.y, m.e[0][2] = a.z;
     m.e[1][0] = b.x, m.e[1][1] = b.y, m.e[1][2] = b.z;
     m.e[2][0] = c.x, m.e[2][1] = c.y, m.e[2][2] = c.z;
@@ -136,7 +163,21 @@ struct Rng {
     __device__ __forceinline__ double open01() { return ((double)(bits() >> 12) + 0.5) * (1.0 / 4503599627370496.0); }
     // rand 0.7 Standard bool: sign bit
     __device__ __forceinline__ bool boolean() { return (bits() >> 63) != 0; }
+    // the same draws in the working precision (float: rand 0.7's f32 rules, 24 / 23 bits, from the same 64-bit word,
+    // so a fast-mode path follows its parity twin as long as no discrete decision flips)
+    template <typename R>
+    __device__ __forceinline__ R uniform();
+    template <typename R>
+    __device__ __forceinline__ R uniform_open();
 };
+template <>
+__device__ __forceinline__ double Rng::uniform<double>() { return f64(); }
+template <>
+__device__ __forceinline__ double Rng::uniform_open<double>() { return open01(); }
+template <>
+__device__ __forceinline__ float Rng::uniform<float>() { return (float)(bits() >> 40) * (1.0f / 16777216.0f); }
+template <>
+__device__ __forceinline__ float Rng::uniform_open<float>() { return ((float)(bits() >> 41) + 0.5f) * (1.0f / 8388608.0f); }
 
 // ------------------------------------------------------------------------------------------
 // colour/spectrum.rs
@@ -151,30 +192,33 @@ __device__ const double g_rgb_basis[7][32] = {
 enum { B_WHITE = 0, B_CYAN, B_MAGENTA, B_YELLOW, B_RED, B_GREEN, B_BLUE };
 
 // spectrum.rs:50-79, `sample(i)` supplies sample i
-template <typename F>
-__device__ __forceinline__ double spectrum_lookup(double shortest, double longest, uint32_t n, double wavelength, F sample) {
-    if (wavelength < shortest || wavelength > longest) return 0.0;
-    double range = longest - shortest;
-    double nm1 = (double)(n - 1);
-    double fidx = nm1 * ((wavelength - shortest) / range);
-    uint32_t before = (fidx != fidx || fidx < 0.0) ? 0u : (uint32_t)fidx;
-    double wl_before = (double)before / nm1 * range + shortest;
+template <typename R, typename F>
+__device__ __forceinline__ R spectrum_lookup(R shortest, R longest, uint32_t n, R wavelength, F sample) {
+    if (wavelength < shortest || wavelength > longest) return R(0);
+    R range = longest - shortest;
+    R nm1 = (R)(n - 1);
+    R fidx = nm1 * ((wavelength - shortest) / range);
+    uint32_t before = (fidx != fidx || fidx < R(0)) ? 0u : (uint32_t)fidx;
+    if (before > n - 1) before = n - 1; // cannot happen in binary64; guards binary32 rounding at the upper end
+    R wl_before = (R)before / nm1 * range + shortest;
     if (before == n - 1) return sample(before);
-    double wl_after = (double)(before + 1) / nm1 * range + shortest;
-    double delta = wl_after - wl_before;
-    double ratio = (wavelength - wl_before) / delta;
-    return sample(before) * (1.0 - ratio) + sample(before + 1) * ratio;
+    R wl_after = (R)(before + 1) / nm1 * range + shortest;
+    R delta = wl_after - wl_before;
+    R ratio = (wavelength - wl_before) / delta;
+    return sample(before) * (R(1) - ratio) + sample(before + 1) * ratio;
 }
-__device__ __forceinline__ double spectrum_intensity(const SpectrumDev *__restrict__ spectra,
-                                                     const double *__restrict__ samples, uint32_t id, double wavelength) {
+template <typename R>
+__device__ __forceinline__ R spectrum_intensity(const SpectrumDev *__restrict__ spectra, const double *__restrict__ samples,
+                                                uint32_t id, R wavelength) {
     SpectrumDev s = spectra[id];
     const double *p = samples + s.first;
-    return spectrum_lookup(s.shortest, s.longest, s.n, wavelength, [p](uint32_t i) { return __ldg(p + i); });
+    return spectrum_lookup<R>((R)s.shortest, (R)s.longest, s.n, wavelength, [p](uint32_t i) { return (R)__ldg(p + i); });
 }
 // spectrum.rs:81-165 evaluated lazily: only the (at most two) samples the lookup touches are formed
-__device__ __forceinline__ double rgb_reflection_intensity(double r, double g, double b, double wavelength) {
+template <typename R>
+__device__ __forceinline__ R rgb_reflection_intensity(R r, R g, R b, R wavelength) {
     int second, third;
-    double c0, c1, c2;
+    R c0, c1, c2;
     if (r <= g && r <= b) {
         if (g <= b) { second = B_CYAN, third = B_BLUE, c0 = r, c1 = g - r, c2 = b - g; }
         else        { second = B_CYAN, third = B_GREEN, c0 = r, c1 = b - r, c2 = g - b; }
@@ -185,73 +229,83 @@ __device__ __forceinline__ double rgb_reflection_intensity(double r, double g, d
         if (r <= g) { second = B_YELLOW, third = B_GREEN, c0 = b, c1 = r - b, c2 = g - r; }
         else        { second = B_YELLOW, third = B_RED, c0 = b, c1 = g - b, c2 = r - g; }
     }
-    return spectrum_lookup(380.0, 720.0, 32u, wavelength, [=](uint32_t i) {
-        return c0 * g_rgb_basis[B_WHITE][i] + c1 * g_rgb_basis[second][i] + c2 * g_rgb_basis[third][i];
+    return spectrum_lookup<R>(R(380), R(720), 32u, wavelength, [=](uint32_t i) {
+        return c0 * (R)g_rgb_basis[B_WHITE][i] + c1 * (R)g_rgb_basis[second][i] + c2 * (R)g_rgb_basis[third][i];
     });
 }
-// integrators/simple_random_integrator.rs:57-65
-__device__ __forceinline__ double sky(D3 w, double wavelength) { return rgb_reflection_intensity(w.y, w.y, 1.0, wavelength); }
 
 // colour/colour_xyz.rs:86-103
-__device__ __forceinline__ double gaussian(double w, double alpha, double mu, double s1, double s2) {
-    double sigma = w < mu ? s1 : s2;
-    double denominator = 2.0 * (sigma * sigma);
+template <typename R>
+__device__ __forceinline__ R gaussian(R w, R alpha, R mu, R s1, R s2) {
+    R sigma = w < mu ? s1 : s2;
+    R denominator = R(2) * (sigma * sigma);
     return alpha * exp(-((w - mu) * (w - mu)) / denominator);
 }
-__device__ __forceinline__ D3 cmf(double w) {
-    double x = gaussian(w, 1.056, 599.8, 37.9, 31.0) + gaussian(w, 0.362, 442.0, 16.0, 26.7) +
-               gaussian(w, -0.065, 501.1, 20.4, 26.2);
-    double y = gaussian(w, 0.821, 568.8, 46.9, 40.5) + gaussian(w, 0.286, 530.9, 16.3, 31.1);
-    double z = gaussian(w, 1.217, 437.0, 11.8, 36.0) + gaussian(w, 0.681, 459.0, 26.0, 13.8);
-    return d3(x, y, z);
+template <typename R>
+__device__ __forceinline__ V3<R> cmf(R w) {
+    R x = gaussian<R>(w, R(1.056), R(599.8), R(37.9), R(31.0)) + gaussian<R>(w, R(0.362), R(442.0), R(16.0), R(26.7)) +
+          gaussian<R>(w, R(-0.065), R(501.1), R(20.4), R(26.2));
+    R y = gaussian<R>(w, R(0.821), R(568.8), R(46.9), R(40.5)) + gaussian<R>(w, R(0.286), R(530.9), R(16.3), R(31.1));
+    R z = gaussian<R>(w, R(1.217), R(437.0), R(11.8), R(36.0)) + gaussian<R>(w, R(0.681), R(459.0), R(26.0), R(13.8));
+    return V3<R>{x, y, z};
 }
 
 // ------------------------------------------------------------------------------------------
-// raycasting: exact primitive tests (binary64)
-struct HitFrame {
-    double distance;
-    D3 location, normal, tangent, cotangent, retro;
+// raycasting: the primitives' own intersection arithmetic (exact in the reference's sense when R = double)
+template <typename R>
+struct HitFrameT {
+    R distance;
+    V3<R> location, normal, tangent, cotangent, retro;
     uint32_t material;
 };
+typedef HitFrameT<double> HitFrame;
 
 // Per-ray constants of Triangle::intersect: permutation (triangle.rs:108-122, SIGNED largest
 // component last, cyclic permutations only) and shear (triangle.rs:133-135).
-struct TriRay {
-    D3 o;
-    double sx, sy, pdz;
+template <typename R>
+struct TriRayT {
+    V3<R> o;
+    R sx, sy, pdz;
     int perm; // 0: (x,y,z)  1: (y,z,x)  2: (z,x,y)
 };
-__device__ __forceinline__ D3 permute(D3 v, int perm) {
-    return perm == 0 ? v : (perm == 1 ? d3(v.y, v.z, v.x) : d3(v.z, v.x, v.y));
+typedef TriRayT<double> TriRay;
+template <typename R>
+__device__ __forceinline__ V3<R> permute(V3<R> v, int perm) {
+    return perm == 0 ? v : (perm == 1 ? V3<R>{v.y, v.z, v.x} : V3<R>{v.z, v.x, v.y});
 }
-__device__ __forceinline__ TriRay tri_ray(D3 o, D3 d) {
-    TriRay r;
+template <typename R>
+__device__ __forceinline__ TriRayT<R> tri_ray(V3<R> o, V3<R> d) {
+    TriRayT<R> r;
     r.o = o;
     if (d.x > d.y) r.perm = (d.z > d.x) ? 0 : 1;
     else r.perm = (d.z > d.y) ? 0 : 2;
-    D3 pd = permute(d, r.perm);
+    V3<R> pd = permute(d, r.perm);
     r.sx = -pd.x / pd.z, r.sy = -pd.y / pd.z, r.pdz = pd.z;
     return r;
 }
-__device__ __forceinline__ double edge_fn(D3 a, D3 b) { return a.x * b.y - b.x * a.y; }
+template <typename R>
+__device__ __forceinline__ R edge_fn(V3<R> a, V3<R> b) { return a.x * b.y - b.x * a.y; }
+__device__ __forceinline__ bool sign_bit(double v) { return __double2hiint(v) < 0; }
+__device__ __forceinline__ bool sign_bit(float v) { return __float_as_int(v) < 0; }
 
 // triangle.rs:35-72: returns true and the barycentrics + distance when the ray hits
-__device__ VRJ_INL_PRIM bool triangle_test(const TriRay &r, D3 v0, D3 v1, D3 v2, double &distance, double &b0,
-                                              double &b1, double &b2, D3 &location) {
-    D3 p0 = permute(v0 - r.o, r.perm), p1 = permute(v1 - r.o, r.perm), p2 = permute(v2 - r.o, r.perm);
-    D3 t0 = d3(p0.x + r.sx * p0.z, p0.y + r.sy * p0.z, p0.z);
-    D3 t1 = d3(p1.x + r.sx * p1.z, p1.y + r.sy * p1.z, p1.z);
-    D3 t2 = d3(p2.x + r.sx * p2.z, p2.y + r.sy * p2.z, p2.z);
-    double e0 = edge_fn(t1, t2), e1 = edge_fn(t2, t0), e2 = edge_fn(t0, t1);
+template <typename R>
+__device__ VRJ_INL_PRIM bool triangle_test(const TriRayT<R> &r, V3<R> v0, V3<R> v1, V3<R> v2, R &distance, R &b0, R &b1, R &b2,
+                                           V3<R> &location) {
+    V3<R> p0 = permute(v0 - r.o, r.perm), p1 = permute(v1 - r.o, r.perm), p2 = permute(v2 - r.o, r.perm);
+    V3<R> t0 = V3<R>{p0.x + r.sx * p0.z, p0.y + r.sy * p0.z, p0.z};
+    V3<R> t1 = V3<R>{p1.x + r.sx * p1.z, p1.y + r.sy * p1.z, p1.z};
+    V3<R> t2 = V3<R>{p2.x + r.sx * p2.z, p2.y + r.sy * p2.z, p2.z};
+    R e0 = edge_fn(t1, t2), e1 = edge_fn(t2, t0), e2 = edge_fn(t0, t1);
     // sign BITS, so +-0 matter (triangle.rs:52-53)
-    int neg = (__double2hiint(e0) < 0) + (__double2hiint(e1) < 0) + (__double2hiint(e2) < 0);
+    int neg = (int)sign_bit(e0) + (int)sign_bit(e1) + (int)sign_bit(e2);
     if (neg != 0 && neg != 3) return false;
-    double a0 = fabs(e0), a1 = fabs(e1), a2 = fabs(e2);
-    double inv = 1.0 / (((0.0 + a0) + a1) + a2);
+    R a0 = fabs(e0), a1 = fabs(e1), a2 = fabs(e2);
+    R inv = R(1) / (((R(0) + a0) + a1) + a2);
     b0 = a0 * inv, b1 = a1 * inv, b2 = a2 * inv;
-    double tz = ((0.0 + t0.z * b0) + t1.z * b1) + t2.z * b2;
-    if ((__double2hiint(tz) < 0) != (__double2hiint(r.pdz) < 0)) return false;
-    location = ((d3(0.0, 0.0, 0.0) + v0 * b0) + v1 * b1) + v2 * b2;
+    R tz = ((R(0) + t0.z * b0) + t1.z * b1) + t2.z * b2;
+    if (sign_bit(tz) != sign_bit(r.pdz)) return false;
+    location = ((V3<R>{R(0), R(0), R(0)} + v0 * b0) + v1 * b1) + v2 * b2;
     distance = norm(r.o - location);
     return true;
 }
@@ -261,28 +315,31 @@ struct SphereDev {
     uint32_t material, pad;
 };
 // sphere.rs:39-75 (distance only)
-__device__ VRJ_INL_PRIM bool sphere_test(const SphereDev &s, D3 o, D3 d, double &distance) {
-    D3 c = d3(s.cx, s.cy, s.cz);
-    double a = ((0.0 + d.x * d.x) + d.y * d.y) + d.z * d.z;
-    double b = ((0.0 + (o.x * d.x - c.x * d.x) * 2.0) + (o.y * d.y - c.y * d.y) * 2.0) + (o.z * d.z - c.z * d.z) * 2.0;
-    double cc = (((0.0 + ((o.x * o.x + c.x * c.x) - c.x * o.x * 2.0)) + ((o.y * o.y + c.y * c.y) - c.y * o.y * 2.0)) +
-                 ((o.z * o.z + c.z * c.z) - c.z * o.z * 2.0)) -
-                s.radius * s.radius;
-    double delta_squared = b * b - 4.0 * a * cc;
-    if (delta_squared < 0.0) return false;
-    double delta = sqrt(delta_squared);
-    double one_over_2a = 1.0 / (2.0 * a);
-    double t1 = (-b - delta) * one_over_2a;
-    double t2 = (-b + delta) * one_over_2a;
-    distance = (t1 < 0.0 || (t2 >= 0.0 && t1 >= t2)) ? t2 : t1;
-    return !(distance <= 0.0);
+template <typename R>
+__device__ VRJ_INL_PRIM bool sphere_test(const SphereDev &s, V3<R> o, V3<R> d, R &distance) {
+    V3<R> c = V3<R>{(R)s.cx, (R)s.cy, (R)s.cz};
+    const R radius = (R)s.radius;
+    R a = ((R(0) + d.x * d.x) + d.y * d.y) + d.z * d.z;
+    R b = ((R(0) + (o.x * d.x - c.x * d.x) * R(2)) + (o.y * d.y - c.y * d.y) * R(2)) + (o.z * d.z - c.z * d.z) * R(2);
+    R cc = (((R(0) + ((o.x * o.x + c.x * c.x) - c.x * o.x * R(2))) + ((o.y * o.y + c.y * c.y) - c.y * o.y * R(2))) +
+            ((o.z * o.z + c.z * c.z) - c.z * o.z * R(2))) -
+           radius * radius;
+    R delta_squared = b * b - R(4) * a * cc;
+    if (delta_squared < R(0)) return false;
+    R delta = sqrt(delta_squared);
+    R one_over_2a = R(1) / (R(2) * a);
+    R t1 = (-b - delta) * one_over_2a;
+    R t2 = (-b + delta) * one_over_2a;
+    distance = (t1 < R(0) || (t2 >= R(0) && t1 >= t2)) ? t2 : t1;
+    return !(distance <= R(0));
 }
 // sphere.rs:76-90
-__device__ __forceinline__ void sphere_frame(const SphereDev &s, D3 o, D3 d, double distance, HitFrame &h) {
+template <typename R>
+__device__ __forceinline__ void sphere_frame(const SphereDev &s, V3<R> o, V3<R> d, R distance, HitFrameT<R> &h) {
     h.distance = distance;
     h.location = o + d * distance;
-    h.normal = normalize(h.location - d3(s.cx, s.cy, s.cz));
-    h.tangent = normalize(cross(h.normal, d3(0.0, 0.0, 1.0)));
+    h.normal = normalize(h.location - V3<R>{(R)s.cx, (R)s.cy, (R)s.cz});
+    h.tangent = normalize(cross(h.normal, V3<R>{R(0), R(0), R(1)}));
     h.cotangent = cross(h.normal, h.tangent);
     h.retro = -d;
     h.material = s.material;
@@ -294,22 +351,24 @@ struct PlaneDev {
     uint32_t material, pad;
 };
 // plane.rs:48-63 (distance only)
-__device__ __forceinline__ bool plane_test(const PlaneDev &p, D3 o, D3 d, double &t) {
-    D3 n = d3(p.n[0], p.n[1], p.n[2]);
-    double d_dot_n = dot(d, n);
-    D3 point_on_plane = n * p.distance;
-    double num = dot(point_on_plane - o, n);
-    if (d_dot_n == 0.0 && num != 0.0) return false;
+template <typename R>
+__device__ __forceinline__ bool plane_test(const PlaneDev &p, V3<R> o, V3<R> d, R &t) {
+    V3<R> n = V3<R>{(R)p.n[0], (R)p.n[1], (R)p.n[2]};
+    R d_dot_n = dot(d, n);
+    V3<R> point_on_plane = n * (R)p.distance;
+    R num = dot(point_on_plane - o, n);
+    if (d_dot_n == R(0) && num != R(0)) return false;
     t = num / d_dot_n;
-    return !(t < 0.0);
+    return !(t < R(0));
 }
 // plane.rs:64-73
-__device__ __forceinline__ void plane_frame(const PlaneDev &p, D3 o, D3 d, double t, HitFrame &h) {
+template <typename R>
+__device__ __forceinline__ void plane_frame(const PlaneDev &p, V3<R> o, V3<R> d, R t, HitFrameT<R> &h) {
     h.distance = t;
     h.location = o + d * t;
-    h.normal = d3(p.n[0], p.n[1], p.n[2]);
-    h.tangent = d3(p.t[0], p.t[1], p.t[2]);
-    h.cotangent = d3(p.c[0], p.c[1], p.c[2]);
+    h.normal = V3<R>{(R)p.n[0], (R)p.n[1], (R)p.n[2]};
+    h.tangent = V3<R>{(R)p.t[0], (R)p.t[1], (R)p.t[2]};
+    h.cotangent = V3<R>{(R)p.c[0], (R)p.c[1], (R)p.c[2]};
     h.retro = -d;
     h.material = p.material;
 }
@@ -320,33 +379,35 @@ struct MaterialDev {
     uint32_t kind, spectrum;
     double p0, p1, p2;
 };
-struct Fresnel {
-    D3 reflection_direction, transmission_direction;
-    double reflection_strength, transmission_strength;
+template <typename R>
+struct FresnelT {
+    V3<R> reflection_direction, transmission_direction;
+    R reflection_strength, transmission_strength;
 };
 // smooth_transparent_dialectric.rs:15-60
-__device__ __forceinline__ Fresnel fresnel(D3 w_i, double eta1, double eta2) {
-    D3 normal = w_i.z > 0.0 ? d3(0.0, 0.0, 1.0) : -d3(0.0, 0.0, 1.0);
-    Fresnel f;
-    f.reflection_direction = d3(-w_i.x, -w_i.y, w_i.z);
-    double r = eta1 / eta2;
-    double cos1 = dot(normal, w_i);
-    double cos2sq = 1.0 - r * r * (1.0 - cos1 * cos1);
-    if (cos2sq >= 0.0) {
-        double cos2 = sqrt(cos2sq);
-        double rpar = (eta1 * cos2 - eta2 * cos1) / (eta1 * cos2 + eta2 * cos1);
-        double rperp = (eta1 * cos1 - eta2 * cos2) / (eta1 * cos1 + eta2 * cos2);
-        f.reflection_strength = 0.5 * (rpar * rpar + rperp * rperp);
+template <typename R>
+__device__ __forceinline__ FresnelT<R> fresnel(V3<R> w_i, R eta1, R eta2) {
+    V3<R> normal = w_i.z > R(0) ? V3<R>{R(0), R(0), R(1)} : -V3<R>{R(0), R(0), R(1)};
+    FresnelT<R> f;
+    f.reflection_direction = V3<R>{-w_i.x, -w_i.y, w_i.z};
+    R r = eta1 / eta2;
+    R cos1 = dot(normal, w_i);
+    R cos2sq = R(1) - r * r * (R(1) - cos1 * cos1);
+    if (cos2sq >= R(0)) {
+        R cos2 = sqrt(cos2sq);
+        R rpar = (eta1 * cos2 - eta2 * cos1) / (eta1 * cos2 + eta2 * cos1);
+        R rperp = (eta1 * cos1 - eta2 * cos2) / (eta1 * cos1 + eta2 * cos2);
+        f.reflection_strength = R(0.5) * (rpar * rpar + rperp * rperp);
         f.transmission_direction = normalize((w_i * (-r)) + (normal * (r * cos1 - cos2)));
-        f.transmission_strength = 1.0 - f.reflection_strength;
+        f.transmission_strength = R(1) - f.reflection_strength;
     } else {
-        f.reflection_strength = 1.0;
-        f.transmission_strength = 0.0;
-        f.transmission_direction = d3(0.0, 0.0, 0.0);
+        f.reflection_strength = R(1);
+        f.transmission_strength = R(0);
+        f.transmission_direction = V3<R>{R(0), R(0), R(0)};
     }
-    if (w_i.z < 0.0) {
-        f.reflection_direction.z *= -1.0;
-        f.transmission_direction.z *= -1.0;
+    if (w_i.z < R(0)) {
+        f.reflection_direction.z *= R(-1);
+        f.transmission_direction.z *= R(-1);
     }
     return f;
 }
@@ -354,80 +415,84 @@ __device__ __forceinline__ Fresnel fresnel(D3 w_i, double eta1, double eta2) {
 #define VRJ_PI 3.14159265358979323846264338327950288
 
 // Material::sample: returns direction (BSDF space) and pdf, consuming draws from rng
-__device__ __forceinline__ void material_sample(const MaterialDev &m, double eta_or_zero, D3 w_i, Rng &rng, D3 &dir, double &pdf) {
+template <typename R>
+__device__ __forceinline__ void material_sample(const MaterialDev &m, R eta_or_zero, V3<R> w_i, Rng &rng, V3<R> &dir, R &pdf) {
+    const R pi = R(VRJ_PI);
     if (m.kind == 0) { // lambertian_material.rs:36-59 (rejection in the unit disc)
-        double x = 2.0 * rng.open01() - 1.0;
-        double y = 2.0 * rng.open01() - 1.0;
-        while (((0.0 + x * x) + y * y) + 0.0 * 0.0 > 1.0) {
-            x = 2.0 * rng.open01() - 1.0;
-            y = 2.0 * rng.open01() - 1.0;
+        R x = R(2) * rng.uniform_open<R>() - R(1);
+        R y = R(2) * rng.uniform_open<R>() - R(1);
+        while (((R(0) + x * x) + y * y) + R(0) * R(0) > R(1)) {
+            x = R(2) * rng.uniform_open<R>() - R(1);
+            y = R(2) * rng.uniform_open<R>() - R(1);
         }
-        double z = fmax(sqrt(1.0 - x * x - y * y), 0.0);
-        double cos_theta = ((0.0 + x * 0.0) + y * 0.0) + z * 1.0;
-        double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
-        dir = normalize(d3(x, y, z));
-        pdf = (cos_theta * sin_theta) / VRJ_PI;
+        R z = fmax(sqrt(R(1) - x * x - y * y), R(0));
+        R cos_theta = ((R(0) + x * R(0)) + y * R(0)) + z * R(1);
+        R sin_theta = sqrt(R(1) - cos_theta * cos_theta);
+        dir = normalize(V3<R>{x, y, z});
+        pdf = (cos_theta * sin_theta) / pi;
     } else if (m.kind == 2) { // reflective_material.rs:42-47
-        dir = d3(-w_i.x, -w_i.y, w_i.z);
-        pdf = 1.0;
+        dir = V3<R>{-w_i.x, -w_i.y, w_i.z};
+        pdf = R(1);
     } else if (m.kind == 3) { // smooth_transparent_dialectric.rs:91-114
-        double eta1 = w_i.z >= 0.0 ? 1.0 : eta_or_zero, eta2 = w_i.z >= 0.0 ? eta_or_zero : 1.0;
-        Fresnel f = fresnel(w_i, eta1, eta2);
-        pdf = 0.5;
-        if (f.transmission_strength <= 0.0000000001) dir = f.reflection_direction;
-        else if (f.reflection_strength <= 0.0000000001 || rng.boolean()) dir = f.transmission_direction;
+        R eta1 = w_i.z >= R(0) ? R(1) : eta_or_zero, eta2 = w_i.z >= R(0) ? eta_or_zero : R(1);
+        FresnelT<R> f = fresnel(w_i, eta1, eta2);
+        pdf = R(0.5);
+        if (f.transmission_strength <= R(0.0000000001)) dir = f.reflection_direction;
+        else if (f.reflection_strength <= R(0.0000000001) || rng.boolean()) dir = f.transmission_direction;
         else dir = f.reflection_direction;
     } else { // materials/mod.rs:28-33 -> cosine_weighted_hemisphere.rs:19-33, unit_disc.rs:27-44, uniform_square.rs:20-25
-        double sx = -1.0 + rng.open01() * 2.0;
-        double sy = -1.0 + rng.open01() * 2.0;
-        double dx, dy;
-        if (sx == 0.0 && sy == 0.0) {
+        R sx = R(-1) + rng.uniform_open<R>() * R(2);
+        R sy = R(-1) + rng.uniform_open<R>() * R(2);
+        R dx, dy;
+        if (sx == R(0) && sy == R(0)) {
             dx = sx, dy = sy;
         } else {
-            double radius, angle;
-            if (fabs(sx) > fabs(sy)) radius = sx, angle = (VRJ_PI / 4.0) * sy / sx;
-            else radius = sy, angle = VRJ_PI / 2.0 - (VRJ_PI / 4.0) * sx / sy;
+            R radius, angle;
+            if (fabs(sx) > fabs(sy)) radius = sx, angle = (pi / R(4)) * sy / sx;
+            else radius = sy, angle = pi / R(2) - (pi / R(4)) * sx / sy;
             dx = cos(angle) * radius, dy = sin(angle) * radius;
         }
-        double z = sqrt(fmax(0.0, 1.0 - dx * dx - dy * dy));
-        dir = d3(dx, dy, z);
-        pdf = sqrt(dx * dx + dy * dy) / VRJ_PI;
+        R z = sqrt(fmax(R(0), R(1) - dx * dx - dy * dy));
+        dir = V3<R>{dx, dy, z};
+        pdf = sqrt(dx * dx + dy * dy) / pi;
     }
 }
 
 // Material::bsdf as an affine map of the incoming intensity: out = a * in + b.
 // `s` is the material spectrum at the photon's wavelength (colour, or eta for the dielectric).
-__device__ __forceinline__ void material_bsdf_affine(const MaterialDev &m, double s, D3 w_o, D3 w_i, double &a, double &b) {
+template <typename R>
+__device__ __forceinline__ void material_bsdf_affine(const MaterialDev &m, R s, V3<R> w_o, V3<R> w_i, R &a, R &b) {
+    const R p0 = (R)m.p0, p1 = (R)m.p1, p2 = (R)m.p2;
     if (m.kind == 0) { // lambertian_material.rs:27-34
-        a = s * m.p0, b = 0.0;
+        a = s * p0, b = R(0);
     } else if (m.kind == 1) { // phong_material.rs:16-36
-        if (w_i.z < 0.0 || w_o.z < 0.0) {
-            a = 0.0, b = 0.0;
+        if (w_i.z < R(0) || w_o.z < R(0)) {
+            a = R(0), b = R(0);
         } else {
-            D3 refl = d3(-w_i.x, -w_i.y, w_i.z);
-            a = s * m.p0;
-            b = pow(fabs(dot(w_o, refl)), m.p2) * (m.p1 / dot(w_i, d3(0.0, 0.0, 1.0)));
+            V3<R> refl = V3<R>{-w_i.x, -w_i.y, w_i.z};
+            a = s * p0;
+            b = pow(fabs(dot(w_o, refl)), p2) * (p1 / dot(w_i, V3<R>{R(0), R(0), R(1)}));
         }
     } else if (m.kind == 2) { // reflective_material.rs:15-40
-        if (w_i.z <= 0.0 || w_o.z <= 0.0) {
-            a = 0.0, b = 0.0;
+        if (w_i.z <= R(0) || w_o.z <= R(0)) {
+            a = R(0), b = R(0);
         } else {
-            D3 refl = d3(-w_o.x, -w_o.y, w_o.z);
-            double c = dot(w_i, refl);
-            c = c < 0.0 ? 0.0 : (c > 1.0 ? 1.0 : c);
-            double theta = acos(fabs(c));
-            double sigma = 0.05, two = 2.0;
-            double rf = m.p1 * exp(-(theta * theta) / (two * sigma * sigma));
-            a = (s * m.p0) * (1.0 - rf), b = rf;
+            V3<R> refl = V3<R>{-w_o.x, -w_o.y, w_o.z};
+            R c = dot(w_i, refl);
+            c = c < R(0) ? R(0) : (c > R(1) ? R(1) : c);
+            R theta = acos(fabs(c));
+            R sigma = R(0.05), two = R(2);
+            R rf = p1 * exp(-(theta * theta) / (two * sigma * sigma));
+            a = (s * p0) * (R(1) - rf), b = rf;
         }
     } else { // smooth_transparent_dialectric.rs:74-89
-        double eta1 = w_i.z >= 0.0 ? 1.0 : s, eta2 = w_i.z >= 0.0 ? s : 1.0;
-        Fresnel f = fresnel(w_i, eta1, eta2);
-        D3 dr = w_o - f.reflection_direction, dt = w_o - f.transmission_direction;
-        b = 0.0;
-        if (dot(dr, dr) < 0.0000000001) a = f.reflection_strength;
-        else if (dot(dt, dt) < 0.0000000001) a = f.transmission_strength;
-        else a = 0.0;
+        R eta1 = w_i.z >= R(0) ? R(1) : s, eta2 = w_i.z >= R(0) ? s : R(1);
+        FresnelT<R> f = fresnel(w_i, eta1, eta2);
+        V3<R> dr = w_o - f.reflection_direction, dt = w_o - f.transmission_direction;
+        b = R(0);
+        if (dot(dr, dr) < R(0.0000000001)) a = f.reflection_strength;
+        else if (dot(dt, dt) < R(0.0000000001)) a = f.transmission_strength;
+        else a = R(0);
     }
 }
 

@@ -29,6 +29,15 @@
 #ifndef VRJ_TRACE4_MINB
 #define VRJ_TRACE4_MINB 5
 #endif
+// VRJ_PRECISION_F32_FAST: half the register footprint, so more resident CTAs
+#ifndef VRJ_SHADE_MINB_F32
+#define VRJ_SHADE_MINB_F32 8
+#endif
+#ifndef VRJ_TRACE_MINB_F32
+#define VRJ_TRACE_MINB_F32 8
+#endif
+#define VRJ_SHADE_BOUNDS(R) __launch_bounds__(128, sizeof(R) == 4 ? VRJ_SHADE_MINB_F32 : VRJ_SHADE_MINB)
+#define VRJ_TRACE_BOUNDS(R) __launch_bounds__(128, sizeof(R) == 4 ? VRJ_TRACE_MINB_F32 : VRJ_TRACE_MINB)
 
 namespace vrj {
 
@@ -66,9 +75,10 @@ struct RenderConst {
     const double *light_samples;
 };
 
-__device__ __forceinline__ double light_intensity(const RenderConst &rc, const SpectrumDev &s, double wavelength) {
+template <typename R>
+__device__ __forceinline__ R light_intensity(const RenderConst &rc, const SpectrumDev &s, R wavelength) {
     const double *p = rc.light_samples + s.first;
-    return spectrum_lookup(s.shortest, s.longest, s.n, wavelength, [p](uint32_t i) { return __ldg(p + i); });
+    return spectrum_lookup<R>((R)s.shortest, (R)s.longest, s.n, wavelength, [p](uint32_t i) { return (R)__ldg(p + i); });
 }
 
 enum { ST_PRIMARY = 0, ST_BOUNCE, ST_SHADOW, ST_MISSED, ST_ESCAPED, ST_LIMITED, ST_NODES, ST_TRIS, ST_STAGED, ST_COUNT };
@@ -98,19 +108,27 @@ __device__ __forceinline__ uint32_t queue_reserve(bool alive, uint32_t *count) {
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
 
-__device__ __forceinline__ void queue_store(const PathQueue &q, uint32_t idx, D3 o, D3 d, double wl, double A, double B,
-                                            double aux, uint32_t slot, uint32_t ordinal, uint32_t limit, uint32_t flags) {
-    q.q0[idx] = make_double2(o.x, o.y);
-    q.q1[idx] = make_double2(o.z, d.x);
-    q.q2[idx] = make_double2(d.y, d.z);
-    q.q3[idx] = make_double2(wl, A);
-    q.q4[idx] = make_double2(B, aux);
+// the queue keeps binary64 slots in both precisions (binary32 values widen exactly)
+template <typename R>
+__device__ __forceinline__ void queue_store(const PathQueue &q, uint32_t idx, V3<R> o, V3<R> d, R wl, R A, R B, R aux, uint32_t slot,
+                                            uint32_t ordinal, uint32_t limit, uint32_t flags) {
+    q.q0[idx] = make_double2((double)o.x, (double)o.y);
+    q.q1[idx] = make_double2((double)o.z, (double)d.x);
+    q.q2[idx] = make_double2((double)d.y, (double)d.z);
+    q.q3[idx] = make_double2((double)wl, (double)A);
+    q.q4[idx] = make_double2((double)B, (double)aux);
     q.q5[idx] = make_uint4(slot, ordinal, limit, flags);
+}
+template <typename R>
+__device__ __forceinline__ void queue_load_ray(const PathQueue &q, uint32_t j, V3<R> &o, V3<R> &d) {
+    const double2 a0 = q.q0[j], a1 = q.q1[j], a2 = q.q2[j];
+    o = V3<R>{(R)a0.x, (R)a0.y, (R)a1.x}, d = V3<R>{(R)a1.y, (R)a2.x, (R)a2.y};
 }
 
 // Ray::new (raycasting/mod.rs:41-46) then .bias(amount) (raycasting/mod.rs:58-60): normalise, offset, normalise again
-__device__ __forceinline__ void biased_ray(D3 origin, D3 direction, double amount, D3 &o, D3 &d) {
-    D3 d1 = normalize(direction);
+template <typename R>
+__device__ __forceinline__ void biased_ray(V3<R> origin, V3<R> direction, R amount, V3<R> &o, V3<R> &d) {
+    V3<R> d1 = normalize(direction);
     o = origin + d1 * amount;
     d = normalize(d1);
 }
@@ -132,16 +150,16 @@ struct TraceBuffers {
 };
 
 // analytic objects + BVH root pre-test for the ray just written to queue entry `idx`; all 32 lanes call
-template <bool COUNT>
-__device__ __forceinline__ void stage_ray(const DevScene &sc, bool have_ray, uint32_t idx, D3 o, D3 d, const TraceBuffers &tb,
+template <bool COUNT, typename R>
+__device__ __forceinline__ void stage_ray(const DevScene &sc, bool have_ray, uint32_t idx, V3<R> o, V3<R> d, const TraceBuffers &tb,
                                           uint32_t *list_count, LocalStats &ls) {
     bool need = false;
     if (have_ray) {
-        Hit best;
+        HitT<R> best;
         TraceCounters tc = {0, 0};
         need = pretrace<COUNT>(sc, o, d, best, tc);
         tb.hits[idx] = make_int2(best.item, best.tri);
-        tb.tbest[idx] = best.t;
+        tb.tbest[idx] = (double)best.t;
         if (COUNT) ls.v[ST_TRIS] += tc.tri_tests;
     }
     uint32_t pos = queue_reserve(need, list_count);
@@ -149,8 +167,8 @@ __device__ __forceinline__ void stage_ray(const DevScene &sc, bool have_ray, uin
 }
 
 // ---- k_raygen: camera rays (camera.rs:45-66) into queue 0, staged for traversal ----
-template <bool COUNT>
-__global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_raygen(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, uint32_t *list_count,
+template <typename R, bool COUNT>
+__global__ void VRJ_SHADE_BOUNDS(R) k_raygen(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, uint32_t *list_count,
                                                 uint32_t *work, unsigned long long *stats) {
     const uint32_t n = rc.npix * rc.batch_samples;
     const uint32_t lane = threadIdx.x & 31;
@@ -162,21 +180,22 @@ __global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_raygen(DevScene sc, Ren
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         uint32_t j = base + lane;
-        D3 o = d3(0, 0, 0), d = d3(0, 0, 1);
+        V3<R> o = V3<R>{R(0), R(0), R(0)}, d = V3<R>{R(0), R(0), R(1)};
         if (j < n) {
             uint32_t pixel;
             uint64_t sample, grow, gcol;
             slot_to_pixel(rc, j, pixel, sample, grow, gcol);
             Rng rng;
             rng.init(rc.seed, pixel, sample, 0);
-            double ux = rng.f64(), uy = rng.f64();
-            double px = ((double)gcol + ux) * (rc.film_w * (1.0 / (double)rc.width)) - rc.film_w * 0.5;
-            double py = ((double)(rc.height - (grow + 1)) + uy) * (rc.film_h * (1.0 / (double)rc.height)) - rc.film_h * 0.5;
-            o = d3(sc.cam[0], sc.cam[1], sc.cam[2]);
-            d = normalize(d3(px, py, 1.0));
-            q.q0[j] = make_double2(o.x, o.y);
-            q.q1[j] = make_double2(o.z, d.x);
-            q.q2[j] = make_double2(d.y, d.z);
+            R ux = rng.uniform<R>(), uy = rng.uniform<R>();
+            const R film_w = (R)rc.film_w, film_h = (R)rc.film_h;
+            R px = ((R)gcol + ux) * (film_w * (R(1) / (R)rc.width)) - film_w * R(0.5);
+            R py = ((R)(rc.height - (grow + 1)) + uy) * (film_h * (R(1) / (R)rc.height)) - film_h * R(0.5);
+            o = V3<R>{(R)sc.cam[0], (R)sc.cam[1], (R)sc.cam[2]};
+            d = normalize(V3<R>{px, py, R(1)});
+            q.q0[j] = make_double2((double)o.x, (double)o.y);
+            q.q1[j] = make_double2((double)o.z, (double)d.x);
+            q.q2[j] = make_double2((double)d.y, (double)d.z);
             ls.v[ST_PRIMARY]++;
         }
         stage_ray<COUNT>(sc, j < n, j, o, d, tb, list_count, ls);
@@ -188,33 +207,34 @@ __global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_raygen(DevScene sc, Ren
 struct ListRaySource {
     const PathQueue &q;
     const TraceBuffers &tb;
-    __device__ __forceinline__ void load(uint32_t r, D3 &o, D3 &d, Hit &best) {
+    template <typename R>
+    __device__ __forceinline__ void load(uint32_t r, V3<R> &o, V3<R> &d, HitT<R> &best) {
         uint32_t j = tb.list[r];
-        double2 a0 = q.q0[j], a1 = q.q1[j], a2 = q.q2[j];
-        o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
+        queue_load_ray(q, j, o, d);
         int2 h = tb.hits[j];
-        best.item = h.x, best.tri = h.y, best.t = tb.tbest[j];
+        best.item = h.x, best.tri = h.y, best.t = (R)tb.tbest[j];
     }
 };
 struct ListHitSink {
     const TraceBuffers &tb;
-    __device__ __forceinline__ void store(uint32_t r, const Hit &best, bool improved) {
+    template <typename R>
+    __device__ __forceinline__ void store(uint32_t r, const HitT<R> &best, bool improved) {
         if (!improved) return;
         uint32_t j = tb.list[r];
         tb.hits[j] = make_int2(best.item, best.tri);
-        tb.tbest[j] = best.t;
+        tb.tbest[j] = (double)best.t;
     }
 };
 
-template <typename NT, bool COUNT>
-__global__ void __launch_bounds__(128, VRJ_TRACE_MINB) k_trace(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
+template <typename NT, typename R, bool COUNT>
+__global__ void VRJ_TRACE_BOUNDS(R) k_trace(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
                                                uint32_t *work, unsigned long long *stats, const uint32_t *tail_done) {
     if (tail_done && *tail_done) return;
     const uint32_t n = *list_count;
     ListRaySource source{q, tb};
     ListHitSink sink{tb};
     TraceCounters tc = {0, 0};
-    trace_persistent<NT, COUNT>(sc, n, work, source, sink, tc);
+    trace_persistent<NT, R, COUNT>(sc, n, work, source, sink, tc);
     if (COUNT) {
         LocalStats ls;
         ls.clear();
@@ -242,20 +262,25 @@ __global__ void __launch_bounds__(128, VRJ_TRACE4_MINB) k_trace4(DevScene sc, Pa
 }
 
 // ---- one level of the integrator for one path (shared by k_shade and k_tail) ----
-struct PathRegs {
-    D3 o, d;                 // in: the ray that produced `hit`; out: the bounce ray
-    double wl, A, B, aux;    // wavelength, affine accumulator, aux (SimpleRandom: W.y; Whitted: B before the bounce term)
+template <typename R>
+struct PathRegsT {
+    V3<R> o, d;         // in: the ray that produced `hit`; out: the bounce ray
+    R wl, A, B, aux;    // wavelength, affine accumulator, aux (SimpleRandom: W.y; Whitted: B before the bounce term)
     uint32_t slot, ordinal, limit, flags;
 };
+// a finished sample: (wavelength, intensity * 360); binary64 slots in both precisions
+template <typename R>
+__device__ __forceinline__ double2 photon_out(R wavelength, R intensity) { return make_double2((double)wavelength, (double)intensity); }
 
 // Consumes the closest hit of p's ray: finishes the path (miss: black / sky; depth limit) and returns false, or
 // runs one level of Integrator::integrate -- rebuild the IntersectionInfo, sample the material (Whitted: trace the
 // shadow rays), update the affine accumulator -- leaves the bounce ray and the new state in p and returns true.
 // `first`: p.slot is set, the rest of the state is initialised here (camera.rs:108-119).
 // `load_ray(o, d)` fetches the ray only when it is needed.
-template <typename NT, bool COUNT, bool WHITTED, typename RayLoader>
-__device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderConst &rc, PathRegs &p, int2 hit, bool first,
+template <typename NT, bool COUNT, bool WHITTED, typename R, typename RayLoader>
+__device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderConst &rc, PathRegsT<R> &p, int2 hit, bool first,
                                             RayLoader load_ray, double2 *photons, LocalStats &ls) {
+    const R span = R(740.0) - R(380.0); // photon.rs:18-24, colour/mod.rs:13-14
     if (first) {
         if (hit.x < 0) {
             photons[p.slot] = make_double2(0.0, 0.0); // camera.rs:110-113
@@ -267,8 +292,8 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
         slot_to_pixel(rc, p.slot, pixel, sample, grow, gcol);
         Rng rng;
         rng.init(rc.seed, pixel, sample, 2);
-        p.wl = 380.0 + (740.0 - 380.0) * rng.f64(); // photon.rs:18-24
-        p.ordinal = 4, p.A = 1.0, p.B = 0.0, p.aux = 0.0, p.limit = rc.max_depth, p.flags = 0; // ordinal 3 unused: draws pair up per Philox block
+        p.wl = R(380.0) + span * rng.uniform<R>(); // photon.rs:18-24
+        p.ordinal = 4, p.A = R(1), p.B = R(0), p.aux = R(0), p.limit = rc.max_depth, p.flags = 0; // ordinal 3 unused: draws pair up per Philox block
         if (!WHITTED && p.limit == 0) {
             photons[p.slot] = make_double2(0.0, 0.0); // simple_random_integrator.rs:20-25
             ls.v[ST_LIMITED]++;
@@ -277,14 +302,14 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
     } else if (WHITTED) {
         // whitted_integrator.rs:52-79: the bounce term counts only if the ray hit and the level had limit > 0
         if (hit.x < 0 || (p.flags & 1u)) {
-            photons[p.slot] = make_double2(p.wl, p.aux * (740.0 - 380.0));
+            photons[p.slot] = photon_out(p.wl, p.aux * span);
             if (hit.x < 0) ls.v[ST_ESCAPED]++;
             else ls.v[ST_LIMITED]++;
             return false;
         }
     } else if (hit.x < 0) {
-        double L = rgb_reflection_intensity(p.aux, p.aux, 1.0, p.wl); // sky(W): simple_random_integrator.rs:43-46,57-65
-        photons[p.slot] = make_double2(p.wl, (p.A * L + p.B) * (740.0 - 380.0));
+        R L = rgb_reflection_intensity<R>(p.aux, p.aux, R(1), p.wl); // sky(W): simple_random_integrator.rs:43-46,57-65
+        photons[p.slot] = photon_out(p.wl, (p.A * L + p.B) * span);
         ls.v[ST_ESCAPED]++;
         return false;
     } else if (p.limit == 0) {
@@ -294,37 +319,37 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
         return false;
     }
     load_ray(p.o, p.d);
-    HitFrame h;
+    HitFrameT<R> h;
     bool ok = rebuild_hit(sc, p.o, p.d, hit.x, hit.y, h);
     // algebra_utils.rs:3-5, mat3.rs:111-118
-    M3 w2b = from_rows(h.tangent, h.cotangent, h.normal), b2w;
+    M3T<R> w2b = from_rows(h.tangent, h.cotangent, h.normal), b2w;
     ok = try_inverse(w2b, b2w) && ok;
     if (!ok) {
         // the reference panics here (simple_random_integrator.rs:28,31); report a NaN sample
-        photons[p.slot] = make_double2(p.wl, CUDART_NAN);
+        photons[p.slot] = make_double2((double)p.wl, CUDART_NAN);
         return false;
     }
     MaterialDev m = sc.materials[h.material];
-    double s = spectrum_intensity(sc.spectra, sc.spectrum_samples, m.spectrum, p.wl);
-    D3 w_retro = mul(w2b, h.retro);
+    R s = spectrum_intensity<R>(sc.spectra, sc.spectrum_samples, m.spectrum, p.wl);
+    V3<R> w_retro = mul(w2b, h.retro);
     if (WHITTED) {
         // whitted_integrator.rs:33-50: one shadow ray per light
         TraceCounters tc = {0, 0};
-        double direct = 0.0; // fold starts from photon.intensity == 0
+        R direct = R(0); // fold starts from photon.intensity == 0
         for (uint32_t li = 0; li < rc.n_lights; li++) {
             LightDev Lt = rc.lights[li];
-            D3 ldir = d3(Lt.dir[0], Lt.dir[1], Lt.dir[2]);
-            D3 so, sd;
-            biased_ray(h.location, ldir, rc.bias, so, sd);
-            Hit sh = trace_closest<NT, COUNT, true>(sc, so, sd, tc);
+            V3<R> ldir = V3<R>{(R)Lt.dir[0], (R)Lt.dir[1], (R)Lt.dir[2]};
+            V3<R> so, sd;
+            biased_ray(h.location, ldir, (R)rc.bias, so, sd);
+            HitT<R> sh = trace_closest<NT, COUNT, true>(sc, so, sd, tc);
             ls.v[ST_SHADOW]++;
-            double term;
+            R term;
             if (sh.item >= 0) {
-                term = rc.has_ambient ? light_intensity(rc, rc.lights[rc.n_lights].spectrum, p.wl) : 0.0;
+                term = rc.has_ambient ? light_intensity<R>(rc, rc.lights[rc.n_lights].spectrum, p.wl) : R(0);
             } else {
-                double emitted = light_intensity(rc, Lt.spectrum, p.wl);
+                R emitted = light_intensity<R>(rc, Lt.spectrum, p.wl);
                 emitted = emitted * fabs(dot(ldir, h.normal));
-                double la, lb;
+                R la, lb;
                 material_bsdf_affine(m, s, w_retro, mul(w2b, ldir), la, lb); // (retro, incoming) order
                 term = la * emitted + lb;
             }
@@ -338,14 +363,14 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
     uint64_t sample, grow, gcol;
     slot_to_pixel(rc, p.slot, pixel, sample, grow, gcol);
     rng.init(rc.seed, pixel, sample, p.ordinal);
-    D3 w_s;
-    double pdf;
+    V3<R> w_s;
+    R pdf;
     material_sample(m, s, w_retro, rng, w_s, pdf);
     p.ordinal = rng.ordinal;
-    D3 W = mul(b2w, w_s);
-    biased_ray(h.location, W, rc.bias, p.o, p.d);
-    double cosine = fabs(dot(W, h.normal));
-    double ba, bb;
+    V3<R> W = mul(b2w, w_s);
+    biased_ray(h.location, W, (R)rc.bias, p.o, p.d);
+    R cosine = fabs(dot(W, h.normal));
+    R ba, bb;
     if (WHITTED) {
         // bsdf(retro, sampled, L_in) * |W.n|, pdf unused; B before the bounce term is kept in aux
         material_bsdf_affine(m, s, w_retro, w_s, ba, bb);
@@ -367,8 +392,8 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
 }
 
 // ---- k_shade: consume the hits of a queue; survivors are enqueued warp-ballot compacted and staged ----
-template <typename NT, bool COUNT, bool WHITTED, bool FIRST>
-__global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_shade(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
+template <typename NT, typename R, bool COUNT, bool WHITTED, bool FIRST>
+__global__ void VRJ_SHADE_BOUNDS(R) k_shade(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
                                                TraceBuffers tb_in, PathQueue out, uint32_t *out_count, TraceBuffers tb_out,
                                                uint32_t *list_count, uint32_t *work, double2 *photons,
                                                unsigned long long *stats, const uint32_t *tail_done) {
@@ -408,9 +433,9 @@ __global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_shade(DevScene sc, Rend
         for (uint32_t k = threadIdx.x; k < ((total + 31u) & ~31u); k += 128) {
             const uint32_t j = k < total ? s_sorted[k] : n;
             bool alive = false;
-            PathRegs p;
-            p.o = d3(0, 0, 0), p.d = d3(0, 0, 1);
-            p.wl = p.A = p.B = p.aux = 0.0;
+            PathRegsT<R> p;
+            p.o = V3<R>{R(0), R(0), R(0)}, p.d = V3<R>{R(0), R(0), R(1)};
+            p.wl = p.A = p.B = p.aux = R(0);
             p.slot = p.ordinal = p.limit = p.flags = 0;
             if (j < n) {
                 int2 hit = tb_in.hits[j];
@@ -419,16 +444,11 @@ __global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_shade(DevScene sc, Rend
                 } else {
                     double2 a3 = in.q3[j], a4 = in.q4[j];
                     uint4 a5 = in.q5[j];
-                    p.wl = a3.x, p.A = a3.y, p.B = a4.x, p.aux = a4.y;
+                    p.wl = (R)a3.x, p.A = (R)a3.y, p.B = (R)a4.x, p.aux = (R)a4.y;
                     p.slot = a5.x, p.ordinal = a5.y, p.limit = a5.z, p.flags = a5.w;
                 }
                 alive = shade_entry<NT, COUNT, WHITTED>(
-                    sc, rc, p, hit, FIRST,
-                    [&in, j](D3 &o, D3 &d) {
-                        double2 a0 = in.q0[j], a1 = in.q1[j], a2 = in.q2[j];
-                        o = d3(a0.x, a0.y, a1.x), d = d3(a1.y, a2.x, a2.y);
-                    },
-                    photons, ls);
+                    sc, rc, p, hit, FIRST, [&in, j](V3<R> &o, V3<R> &d) { queue_load_ray(in, j, o, d); }, photons, ls);
             }
             uint32_t idx = queue_reserve(alive, out_count);
             if (alive) queue_store(out, idx, p.o, p.d, p.wl, p.A, p.B, p.aux, p.slot, p.ordinal, p.limit, p.flags);
@@ -444,7 +464,7 @@ __global__ void __launch_bounds__(128, VRJ_SHADE_MINB) k_shade(DevScene sc, Rend
 // here every thread follows one path (trace -> shade -> trace ...) to its end, so the remaining levels overlap.
 // Runs before T_k on queue k; does nothing unless the queue is at most `tail_max` long; sets *tail_done so the
 // remaining T / S launches of the batch return immediately.
-template <typename NT, bool COUNT, bool WHITTED>
+template <typename NT, typename R, bool COUNT, bool WHITTED>
 __global__ void __launch_bounds__(128, 2) k_tail(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
                                               uint32_t tail_max, double2 *photons, unsigned long long *stats,
                                               uint32_t *tail_done) {
@@ -455,18 +475,18 @@ __global__ void __launch_bounds__(128, 2) k_tail(DevScene sc, RenderConst rc, Pa
     const uint32_t padded = (n + 31u) & ~31u;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < padded; j += gridDim.x * blockDim.x) {
         if (j < n) {
-            PathRegs p;
-            double2 a0 = in.q0[j], a1 = in.q1[j], a2 = in.q2[j], a3 = in.q3[j], a4 = in.q4[j];
+            PathRegsT<R> p;
+            double2 a3 = in.q3[j], a4 = in.q4[j];
             uint4 a5 = in.q5[j];
-            p.o = d3(a0.x, a0.y, a1.x), p.d = d3(a1.y, a2.x, a2.y);
-            p.wl = a3.x, p.A = a3.y, p.B = a4.x, p.aux = a4.y;
+            queue_load_ray(in, j, p.o, p.d);
+            p.wl = (R)a3.x, p.A = (R)a3.y, p.B = (R)a4.x, p.aux = (R)a4.y;
             p.slot = a5.x, p.ordinal = a5.y, p.limit = a5.z, p.flags = a5.w;
             bool alive = true;
             while (alive) {
                 TraceCounters tc = {0, 0};
-                Hit h = trace_closest<NT, COUNT, false>(sc, p.o, p.d, tc);
+                HitT<R> h = trace_closest<NT, COUNT, false>(sc, p.o, p.d, tc);
                 if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
-                alive = shade_entry<NT, COUNT, WHITTED>(sc, rc, p, make_int2(h.item, h.tri), false, [](D3 &, D3 &) {}, photons, ls);
+                alive = shade_entry<NT, COUNT, WHITTED>(sc, rc, p, make_int2(h.item, h.tri), false, [](V3<R> &, V3<R> &) {}, photons, ls);
             }
         }
     }
@@ -481,6 +501,8 @@ struct AccumDev {
 };
 
 // accumulation_buffer.rs:44-60 applied for the batch's samples in sample order
+// R: precision of ColourXyz::from_photon (the colour matching functions); the accumulators are binary64 in both modes
+template <typename R>
 __global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t npix, uint32_t batch_samples) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npix) return;
@@ -489,7 +511,7 @@ __global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t npix, u
     double w = acc.weight[p], wb = acc.weight_bias[p];
     for (uint32_t s = 0; s < batch_samples; s++) {
         double2 ph = photons[(size_t)s * npix + p];
-        D3 c = cmf(ph.x) * ph.y; // colour_xyz.rs:31-35
+        D3 c = convert<double>(cmf<R>((R)ph.x) * (R)ph.y); // colour_xyz.rs:31-35
         const double weight = 1.0;
         double wy = weight - wb;
         double wt = w + wy;

@@ -18,7 +18,7 @@ struct RawTriangles {
 };
 
 __global__ void k_pack_triangles(uint32_t n, RawTriangles raw, const uint32_t *__restrict__ perm, double *__restrict__ tri_pos,
-                                 double *__restrict__ tri_nrm) {
+                                 double *__restrict__ tri_nrm, float *__restrict__ tri_pos32, float *__restrict__ tri_nrm32) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const size_t src = perm ? perm[t] : t;
@@ -34,6 +34,12 @@ __global__ void k_pack_triangles(uint32_t n, RawTriangles raw, const uint32_t *_
     const unsigned long long bits = ((unsigned long long)raw.prim_id[src] << 32) | raw.material[src];
     tp[9] = __longlong_as_double((long long)bits);
     tp[10] = tp[11] = 0.0, tn[9] = tn[10] = tn[11] = 0.0;
+    // the binary32 copies of VRJ_PRECISION_F32_FAST: 48-byte records (round to nearest; OBJ vertices are f32 already)
+    float *fp = tri_pos32 + (size_t)t * 12, *fn = tri_nrm32 + (size_t)t * 12;
+#pragma unroll
+    for (int k = 0; k < 9; k++) fp[k] = (float)tp[k], fn[k] = (float)tn[k];
+    fp[9] = __uint_as_float(raw.material[src]), fp[10] = __uint_as_float(raw.prim_id[src]), fp[11] = 0.f;
+    fn[9] = fn[10] = fn[11] = 0.f;
 }
 
 // input-order triangle index of every leaf position of a BVH built on the device

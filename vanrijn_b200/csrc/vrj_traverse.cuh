@@ -25,6 +25,8 @@ struct DevScene {
     const float4 *__restrict__ nodes4;   // 8 x float4 per 4-wide node (128 B): 4 boxes, 4 refs (VRJ_FILTER_F32X4)
     const double2 *__restrict__ tri_pos; // 96-byte records (3 x 256-bit loads): 9 coords + {material, prim_id} + pad
     const double2 *__restrict__ tri_nrm; // 96-byte records: 9 coords + pad
+    const float4 *__restrict__ tri_pos32; // f32-fast mode: 48-byte records, 9 coords + {material, prim_id} + pad
+    const float4 *__restrict__ tri_nrm32; // 48-byte records: 9 coords + pad
     const SphereDev *__restrict__ spheres;
     const PlaneDev *__restrict__ planes;
     const MaterialDev *__restrict__ materials;
@@ -41,11 +43,19 @@ struct DevScene {
     double cam[3];
 };
 
-struct Hit {
-    double t;
+template <typename R>
+struct HitT {
+    R t;
     int item; // -1 = miss
     int tri;  // triangle index (absolute) for triangle hits
 };
+typedef HitT<double> Hit;
+template <typename R>
+__device__ __forceinline__ R real_inf();
+template <>
+__device__ __forceinline__ double real_inf<double>() { return CUDART_INF; }
+template <>
+__device__ __forceinline__ float real_inf<float>() { return CUDART_INF_F; }
 
 struct TraceCounters {
     uint32_t node_visits, tri_tests;
@@ -63,6 +73,10 @@ struct FilterTraits<float> {
     static __device__ __forceinline__ float down(double v) { return __double2float_rd(v); }
     static __device__ __forceinline__ float up(double v) { return __double2float_ru(v); }
     static __device__ __forceinline__ float near(double v) { return __double2float_rn(v); }
+    // f32-fast mode: the ray constants are already binary32; the relative pads absorb the missing directed rounding
+    static __device__ __forceinline__ float down(float v) { return v; }
+    static __device__ __forceinline__ float up(float v) { return v; }
+    static __device__ __forceinline__ float near(float v) { return v; }
     static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
     static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
     static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
@@ -89,22 +103,28 @@ template <typename T>
 struct FilterRay {
     T id[3], cn[3], cf[3];
 };
-template <typename T>
-__device__ __forceinline__ FilterRay<T> filter_ray(D3 o, D3 d) {
+template <typename T, typename R>
+__device__ __forceinline__ FilterRay<T> filter_ray(V3<R> o, V3<R> d) {
     typedef FilterTraits<T> F;
     FilterRay<T> f;
-    const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    const R oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        double id = 1.0 / dd[k];
-        if (!(fabs(id) <= F::big())) id = copysign(F::big(), dd[k]);
-        double ood = oo[k] * id;
-        double pad = fabs(ood) * F::abs_factor() + 1e-300;
+        R id = R(1) / dd[k];
+        if (!(fabs(id) <= (R)F::big())) id = copysign((R)F::big(), dd[k]);
+        R ood = oo[k] * id;
+        R pad = fabs(ood) * (R)F::abs_factor() + (sizeof(R) == 8 ? R(1e-300) : R(1e-30));
         f.id[k] = F::near(id);
         f.cn[k] = F::down(-(ood + pad));
         f.cf[k] = F::up(-(ood - pad));
     }
     return f;
+}
+// the prune bound of the filter for a best distance t: rounded up in the node type with the filter's relative slack
+template <typename T, typename R>
+__device__ __forceinline__ T filter_limit(R t) {
+    typedef FilterTraits<T> F;
+    return F::up(t * (R(1) + R(4) * (R)F::rel()));
 }
 template <typename T>
 __device__ __forceinline__ bool box_filter(const FilterRay<T> &f, T lox, T hix, T loy, T hiy, T loz, T hiz, T t_limit,
@@ -174,18 +194,29 @@ __device__ __forceinline__ void load_tri_nrm(const DevScene &sc, int tri, D3 &n0
     n0 = d3(a.x, a.y, b.x), n1 = d3(b.y, c.x, c.y), n2 = d3(d.x, d.y, e.x);
 }
 
+__device__ __forceinline__ void load_tri_pos(const DevScene &sc, int tri, F3 &v0, F3 &v1, F3 &v2, uint32_t &material, uint32_t &prim_id) {
+    const float4 *p = sc.tri_pos32 + (size_t)tri * 3;
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    v0 = F3{a.x, a.y, a.z}, v1 = F3{a.w, b.x, b.y}, v2 = F3{b.z, b.w, c.x};
+    material = __float_as_uint(c.y), prim_id = __float_as_uint(c.z);
+}
+__device__ __forceinline__ void load_tri_nrm(const DevScene &sc, int tri, F3 &n0, F3 &n1, F3 &n2) {
+    const float4 *p = sc.tri_nrm32 + (size_t)tri * 3;
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    n0 = F3{a.x, a.y, a.z}, n1 = F3{a.w, b.x, b.y}, n2 = F3{b.z, b.w, c.x};
+}
+
 // One BoundingVolumeHierarchy::intersect: closest triangle with distance rule "later DFS leaf wins ties".
 // `t_limit` (distance of the best hit found in EARLIER objects) only prunes; the caller merges.
-template <typename NT, bool COUNT, bool ANY>
-__device__ __forceinline__ void bvh_closest(const DevScene &sc, int root, const TriRay &tr, const FilterRay<NT> &fr,
-                                            double t_limit, double &best_t, int &best_tri, TraceCounters &cnt) {
-    typedef FilterTraits<NT> F;
+template <typename NT, bool COUNT, bool ANY, typename R>
+__device__ __forceinline__ void bvh_closest(const DevScene &sc, int root, const TriRayT<R> &tr, const FilterRay<NT> &fr,
+                                            R t_limit, R &best_t, int &best_tri, TraceCounters &cnt) {
     int stack[32];
     int sp = 0;
     int cur = root;
-    best_t = CUDART_INF, best_tri = -1;
+    best_t = real_inf<R>(), best_tri = -1;
     // prune bound in NodeT, rounded up, with the relative slack of the filter
-    NT limit = F::up(t_limit * (1.0 + 4.0 * (double)F::rel()));
+    NT limit = filter_limit<NT>(t_limit);
     while (true) {
         while (cur >= 0) {
             WideNode<NT> n;
@@ -207,16 +238,16 @@ __device__ __forceinline__ void bvh_closest(const DevScene &sc, int root, const 
         if (cur == VRJ_LEAF_DONE) break;
         {
             int tri = ~cur;
-            D3 v0, v1, v2, loc;
+            V3<R> v0, v1, v2, loc;
             uint32_t mat, pid;
             load_tri_pos(sc, tri, v0, v1, v2, mat, pid);
             if (COUNT) cnt.tri_tests += 1;
-            double dist, b0, b1, b2;
+            R dist, b0, b1, b2;
             if (triangle_test(tr, v0, v1, v2, dist, b0, b1, b2, loc)) {
                 if (dist < best_t || (dist == best_t && tri > best_tri)) {
                     best_t = dist, best_tri = tri;
                     if (ANY) return;
-                    limit = F::up(fmin(best_t, t_limit) * (1.0 + 4.0 * (double)F::rel()));
+                    limit = filter_limit<NT>(fmin(best_t, t_limit));
                 }
             }
         }
@@ -226,15 +257,15 @@ __device__ __forceinline__ void bvh_closest(const DevScene &sc, int root, const 
 }
 
 // Sampler::sample.  ANY = true stops at the first hit found (shadow rays: only Some/None is used).
-template <typename NT, bool COUNT, bool ANY>
-__device__ __forceinline__ Hit trace_closest(const DevScene &sc, D3 o, D3 d, TraceCounters &cnt) {
-    Hit best;
-    best.t = CUDART_INF, best.item = -1, best.tri = -1;
+template <typename NT, bool COUNT, bool ANY, typename R>
+__device__ __forceinline__ HitT<R> trace_closest(const DevScene &sc, V3<R> o, V3<R> d, TraceCounters &cnt) {
+    HitT<R> best;
+    best.t = real_inf<R>(), best.item = -1, best.tri = -1;
     bool have_tri_ray = false;
-    TriRay tr;
+    TriRayT<R> tr;
     for (uint32_t i = 0; i < sc.n_items; i++) {
         ItemDev it = sc.items[i];
-        double t;
+        R t;
         int tri = -1;
         bool hit = false;
         if (it.kind == 0) {
@@ -244,16 +275,16 @@ __device__ __forceinline__ Hit trace_closest(const DevScene &sc, D3 o, D3 d, Tra
         } else {
             if (!have_tri_ray) tr = tri_ray(o, d), have_tri_ray = true;
             if (it.kind == 2) {
-                D3 v0, v1, v2, loc;
+                V3<R> v0, v1, v2, loc;
                 uint32_t mat, pid;
-                double b0, b1, b2;
+                R b0, b1, b2;
                 load_tri_pos(sc, (int)it.index, v0, v1, v2, mat, pid);
                 if (COUNT) cnt.tri_tests += 1;
                 hit = triangle_test(tr, v0, v1, v2, t, b0, b1, b2, loc);
                 tri = (int)it.index;
             } else {
                 FilterRay<NT> fr = filter_ray<NT>(o, d);
-                bvh_closest<NT, COUNT, ANY>(sc, (int)it.root, tr, fr, best.item < 0 ? CUDART_INF : best.t, t, tri, cnt);
+                bvh_closest<NT, COUNT, ANY>(sc, (int)it.root, tr, fr, best.item < 0 ? real_inf<R>() : best.t, t, tri, cnt);
                 hit = tri >= 0;
             }
         }
@@ -270,22 +301,22 @@ __device__ __forceinline__ Hit trace_closest(const DevScene &sc, D3 o, D3 d, Tra
 // Closest hit, stage 1 (runs inside the fully-SIMD ray-producing kernels): the analytic objects
 // (spheres, planes, flat-list triangles) and a conservative pre-test of every BVH's root box.
 // Returns the best analytic hit and whether the ray has to be queued for BVH traversal.
-template <bool COUNT>
-__device__ __forceinline__ bool pretrace(const DevScene &sc, D3 o, D3 d, Hit &best, TraceCounters &cnt) {
-    best.t = CUDART_INF, best.item = -1, best.tri = -1;
+template <bool COUNT, typename R>
+__device__ __forceinline__ bool pretrace(const DevScene &sc, V3<R> o, V3<R> d, HitT<R> &best, TraceCounters &cnt) {
+    best.t = real_inf<R>(), best.item = -1, best.tri = -1;
     for (uint32_t a = 0; a < sc.n_analytic; a++) {
         uint32_t i = sc.analytic_items[a];
         ItemDev it = sc.items[i];
-        double t;
+        R t;
         int tri = -1;
         bool hit;
         if (it.kind == 0) hit = sphere_test(sc.spheres[it.index], o, d, t);
         else if (it.kind == 1) hit = plane_test(sc.planes[it.index], o, d, t);
         else {
-            TriRay tr = tri_ray(o, d);
-            D3 v0, v1, v2, loc;
+            TriRayT<R> tr = tri_ray(o, d);
+            V3<R> v0, v1, v2, loc;
             uint32_t mat, pid;
-            double b0, b1, b2;
+            R b0, b1, b2;
             load_tri_pos(sc, (int)it.index, v0, v1, v2, mat, pid);
             if (COUNT) cnt.tri_tests += 1;
             hit = triangle_test(tr, v0, v1, v2, t, b0, b1, b2, loc);
@@ -297,7 +328,7 @@ __device__ __forceinline__ bool pretrace(const DevScene &sc, D3 o, D3 d, Hit &be
     bool need = false;
     if (sc.n_bvh_items) {
         FilterRay<float> fr = filter_ray<float>(o, d);
-        float limit = FilterTraits<float>::up(best.t * (1.0 + 4.0 * (double)FilterTraits<float>::rel()));
+        float limit = filter_limit<float>(best.t);
         for (uint32_t b = 0; b < sc.n_bvh_items; b++) {
             ItemDev it = sc.items[sc.bvh_items[b]];
             float e;
@@ -319,10 +350,9 @@ __device__ __forceinline__ bool pretrace(const DevScene &sc, D3 o, D3 d, Hit &be
 //
 // Source:  void load(uint32_t r, D3 &o, D3 &d, Hit &best)   -- ray r of the list and its best analytic hit
 // Sink:    void store(uint32_t r, const Hit &best, bool improved)
-template <typename NT, bool COUNT, typename Source, typename Sink>
+template <typename NT, typename R, bool COUNT, typename Source, typename Sink>
 __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n, uint32_t *work, Source &source, Sink &sink,
                                                  TraceCounters &cnt) {
-    typedef FilterTraits<NT> F;
     const unsigned FULL = 0xffffffffu;
     const uint32_t NONE = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
@@ -332,15 +362,15 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
     int sp = 0, cur = VRJ_LEAF_DONE;
     uint32_t r = NONE, bcur = 0;
     bool improved = false;
-    TriRay tr;
+    TriRayT<R> tr;
     FilterRay<NT> fr;
-    Hit best;
-    double loc_t = CUDART_INF;
+    HitT<R> best;
+    R loc_t = real_inf<R>();
     int loc_tri = -1;
     NT limit = (NT)0;
     bool exhausted = false;
-    tr.o = d3(0, 0, 0), tr.sx = tr.sy = tr.pdz = 0.0, tr.perm = 0;
-    best.t = CUDART_INF, best.item = -1, best.tri = -1;
+    tr.o = V3<R>{R(0), R(0), R(0)}, tr.sx = tr.sy = tr.pdz = R(0), tr.perm = 0;
+    best.t = real_inf<R>(), best.item = -1, best.tri = -1;
 #pragma unroll
     for (int k = 0; k < 3; k++) fr.id[k] = fr.cn[k] = fr.cf[k] = (NT)0;
 
@@ -352,8 +382,8 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
         bcur++;
         if (bcur < sc.n_bvh_items) {
             cur = (int)sc.items[sc.bvh_items[bcur]].root;
-            sp = 0, loc_t = CUDART_INF, loc_tri = -1;
-            limit = F::up(best.t * (1.0 + 4.0 * (double)F::rel()));
+            sp = 0, loc_t = real_inf<R>(), loc_tri = -1;
+            limit = filter_limit<NT>(best.t);
         } else {
             cur = VRJ_LEAF_DONE;
         }
@@ -398,15 +428,15 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
                 if (idle) {
                     uint32_t my = base + (uint32_t)__popc(idle_mask & ((1u << lane) - 1u));
                     if (my < n) {
-                        D3 o, d;
+                        V3<R> o, d;
                         source.load(my, o, d, best);
                         r = my, improved = false;
                         tr = tri_ray(o, d);
                         fr = filter_ray<NT>(o, d);
                         bcur = 0;
                         cur = (int)sc.items[sc.bvh_items[0]].root;
-                        sp = 0, loc_t = CUDART_INF, loc_tri = -1;
-                        limit = F::up(best.t * (1.0 + 4.0 * (double)F::rel()));
+                        sp = 0, loc_t = real_inf<R>(), loc_tri = -1;
+                        limit = filter_limit<NT>(best.t);
                     }
                 }
             }
@@ -423,15 +453,15 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
             if (leaf_mask && (node_mask == 0 || __popc(leaf_mask) >= leaf_threshold)) {
                 if (at_leaf) {
                     int tri = ~cur;
-                    D3 v0, v1, v2, loc;
+                    V3<R> v0, v1, v2, loc;
                     uint32_t mat, pid;
                     load_tri_pos(sc, tri, v0, v1, v2, mat, pid);
                     if (COUNT) cnt.tri_tests += 1;
-                    double dist, b0, b1, b2;
+                    R dist, b0, b1, b2;
                     if (triangle_test(tr, v0, v1, v2, dist, b0, b1, b2, loc)) {
                         if (dist < loc_t || (dist == loc_t && tri > loc_tri)) {
                             loc_t = dist, loc_tri = tri;
-                            limit = F::up(fmin(loc_t, best.t) * (1.0 + 4.0 * (double)F::rel()));
+                            limit = filter_limit<NT>(fmin(loc_t, best.t));
                         }
                     }
                     if (sp) cur = stack[--sp];
@@ -488,7 +518,7 @@ __device__ __forceinline__ void trace_persistent_quad(const DevScene &sc, uint32
         if (bcur < sc.n_bvh_items) {
             cur = (int)sc.items[sc.bvh_items[bcur]].root;
             sp = 0, loc_t = CUDART_INF, loc_tri = -1;
-            limit = F::up(best.t * (1.0 + 4.0 * (double)F::rel()));
+            limit = filter_limit<float>(best.t);
         } else {
             cur = VRJ_LEAF_DONE;
         }
@@ -589,31 +619,32 @@ __device__ __forceinline__ void trace_persistent_quad(const DevScene &sc, uint32
 
 // Rebuild the IntersectionInfo (raycasting/mod.rs:67-97) of a known hit with the exact arithmetic
 // of the primitive's intersect(): the wavefront stores only (ray, item, triangle).
-__device__ __forceinline__ bool rebuild_hit(const DevScene &sc, D3 o, D3 d, int item, int tri, HitFrame &h) {
+template <typename R>
+__device__ __forceinline__ bool rebuild_hit(const DevScene &sc, V3<R> o, V3<R> d, int item, int tri, HitFrameT<R> &h) {
     ItemDev it = sc.items[item];
     if (it.kind == 0) {
         SphereDev s = sc.spheres[it.index];
-        double t;
+        R t;
         if (!sphere_test(s, o, d, t)) return false;
         sphere_frame(s, o, d, t, h);
         return true;
     }
     if (it.kind == 1) {
         PlaneDev p = sc.planes[it.index];
-        double t;
+        R t;
         if (!plane_test(p, o, d, t)) return false;
         plane_frame(p, o, d, t, h);
         return true;
     }
-    TriRay tr = tri_ray(o, d);
-    D3 v0, v1, v2, n0, n1, n2;
+    TriRayT<R> tr = tri_ray(o, d);
+    V3<R> v0, v1, v2, n0, n1, n2;
     uint32_t mat, pid;
-    double b0, b1, b2;
+    R b0, b1, b2;
     load_tri_pos(sc, tri, v0, v1, v2, mat, pid);
     if (!triangle_test(tr, v0, v1, v2, h.distance, b0, b1, b2, h.location)) return false;
     load_tri_nrm(sc, tri, n0, n1, n2);
     // triangle.rs:73-83
-    h.normal = normalize(((d3(0.0, 0.0, 0.0) + n0 * b0) + n1 * b1) + n2 * b2);
+    h.normal = normalize(((V3<R>{R(0), R(0), R(0)} + n0 * b0) + n1 * b1) + n2 * b2);
     h.cotangent = normalize(cross(v0 - v1, h.normal));
     h.tangent = normalize(cross(h.cotangent, h.normal));
     h.retro = normalize(o - h.location);

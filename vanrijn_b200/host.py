@@ -116,7 +116,8 @@ class HostScene:
         return obj, prim, t, st
 
     def make_params(self, spp=1, max_depth=128, sample_offset=0, seed=1, integrator=capi.INTEGRATOR_SIMPLE_RANDOM,
-                    bvh_filter=capi.FILTER_F32, bias=1e-7, lights=(), ambient=-1, sample_stride=1, count_traversal=False):
+                    bvh_filter=capi.FILTER_F32, bias=1e-7, lights=(), ambient=-1, sample_stride=1, count_traversal=False,
+                    precision=capi.PRECISION_F64):
         keep = []
         larr = (capi.Light * max(1, len(lights)))()
         for i, (direction, spectrum_id) in enumerate(lights):
@@ -131,7 +132,7 @@ class HostScene:
         p = capi.RenderParams(spp=spp, max_depth=max_depth, sample_offset=sample_offset, seed=seed, integrator=integrator,
                               bvh_filter=bvh_filter, bias=bias, lights=larr,
                               ambient_light=C.pointer(amb) if amb is not None else None, n_lights=len(lights),
-                              sample_stride=sample_stride, count_traversal=1 if count_traversal else 0)
+                              sample_stride=sample_stride, count_traversal=1 if count_traversal else 0, precision=precision)
         keep.extend([larr, amb])
         return p, keep
 
