@@ -9,6 +9,7 @@
 // Additions: --obj FILE (default $VANRIJN_BUNNY_OBJ; the reference hard-codes test_data/stanford_bunny.obj),
 // --spp N samples per partial_render_scene call (the reference: 1), --passes N, --depth N (RECURSION_LIMIT, 128),
 // --builder host|device|upload, --seed N, --preview-every N (rewrite --out every N passes: the progressive view),
+// --cache FILE: the flattened scene on disk (load_scene_cache if FILE exists, else build the scene and save_scene_cache),
 // --resident: keep the frame's AccumulationBuffer on the GPU (DeviceAccumulationBuffer) instead of downloading a
 // buffer per tile and merging on the host; previews then move 3 bytes per pixel.
 #include <chrono>
@@ -25,7 +26,7 @@ using namespace vanrijn;
 namespace {
 struct CommandLineParameters {
     size_t width = 0, height = 0;
-    std::string output_file, obj;
+    std::string output_file, obj, cache;
     double time = 0.0;
     uint32_t spp = 1, passes = 0, depth = 128, preview_every = 0;
     uint64_t seed = 1;
@@ -35,7 +36,7 @@ struct CommandLineParameters {
 
 [[noreturn]] void usage(const char *why) {
     std::fprintf(stderr, "error: %s\nUSAGE: vanrijn --size <WIDTH> <HEIGHT> [--out <FILENAME>] [--time <SECONDS>] [--obj <FILE>] [--spp N] "
-                         "[--passes N] [--depth N] [--builder host|device|upload] [--seed N] [--preview-every N] [--resident]\n", why);
+                         "[--passes N] [--depth N] [--builder host|device|upload] [--seed N] [--preview-every N] [--resident] [--cache FILE]\n", why);
     std::exit(2);
 }
 
@@ -52,6 +53,7 @@ CommandLineParameters parse_args(int argc, char **argv) {
         else if (a == "--out") p.output_file = value(), i++;
         else if (a == "--time") p.time = std::strtod(value(), nullptr), i++;
         else if (a == "--obj") p.obj = value(), i++;
+        else if (a == "--cache") p.cache = value(), i++;
         else if (a == "--spp") p.spp = (uint32_t)std::strtoul(value(), nullptr, 10), i++;
         else if (a == "--passes") p.passes = (uint32_t)std::strtoul(value(), nullptr, 10), i++;
         else if (a == "--depth") p.depth = (uint32_t)std::strtoul(value(), nullptr, 10), i++;
@@ -86,6 +88,18 @@ int main(int argc, char **argv) {
     try {
         AccumulationBuffer rendered_image(image_width, image_height);
         Scene scene;
+        bool from_cache = false;
+        if (!parameters.cache.empty()) {
+            if (FILE *probe = std::fopen(parameters.cache.c_str(), "rb")) {
+                std::fclose(probe);
+                const auto t_cache = std::chrono::steady_clock::now();
+                scene = load_scene_cache(parameters.cache);
+                from_cache = true;
+                std::printf("Loaded the flattened scene from %s (%.3f s)\n", parameters.cache.c_str(), seconds_since(t_cache));
+            }
+        }
+        auto t_load = std::chrono::steady_clock::now();
+        if (!from_cache) {
         scene.camera_location = Vec3(-2.0, 1.0, -5.0);
         auto list = std::unique_ptr<PrimitiveList>(new PrimitiveList());
         list->primitives.push_back(std::make_shared<Plane>(Vec3(0.0, 1.0, 0.0), -2.0, lambertian(ColourRgbF(0.55, 0.27, 0.04), 0.1)));
@@ -93,7 +107,6 @@ int main(int argc, char **argv) {
         list->primitives.push_back(std::make_shared<Sphere>(Vec3(-4.25, -0.5, 2.0), 1.0, lambertian(ColourRgbF::from_named(NamedColour::Blue), 0.1)));
         list->primitives.push_back(std::make_shared<Sphere>(Vec3(-5.0, 1.5, 1.0), 1.0, lambertian(ColourRgbF::from_named(NamedColour::Red), 0.05)));
         scene.objects.push_back(std::move(list));
-        auto t_load = std::chrono::steady_clock::now();
         if (!parameters.obj.empty()) {
             std::printf("Loading object...\n");
             const TriangleMesh mesh = load_obj_mesh(parameters.obj);
@@ -102,6 +115,11 @@ int main(int argc, char **argv) {
         } else {
             std::printf("No --obj and no $VANRIJN_BUNNY_OBJ: rendering the scene without the model.\n");
         }
+        if (!parameters.cache.empty()) {
+            save_scene_cache(scene, parameters.cache);
+            std::printf("Saved the flattened scene to %s\n", parameters.cache.c_str());
+        }
+        } // !from_cache
         std::printf("Constructing Scene...\n");
         device_scene(scene, 0); // flatten + upload (+ BVH build on the device with --builder upload)
         std::printf("Done. (%.3f s)\n", seconds_since(t_load));

@@ -166,12 +166,41 @@ class BoundingVolumeHierarchy : public Aggregate {
     uint32_t depth_ = 0;
 };
 
+// A VrjSceneDesc that owns its arrays: what the scene cache file holds ("on-disk cache of the flattened scene").
+class FlatScene {
+  public:
+    explicit FlatScene(const VrjSceneDesc &desc); // deep copy
+    FlatScene(FlatScene &&) = default;            // (desc() points into the vectors: movable, not copyable)
+    FlatScene(const FlatScene &) = delete;
+    static FlatScene load(const std::string &filename); // throws std::runtime_error on a missing, truncated or corrupt file
+    void save(const std::string &filename) const;
+    const VrjSceneDesc &desc() const { return desc_; }
+
+  private:
+    FlatScene() = default;
+    void bind();
+    std::vector<VrjSpectrum> spectra_;
+    std::vector<double> samples_;
+    std::vector<VrjMaterial> materials_;
+    std::vector<VrjSphere> spheres_;
+    std::vector<VrjPlane> planes_;
+    std::vector<VrjBvh> bvhs_;
+    std::vector<VrjItem> items_;
+    std::vector<double> tri_[6], node_min_, node_max_;
+    std::vector<uint32_t> tri_material_, tri_prim_id_;
+    std::vector<int32_t> node_child_;
+    VrjSceneDesc desc_{};
+};
+
 // scene.rs:5-8
 struct Scene {
     Vec3 camera_location;
     std::vector<std::unique_ptr<Aggregate>> objects;
+    // set by load_scene_cache: the flattened form read from disk; `objects` is then empty and the scene can only be rendered
+    std::shared_ptr<const FlatScene> flattened;
     Scene() = default;
     Scene(Scene &&) = default;
+    Scene &operator=(Scene &&) = default;
     ~Scene();
     // device copy, created on first use and reused (the scene is immutable while it renders)
     struct DeviceCache;
@@ -349,6 +378,10 @@ class FlatSceneBuilder {
     UploadVector<int32_t> node_child_;
     VrjSceneDesc desc_{};
 };
+
+// The flattened form of a scene on disk: save once (OBJ parsed, tree built or left to the device), load in milliseconds.
+void save_scene_cache(const Scene &scene, const std::string &filename);
+Scene load_scene_cache(const std::string &filename);
 
 // Flatten + upload (cached on the scene).  Exposed for callers that want the raw C ABI.
 const VrjScene *device_scene(const Scene &scene, int device = 0);

@@ -63,3 +63,28 @@ def test_harness_time_limit_and_usage_errors(tmp_path):
     passes = int(r.stdout.split(" passes")[0].split()[-1])
     assert passes >= 1
     assert helpers.read_png_rgb8(out).shape == (36, 64, 3)
+
+
+def test_scene_cache_renders_the_same_frame(tmp_path):
+    """--cache: the first run parses the OBJ and saves the flattened scene, the second run loads it (no OBJ, no primitive
+    objects) and must write the same PNG; the library renders the cached scene bit-identically too."""
+    exe = os.path.join(ROOT, "build", "vanrijn")
+    obj, _ = scenes.bunny_obj_path(subdivisions=3)
+    cache = str(tmp_path / "scene.vrjscene")
+    outs = []
+    for run in range(2):
+        out = str(tmp_path / ("c%d.png" % run))
+        args = [exe, "--size", "160", "90", "--out", out, "--spp", "3", "--depth", "6", "--cache", cache]
+        r = subprocess.run(args + (["--obj", obj] if run == 0 else []), capture_output=True, text=True, timeout=300,
+                           env={k: v for k, v in os.environ.items() if k != "VANRIJN_BUNNY_OBJ"})
+        assert r.returncode == 0, r.stderr
+        assert ("Saved the flattened scene" in r.stdout) if run == 0 else ("Loaded the flattened scene" in r.stdout)
+        outs.append(helpers.read_png_rgb8(out))
+    assert np.array_equal(outs[0], outs[1]) and outs[0].max() > 0
+    spec = scenes.scene_main(subdivisions=3, obj=True)
+    a = V.build_scene(spec)
+    a.save_cache(tmp_path / "lib.vrjscene")
+    b = V.HostScene.from_cache(tmp_path / "lib.vrjscene")
+    ra = a.render((0, 96, 0, 54), 54, 96, spp=2, max_depth=6, seed=2, want=("colour_sum",), want_photons=True)
+    rb = b.render((0, 96, 0, 54), 54, 96, spp=2, max_depth=6, seed=2, want=("colour_sum",), want_photons=True)
+    assert np.array_equal(ra["photons"], rb["photons"])

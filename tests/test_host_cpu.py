@@ -248,3 +248,38 @@ def test_write_png_round_trips(tmp_path, w, h):
     path = str(tmp_path / "t.png")
     assert capi.host().vrjh_write_png(path.encode(), w, h, rgb.ctypes.data) == 0
     assert np.array_equal(helpers.read_png_rgb8(path), rgb)
+
+
+def test_scene_cache_round_trip_and_corruption(tmp_path):
+    """the flattened scene saved to disk reloads to the same VrjSceneDesc, for a host-built tree and for a
+    tree left to the device (n_nodes == 0); a flipped byte or a truncated file is refused."""
+    for builder in (False, "upload"):
+        hs = V.build_scene(scenes.scene_main(subdivisions=3, obj=False, variant="mixed"), device_builder=builder)
+        path = tmp_path / ("scene_%s.vrjscene" % builder)
+        hs.save_cache(path)
+        back = V.HostScene.from_cache(path)
+        a, b = hs.desc(), back.desc()
+        for f in ("n_spectra", "n_spectrum_samples", "n_materials", "n_spheres", "n_planes", "n_bvhs", "n_triangles", "n_nodes", "n_items"):
+            assert int(getattr(a, f)) == int(getattr(b, f)), f
+        assert list(a.camera_location) == list(b.camera_location)
+        n, nn = int(a.n_triangles), int(a.n_nodes)
+        arr = lambda p, count, dt=None: np.ctypeslib.as_array(p, shape=(count,)) if count else np.zeros(0)
+        for name, count in (("tri_v0", 4 * n), ("tri_v2", 4 * n), ("tri_n1", 4 * n), ("tri_material", n), ("tri_prim_id", n),
+                            ("node_min", 4 * nn), ("node_max", 4 * nn), ("node_child", 2 * nn), ("spectrum_samples", int(a.n_spectrum_samples))):
+            assert np.array_equal(arr(getattr(a, name), count), arr(getattr(b, name), count)), name
+        raw = lambda p, count, T: bytes(C.string_at(C.cast(p, C.c_void_p), count * C.sizeof(T)))
+        for name, count, T in (("spectra", a.n_spectra, capi.Spectrum), ("materials", a.n_materials, capi.Material),
+                               ("spheres", a.n_spheres, capi.Sphere), ("planes", a.n_planes, capi.Plane),
+                               ("bvhs", a.n_bvhs, capi.Bvh), ("items", a.n_items, capi.Item)):
+            assert raw(getattr(a, name), int(count), T) == raw(getattr(b, name), int(count), T), name
+        data = bytearray(open(path, "rb").read())
+        data[len(data) // 2] ^= 0x40
+        bad = tmp_path / "bad.vrjscene"
+        bad.write_bytes(bytes(data))
+        with pytest.raises(capi.VrjError, match="checksum"):
+            V.HostScene.from_cache(bad)
+        bad.write_bytes(bytes(data[:100]))
+        with pytest.raises(capi.VrjError):
+            V.HostScene.from_cache(bad)
+    with pytest.raises(capi.VrjError):
+        V.HostScene.from_cache(tmp_path / "missing.vrjscene")

@@ -213,6 +213,9 @@ def host():
         L.vrjh_partial_render_scene.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                                 dp, dp, dp, dp, dp]
         L.vrjh_merge_tile.argtypes = [dp, dp, C.c_uint64, C.c_uint64, u64p, dp, dp]
+        L.vrjh_scene_save_cache.argtypes = [C.c_void_p, C.c_char_p]
+        L.vrjh_scene_load_cache.restype = C.c_void_p
+        L.vrjh_scene_load_cache.argtypes = [C.c_char_p]
         L.vrjh_write_png.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.vrjh_tile_iterator.restype = C.c_int64
         L.vrjh_tile_iterator.argtypes = [C.c_uint64] * 3 + [u64p, C.c_int64]

@@ -179,6 +179,10 @@ const VrjSceneDesc *vrjh_flatten(void *p) {
     HostScene *h = static_cast<HostScene *>(p);
     const VrjSceneDesc *d = nullptr;
     guarded([&] {
+        if (h->scene.flattened) {
+            d = &h->scene.flattened->desc();
+            return;
+        }
         if (!h->flattened) {
             for (size_t i = 0; i < h->scene.objects.size(); i++) h->scene.objects[i]->flatten(h->flat, (uint32_t)i);
             h->flattened = true;
@@ -227,6 +231,19 @@ int vrjh_merge_tile(double *dst_colour, double *dst_weight, uint64_t dst_w, uint
         std::memcpy(dst_colour, dst.colour.data(), 3 * dst_w * dst_h * sizeof(double));
         std::memcpy(dst_weight, dst.weight.data(), dst_w * dst_h * sizeof(double));
     });
+}
+/* save_scene_cache / load_scene_cache: the flattened scene on disk.  vrjh_scene_load_cache returns a new scene handle or NULL. */
+int vrjh_scene_save_cache(void *p, const char *path) {
+    HostScene *h = static_cast<HostScene *>(p);
+    return guarded([&] { save_scene_cache(h->scene, path); });
+}
+void *vrjh_scene_load_cache(const char *path) {
+    HostScene *h = new HostScene();
+    if (guarded([&] { h->scene = load_scene_cache(path); })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
 }
 /* ImageRgbU8::write_png on a raw RGB array */
 int vrjh_write_png(const char *path, uint64_t width, uint64_t height, const uint8_t *rgb) {

@@ -551,6 +551,122 @@ void AccumulationBuffer::merge_tile(const Tile &tile, const AccumulationBuffer &
         }
 }
 
+// ------------------------------------------------------------------------------ scene cache
+namespace {
+const char kCacheMagic[8] = {'V', 'R', 'J', 'S', 'C', 'N', '1', 0};
+template <typename T>
+void put_array(std::vector<uint8_t> &out, const std::vector<T> &v) {
+    const uint64_t n = v.size();
+    const uint8_t *pn = reinterpret_cast<const uint8_t *>(&n);
+    out.insert(out.end(), pn, pn + 8);
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(v.data());
+    out.insert(out.end(), p, p + n * sizeof(T));
+}
+template <typename T>
+void get_array(const std::vector<uint8_t> &in, size_t &pos, std::vector<T> &v) {
+    if (pos + 8 > in.size()) throw std::runtime_error("scene cache: truncated");
+    uint64_t n;
+    std::memcpy(&n, &in[pos], 8);
+    pos += 8;
+    if (n > (in.size() - pos) / sizeof(T)) throw std::runtime_error("scene cache: truncated");
+    v.resize(n);
+    if (n) std::memcpy(v.data(), &in[pos], n * sizeof(T));
+    pos += n * sizeof(T);
+}
+} // namespace
+
+FlatScene::FlatScene(const VrjSceneDesc &d) {
+    desc_ = d;
+    spectra_.assign(d.spectra, d.spectra + d.n_spectra), samples_.assign(d.spectrum_samples, d.spectrum_samples + d.n_spectrum_samples);
+    materials_.assign(d.materials, d.materials + d.n_materials), spheres_.assign(d.spheres, d.spheres + d.n_spheres);
+    planes_.assign(d.planes, d.planes + d.n_planes), bvhs_.assign(d.bvhs, d.bvhs + d.n_bvhs), items_.assign(d.items, d.items + d.n_items);
+    const double *tri[6] = {d.tri_v0, d.tri_v1, d.tri_v2, d.tri_n0, d.tri_n1, d.tri_n2};
+    for (int k = 0; k < 6; k++) tri_[k].assign(tri[k], tri[k] + 4 * d.n_triangles);
+    tri_material_.assign(d.tri_material, d.tri_material + d.n_triangles), tri_prim_id_.assign(d.tri_prim_id, d.tri_prim_id + d.n_triangles);
+    node_min_.assign(d.node_min, d.node_min + 4 * d.n_nodes), node_max_.assign(d.node_max, d.node_max + 4 * d.n_nodes);
+    node_child_.assign(d.node_child, d.node_child + 2 * d.n_nodes);
+    bind();
+}
+void FlatScene::bind() {
+    VrjSceneDesc &d = desc_;
+    d.n_spectra = (uint32_t)spectra_.size(), d.n_spectrum_samples = (uint32_t)samples_.size();
+    d.spectra = spectra_.data(), d.spectrum_samples = samples_.data();
+    d.n_materials = (uint32_t)materials_.size(), d.materials = materials_.data();
+    d.n_spheres = (uint32_t)spheres_.size(), d.spheres = spheres_.data();
+    d.n_planes = (uint32_t)planes_.size(), d.planes = planes_.data();
+    d.n_bvhs = (uint32_t)bvhs_.size(), d.bvhs = bvhs_.data();
+    d.n_triangles = tri_material_.size();
+    d.tri_v0 = tri_[0].data(), d.tri_v1 = tri_[1].data(), d.tri_v2 = tri_[2].data();
+    d.tri_n0 = tri_[3].data(), d.tri_n1 = tri_[4].data(), d.tri_n2 = tri_[5].data();
+    d.tri_material = tri_material_.data(), d.tri_prim_id = tri_prim_id_.data();
+    d.n_nodes = node_child_.size() / 2;
+    d.node_min = node_min_.data(), d.node_max = node_max_.data(), d.node_child = node_child_.data();
+    d.n_items = (uint32_t)items_.size(), d.items = items_.data();
+}
+void FlatScene::save(const std::string &filename) const {
+    std::vector<uint8_t> out(kCacheMagic, kCacheMagic + 8);
+    const uint32_t head[2] = {VRJ_ABI_VERSION, 0};
+    out.insert(out.end(), reinterpret_cast<const uint8_t *>(head), reinterpret_cast<const uint8_t *>(head) + 8);
+    out.insert(out.end(), reinterpret_cast<const uint8_t *>(desc_.camera_location), reinterpret_cast<const uint8_t *>(desc_.camera_location) + 24);
+    put_array(out, spectra_), put_array(out, samples_), put_array(out, materials_), put_array(out, spheres_), put_array(out, planes_);
+    put_array(out, bvhs_), put_array(out, items_);
+    for (int k = 0; k < 6; k++) put_array(out, tri_[k]);
+    put_array(out, tri_material_), put_array(out, tri_prim_id_), put_array(out, node_min_), put_array(out, node_max_), put_array(out, node_child_);
+    static const Crc32 crc;
+    const uint32_t sum = crc.update(0xffffffffu, out.data(), out.size()) ^ 0xffffffffu;
+    out.insert(out.end(), reinterpret_cast<const uint8_t *>(&sum), reinterpret_cast<const uint8_t *>(&sum) + 4);
+    FILE *f = std::fopen(filename.c_str(), "wb");
+    if (!f) throw std::runtime_error("scene cache: cannot open " + filename);
+    const bool ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
+    if (std::fclose(f) != 0 || !ok) throw std::runtime_error("scene cache: write failed: " + filename);
+}
+FlatScene FlatScene::load(const std::string &filename) {
+    FILE *f = std::fopen(filename.c_str(), "rb");
+    if (!f) throw std::runtime_error("scene cache: cannot open " + filename);
+    std::vector<uint8_t> in;
+    uint8_t buf[1 << 16];
+    for (size_t n; (n = std::fread(buf, 1, sizeof buf, f)) > 0;) in.insert(in.end(), buf, buf + n);
+    std::fclose(f);
+    if (in.size() < 8 + 8 + 24 + 4 || std::memcmp(in.data(), kCacheMagic, 8) != 0) throw std::runtime_error("scene cache: not a scene cache file: " + filename);
+    static const Crc32 crc;
+    uint32_t stored;
+    std::memcpy(&stored, &in[in.size() - 4], 4);
+    if ((crc.update(0xffffffffu, in.data(), in.size() - 4) ^ 0xffffffffu) != stored) throw std::runtime_error("scene cache: checksum mismatch: " + filename);
+    in.resize(in.size() - 4);
+    uint32_t head[2];
+    std::memcpy(head, &in[8], 8);
+    if (head[0] != VRJ_ABI_VERSION) throw std::runtime_error("scene cache: written for another ABI version");
+    FlatScene s;
+    s.desc_.abi_version = VRJ_ABI_VERSION;
+    std::memcpy(s.desc_.camera_location, &in[16], 24);
+    size_t pos = 40;
+    get_array(in, pos, s.spectra_), get_array(in, pos, s.samples_), get_array(in, pos, s.materials_), get_array(in, pos, s.spheres_);
+    get_array(in, pos, s.planes_), get_array(in, pos, s.bvhs_), get_array(in, pos, s.items_);
+    for (int k = 0; k < 6; k++) get_array(in, pos, s.tri_[k]);
+    get_array(in, pos, s.tri_material_), get_array(in, pos, s.tri_prim_id_), get_array(in, pos, s.node_min_), get_array(in, pos, s.node_max_);
+    get_array(in, pos, s.node_child_);
+    const size_t nt = s.tri_material_.size();
+    for (int k = 0; k < 6; k++)
+        if (s.tri_[k].size() != 4 * nt) throw std::runtime_error("scene cache: inconsistent triangle arrays");
+    if (s.tri_prim_id_.size() != nt || s.node_min_.size() != 2 * s.node_child_.size() || s.node_max_.size() != s.node_min_.size() || pos != in.size())
+        throw std::runtime_error("scene cache: inconsistent arrays");
+    s.bind();
+    return s;
+}
+void save_scene_cache(const Scene &scene, const std::string &filename) {
+    if (scene.flattened) return scene.flattened->save(filename);
+    FlatSceneBuilder fb;
+    for (size_t i = 0; i < scene.objects.size(); i++) scene.objects[i]->flatten(fb, (uint32_t)i);
+    FlatScene(fb.desc(scene.camera_location)).save(filename);
+}
+Scene load_scene_cache(const std::string &filename) {
+    Scene scene;
+    auto flat = std::make_shared<FlatScene>(FlatScene::load(filename));
+    scene.camera_location = Vec3(flat->desc().camera_location[0], flat->desc().camera_location[1], flat->desc().camera_location[2]);
+    scene.flattened = std::move(flat);
+    return scene;
+}
+
 // ------------------------------------------------------------------------------ device scene + render
 struct Scene::DeviceCache {
     std::mutex mutex;
@@ -571,9 +687,15 @@ const VrjScene *device_scene(const Scene &scene, int device) {
     for (auto &e : scene.device_cache->scenes)
         if (e.first == device) return e.second;
     FlatSceneBuilder fb;
-    for (size_t i = 0; i < scene.objects.size(); i++) scene.objects[i]->flatten(fb, (uint32_t)i);
+    const VrjSceneDesc *desc = nullptr;
+    if (scene.flattened) {
+        desc = &scene.flattened->desc();
+    } else {
+        for (size_t i = 0; i < scene.objects.size(); i++) scene.objects[i]->flatten(fb, (uint32_t)i);
+        desc = &fb.desc(scene.camera_location);
+    }
     VrjScene *dev = nullptr;
-    if (vrj_scene_create(&fb.desc(scene.camera_location), device, &dev) != VRJ_OK)
+    if (vrj_scene_create(desc, device, &dev) != VRJ_OK)
         throw std::runtime_error(std::string("vrj_scene_create: ") + vrj_last_error());
     scene.device_cache->scenes.push_back({device, dev});
     return dev;

@@ -64,6 +64,22 @@ class HostScene:
                     raise capi.VrjError(H.vrjh_last_error().decode())
         self._dev = {}
 
+    def save_cache(self, path):
+        """save_scene_cache: the flattened scene (primitives, triangles, tree if built on the host) to one file."""
+        if self.H.vrjh_scene_save_cache(self.h, str(path).encode()) != 0:
+            raise capi.VrjError(self.H.vrjh_last_error().decode())
+
+    @classmethod
+    def from_cache(cls, path, spec=None):
+        """load_scene_cache: a scene that can be rendered (and flattened) but holds no primitive objects."""
+        self = cls.__new__(cls)
+        self.H = capi.host()
+        h = self.H.vrjh_scene_load_cache(str(path).encode())
+        if not h:
+            raise capi.VrjError(self.H.vrjh_last_error().decode())
+        self.h, self.spec, self._keep, self._dev, self.device_builder = C.c_void_p(h), spec, [], {}, 0
+        return self
+
     def __del__(self):
         try:
             for comm, ms in getattr(self, "_comm", {}).values():
