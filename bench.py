@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--spp", type=int, default=32, help="samples per pixel per step per GPU (one wavefront batch up to 32 at 1080p)")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
-    ap.add_argument("--filter", default="f32", choices=["f32", "f64", "f32x4"],
+    ap.add_argument("--filter", default="f32", choices=["f32", "f64", "f32x4", "q16"],
                     help="conservative BVH box filter: 2-wide f32, 2-wide f64, or 4-wide f32 nodes (results identical)")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
                     help="f64 = the reference's type (parity path, the headline); f32 = VRJ_PRECISION_F32_FAST, reported separately")
@@ -178,7 +178,7 @@ def main():
 
     W, H, spp = args.width, args.height, args.spp
     npix = W * H
-    bvh_filter = {"f64": capi.FILTER_F64, "f32x4": capi.FILTER_F32X4}.get(args.filter, capi.FILTER_F32)
+    bvh_filter = {"f64": capi.FILTER_F64, "f32x4": capi.FILTER_F32X4, "q16": capi.FILTER_Q16}.get(args.filter, capi.FILTER_F32)
     precision = capi.PRECISION_F32_FAST if args.precision == "f32" else capi.PRECISION_F64
     hs = V.build_scene(spec)
     hs.device_scene(local)

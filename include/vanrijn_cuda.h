@@ -61,8 +61,9 @@ enum { VRJ_INTEGRATOR_SIMPLE_RANDOM = 0, VRJ_INTEGRATOR_WHITTED = 1 };
 /* top-level traversal items, in Scene.objects order (sampler.rs:12-19: first object wins ties) */
 enum { VRJ_ITEM_SPHERE = 0, VRJ_ITEM_PLANE = 1, VRJ_ITEM_TRIANGLE = 2, VRJ_ITEM_BVH = 3 };
 /* precision / shape of the conservative box culling in front of the exact triangle test; results are identical in all modes.
- * F32: 2-wide nodes, f32 boxes; F64: 2-wide, f64 boxes (cross-check); F32X4: 4-wide nodes (two reference levels per fetch) */
-enum { VRJ_FILTER_F32 = 0, VRJ_FILTER_F64 = 1, VRJ_FILTER_F32X4 = 2 };
+ * F32: 2-wide nodes, f32 boxes; F64: 2-wide, f64 boxes (cross-check); F32X4: 4-wide nodes (two reference levels per fetch);
+ * Q16: 2-wide nodes, boxes rounded outward onto a 16-bit grid over the scene's meshes (32-byte nodes, half the bytes per step) */
+enum { VRJ_FILTER_F32 = 0, VRJ_FILTER_F64 = 1, VRJ_FILTER_F32X4 = 2, VRJ_FILTER_Q16 = 3 };
 enum { VRJ_MEM_HOST = 0, VRJ_MEM_DEVICE = 1 };
 /* VRJ_PRECISION_F64: every hit, shading and accumulation operation in binary64, the reference's type and operation order.
  * VRJ_PRECISION_F32_FAST: the same formulas in binary32 (accumulators stay binary64).  The reference has no binary32 build

@@ -43,7 +43,7 @@ def assert_ids_bit_exact(hs, orc, o, d, bvh_filter, min_expected_hits=1):
     return st, cnt
 
 
-@pytest.mark.parametrize("bvh_filter", [capi.FILTER_F32, capi.FILTER_F64, capi.FILTER_F32X4])
+@pytest.mark.parametrize("bvh_filter", [capi.FILTER_F32, capi.FILTER_F64, capi.FILTER_F32X4, capi.FILTER_Q16])
 def test_ids_bit_exact_small_scene(bvh_filter):
     spec = scenes.scene_main(subdivisions=3, obj=False)
     hs, orc = both(spec)
@@ -53,7 +53,7 @@ def test_ids_bit_exact_small_scene(bvh_filter):
     assert_ids_bit_exact(hs, orc, o, d, bvh_filter, 1000)
 
 
-@pytest.mark.parametrize("bvh_filter", [capi.FILTER_F32, capi.FILTER_F64, capi.FILTER_F32X4])
+@pytest.mark.parametrize("bvh_filter", [capi.FILTER_F32, capi.FILTER_F64, capi.FILTER_F32X4, capi.FILTER_Q16])
 def test_ids_bit_exact_bunny_1080p_pixel_centres(bvh_filter):
     """The fixed ray set of SURVEY.md 8(d): the 2 073 600 pixel-centre rays of C2 + 1M sphere rays."""
     spec = scenes.scene_bench(subdivisions=6, obj=True)
@@ -91,7 +91,7 @@ def photons_close(g, r, rtol, max_diverged=0):
     return int((~same).sum() + (rel > rtol).sum())
 
 
-@pytest.mark.parametrize("bvh_filter", [capi.FILTER_F32, capi.FILTER_F64, capi.FILTER_F32X4])
+@pytest.mark.parametrize("bvh_filter", [capi.FILTER_F32, capi.FILTER_F64, capi.FILTER_F32X4, capi.FILTER_Q16])
 def test_path_traced_samples_lambertian(bvh_filter):
     """C1b (main.rs scene, Lambertian) at reduced size: per-sample photons against the oracle, 1e-12."""
     spec = scenes.scene_main(subdivisions=3, obj=False)
@@ -242,7 +242,7 @@ def test_filter_modes_render_identical_frames():
         hs = V.build_scene(spec)
         W, H = (1920, 1080) if depth == 8 else (480, 270)
         ref = None
-        for f in (capi.FILTER_F32, capi.FILTER_F64, capi.FILTER_F32X4):
+        for f in (capi.FILTER_F32, capi.FILTER_F64, capi.FILTER_F32X4, capi.FILTER_Q16):
             r = hs.render((0, W, 0, H), H, W, spp=1, max_depth=depth, seed=7, want=("colour_sum",), want_photons=True, bvh_filter=f)
             if ref is None:
                 ref = r

@@ -16,7 +16,7 @@ ap.add_argument("--variant", default="lambertian")
 ap.add_argument("--count", action="store_true")
 a = ap.parse_args()
 hs = V.build_scene(scenes.scene_main(subdivisions=6, obj=True, variant=a.variant))
-f = {"f64": capi.FILTER_F64, "f32x4": capi.FILTER_F32X4}.get(a.filter, capi.FILTER_F32)
+f = {"f64": capi.FILTER_F64, "f32x4": capi.FILTER_F32X4, "q16": capi.FILTER_Q16}.get(a.filter, capi.FILTER_F32)
 for i in range(a.reps):
     r = hs.render((0, a.width, 0, a.height), a.height, a.width, spp=a.spp, max_depth=a.depth, seed=1, sample_offset=i * a.spp,
                   bvh_filter=f, want=("colour_sum", "weight"), count_traversal=a.count,

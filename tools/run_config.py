@@ -18,7 +18,7 @@ ap.add_argument("--filter", default="f32")
 ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="f32 = VRJ_PRECISION_F32_FAST (not a parity mode)")
 ap.add_argument("--device-builder", action="store_true", help="BoundingVolumeHierarchy::build on the GPU (vrj_bvh_build)")
 a = ap.parse_args()
-kw = dict(seed=1, precision=capi.PRECISION_F32_FAST if a.precision == "f32" else capi.PRECISION_F64, bvh_filter={"f64": capi.FILTER_F64, "f32x4": capi.FILTER_F32X4}.get(a.filter, capi.FILTER_F32))
+kw = dict(seed=1, precision=capi.PRECISION_F32_FAST if a.precision == "f32" else capi.PRECISION_F64, bvh_filter={"f64": capi.FILTER_F64, "f32x4": capi.FILTER_F32X4, "q16": capi.FILTER_Q16}.get(a.filter, capi.FILTER_F32))
 t0 = time.time()
 if a.config == "C2":
     spec, lights, amb = scenes.scene_direct(subdivisions=6, obj=True)

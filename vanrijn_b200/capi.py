@@ -17,7 +17,7 @@ u64p = C.POINTER(C.c_uint64)
 
 MAT_LAMBERTIAN, MAT_PHONG, MAT_REFLECTIVE, MAT_DIELECTRIC = 0, 1, 2, 3
 INTEGRATOR_SIMPLE_RANDOM, INTEGRATOR_WHITTED = 0, 1
-FILTER_F32, FILTER_F64, FILTER_F32X4 = 0, 1, 2
+FILTER_F32, FILTER_F64, FILTER_F32X4, FILTER_Q16 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 PRECISION_F64, PRECISION_F32_FAST = 0, 1
 TONEMAP_XYZ, TONEMAP_LINEAR_RGB = 0, 1

@@ -406,7 +406,8 @@ int persistent_grid(const VrjScene *sc, K kernel) {
 }
 
 template <typename NT, typename R, bool COUNT>
-VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, bool quad, uint64_t *launches) {
+VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, int walk, uint64_t *launches) {
+    const bool quad = walk == 1, q16 = walk == 2; // 0: the 2-wide tree in NT boxes; 1: 4-wide f32; 2: 2-wide on the 16-bit grid
     // launch sequence: G T S_0 [X_k T_k S_k]*, k = 1..levels (X = k_tail, a no-op until the queue is short);
     // SimpleRandom needs max_depth levels, Whitted one more (its limit-0 level still shades and traces);
     // the final S only finishes paths.
@@ -420,7 +421,7 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 4 + 1) * sizeof(uint32_t), s->stream));
     unsigned long long *stats = s->stats.as<unsigned long long>();
     double2 *photons = s->photons.as<double2>();
-    const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
+    const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT>) : q16 ? persistent_grid(sc, k_traceq<COUNT>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
     const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, true>);
     const int g_s = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, false>);
     // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
@@ -435,6 +436,7 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     VRJ_CUDA(s->mark(4));
     if (has_bvh) {
         if (quad) k_trace4<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
+        else if (q16) k_traceq<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
         else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
         (*launches)++;
         VRJ_CUDA(s->mark(0));
@@ -458,6 +460,7 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
         }
         if (has_bvh) {
             if (quad) k_trace4<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            else if (q16) k_traceq<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
             else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
             (*launches)++;
             VRJ_CUDA(s->mark(1));
@@ -589,6 +592,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     const size_t small_bytes = std::max<size_t>(cursor, 256);
     const Section s_n32 = reserve_section(n_wide * 64), s_n64 = reserve_section(n_wide * 112);
     const Section s_n4 = reserve_section(n_wide * 128); // upper bound: at most every internal node becomes a 4-wide node
+    const Section s_nq = reserve_section(n_wide * 32);
     const Section s_tp = reserve_section((size_t)d->n_triangles * 96), s_tn = reserve_section((size_t)d->n_triangles * 96);
     const Section s_tp32 = reserve_section((size_t)d->n_triangles * 48), s_tn32 = reserve_section((size_t)d->n_triangles * 48);
     const size_t arena_bytes = std::max<size_t>(cursor, 256);
@@ -684,6 +688,26 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
             VRJ_TRY_CUDA(cudaMemcpyAsync(&built_root[b * 8 + 4], dn_max + 4 * plan[b].first_node, 32, cudaMemcpyDeviceToHost, stream));
         }
     }
+    // the 16-bit grid of VRJ_FILTER_Q16 spans the root boxes of all meshes (those built above are read back first)
+    QGrid grid_q;
+    {
+        QGrid &grid = grid_q;
+        if (any_build) VRJ_TRY_CUDA(cudaStreamSynchronize(stream));
+        double glo[3] = {std::numeric_limits<double>::infinity(), std::numeric_limits<double>::infinity(), std::numeric_limits<double>::infinity()};
+        double ghi[3] = {-glo[0], -glo[1], -glo[2]};
+        for (uint32_t b = 0; b < d->n_bvhs; b++) {
+            if (plan[b].empty) continue;
+            const double *rmin = plan[b].build ? &built_root[b * 8] : d->node_min + d->bvhs[b].first_node * 4;
+            const double *rmax = plan[b].build ? &built_root[b * 8 + 4] : d->node_max + d->bvhs[b].first_node * 4;
+            for (int k = 0; k < 3; k++) glo[k] = std::fmin(glo[k], rmin[k]), ghi[k] = std::fmax(ghi[k], rmax[k]);
+        }
+        for (int k = 0; k < 3; k++) {
+            const bool ok = std::isfinite(glo[k]) && std::isfinite(ghi[k]) && ghi[k] > glo[k];
+            grid.lo[k] = std::isfinite(glo[k]) ? glo[k] : 0.0;
+            grid.cell[k] = ok ? (ghi[k] - glo[k]) / 65534.0 : 1e-30;
+            sc->dev.qlo[k] = grid.lo[k], sc->dev.qcell[k] = grid.cell[k];
+        }
+    }
     if (nt)
         k_pack_triangles<<<(unsigned)((nt + 127) / 128), 128, 0, stream>>>((uint32_t)nt, rt, perm, reinterpret_cast<double *>(base + s_tp.offset),
                                                                            reinterpret_cast<double *>(base + s_tn.offset),
@@ -706,6 +730,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
             return ss;
         }
         k_wide_nodes<<<grid, 256, 0, stream>>>(bn, flags, reinterpret_cast<float *>(base + s_n32.offset), reinterpret_cast<double *>(base + s_n64.offset));
+        k_q16_nodes<<<grid, 256, 0, stream>>>(bn, flags, grid_q, reinterpret_cast<uint4 *>(base + s_nq.offset));
         // the 4-wide form of the same tree (VRJ_FILTER_F32X4); its nodes are numbered from the same base (there are fewer of them)
         uint32_t *parent = reinterpret_cast<uint32_t *>(rb + r_parent), *is_quad = reinterpret_cast<uint32_t *>(rb + r_isquad);
         k_parents<<<grid, 256, 0, stream>>>(bn, parent);
@@ -768,6 +793,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     sc->dev.nodes32 = reinterpret_cast<const float4 *>(base + s_n32.offset);
     sc->dev.nodes64 = reinterpret_cast<const double2 *>(base + s_n64.offset);
     sc->dev.nodes4 = reinterpret_cast<const float4 *>(base + s_n4.offset);
+    sc->dev.nodesq = reinterpret_cast<const uint4 *>(base + s_nq.offset);
     sc->dev.tri_pos = reinterpret_cast<const double2 *>(base + s_tp.offset);
     sc->dev.tri_nrm = reinterpret_cast<const double2 *>(base + s_tn.offset);
     sc->dev.tri_pos32 = reinterpret_cast<const float4 *>(base + s_tp32.offset);
@@ -897,7 +923,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         return fail(VRJ_ERR_INVALID_ARGUMENT, "tile outside the image");
     if (width * height > 0xffffffffull) return fail(VRJ_ERR_UNSUPPORTED, "image larger than 2^32 pixels");
     if (p->integrator > VRJ_INTEGRATOR_WHITTED) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown integrator");
-    if (p->bvh_filter > VRJ_FILTER_F32X4) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
+    if (p->bvh_filter > VRJ_FILTER_Q16) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
     if (p->precision > VRJ_PRECISION_F32_FAST) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown precision");
     if (p->max_depth > 65535) return fail(VRJ_ERR_INVALID_ARGUMENT, "max_depth exceeds u16 (RECURSION_LIMIT is a u16)");
     if (p->n_lights && !p->lights) return fail(VRJ_ERR_INVALID_ARGUMENT, "lights is NULL");
@@ -984,7 +1010,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     rc.light_samples = s->light_samples.as<double>();
 
     // F32X4: the staged rays walk the 4-wide tree; inline any-hit queries (Whitted shadow rays, k_tail) use the 2-wide f32 tree
-    const bool quad = p->bvh_filter == VRJ_FILTER_F32X4;
+    const int quad = p->bvh_filter == VRJ_FILTER_F32X4 ? 1 : p->bvh_filter == VRJ_FILTER_Q16 ? 2 : 0;
     // VRJ_PRECISION_F32_FAST: the whole sample in binary32 over the 2-wide f32 tree (no reference counterpart; not a parity mode)
     const bool fast = p->precision == VRJ_PRECISION_F32_FAST;
     uint64_t launches = 0;
@@ -994,12 +1020,12 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         rc.batch_samples = std::min(batch, p->spp - done);
         rc.first_sample = p->sample_offset + (uint64_t)done * rc.sample_stride;
         if (p->count_traversal) {
-            st = fast ? run_batch<float, float, true>(scene, s, rc, whitted, false, &launches)
-                 : p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, double, true>(scene, s, rc, whitted, false, &launches)
+            st = fast ? run_batch<float, float, true>(scene, s, rc, whitted, 0, &launches)
+                 : p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, double, true>(scene, s, rc, whitted, 0, &launches)
                                                    : run_batch<float, double, true>(scene, s, rc, whitted, quad, &launches);
         } else {
-            st = fast ? run_batch<float, float, false>(scene, s, rc, whitted, false, &launches)
-                 : p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, double, false>(scene, s, rc, whitted, false, &launches)
+            st = fast ? run_batch<float, float, false>(scene, s, rc, whitted, 0, &launches)
+                 : p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, double, false>(scene, s, rc, whitted, 0, &launches)
                                                    : run_batch<float, double, false>(scene, s, rc, whitted, quad, &launches);
         }
         if (st != VRJ_OK) return st;
@@ -1071,7 +1097,7 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     VrjScene *scene = const_cast<VrjScene *>(scene_c);
     if (!scene || (n && (!origins || !directions || !object_id || !prim_id || !t)))
         return fail(VRJ_ERR_INVALID_ARGUMENT, "NULL argument");
-    if (bvh_filter > VRJ_FILTER_F32X4) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
+    if (bvh_filter > VRJ_FILTER_Q16) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown bvh_filter");
     if (stats) std::memset(stats, 0, sizeof(VrjStats));
     if (n == 0) return VRJ_OK;
     if (n > 0xfffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "more than 2^32 rays in one call");
@@ -1115,6 +1141,8 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
             k_trace<double, double, true><<<persistent_grid(scene, k_trace<double, double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
         else if (bvh_filter == VRJ_FILTER_F32X4)
             k_trace4<true><<<persistent_grid(scene, k_trace4<true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
+        else if (bvh_filter == VRJ_FILTER_Q16)
+            k_traceq<true><<<persistent_grid(scene, k_traceq<true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
         else
             k_trace<float, double, true><<<persistent_grid(scene, k_trace<float, double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
     }

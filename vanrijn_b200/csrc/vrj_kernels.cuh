@@ -261,6 +261,24 @@ __global__ void __launch_bounds__(128, VRJ_TRACE4_MINB) k_trace4(DevScene sc, Pa
     }
 }
 
+// the same launch over 16-bit nodes (VRJ_FILTER_Q16)
+template <bool COUNT>
+__global__ void __launch_bounds__(128, VRJ_TRACE_MINB) k_traceq(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
+                                                                uint32_t *work, unsigned long long *stats, const uint32_t *tail_done) {
+    if (tail_done && *tail_done) return;
+    const uint32_t n = *list_count;
+    ListRaySource source{q, tb};
+    ListHitSink sink{tb};
+    TraceCounters tc = {0, 0};
+    trace_persistent_q16<COUNT>(sc, n, work, source, sink, tc);
+    if (COUNT) {
+        LocalStats ls;
+        ls.clear();
+        ls.v[ST_NODES] = tc.node_visits, ls.v[ST_TRIS] = tc.tri_tests;
+        ls.flush(stats);
+    }
+}
+
 // ---- one level of the integrator for one path (shared by k_shade and k_tail) ----
 template <typename R>
 struct PathRegsT {

@@ -135,6 +135,66 @@ __global__ void k_wide_nodes(BvhNodes b, const uint32_t *__restrict__ rank, floa
     g[13] = 0.0;
 }
 
+// ---- 16-bit nodes (VRJ_FILTER_Q16): the 2-wide tree with both children's boxes quantised OUTWARD onto one 65536^3 grid over
+// the scene's meshes -- 32-byte records, one 256-bit load per step instead of two: {lo.x, hi.x, lo.y, hi.y} {lo.z, hi.z, l, r},
+// each coordinate word = child 0 in the low half, child 1 in the high half.  A plane sits at grid.lo + q * grid.cell.
+struct QGrid {
+    double lo[3], cell[3];
+};
+__device__ __forceinline__ uint32_t quantise_lo(double v, double glo, double cell) {
+    double x = floor((v - glo) / cell);
+    x = x < 0.0 ? 0.0 : (x > 65535.0 ? 65535.0 : x);
+    uint32_t q = (uint32_t)x;
+    if (q > 0 && glo + (double)q * cell > v) q--; // the division rounded up across a grid line
+    return q;
+}
+__device__ __forceinline__ uint32_t quantise_hi(double v, double glo, double cell) {
+    double x = ceil((v - glo) / cell);
+    x = x < 0.0 ? 0.0 : (x > 65535.0 ? 65535.0 : x);
+    uint32_t q = (uint32_t)x;
+    if (q < 65535u && glo + (double)q * cell < v) q++;
+    return q;
+}
+__device__ __forceinline__ void q16_child(const BvhNodes &b, const uint32_t *__restrict__ rank, const QGrid &g, int64_t node, uint32_t qlo[3],
+                                          uint32_t qhi[3], int32_t &ref) {
+    ref = -1;
+    bool empty = node < 0;
+    if (!empty) {
+        const int32_t l = b.node_child[2 * node], r = b.node_child[2 * node + 1];
+        if (l >= 0) ref = (int32_t)(b.wide_base + rank[node - b.first_node]);
+        else if (r == 0) empty = true;
+        else ref = ~((~l) + b.triangle_offset);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        qlo[k] = empty ? 65535u : quantise_lo(b.node_min[4 * node + k], g.lo[k], g.cell[k]);
+        qhi[k] = empty ? 0u : quantise_hi(b.node_max[4 * node + k], g.lo[k], g.cell[k]);
+    }
+}
+__global__ void k_q16_nodes(BvhNodes b, const uint32_t *__restrict__ rank, QGrid g, uint4 *__restrict__ nodesq) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_nodes) return;
+    const int64_t me = (int64_t)b.first_node + i;
+    const int32_t l = b.node_child[2 * me], r = b.node_child[2 * me + 1];
+    int64_t c0, c1;
+    uint32_t w;
+    if (l >= 0) {
+        w = b.wide_base + rank[i];
+        c0 = (int64_t)l + b.child_offset, c1 = (int64_t)r + b.child_offset;
+    } else if (i == 0) {
+        w = b.wide_base;
+        c0 = me, c1 = -1;
+    } else {
+        return;
+    }
+    uint32_t lo0[3], hi0[3], lo1[3], hi1[3];
+    int32_t r0, r1;
+    q16_child(b, rank, g, c0, lo0, hi0, r0);
+    q16_child(b, rank, g, c1, lo1, hi1, r1);
+    nodesq[(size_t)w * 2] = make_uint4(lo0[0] | (lo1[0] << 16), hi0[0] | (hi1[0] << 16), lo0[1] | (lo1[1] << 16), hi0[1] | (hi1[1] << 16));
+    nodesq[(size_t)w * 2 + 1] = make_uint4(lo0[2] | (lo1[2] << 16), hi0[2] | (hi1[2] << 16), (uint32_t)r0, (uint32_t)r1);
+}
+
 // ---- 4-wide nodes (VRJ_FILTER_F32X4): every second level of the reference tree is folded away, so a node carries
 // the f32 boxes (rounded outward) of its up to four grandchildren and a ray makes half as many dependent fetches.
 // 128-byte records: 24 floats [child][lo.x hi.x lo.y hi.y lo.z hi.z], 4 child refs (>= 0: 4-wide node, < 0: ~triangle,

@@ -23,6 +23,8 @@ struct DevScene {
     const float4 *__restrict__ nodes32;  // 4 x float4 per wide node (64 B)
     const double2 *__restrict__ nodes64; // 7 x double2 per wide node (112 B)
     const float4 *__restrict__ nodes4;   // 8 x float4 per 4-wide node (128 B): 4 boxes, 4 refs (VRJ_FILTER_F32X4)
+    const uint4 *__restrict__ nodesq;    // 2 x uint4 per 2-wide node (32 B): boxes on a 16-bit grid, 2 refs (VRJ_FILTER_Q16)
+    double qlo[3], qcell[3];             // that grid: plane coordinate = qlo + q * qcell
     const double2 *__restrict__ tri_pos; // 96-byte records (3 x 256-bit loads): 9 coords + {material, prim_id} + pad
     const double2 *__restrict__ tri_nrm; // 96-byte records: 9 coords + pad
     const float4 *__restrict__ tri_pos32; // f32-fast mode: 48-byte records, 9 coords + {material, prim_id} + pad
@@ -462,6 +464,177 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
                         if (dist < loc_t || (dist == loc_t && tri > loc_tri)) {
                             loc_t = dist, loc_tri = tri;
                             limit = filter_limit<NT>(fmin(loc_t, best.t));
+                        }
+                    }
+                    if (sp) cur = stack[--sp];
+                    else finish_bvh();
+                }
+            }
+            unsigned done_mask = __ballot_sync(FULL, cur == VRJ_LEAF_DONE);
+            if (done_mask == FULL || (!exhausted && __popc(done_mask) >= refill_threshold)) break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The same engine over 16-bit nodes (VRJ_FILTER_Q16): half the bytes per step.  A box plane is qlo + q * qcell; with
+// A = qcell / d (binary32) and B = (qlo - o) / d - 2^23 * A (formed in binary64 from the ROUNDED A, then rounded to binary32
+// away from the ray's interval, with a pad for q * (A - qcell / d)), the parameter of the plane is fma(2^23 + q, A, B):
+// one PRMT builds the float 2^23 + q from a 16-bit field, the bias cancels inside the fused multiply-add.  The box a ray
+// sees is at most two cells larger per side than the real one (one from the outward quantisation, one from rounding B),
+// never smaller; every triangle is still decided by the exact binary64 test, so results do not change.
+struct FilterRayQ {
+    float A[3], Bn[3], Bf[3];
+    uint32_t neg; // bit k: the direction is negative on axis k (the near plane is the box's hi plane)
+};
+__device__ __forceinline__ FilterRayQ filter_ray_q(const DevScene &sc, D3 o, D3 d) {
+    FilterRayQ f;
+    const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    f.neg = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double id = 1.0 / dd[k];
+        if (!(fabs(id) <= 1e18)) id = copysign(1e18, dd[k]);
+        const float A = __double2float_rn(sc.qcell[k] * id);
+        const double shift = (sc.qlo[k] - oo[k]) * id;
+        const double B = shift - 8388608.0 * (double)A;
+        // q * (A - cell/d) <= 65535 * 2^-24 * |A|;  binary64 rounding of `shift` and B;  a floor so the pad is never zero
+        const double pad = fabs((double)A) * 0.0079 + (fabs(shift) + fabs(B)) * 1e-15 + 1e-300;
+        f.A[k] = A, f.Bn[k] = __double2float_rd(B - pad), f.Bf[k] = __double2float_ru(B + pad);
+        if (id < 0.0) f.neg |= 1u << k;
+    }
+    return f;
+}
+template <bool COUNT, typename Source, typename Sink>
+__device__ __forceinline__ void trace_persistent_q16(const DevScene &sc, uint32_t n, uint32_t *work, Source &source, Sink &sink,
+                                                     TraceCounters &cnt) {
+    typedef FilterTraits<float> F;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t NONE = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const int refill_threshold = sc.refill_threshold, leaf_threshold = sc.leaf_threshold;
+    const int node_batch = sc.node_batch, max_iters = sc.max_iters;
+    int stack[32];
+    int sp = 0, cur = VRJ_LEAF_DONE;
+    uint32_t r = NONE, bcur = 0;
+    bool improved = false;
+    TriRay tr;
+    FilterRayQ fr;
+    Hit best;
+    double loc_t = CUDART_INF;
+    int loc_tri = -1;
+    float limit = 0.f;
+    bool exhausted = false;
+    tr.o = d3(0, 0, 0), tr.sx = tr.sy = tr.pdz = 0.0, tr.perm = 0;
+    best.t = CUDART_INF, best.item = -1, best.tri = -1;
+    fr.neg = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) fr.A[k] = fr.Bn[k] = fr.Bf[k] = 0.f;
+
+    auto finish_bvh = [&]() {
+        uint32_t item = sc.bvh_items[bcur];
+        if (loc_tri >= 0 && (best.item < 0 || loc_t < best.t || (loc_t == best.t && (int)item < best.item)))
+            best.t = loc_t, best.item = (int)item, best.tri = loc_tri, improved = true;
+        bcur++;
+        if (bcur < sc.n_bvh_items) {
+            cur = (int)sc.items[sc.bvh_items[bcur]].root; // all meshes share the scene's grid: the ray constants stay
+            sp = 0, loc_t = CUDART_INF, loc_tri = -1;
+            limit = filter_limit<float>(best.t);
+        } else {
+            cur = VRJ_LEAF_DONE;
+        }
+    };
+    // parameter interval of child `hi16` (0: low halves, 1: high halves) of the node words
+    auto child_test = [&](uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz, uint32_t sel, float &enter) {
+        const float qnx = __uint_as_float(__byte_perm(nx, 0x4b000000u, sel)), qfx = __uint_as_float(__byte_perm(fx, 0x4b000000u, sel));
+        const float qny = __uint_as_float(__byte_perm(ny, 0x4b000000u, sel)), qfy = __uint_as_float(__byte_perm(fy, 0x4b000000u, sel));
+        const float qnz = __uint_as_float(__byte_perm(nz, 0x4b000000u, sel)), qfz = __uint_as_float(__byte_perm(fz, 0x4b000000u, sel));
+        const float tn = fmaxf(fmaxf(fmaf(qnx, fr.A[0], fr.Bn[0]), fmaf(qny, fr.A[1], fr.Bn[1])), fmaf(qnz, fr.A[2], fr.Bn[2]));
+        const float tf = fminf(fminf(fmaf(qfx, fr.A[0], fr.Bf[0]), fmaf(qfy, fr.A[1], fr.Bf[1])), fmaf(qfz, fr.A[2], fr.Bf[2]));
+        const float ep = fmaf(-F::rel(), fabsf(tn), tn), xp = fmaf(F::rel(), fabsf(tf), tf);
+        enter = ep;
+        return (ep <= xp) && (xp >= 0.f) && (ep <= limit);
+    };
+    auto node_step = [&]() {
+        const uint4 *p = sc.nodesq + (size_t)cur * 2;
+        uint4 a, b;
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                     : "l"(p));
+        if (COUNT) cnt.node_visits += 2;
+        const bool ngx = fr.neg & 1u, ngy = fr.neg & 2u, ngz = fr.neg & 4u;
+        const uint32_t nx = ngx ? a.y : a.x, fx = ngx ? a.x : a.y;
+        const uint32_t ny = ngy ? a.w : a.z, fy = ngy ? a.z : a.w;
+        const uint32_t nz = ngz ? b.y : b.x, fz = ngz ? b.x : b.y;
+        float e0, e1;
+        const bool h0 = child_test(nx, fx, ny, fy, nz, fz, 0x7610u, e0);
+        const bool h1 = child_test(nx, fx, ny, fy, nz, fz, 0x7632u, e1);
+        const int left = (int)b.z, right = (int)b.w;
+        if (h0 && h1) {
+            bool swap = e1 < e0;
+            stack[sp++] = swap ? left : right;
+            cur = swap ? right : left;
+        } else if (h0 || h1) {
+            cur = h0 ? left : right;
+        } else if (sp) {
+            cur = stack[--sp];
+        } else {
+            finish_bvh();
+        }
+    };
+
+    while (true) {
+        bool idle = cur == VRJ_LEAF_DONE;
+        unsigned idle_mask = __ballot_sync(FULL, idle);
+        if (idle_mask) {
+            if (idle && r != NONE) {
+                sink.store(r, best, improved);
+                r = NONE;
+            }
+            if (exhausted) {
+                if (idle_mask == FULL) break;
+            } else if (idle_mask == FULL || __popc(idle_mask) >= refill_threshold) {
+                uint32_t want = (uint32_t)__popc(idle_mask), base = 0;
+                int leader = __ffs(idle_mask) - 1;
+                if ((int)lane == leader) base = atomicAdd(work, want);
+                base = __shfl_sync(FULL, base, leader);
+                if (base + want >= n) exhausted = true;
+                if (idle) {
+                    uint32_t my = base + (uint32_t)__popc(idle_mask & ((1u << lane) - 1u));
+                    if (my < n) {
+                        D3 o, d;
+                        source.load(my, o, d, best);
+                        r = my, improved = false;
+                        tr = tri_ray(o, d);
+                        fr = filter_ray_q(sc, o, d);
+                        bcur = 0;
+                        cur = (int)sc.items[sc.bvh_items[0]].root;
+                        sp = 0, loc_t = CUDART_INF, loc_tri = -1;
+                        limit = filter_limit<float>(best.t);
+                    }
+                }
+            }
+        }
+#pragma unroll 1
+        for (int it = 0; it < max_iters; it++) {
+#pragma unroll 1
+            for (int u = 0; u < node_batch; u++)
+                if (cur >= 0) node_step();
+            bool at_leaf = cur < 0 && cur != VRJ_LEAF_DONE;
+            unsigned leaf_mask = __ballot_sync(FULL, at_leaf);
+            unsigned node_mask = __ballot_sync(FULL, cur >= 0);
+            if (leaf_mask && (node_mask == 0 || __popc(leaf_mask) >= leaf_threshold)) {
+                if (at_leaf) {
+                    int tri = ~cur;
+                    D3 v0, v1, v2, loc;
+                    uint32_t mat, pid;
+                    load_tri_pos(sc, tri, v0, v1, v2, mat, pid);
+                    if (COUNT) cnt.tri_tests += 1;
+                    double dist, b0, b1, b2;
+                    if (triangle_test(tr, v0, v1, v2, dist, b0, b1, b2, loc)) {
+                        if (dist < loc_t || (dist == loc_t && tri > loc_tri)) {
+                            loc_t = dist, loc_tri = tri;
+                            limit = filter_limit<float>(fmin(loc_t, best.t));
                         }
                     }
                     if (sp) cur = stack[--sp];
