@@ -45,6 +45,9 @@ struct DevScene {
     double cam[3];
 };
 
+#ifndef VRJ_TRACE_TRIRAY_SMEM
+#define VRJ_TRACE_TRIRAY_SMEM 0
+#endif
 template <typename R>
 struct HitT {
     R t;
@@ -364,7 +367,14 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
     int sp = 0, cur = VRJ_LEAF_DONE;
     uint32_t r = NONE, bcur = 0;
     bool improved = false;
+#if VRJ_TRACE_TRIRAY_SMEM
+    // the triangle-test constants of the lane's ray live in shared memory: they are touched once per leaf, not per node
+    // step, and their 13 (binary64) registers are what keeps the kernel from 8 resident CTAs per SM
+    __shared__ TriRayT<R> s_tr[128];
+    TriRayT<R> &tr = s_tr[threadIdx.x];
+#else
     TriRayT<R> tr;
+#endif
     FilterRay<NT> fr;
     HitT<R> best;
     R loc_t = real_inf<R>();
