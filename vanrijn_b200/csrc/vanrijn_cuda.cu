@@ -398,10 +398,22 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
     return VRJ_OK;
 }
 
+// resident CTAs per SM of a kernel at 128 threads; asked once per kernel (the query costs tens of microseconds and a
+// 1-spp call makes five of them)
 template <typename K>
 int persistent_grid(const VrjScene *sc, K kernel) {
+    static std::mutex m;
+    static std::unordered_map<const void *, int> cache;
+    const void *key = reinterpret_cast<const void *>(kernel);
+    {
+        std::lock_guard<std::mutex> g(m);
+        auto it = cache.find(key);
+        if (it != cache.end()) return sc->sm_count * it->second;
+    }
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    std::lock_guard<std::mutex> g(m);
+    cache[key] = per_sm;
     return sc->sm_count * per_sm;
 }
 
@@ -938,6 +950,8 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     }
     const uint64_t tw = tile->end_column - tile->start_column, th = tile->end_row - tile->start_row;
     const uint64_t npix = tw * th;
+    static const bool timing = std::getenv("VRJ_TIMING") != nullptr;
+    const auto t_call0 = std::chrono::steady_clock::now();
     if (out->stats) std::memset(out->stats, 0, sizeof(VrjStats));
     if (npix == 0 || p->spp == 0) return VRJ_OK;
     VRJ_CUDA(cudaSetDevice(scene->device));
@@ -1015,6 +1029,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     const bool fast = p->precision == VRJ_PRECISION_F32_FAST;
     uint64_t launches = 0;
     s->n_marks = 0;
+    const auto t_call1 = std::chrono::steady_clock::now();
     VRJ_CUDA(cudaEventRecord(s->ev0, s->stream));
     for (uint32_t done = 0; done < p->spp; done += batch) {
         rc.batch_samples = std::min(batch, p->spp - done);
@@ -1050,9 +1065,18 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     }
     unsigned long long hstats[ST_COUNT];
     VRJ_CUDA(cudaMemcpyAsync(hstats, s->stats.p, sizeof hstats, cudaMemcpyDeviceToHost, s->stream));
+    const auto t_call2 = std::chrono::steady_clock::now();
     VRJ_CUDA(cudaStreamSynchronize(s->stream));
+    const auto t_call3 = std::chrono::steady_clock::now();
     float ms = 0.f;
     VRJ_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    if (timing) {
+        auto msd = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        std::fprintf(stderr, "vrj_render_tile: setup %.3f ms, enqueue %.3f ms, wait %.3f ms (device %.3f ms, %llu launches)\n",
+                     msd(t_call0, t_call1), msd(t_call1, t_call2), msd(t_call2, t_call3), ms, (unsigned long long)launches);
+    }
     if (out->stats) {
         fill_stats(out->stats, hstats, launches, ms);
         double cls_ms[6] = {0, 0, 0, 0, 0, 0}; // 0 T (camera rays), 1 T (bounce rays), 2 resolve, 3 shade, 4 raygen, 5 tail
