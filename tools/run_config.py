@@ -49,4 +49,5 @@ for i in range(a.reps):
                       "device_ms": st.device_ms, "rays": st.rays, "primary": int(st.primary_rays), "bounce": int(st.bounce_rays),
                       "shadow": int(st.shadow_rays), "staged": int(st.staged_rays), "launches": int(st.kernel_launches),
                       "trace_ms": st.primary_ms + st.bounce_ms, "shade_ms": st.shade_ms, "resolve_ms": st.resolve_ms,
+                      "tail_ms": st.tail_ms, "tail_launches": int(st.tail_launches), "depth_limited": int(st.paths_depth_limited),
                       "weights_ok_finite": ok, "mean_Y": float(r["colour_sum"].reshape(-1, 3)[:, 1].mean() / spp)}), flush=True)

@@ -197,7 +197,7 @@ struct VrjScene {
     DevScene dev{};
     std::vector<DeviceBuffer *> owned;
     uint32_t n_spectra = 0;
-    uint32_t tail_max = 1u << 17; // queue length at which k_tail finishes the batch in one launch (0 = never)
+    uint32_t tail_max = 1u << 18; // queue length at which k_tail finishes the batch in one launch (0 = never)
     ~VrjScene() {
         for (auto *b : owned) delete b;
     }

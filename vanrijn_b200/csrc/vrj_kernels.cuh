@@ -26,6 +26,9 @@
 #ifndef VRJ_TRACE_MINB
 #define VRJ_TRACE_MINB 6
 #endif
+#ifndef VRJ_TAIL_QUAD
+#define VRJ_TAIL_QUAD 1
+#endif
 #ifndef VRJ_TRACE4_MINB
 #define VRJ_TRACE4_MINB 5
 #endif
@@ -502,7 +505,8 @@ __global__ void __launch_bounds__(128, 2) k_tail(DevScene sc, RenderConst rc, Pa
             bool alive = true;
             while (alive) {
                 TraceCounters tc = {0, 0};
-                HitT<R> h = trace_closest<NT, COUNT, false>(sc, p.o, p.d, tc);
+                // one thread, one path: what it waits on is the chain of dependent node fetches, and the 4-wide tree halves it
+                HitT<R> h = trace_closest<NT, COUNT, false, R, VRJ_TAIL_QUAD != 0>(sc, p.o, p.d, tc);
                 if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
                 alive = shade_entry<NT, COUNT, WHITTED>(sc, rc, p, make_int2(h.item, h.tri), false, [](V3<R> &, V3<R> &) {}, photons, ls);
             }

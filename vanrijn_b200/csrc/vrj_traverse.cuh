@@ -261,8 +261,72 @@ __device__ __forceinline__ void bvh_closest(const DevScene &sc, int root, const 
     }
 }
 
+// The same query over the 4-wide form of the tree: half the dependent fetches, which is what a single thread following one
+// path to its end (k_tail) waits on.  Same filter, same exact test, same tie rule.
+__device__ __forceinline__ void cswap4(float &ka, int &ra, float &kb, int &rb) {
+    const bool sw = kb < ka;
+    const float k = sw ? kb : ka, K = sw ? ka : kb;
+    const int r = sw ? rb : ra, R = sw ? ra : rb;
+    ka = k, kb = K, ra = r, rb = R;
+}
+template <bool COUNT, typename R>
+__device__ __forceinline__ void bvh_closest_quad(const DevScene &sc, int root, const TriRayT<R> &tr, const FilterRay<float> &fr, R t_limit,
+                                                 R &best_t, int &best_tri, TraceCounters &cnt) {
+    int stack[48];
+    int sp = 0;
+    int cur = root;
+    best_t = real_inf<R>(), best_tri = -1;
+    float limit = filter_limit<float>(t_limit);
+    while (true) {
+        while (cur >= 0) {
+            const float4 *p = sc.nodes4 + (size_t)cur * 8;
+            float4 a, b, c, d, e, f, g, h;
+            ldg256(p, a, b);
+            ldg256(p + 2, c, d);
+            ldg256(p + 4, e, f);
+            ldg256(p + 6, g, h);
+            if (COUNT) cnt.node_visits += 4;
+            float k0, k1, k2, k3;
+            const bool h0 = box_filter(fr, a.x, a.y, a.z, a.w, b.x, b.y, limit, k0);
+            const bool h1 = box_filter(fr, b.z, b.w, c.x, c.y, c.z, c.w, limit, k1);
+            const bool h2 = box_filter(fr, d.x, d.y, d.z, d.w, e.x, e.y, limit, k2);
+            const bool h3 = box_filter(fr, e.z, e.w, f.x, f.y, f.z, f.w, limit, k3);
+            int r0 = __float_as_int(g.x), r1 = __float_as_int(g.y), r2 = __float_as_int(g.z), r3 = __float_as_int(g.w);
+            const float inf = CUDART_INF_F;
+            k0 = h0 ? k0 : inf, k1 = h1 ? k1 : inf, k2 = h2 ? k2 : inf, k3 = h3 ? k3 : inf;
+            const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+            cswap4(k0, r0, k1, r1), cswap4(k2, r2, k3, r3), cswap4(k0, r0, k2, r2), cswap4(k1, r1, k3, r3), cswap4(k1, r1, k2, r2);
+            if (nh == 0) {
+                cur = sp ? stack[--sp] : VRJ_LEAF_DONE;
+            } else {
+                if (nh > 3) stack[sp++] = r3;
+                if (nh > 2) stack[sp++] = r2;
+                if (nh > 1) stack[sp++] = r1;
+                cur = r0;
+            }
+        }
+        if (cur == VRJ_LEAF_DONE) break;
+        {
+            int tri = ~cur;
+            V3<R> v0, v1, v2, loc;
+            uint32_t mat, pid;
+            load_tri_pos(sc, tri, v0, v1, v2, mat, pid);
+            if (COUNT) cnt.tri_tests += 1;
+            R dist, b0, b1, b2;
+            if (triangle_test(tr, v0, v1, v2, dist, b0, b1, b2, loc)) {
+                if (dist < best_t || (dist == best_t && tri > best_tri)) {
+                    best_t = dist, best_tri = tri;
+                    limit = filter_limit<float>(fmin(best_t, t_limit));
+                }
+            }
+        }
+        cur = sp ? stack[--sp] : VRJ_LEAF_DONE;
+        if (cur == VRJ_LEAF_DONE) break;
+    }
+}
+
 // Sampler::sample.  ANY = true stops at the first hit found (shadow rays: only Some/None is used).
-template <typename NT, bool COUNT, bool ANY, typename R>
+template <typename NT, bool COUNT, bool ANY, typename R, bool QUAD = false>
 __device__ __forceinline__ HitT<R> trace_closest(const DevScene &sc, V3<R> o, V3<R> d, TraceCounters &cnt) {
     HitT<R> best;
     best.t = real_inf<R>(), best.item = -1, best.tri = -1;
@@ -288,8 +352,13 @@ __device__ __forceinline__ HitT<R> trace_closest(const DevScene &sc, V3<R> o, V3
                 hit = triangle_test(tr, v0, v1, v2, t, b0, b1, b2, loc);
                 tri = (int)it.index;
             } else {
-                FilterRay<NT> fr = filter_ray<NT>(o, d);
-                bvh_closest<NT, COUNT, ANY>(sc, (int)it.root, tr, fr, best.item < 0 ? real_inf<R>() : best.t, t, tri, cnt);
+                if (QUAD) {
+                    FilterRay<float> fr = filter_ray<float>(o, d);
+                    bvh_closest_quad<COUNT>(sc, (int)it.root, tr, fr, best.item < 0 ? real_inf<R>() : best.t, t, tri, cnt);
+                } else {
+                    FilterRay<NT> fr = filter_ray<NT>(o, d);
+                    bvh_closest<NT, COUNT, ANY>(sc, (int)it.root, tr, fr, best.item < 0 ? real_inf<R>() : best.t, t, tri, cnt);
+                }
                 hit = tri >= 0;
             }
         }
