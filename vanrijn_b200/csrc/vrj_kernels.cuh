@@ -26,6 +26,9 @@
 #ifndef VRJ_TRACE_MINB
 #define VRJ_TRACE_MINB 6
 #endif
+#ifndef VRJ_SHADOW_QUAD
+#define VRJ_SHADOW_QUAD 1
+#endif
 #ifndef VRJ_TAIL_QUAD
 #define VRJ_TAIL_QUAD 1
 #endif
@@ -362,7 +365,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
             V3<R> ldir = V3<R>{(R)Lt.dir[0], (R)Lt.dir[1], (R)Lt.dir[2]};
             V3<R> so, sd;
             biased_ray(h.location, ldir, (R)rc.bias, so, sd);
-            HitT<R> sh = trace_closest<NT, COUNT, true>(sc, so, sd, tc);
+            HitT<R> sh = trace_closest<NT, COUNT, true, R, VRJ_SHADOW_QUAD != 0>(sc, so, sd, tc);
             ls.v[ST_SHADOW]++;
             R term;
             if (sh.item >= 0) {

@@ -269,7 +269,7 @@ __device__ __forceinline__ void cswap4(float &ka, int &ra, float &kb, int &rb) {
     const int r = sw ? rb : ra, R = sw ? ra : rb;
     ka = k, kb = K, ra = r, rb = R;
 }
-template <bool COUNT, typename R>
+template <bool COUNT, bool ANY, typename R>
 __device__ __forceinline__ void bvh_closest_quad(const DevScene &sc, int root, const TriRayT<R> &tr, const FilterRay<float> &fr, R t_limit,
                                                  R &best_t, int &best_tri, TraceCounters &cnt) {
     int stack[48];
@@ -316,6 +316,7 @@ __device__ __forceinline__ void bvh_closest_quad(const DevScene &sc, int root, c
             if (triangle_test(tr, v0, v1, v2, dist, b0, b1, b2, loc)) {
                 if (dist < best_t || (dist == best_t && tri > best_tri)) {
                     best_t = dist, best_tri = tri;
+                    if (ANY) return;
                     limit = filter_limit<float>(fmin(best_t, t_limit));
                 }
             }
@@ -354,7 +355,7 @@ __device__ __forceinline__ HitT<R> trace_closest(const DevScene &sc, V3<R> o, V3
             } else {
                 if (QUAD) {
                     FilterRay<float> fr = filter_ray<float>(o, d);
-                    bvh_closest_quad<COUNT>(sc, (int)it.root, tr, fr, best.item < 0 ? real_inf<R>() : best.t, t, tri, cnt);
+                    bvh_closest_quad<COUNT, ANY>(sc, (int)it.root, tr, fr, best.item < 0 ? real_inf<R>() : best.t, t, tri, cnt);
                 } else {
                     FilterRay<NT> fr = filter_ray<NT>(o, d);
                     bvh_closest<NT, COUNT, ANY>(sc, (int)it.root, tr, fr, best.item < 0 ? real_inf<R>() : best.t, t, tri, cnt);
