@@ -198,6 +198,7 @@ struct VrjScene {
     std::vector<DeviceBuffer *> owned;
     uint32_t n_spectra = 0;
     uint32_t tail_max = 1u << 18; // queue length at which k_tail finishes the batch in one launch (0 = never)
+    uint32_t tail_max_shallow = 0; // the same for recursion limits <= 12
     ~VrjScene() {
         for (auto *b : owned) delete b;
     }
@@ -438,7 +439,7 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     const int g_s = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, false>);
     // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
     // per-level latency it removes is smaller than what its one-thread-per-path traversal costs (measured)
-    const uint32_t tail_max = levels > 12 ? sc->tail_max : 0u;
+    const uint32_t tail_max = levels > 12 ? sc->tail_max : sc->tail_max_shallow;
     const int g_x = (int)std::max<uint32_t>(1, (tail_max + 127) / 128);
     const bool has_bvh = sc->dev.n_bvh_items > 0;
     VRJ_CUDA(s->mark(-1));
@@ -824,6 +825,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     if (const char *tune = std::getenv("VRJ_TUNE")) // experiments only: "refill,leaf,node_batch,max_iters,tail_max,node_batch4"
         std::sscanf(tune, "%d,%d,%d,%d,%u,%d", &sc->dev.refill_threshold, &sc->dev.leaf_threshold, &sc->dev.node_batch, &sc->dev.max_iters, &sc->tail_max,
                     &sc->dev.node_batch4);
+    if (const char *ts = std::getenv("VRJ_TAIL_SHALLOW")) sc->tail_max_shallow = (uint32_t)std::strtoul(ts, nullptr, 10); // experiments only
     if (std::getenv("VRJ_TIMING")) {
         auto t_end = std::chrono::steady_clock::now();
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -1045,9 +1047,13 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         }
         if (st != VRJ_OK) return st;
         if (out->photons) {
-            // debug output, batch-major: [(sample * npix + pixel) * 2]
-            VRJ_CUDA(cudaMemcpyAsync(out->photons + (size_t)done * npix * 2, s->photons.p,
-                                     (size_t)rc.batch_samples * npix * sizeof(double2), out_kind, s->stream));
+            // debug output, batch-major: [(sample * npix + pixel) * 2]; the device keeps the batch pixel-major, so transpose
+            // into queue 0's storage (free at this point: 6 x 16 bytes per path >= 16 bytes per sample)
+            double2 *tmp = s->queues[0][0].as<double2>();
+            const size_t count = (size_t)rc.batch_samples * npix;
+            k_photons_sample_major<<<(unsigned)((count + 255) / 256), 256, 0, s->stream>>>(s->photons.as<double2>(), tmp, (uint32_t)npix, rc.batch_samples);
+            launches++;
+            VRJ_CUDA(cudaMemcpyAsync(out->photons + (size_t)done * npix * 2, tmp, count * sizeof(double2), out_kind, s->stream));
         }
     }
     VRJ_CUDA(cudaEventRecord(s->ev1, s->stream));
