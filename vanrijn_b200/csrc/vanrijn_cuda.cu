@@ -434,7 +434,8 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 4 + 1) * sizeof(uint32_t), s->stream));
     unsigned long long *stats = s->stats.as<unsigned long long>();
     double2 *photons = s->photons.as<double2>();
-    const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT>) : q16 ? persistent_grid(sc, k_traceq<COUNT>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
+    const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT, false>) : q16 ? persistent_grid(sc, k_traceq<COUNT, false>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
+    const int g_t0 = quad ? persistent_grid(sc, k_trace4<COUNT, true>) : q16 ? persistent_grid(sc, k_traceq<COUNT, true>) : persistent_grid(sc, k_trace_primary<NT, R, COUNT>);
     const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, true>);
     const int g_s = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, false>);
     // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
@@ -448,9 +449,9 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     (*launches)++;
     VRJ_CUDA(s->mark(4));
     if (has_bvh) {
-        if (quad) k_trace4<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
-        else if (q16) k_traceq<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
-        else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
+        if (quad) k_trace4<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
+        else if (q16) k_traceq<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
+        else k_trace_primary<NT, R, COUNT><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->trace_buffers(0), lcount + 0, work_t + 0, stats);
         (*launches)++;
         VRJ_CUDA(s->mark(0));
     }
@@ -472,8 +473,8 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
             VRJ_CUDA(s->mark(5));
         }
         if (has_bvh) {
-            if (quad) k_trace4<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
-            else if (q16) k_traceq<COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            if (quad) k_trace4<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            else if (q16) k_traceq<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
             else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
             (*launches)++;
             VRJ_CUDA(s->mark(1));
@@ -1170,9 +1171,9 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
         if (bvh_filter == VRJ_FILTER_F64)
             k_trace<double, double, true><<<persistent_grid(scene, k_trace<double, double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
         else if (bvh_filter == VRJ_FILTER_F32X4)
-            k_trace4<true><<<persistent_grid(scene, k_trace4<true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
+            k_trace4<true, false><<<persistent_grid(scene, k_trace4<true, false>), 128, 0, stream>>>(scene->dev, RenderConst{}, q, tb, d_lcount, d_work, dstats, nullptr);
         else if (bvh_filter == VRJ_FILTER_Q16)
-            k_traceq<true><<<persistent_grid(scene, k_traceq<true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
+            k_traceq<true, false><<<persistent_grid(scene, k_traceq<true, false>), 128, 0, stream>>>(scene->dev, RenderConst{}, q, tb, d_lcount, d_work, dstats, nullptr);
         else
             k_trace<float, double, true><<<persistent_grid(scene, k_trace<float, double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
     }

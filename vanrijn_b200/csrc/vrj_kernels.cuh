@@ -177,7 +177,25 @@ __device__ __forceinline__ void stage_ray(const DevScene &sc, bool have_ray, uin
     if (need) tb.list[pos] = idx, ls.v[ST_STAGED]++;
 }
 
-// ---- k_raygen: camera rays (camera.rs:45-66) into queue 0, staged for traversal ----
+// The camera ray of a result slot (camera.rs:45-66): two Philox draws, the film point, Ray::new.  It is a pure function of
+// the slot, so the primary level never stores it: k_raygen, k_trace on camera rays and the first k_shade each form it again
+// (one Philox block + one normalisation) instead of moving 48 bytes per ray through HBM three times.
+template <typename R>
+__device__ __forceinline__ void camera_ray(const DevScene &sc, const RenderConst &rc, uint32_t slot, V3<R> &o, V3<R> &d) {
+    uint32_t pixel;
+    uint64_t sample, grow, gcol;
+    slot_to_pixel(rc, slot, pixel, sample, grow, gcol);
+    Rng rng;
+    rng.init(rc.seed, pixel, sample, 0);
+    R ux = rng.uniform<R>(), uy = rng.uniform<R>();
+    const R film_w = (R)rc.film_w, film_h = (R)rc.film_h;
+    R px = ((R)gcol + ux) * (film_w * (R(1) / (R)rc.width)) - film_w * R(0.5);
+    R py = ((R)(rc.height - (grow + 1)) + uy) * (film_h * (R(1) / (R)rc.height)) - film_h * R(0.5);
+    o = V3<R>{(R)sc.cam[0], (R)sc.cam[1], (R)sc.cam[2]};
+    d = normalize(V3<R>{px, py, R(1)});
+}
+
+// ---- k_raygen: camera rays (camera.rs:45-66), staged for traversal ----
 template <typename R, bool COUNT>
 __global__ void VRJ_SHADE_BOUNDS(R) k_raygen(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, uint32_t *list_count,
                                                 uint32_t *work, unsigned long long *stats) {
@@ -193,20 +211,7 @@ __global__ void VRJ_SHADE_BOUNDS(R) k_raygen(DevScene sc, RenderConst rc, PathQu
         uint32_t j = base + lane;
         V3<R> o = V3<R>{R(0), R(0), R(0)}, d = V3<R>{R(0), R(0), R(1)};
         if (j < n) {
-            uint32_t pixel;
-            uint64_t sample, grow, gcol;
-            slot_to_pixel(rc, j, pixel, sample, grow, gcol);
-            Rng rng;
-            rng.init(rc.seed, pixel, sample, 0);
-            R ux = rng.uniform<R>(), uy = rng.uniform<R>();
-            const R film_w = (R)rc.film_w, film_h = (R)rc.film_h;
-            R px = ((R)gcol + ux) * (film_w * (R(1) / (R)rc.width)) - film_w * R(0.5);
-            R py = ((R)(rc.height - (grow + 1)) + uy) * (film_h * (R(1) / (R)rc.height)) - film_h * R(0.5);
-            o = V3<R>{(R)sc.cam[0], (R)sc.cam[1], (R)sc.cam[2]};
-            d = normalize(V3<R>{px, py, R(1)});
-            q.q0[j] = make_double2((double)o.x, (double)o.y);
-            q.q1[j] = make_double2((double)o.z, (double)d.x);
-            q.q2[j] = make_double2((double)d.y, (double)d.z);
+            camera_ray(sc, rc, j, o, d);
             ls.v[ST_PRIMARY]++;
         }
         stage_ray<COUNT>(sc, j < n, j, o, d, tb, list_count, ls);
@@ -222,6 +227,19 @@ struct ListRaySource {
     __device__ __forceinline__ void load(uint32_t r, V3<R> &o, V3<R> &d, HitT<R> &best) {
         uint32_t j = tb.list[r];
         queue_load_ray(q, j, o, d);
+        int2 h = tb.hits[j];
+        best.item = h.x, best.tri = h.y, best.t = (R)tb.tbest[j];
+    }
+};
+// the same for the camera rays of a batch: the ray is formed from its slot, nothing is read from the queue
+struct PrimaryRaySource {
+    const DevScene &sc;
+    const RenderConst &rc;
+    const TraceBuffers &tb;
+    template <typename R>
+    __device__ __forceinline__ void load(uint32_t r, V3<R> &o, V3<R> &d, HitT<R> &best) {
+        uint32_t j = tb.list[r];
+        camera_ray(sc, rc, j, o, d);
         int2 h = tb.hits[j];
         best.item = h.x, best.tri = h.y, best.t = (R)tb.tbest[j];
     }
@@ -254,16 +272,38 @@ __global__ void VRJ_TRACE_BOUNDS(R) k_trace(DevScene sc, PathQueue q, TraceBuffe
     }
 }
 
+// k_trace for the camera rays of a batch
+template <typename NT, typename R, bool COUNT>
+__global__ void VRJ_TRACE_BOUNDS(R) k_trace_primary(DevScene sc, RenderConst rc, TraceBuffers tb, const uint32_t *list_count, uint32_t *work,
+                                                    unsigned long long *stats) {
+    const uint32_t n = *list_count;
+    PrimaryRaySource source{sc, rc, tb};
+    ListHitSink sink{tb};
+    TraceCounters tc = {0, 0};
+    trace_persistent<NT, R, COUNT>(sc, n, work, source, sink, tc);
+    if (COUNT) {
+        LocalStats ls;
+        ls.clear();
+        ls.v[ST_NODES] = tc.node_visits, ls.v[ST_TRIS] = tc.tri_tests;
+        ls.flush(stats);
+    }
+}
+
 // the same launch over the 4-wide form of the tree (VRJ_FILTER_F32X4)
-template <bool COUNT>
-__global__ void __launch_bounds__(128, VRJ_TRACE4_MINB) k_trace4(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
+template <bool COUNT, bool PRIMARY>
+__global__ void __launch_bounds__(128, VRJ_TRACE4_MINB) k_trace4(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
                                                                  uint32_t *work, unsigned long long *stats, const uint32_t *tail_done) {
     if (tail_done && *tail_done) return;
     const uint32_t n = *list_count;
-    ListRaySource source{q, tb};
     ListHitSink sink{tb};
     TraceCounters tc = {0, 0};
-    trace_persistent_quad<COUNT>(sc, n, work, source, sink, tc);
+    if (PRIMARY) {
+        PrimaryRaySource source{sc, rc, tb};
+        trace_persistent_quad<COUNT>(sc, n, work, source, sink, tc);
+    } else {
+        ListRaySource source{q, tb};
+        trace_persistent_quad<COUNT>(sc, n, work, source, sink, tc);
+    }
     if (COUNT) {
         LocalStats ls;
         ls.clear();
@@ -273,15 +313,20 @@ __global__ void __launch_bounds__(128, VRJ_TRACE4_MINB) k_trace4(DevScene sc, Pa
 }
 
 // the same launch over 16-bit nodes (VRJ_FILTER_Q16)
-template <bool COUNT>
-__global__ void __launch_bounds__(128, VRJ_TRACE_MINB) k_traceq(DevScene sc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
+template <bool COUNT, bool PRIMARY>
+__global__ void __launch_bounds__(128, VRJ_TRACE_MINB) k_traceq(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, const uint32_t *list_count,
                                                                 uint32_t *work, unsigned long long *stats, const uint32_t *tail_done) {
     if (tail_done && *tail_done) return;
     const uint32_t n = *list_count;
-    ListRaySource source{q, tb};
     ListHitSink sink{tb};
     TraceCounters tc = {0, 0};
-    trace_persistent_q16<COUNT>(sc, n, work, source, sink, tc);
+    if (PRIMARY) {
+        PrimaryRaySource source{sc, rc, tb};
+        trace_persistent_q16<COUNT>(sc, n, work, source, sink, tc);
+    } else {
+        ListRaySource source{q, tb};
+        trace_persistent_q16<COUNT>(sc, n, work, source, sink, tc);
+    }
     if (COUNT) {
         LocalStats ls;
         ls.clear();
@@ -477,7 +522,12 @@ __global__ void VRJ_SHADE_BOUNDS(R) k_shade(DevScene sc, RenderConst rc, PathQue
                     p.slot = a5.x, p.ordinal = a5.y, p.limit = a5.z, p.flags = a5.w;
                 }
                 alive = shade_entry<NT, COUNT, WHITTED>(
-                    sc, rc, p, hit, FIRST, [&in, j](V3<R> &o, V3<R> &d) { queue_load_ray(in, j, o, d); }, photons, ls);
+                    sc, rc, p, hit, FIRST,
+                    [&in, &sc, &rc, j](V3<R> &o, V3<R> &d) {
+                        if (FIRST) camera_ray(sc, rc, j, o, d); // never stored: see camera_ray
+                        else queue_load_ray(in, j, o, d);
+                    },
+                    photons, ls);
             }
             uint32_t idx = queue_reserve(alive, out_count);
             if (alive) queue_store(out, idx, p.o, p.d, p.wl, p.A, p.B, p.aux, p.slot, p.ordinal, p.limit, p.flags);
