@@ -26,6 +26,9 @@
 #ifndef VRJ_TRACE_MINB
 #define VRJ_TRACE_MINB 6
 #endif
+#ifndef VRJ_FIRST_UNSORTED
+#define VRJ_FIRST_UNSORTED 1
+#endif
 #ifndef VRJ_SHADOW_QUAD
 #define VRJ_SHADOW_QUAD 1
 #endif
@@ -486,22 +489,28 @@ __global__ void VRJ_SHADE_BOUNDS(R) k_shade(DevScene sc, RenderConst rc, PathQue
         const uint32_t base = s_base;
         if (base >= n) break;
         const uint32_t total = min((uint32_t)SHADE_CHUNK, n - base);
-        uint32_t cls[SHADE_CHUNK / 128], pos[SHADE_CHUNK / 128];
+        if (FIRST && VRJ_FIRST_UNSORTED) {
+            // camera rays arrive pixel-major: a warp's 32 entries are samples of one pixel and already share a hit class
 #pragma unroll
-        for (int e = 0; e < SHADE_CHUNK / 128; e++) {
-            uint32_t k = threadIdx.x + e * 128;
-            cls[e] = 4;
-            if (k < total) {
-                int item = tb_in.hits[base + k].x;
-                cls[e] = item < 0 ? 0u : 1u + min(sc.items[item].kind, 2u);
-                pos[e] = atomicAdd(&s_count[cls[e]], 1u);
+            for (int e = 0; e < SHADE_CHUNK / 128; e++) s_sorted[threadIdx.x + e * 128] = base + threadIdx.x + e * 128;
+        } else {
+            uint32_t cls[SHADE_CHUNK / 128], pos[SHADE_CHUNK / 128];
+#pragma unroll
+            for (int e = 0; e < SHADE_CHUNK / 128; e++) {
+                uint32_t k = threadIdx.x + e * 128;
+                cls[e] = 4;
+                if (k < total) {
+                    int item = tb_in.hits[base + k].x;
+                    cls[e] = item < 0 ? 0u : 1u + min(sc.items[item].kind, 2u);
+                    pos[e] = atomicAdd(&s_count[cls[e]], 1u);
+                }
             }
-        }
-        __syncthreads();
-        const uint32_t c0 = s_count[0], c1 = c0 + s_count[1], c2 = c1 + s_count[2];
+            __syncthreads();
+            const uint32_t c0 = s_count[0], c1 = c0 + s_count[1], c2 = c1 + s_count[2];
 #pragma unroll
-        for (int e = 0; e < SHADE_CHUNK / 128; e++)
-            if (cls[e] < 4) s_sorted[(cls[e] == 0 ? 0u : cls[e] == 1 ? c0 : cls[e] == 2 ? c1 : c2) + pos[e]] = base + threadIdx.x + e * 128;
+            for (int e = 0; e < SHADE_CHUNK / 128; e++)
+                if (cls[e] < 4) s_sorted[(cls[e] == 0 ? 0u : cls[e] == 1 ? c0 : cls[e] == 2 ? c1 : c2) + pos[e]] = base + threadIdx.x + e * 128;
+        }
         __syncthreads();
 #pragma unroll 1
         for (uint32_t k = threadIdx.x; k < ((total + 31u) & ~31u); k += 128) {
