@@ -355,7 +355,7 @@ __device__ __forceinline__ double2 photon_out(R wavelength, R intensity) { retur
 // `first`: p.slot is set, the rest of the state is initialised here (camera.rs:108-119).
 // `load_ray(o, d)` fetches the ray only when it is needed.
 template <typename NT, bool COUNT, bool WHITTED, typename R, typename RayLoader>
-__device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderConst &rc, PathRegsT<R> &p, int2 hit, bool first,
+__device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderConst &rc, PathRegsT<R> &p, int2 hit, R hit_t, bool first,
                                             RayLoader load_ray, double2 *photons, LocalStats &ls) {
     const R span = R(740.0) - R(380.0); // photon.rs:18-24, colour/mod.rs:13-14
     if (first) {
@@ -397,7 +397,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
     }
     load_ray(p.o, p.d);
     HitFrameT<R> h;
-    bool ok = rebuild_hit(sc, p.o, p.d, hit.x, hit.y, h);
+    bool ok = rebuild_hit(sc, p.o, p.d, hit.x, hit.y, hit_t, h);
     // algebra_utils.rs:3-5, mat3.rs:111-118
     M3T<R> w2b = from_rows(h.tangent, h.cotangent, h.normal), b2w;
     ok = try_inverse(w2b, b2w) && ok;
@@ -531,7 +531,7 @@ __global__ void VRJ_SHADE_BOUNDS(R) k_shade(DevScene sc, RenderConst rc, PathQue
                     p.slot = a5.x, p.ordinal = a5.y, p.limit = a5.z, p.flags = a5.w;
                 }
                 alive = shade_entry<NT, COUNT, WHITTED>(
-                    sc, rc, p, hit, FIRST,
+                    sc, rc, p, hit, hit.x >= 0 ? (R)tb_in.tbest[j] : R(0), FIRST,
                     [&in, &sc, &rc, j](V3<R> &o, V3<R> &d) {
                         if (FIRST) camera_ray(sc, rc, j, o, d); // never stored: see camera_ray
                         else queue_load_ray(in, j, o, d);
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(128, 2) k_tail(DevScene sc, RenderConst rc, Pa
                 // one thread, one path: what it waits on is the chain of dependent node fetches, and the 4-wide tree halves it
                 HitT<R> h = trace_closest<NT, COUNT, false, R, VRJ_TAIL_QUAD != 0>(sc, p.o, p.d, tc);
                 if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
-                alive = shade_entry<NT, COUNT, WHITTED>(sc, rc, p, make_int2(h.item, h.tri), false, [](V3<R> &, V3<R> &) {}, photons, ls);
+                alive = shade_entry<NT, COUNT, WHITTED>(sc, rc, p, make_int2(h.item, h.tri), h.t, false, [](V3<R> &, V3<R> &) {}, photons, ls);
             }
         }
     }

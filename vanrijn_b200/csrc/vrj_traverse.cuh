@@ -872,21 +872,17 @@ __device__ __forceinline__ void trace_persistent_quad(const DevScene &sc, uint32
 
 // Rebuild the IntersectionInfo (raycasting/mod.rs:67-97) of a known hit with the exact arithmetic
 // of the primitive's intersect(): the wavefront stores only (ray, item, triangle).
+// `t` is the distance the closest-hit query found for this hit (the value of the primitive's own intersect(), computed by the
+// same code on the same ray), so spheres and planes go straight to their frame; triangles need their barycentrics again.
 template <typename R>
-__device__ __forceinline__ bool rebuild_hit(const DevScene &sc, V3<R> o, V3<R> d, int item, int tri, HitFrameT<R> &h) {
+__device__ __forceinline__ bool rebuild_hit(const DevScene &sc, V3<R> o, V3<R> d, int item, int tri, R t, HitFrameT<R> &h) {
     ItemDev it = sc.items[item];
     if (it.kind == 0) {
-        SphereDev s = sc.spheres[it.index];
-        R t;
-        if (!sphere_test(s, o, d, t)) return false;
-        sphere_frame(s, o, d, t, h);
+        sphere_frame(sc.spheres[it.index], o, d, t, h);
         return true;
     }
     if (it.kind == 1) {
-        PlaneDev p = sc.planes[it.index];
-        R t;
-        if (!plane_test(p, o, d, t)) return false;
-        plane_frame(p, o, d, t, h);
+        plane_frame(sc.planes[it.index], o, d, t, h);
         return true;
     }
     TriRayT<R> tr = tri_ray(o, d);
