@@ -11,6 +11,11 @@
  *                        (src/scene.rs:5-8) that the host-side BVH builder
  *                        (src/raycasting/bounding_volume_hierarchy.rs:49-75) and OBJ loader
  *                        (src/mesh.rs:74-88) emit; uploaded once per scene
+ *   vrj_bvh_build     <- BoundingVolumeHierarchy::build (bounding_volume_hierarchy.rs:38-75) on the device,
+ *                        the same tree bit for bit (also done inside vrj_scene_create for a VrjBvh without nodes)
+ *   vrj_tone_map      <- AccumulationBuffer::to_image_rgb_u8 with ClampingToneMapper
+ *                        (src/accumulation_buffer.rs:38-42, src/image.rs:130-187)
+ *   vrj_comm_* / vrj_render_sharded  <- the per-worker sample passes + merge of src/main.rs:197-217 over several GPUs
  *
  * The reference has no FFI today; INTEGRATION.md shows the Rust `extern "C"` block and the
  * `partial_render_scene_cuda` wrapper a maintainer would add.  Everything here is plain
@@ -238,7 +243,9 @@ VRJ_API void vrj_scene_destroy(VrjScene *scene);
 VRJ_API uint64_t vrj_scene_device_bytes(const VrjScene *scene);
 VRJ_API uint64_t vrj_scene_upload_bytes(const VrjScene *scene);
 
-/* Free the per-device scratch blocks (path queues etc.) the library keeps between calls. */
+/* Free what the library keeps between calls: the per-device scratch blocks (path queues etc.) and the pooled device and
+ * page-locked host memory (freed scenes, buffers and vrj_alloc_host / vrj_alloc_device blocks are kept for reuse because
+ * cudaMalloc / cudaFree / cudaMallocHost cost milliseconds each). */
 VRJ_API void vrj_release_scratch(void);
 /* Page-locked host memory for output arrays (optional: any host pointer works, pinned ones copy faster). */
 VRJ_API void *vrj_alloc_host(uint64_t bytes);
