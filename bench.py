@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp", type=int, default=32, help="samples per pixel per step per GPU (one wavefront batch up to 32 at 1080p)")
+    ap.add_argument("--spp", type=int, default=64, help="samples per pixel per step per GPU (one wavefront batch up to 64 at 1080p)")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--filter", default="f32", choices=["f32", "f64", "f32x4", "q16"],
@@ -337,7 +337,7 @@ def main():
                        "precision": "f32-fast (no parity claim)" if args.precision == "f32" else "f64 (the reference's type)",
                        "sharding": "sample index mod n_gpus; NCCL reduce of (sumXYZ, weight) to rank 0 each step",
                        "l2": "inputs larger than L2: %.1f GB of path state per step; the %.0f MB scene is L2-resident by design"
-                             % (min(spp, (1 << 26) // npix) * npix * 240 / 1e9, scene_bytes / 1e6)},
+                             % (min(spp, (1 << 27) // npix) * npix * 240 / 1e9, scene_bytes / 1e6)},
             "e2e": {"value": e2e_rays_all / e2e_max / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(upload_bytes),
                     "d2h_bytes_per_step": int(out_bytes), "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_max / e2e_steps, "scene_upload_ms_per_step": 1e3 * e2e_create / e2e_steps,

@@ -199,6 +199,7 @@ struct VrjScene {
     uint32_t n_spectra = 0;
     uint32_t tail_max = 1u << 18; // queue length at which k_tail finishes the batch in one launch (0 = never)
     uint32_t tail_max_shallow = 0; // the same for recursion limits <= 12
+    uint64_t path_budget = 1ull << 27; // paths in flight per batch
     ~VrjScene() {
         for (auto *b : owned) delete b;
     }
@@ -826,6 +827,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     if (const char *tune = std::getenv("VRJ_TUNE")) // experiments only: "refill,leaf,node_batch,max_iters,tail_max,node_batch4"
         std::sscanf(tune, "%d,%d,%d,%d,%u,%d", &sc->dev.refill_threshold, &sc->dev.leaf_threshold, &sc->dev.node_batch, &sc->dev.max_iters, &sc->tail_max,
                     &sc->dev.node_batch4);
+    if (const char *pb = std::getenv("VRJ_PATH_BUDGET_LOG2")) sc->path_budget = 1ull << std::min(std::max(std::atoi(pb), 16), 31); // experiments only
     if (const char *ts = std::getenv("VRJ_TAIL_SHALLOW")) sc->tail_max_shallow = (uint32_t)std::strtoul(ts, nullptr, 10); // experiments only
     if (std::getenv("VRJ_TIMING")) {
         auto t_end = std::chrono::steady_clock::now();
@@ -960,7 +962,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     VRJ_CUDA(cudaSetDevice(scene->device));
 
     // batch: as many samples of the whole tile in flight as fit the path budget
-    const uint64_t path_budget = 1ull << 26; // 64 Mi paths in flight (~14 GB of queue state: sized for 180 GB of HBM)
+    const uint64_t path_budget = scene->path_budget; // paths in flight: 128 Mi by default = ~31 GB of queue state (sized for 180 GB of HBM)
     uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(p->spp, path_budget / npix));
     if (npix * (uint64_t)batch > 0xfffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "tile too large");
     const bool whitted = p->integrator == VRJ_INTEGRATOR_WHITTED;
