@@ -18,6 +18,10 @@ pub const VRJ_ITEM_TRIANGLE: u32 = 2;
 pub const VRJ_ITEM_BVH: u32 = 3;
 pub const VRJ_FILTER_F32: u32 = 0;
 pub const VRJ_FILTER_F64: u32 = 1;
+pub const VRJ_FILTER_F32X4: u32 = 2;
+pub const VRJ_FILTER_Q16: u32 = 3;
+pub const VRJ_PRECISION_F64: u32 = 0;
+pub const VRJ_PRECISION_F32_FAST: u32 = 1;
 pub const VRJ_MEM_HOST: u32 = 0;
 pub const VRJ_MEM_DEVICE: u32 = 1;
 
@@ -118,6 +122,9 @@ extern "C" {
     pub fn vrj_release_scratch();
     pub fn vrj_alloc_host(bytes: u64) -> *mut c_void;
     pub fn vrj_free_host(p: *mut c_void);
+    pub fn vrj_alloc_device(device: i32, bytes: u64) -> *mut c_void;
+    pub fn vrj_free_device(p: *mut c_void);
+    pub fn vrj_copy_to_host(device: i32, host_dst: *mut c_void, device_src: *const c_void, bytes: u64) -> i32;
     pub fn vrj_render_tile(scene: *const VrjScene, tile: *const VrjTile, height: u64, width: u64,
                            params: *const VrjRenderParams, out: *mut VrjAccumOut) -> i32;
     pub fn vrj_comm_create(n_devices: i32, devices: *const i32, out: *mut *mut VrjComm) -> i32;
