@@ -24,6 +24,8 @@ pub const VRJ_PRECISION_F64: u32 = 0;
 pub const VRJ_PRECISION_F32_FAST: u32 = 1;
 pub const VRJ_MEM_HOST: u32 = 0;
 pub const VRJ_MEM_DEVICE: u32 = 1;
+pub const VRJ_TONEMAP_XYZ: u32 = 0;
+pub const VRJ_TONEMAP_LINEAR_RGB: u32 = 1;
 
 #[repr(C)] pub struct VrjScene { _private: [u8; 0] }
 #[repr(C)] pub struct VrjComm { _private: [u8; 0] }

@@ -283,3 +283,14 @@ def test_scene_cache_round_trip_and_corruption(tmp_path):
             V.HostScene.from_cache(bad)
     with pytest.raises(capi.VrjError):
         V.HostScene.from_cache(tmp_path / "missing.vrjscene")
+
+
+def test_rust_sys_crate_declares_every_header_symbol():
+    """rust/vanrijn-cuda-sys cannot be compiled here (no cargo), so at least keep its extern block in step with the header."""
+    header = open(os.path.join(ROOT, "include", "vanrijn_cuda.h")).read()
+    crate = open(os.path.join(ROOT, "rust", "vanrijn-cuda-sys", "src", "lib.rs")).read()
+    for name in sorted(set(re.findall(r"VRJ_API[^;(]*?\b(vrj_\w+)\s*\(", header))):
+        assert ("fn %s(" % name) in crate, name
+    for const in re.findall(r"\b(VRJ_(?:FILTER|PRECISION|MEM|ITEM|MAT|INTEGRATOR|TONEMAP)_\w+)\s*=\s*(\d+)", header):
+        m = re.search(r"pub const %s: u32 = (\d+);" % const[0], crate)
+        assert m and m.group(1) == const[1], const
