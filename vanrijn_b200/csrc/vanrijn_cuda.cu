@@ -357,21 +357,23 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
         VRJ_CUDA(cudaMallocHost(&s->host_count, 64 * sizeof(uint32_t)));
     }
     if (s->capacity < capacity) {
+        // all-or-nothing: a failed allocation leaves the block empty (capacity 0), never half-sized, so the caller can retry smaller
+        s->capacity = 0;
+        std::vector<std::pair<DeviceBuffer *, size_t>> want;
         for (int i = 0; i < 2; i++)
-            for (int k = 0; k < 6; k++) {
-                s->queues[i][k].release();
-                VRJ_CUDA(s->queues[i][k].alloc(capacity * 16));
+            for (int k = 0; k < 6; k++) want.push_back({&s->queues[i][k], capacity * 16});
+        want.push_back({&s->photons, capacity * sizeof(double2)});
+        for (int i = 0; i < 2; i++) want.push_back({&s->hits[i], capacity * sizeof(int2)}), want.push_back({&s->tbest[i], capacity * sizeof(double)});
+        want.push_back({&s->list, capacity * sizeof(uint32_t)});
+        for (auto &w : want) w.first->release();
+        for (auto &w : want) {
+            cudaError_t e = w.first->alloc(w.second);
+            if (e != cudaSuccess) {
+                for (auto &v : want) v.first->release();
+                cudaGetLastError();
+                return fail(e == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA, std::string("path queues: ") + cudaGetErrorString(e));
             }
-        s->photons.release();
-        VRJ_CUDA(s->photons.alloc(capacity * sizeof(double2)));
-        for (int i = 0; i < 2; i++) {
-            s->hits[i].release();
-            VRJ_CUDA(s->hits[i].alloc(capacity * sizeof(int2)));
-            s->tbest[i].release();
-            VRJ_CUDA(s->tbest[i].alloc(capacity * sizeof(double)));
         }
-        s->list.release();
-        VRJ_CUDA(s->list.alloc(capacity * sizeof(uint32_t)));
         s->capacity = capacity;
     }
     if (s->npix < npix) {
@@ -973,6 +975,11 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         ~Releaser() { release_scratch(sc, s); }
     } releaser{scene, s};
     VrjStatus st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples);
+    while (st == VRJ_ERR_OUT_OF_MEMORY && batch > 1) { // 240 bytes per path in flight: halve the batch until the queues fit
+        vrj_pool_trim();
+        batch = (batch + 1) / 2;
+        st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples);
+    }
     if (st != VRJ_OK) return st;
 
     const cudaMemcpyKind in_kind = out->memory == VRJ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
