@@ -154,6 +154,7 @@ int main(int argc, char **argv) {
                 o.spp = parameters.spp, o.max_depth = parameters.depth, o.seed = parameters.seed;
                 o.sample_offset = (uint64_t)pass * parameters.spp;
                 o.stats = &stats;
+                o.kahan_state = false; // merge_tile reads colour and weight only (main.rs:216): 66 MB back per 1080p pass, not 182 MB
                 const auto t_call = std::chrono::steady_clock::now();
                 AccumulationBuffer rendered_tile = partial_render_scene(scene, tile, image_height, image_width, o);
                 call_s += seconds_since(t_call);

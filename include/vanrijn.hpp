@@ -293,7 +293,7 @@ class AccumulationBuffer {
     friend AccumulationBuffer partial_render_scene(const Scene &, Tile, size_t, size_t, const struct RenderOptions &);
     friend class DeviceAccumulationBuffer;
     struct Uninitialized {};
-    AccumulationBuffer(size_t width, size_t height, Uninitialized); // arrays about to be overwritten by a render
+    AccumulationBuffer(size_t width, size_t height, Uninitialized, bool kahan_state = true); // arrays about to be overwritten by a render
     size_t width_, height_;
 };
 
@@ -316,6 +316,10 @@ struct RenderOptions {
     uint32_t bvh_filter = VRJ_FILTER_F32;
     uint32_t sample_stride = 1;
     int device = 0;
+    // false: the returned buffer carries only `colour` and `weight` -- all that merge_tile (accumulation_buffer.rs:62-85) and
+    // to_image_rgb_u8 read; the Kahan arrays (colour_sum, colour_bias, weight_bias: 7 of the 11 doubles per pixel) stay empty
+    // and are not copied back.  Such a buffer cannot be continued with update_pixel.
+    bool kahan_state = true;
     std::vector<DirectionalLight> lights; // Whitted
     Spectrum ambient_light = Spectrum::black();
     VrjStats *stats = nullptr;

@@ -454,9 +454,9 @@ AccumulationBuffer::AccumulationBuffer(size_t width, size_t height)
     : colour(3 * width * height, 0.0), colour_sum(3 * width * height, 0.0), colour_bias(3 * width * height, 0.0),
       weight(width * height, 0.0), weight_bias(width * height, 0.0), width_(width), height_(height) {}
 
-AccumulationBuffer::AccumulationBuffer(size_t width, size_t height, Uninitialized)
-    : colour(3 * width * height), colour_sum(3 * width * height), colour_bias(3 * width * height), weight(width * height),
-      weight_bias(width * height), width_(width), height_(height) {}
+AccumulationBuffer::AccumulationBuffer(size_t width, size_t height, Uninitialized, bool kahan_state)
+    : colour(3 * width * height), colour_sum(kahan_state ? 3 * width * height : 0), colour_bias(kahan_state ? 3 * width * height : 0),
+      weight(width * height), weight_bias(kahan_state ? width * height : 0), width_(width), height_(height) {}
 
 ImageRgbU8 AccumulationBuffer::to_image_rgb_u8(int device) const {
     ImageRgbU8 image(width_, height_);
@@ -707,7 +707,7 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
 
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &o) {
     // every element is overwritten by the copies out of vrj_render_tile (which returns early, writing nothing, for 0 spp)
-    AccumulationBuffer buffer = o.spp ? AccumulationBuffer(tile.width(), tile.height(), AccumulationBuffer::Uninitialized{})
+    AccumulationBuffer buffer = o.spp ? AccumulationBuffer(tile.width(), tile.height(), AccumulationBuffer::Uninitialized{}, o.kahan_state)
                                       : AccumulationBuffer(tile.width(), tile.height());
     VrjRenderParams p{};
     p.spp = o.spp, p.max_depth = o.max_depth, p.sample_offset = o.sample_offset, p.seed = o.seed;
@@ -730,8 +730,8 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
     VrjTile t{tile.start_column, tile.end_column, tile.start_row, tile.end_row};
     VrjAccumOut out{};
     out.memory = VRJ_MEM_HOST;
-    out.colour = buffer.colour.data(), out.colour_sum = buffer.colour_sum.data(), out.colour_bias = buffer.colour_bias.data();
-    out.weight = buffer.weight.data(), out.weight_bias = buffer.weight_bias.data();
+    out.colour = buffer.colour.data(), out.weight = buffer.weight.data();
+    if (!buffer.colour_sum.empty()) out.colour_sum = buffer.colour_sum.data(), out.colour_bias = buffer.colour_bias.data(), out.weight_bias = buffer.weight_bias.data();
     out.stats = o.stats;
     if (vrj_render_tile(dev, &t, height, width, &p, &out) != VRJ_OK) throw std::runtime_error(std::string("vrj_render_tile: ") + vrj_last_error());
     return buffer;
