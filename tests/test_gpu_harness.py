@@ -14,6 +14,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.fixture(scope="module", autouse=True)
+def harness_binary():
+    """build/vanrijn is built by `make` / __graft_entry__.build(); if only the libraries travelled, link it here (g++ only)."""
+    exe = os.path.join(ROOT, "build", "vanrijn")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", ROOT, "build/vanrijn"], check=True)
+    return exe
+
+
 @pytest.mark.parametrize("size,builder", [((160, 90), "upload"), ((2100, 6), "host")])
 def test_harness_png_equals_library_frame(tmp_path, size, builder):
     exe = os.path.join(ROOT, "build", "vanrijn")
