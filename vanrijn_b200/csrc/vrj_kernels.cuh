@@ -26,6 +26,9 @@
 #ifndef VRJ_TRACE_MINB
 #define VRJ_TRACE_MINB 6
 #endif
+#ifndef VRJ_RAYGEN_CHUNK
+#define VRJ_RAYGEN_CHUNK 1024
+#endif
 #ifndef VRJ_FIRST_UNSORTED
 #define VRJ_FIRST_UNSORTED 1
 #endif
@@ -203,21 +206,27 @@ template <typename R, bool COUNT>
 __global__ void VRJ_SHADE_BOUNDS(R) k_raygen(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, uint32_t *list_count,
                                                 uint32_t *work, unsigned long long *stats) {
     const uint32_t n = rc.npix * rc.batch_samples;
-    const uint32_t lane = threadIdx.x & 31;
     LocalStats ls;
     ls.clear();
+    // a CTA takes VRJ_RAYGEN_CHUNK slots per fetch: one atomic on the shared counter per 1024 rays, not one per warp of 32
+    __shared__ uint32_t s_base;
     while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = atomicAdd(work, (uint32_t)VRJ_RAYGEN_CHUNK);
+        __syncthreads();
+        const uint32_t base = s_base;
         if (base >= n) break;
-        uint32_t j = base + lane;
-        V3<R> o = V3<R>{R(0), R(0), R(0)}, d = V3<R>{R(0), R(0), R(1)};
-        if (j < n) {
-            camera_ray(sc, rc, j, o, d);
-            ls.v[ST_PRIMARY]++;
+#pragma unroll 1
+        for (uint32_t k = threadIdx.x; k < (uint32_t)VRJ_RAYGEN_CHUNK; k += 128) {
+            const uint32_t j = base + k;
+            if (base + (k & ~31u) >= n) break; // the whole warp is past the end
+            V3<R> o = V3<R>{R(0), R(0), R(0)}, d = V3<R>{R(0), R(0), R(1)};
+            if (j < n) {
+                camera_ray(sc, rc, j, o, d);
+                ls.v[ST_PRIMARY]++;
+            }
+            stage_ray<COUNT>(sc, j < n, j, o, d, tb, list_count, ls);
         }
-        stage_ray<COUNT>(sc, j < n, j, o, d, tb, list_count, ls);
     }
     ls.flush(stats);
 }
