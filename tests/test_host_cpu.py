@@ -211,6 +211,29 @@ def test_tile_iterator_and_merge_tile_match_the_oracle():
                                        np.zeros(60).ctypes.data_as(capi.dp), np.zeros(20).ctypes.data_as(capi.dp)) == 1
 
 
+def test_merge_tile_large_tile_threaded_path():
+    """Tiles of >= 2^18 pixels are merged by several threads: every pixel must still be the blend of accumulation_buffer.rs:81-85
+    ((c1*w1 + c2*w2) * (1/(w1+w2)), weight summed), here checked against the same expression in numpy (binary64, same order)."""
+    rng = np.random.default_rng(4)
+    W, H = 700, 520
+    tile = (20, 660, 10, 510)  # 640 x 500 = 320 000 pixels
+    th, tw = tile[3] - tile[2], tile[1] - tile[0]
+    dc, dw = rng.random((H, W, 3)), rng.random((H, W)) + 0.1
+    sc_, sw = rng.random((th, tw, 3)), rng.random((th, tw)) + 0.1
+    got_c, got_w = dc.copy(), dw.copy()
+    t4 = (C.c_uint64 * 4)(*tile)
+    assert capi.host().vrjh_merge_tile(got_c.ctypes.data_as(capi.dp), got_w.ctypes.data_as(capi.dp), W, H, t4,
+                                       np.ascontiguousarray(sc_).ctypes.data_as(capi.dp), np.ascontiguousarray(sw).ctypes.data_as(capi.dp)) == 0
+    w1 = dw[tile[2]:tile[3], tile[0]:tile[1]]
+    inv = 1.0 / (w1 + sw)
+    want = (dc[tile[2]:tile[3], tile[0]:tile[1]] * w1[..., None] + sc_ * sw[..., None]) * inv[..., None]
+    assert np.array_equal(got_c[tile[2]:tile[3], tile[0]:tile[1]], want)
+    assert np.array_equal(got_w[tile[2]:tile[3], tile[0]:tile[1]], w1 + sw)
+    mask = np.ones((H, W), bool)
+    mask[tile[2]:tile[3], tile[0]:tile[1]] = False
+    assert np.array_equal(got_c[mask], dc[mask]) and np.array_equal(got_w[mask], dw[mask])
+
+
 def test_shard_samples_partition_the_sample_indices():
     for world in (1, 2, 4, 8):
         for spp in (1, 3, 16):
