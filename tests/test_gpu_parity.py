@@ -355,3 +355,25 @@ def test_f32_fast_mode_tracks_the_parity_path():
         assert abs(b["stats"].rays - a["stats"].rays) <= 1e-3 * a["stats"].rays
     with pytest.raises(capi.VrjError):
         hs.render((0, 8, 0, 8), 8, 8, spp=1, precision=7)
+
+
+def test_full_size_properties_c5_mirror_and_glass_1080p():
+    """BASELINE config C5 at full size (mirror + diamond + reflective bunny, 1920x1080, recursion limit 128) through
+    size-independent properties: every pixel gets weight spp, every path ends exactly once, the frame is finite and
+    bit-reproducible (the one-launch tail kernel and its atomically compacted queues must not leak nondeterminism into the
+    per-pixel sums), and a crop equals the oracle."""
+    spec = scenes.scene_main(subdivisions=6, obj=True, variant="mixed")
+    hs, orc = both(spec)
+    W, H, spp = 1920, 1080, 2
+    a = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=4)
+    b = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=4)
+    st = a["stats"]
+    assert np.all(a["weight"] == spp) and np.all(np.isfinite(a["colour"]))
+    assert np.array_equal(a["colour_sum"], b["colour_sum"])
+    assert st.primary_rays == W * H * spp
+    assert st.paths_missed + st.paths_escaped + st.paths_depth_limited == st.primary_rays
+    assert st.tail_launches >= 1 and st.bounce_rays > st.primary_rays // 2
+    tile = (700, 748, 560, 592)  # on the mirror sphere / bunny boundary
+    r = orc.render(tile, H, W, spp=spp, max_depth=128, seed=4)
+    crop = a["colour_sum"].reshape(H, W, 3)[560:592, 700:748].reshape(-1)
+    np.testing.assert_allclose(crop, r["colour_sum"], rtol=1e-9, atol=1e-25)
