@@ -377,3 +377,26 @@ def test_full_size_properties_c5_mirror_and_glass_1080p():
     r = orc.render(tile, H, W, spp=spp, max_depth=128, seed=4)
     crop = a["colour_sum"].reshape(H, W, 3)[560:592, 700:748].reshape(-1)
     np.testing.assert_allclose(crop, r["colour_sum"], rtol=1e-9, atol=1e-25)
+
+
+def test_full_size_properties_c2_direct_lighting_1080p():
+    """BASELINE config C2 at full size (bunny, Whitted, recursion limit 0, one directional light, 1920x1080, 1 spp): ray
+    accounting (one shadow ray and one unused bounce probe per primary hit, whitted_integrator.rs:33-77), a finite frame,
+    and a 96x64 crop within north_star's 1e-4 per-channel relative error of the oracle (reflective material: no RNG in sample())."""
+    spec, lights, ambient = scenes.scene_direct(subdivisions=6, obj=True, reflective=True)
+    hs, orc = both(spec)
+    W, H = 1920, 1080
+    kw = dict(spp=1, max_depth=0, seed=1, lights=lights, ambient=ambient)
+    g = hs.render((0, W, 0, H), H, W, integrator=capi.INTEGRATOR_WHITTED, **kw)
+    st = g["stats"]
+    assert st.primary_rays == W * H and np.all(g["weight"] == 1.0) and np.all(np.isfinite(g["colour"]))
+    hits = st.primary_rays - st.paths_missed
+    assert st.shadow_rays == hits and st.bounce_rays == hits and hits > 100000
+    tile = (1200, 1296, 600, 664)  # on the bunny's silhouette
+    r = orc.render(tile, H, W, integrator=O.WHITTED, **kw)
+    gc = g["colour"].reshape(H, W, 3)[600:664, 1200:1296].reshape(-1, 3)
+    rc = r["colour"].reshape(-1, 3)
+    lit = np.abs(rc) > 1e-12
+    assert lit.sum() > 1000
+    assert np.max(np.abs(gc[lit] - rc[lit]) / np.abs(rc[lit])) < 1e-4
+    assert np.max(np.abs(gc[~lit] - rc[~lit])) < 1e-12
