@@ -216,7 +216,7 @@ def main():
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = {"rays": 0, "launches": 0, "device_ms": 0.0, "trace_ms": 0.0, "trace_launches": 0, "staged": 0,
-           "shade_ms": 0.0, "resolve_ms": 0.0}
+           "shade_ms": 0.0, "resolve_ms": 0.0, "primary": 0, "bounce": 0, "shade_launches": 0}
     fence()
     ev0.record()
     t0 = time.perf_counter()
@@ -230,6 +230,9 @@ def main():
         agg["staged"] += int(st.staged_rays)
         agg["shade_ms"] += st.shade_ms
         agg["resolve_ms"] += st.resolve_ms
+        agg["primary"] += int(st.primary_rays)
+        agg["bounce"] += int(st.bounce_rays)
+        agg["shade_launches"] += int(st.shade_launches)
     ev1.record()
     fence()
     wall = time.perf_counter() - t0
@@ -316,7 +319,15 @@ def main():
                 "whole_step": {"achieved": step_achieved, "frac": step_achieved / peak,
                                "what": "bytes_per_ray x all ray queries / CUDA-event time of all kernels of the step"},
                 "note": "the scene (BVH + triangles) is L2-resident by design, so the traversal kernel can exceed the HBM "
-                        "figure; the HBM roofline is SURVEY 8d's conservative yard-stick"}
+                        "figure; the HBM roofline is SURVEY 8d's conservative yard-stick",
+                # the other half of the step: k_raygen + k_shade stream the path queues through HBM.  Algorithmic bytes: a
+                # primary path reads its 16-byte hit record and writes a 16-byte result; every bounce ray is written once
+                # (96 B state + 16 B stage-1 hit + 4 B list entry) and read once (96 B + 16 B) by the next level
+                "k_shade": (lambda b, t: {"achieved": b / t / 1e9 if t > 0 else 0.0, "frac": (b / t / 1e9 if t > 0 else 0.0) / peak,
+                                          "unit": "GB/s", "algorithmic_bytes_per_step": b / max(1, args.steps),
+                                          "share_of_step": agg["shade_ms"] / max(1e-9, agg["device_ms"]),
+                                          "what": "k_raygen + k_shade: 32 B per primary path + 228 B per bounce ray / their CUDA-event time"})(
+                    32.0 * agg["primary"] + 228.0 * agg["bounce"], agg["shade_ms"] / 1e3)}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
