@@ -11,23 +11,28 @@ NVFLAGS = -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std
 LIBDIR ?= vanrijn_b200/lib
 EXTRA ?=
 CSRC = vanrijn_b200/csrc
-CUDA_DEPS = $(CSRC)/vanrijn_cuda.cu $(CSRC)/vrj_kernels.cuh $(CSRC)/vrj_traverse.cuh $(CSRC)/vrj_device.cuh \
-            $(CSRC)/rgb_basis_tables.inc include/vanrijn_cuda.h
+CUDA_DEPS = $(CSRC)/vrj_batch.cuh $(CSRC)/vrj_kernels.cuh $(CSRC)/vrj_traverse.cuh $(CSRC)/vrj_device.cuh \
+            $(CSRC)/vrj_internal.h $(CSRC)/rgb_basis_tables.inc include/vanrijn_cuda.h
 HOST_DEPS = $(CSRC)/host/vanrijn_host.cpp $(CSRC)/host/host_capi.cpp include/vanrijn.hpp include/vanrijn_cuda.h
 
 all: $(LIBDIR)/libvanrijn_cuda.so $(LIBDIR)/libvanrijn_host.so oracle examples
 
-# two translation units (the render loop; the device BVH builder), compiled separately so a change to one
-# does not recompile the other
+# translation units: the C ABI + scene upload; the device BVH builder; and one object per instantiation of the wavefront
+# batch (vrj_batch_inst.cu with -DVRJ_INST=0..5), so `make -j` compiles the kernel variants in parallel
 OBJDIR ?= build/obj
-$(OBJDIR)/vanrijn_cuda.o: $(CUDA_DEPS)
+BATCH_OBJS = $(OBJDIR)/vrj_batch_0.o $(OBJDIR)/vrj_batch_1.o $(OBJDIR)/vrj_batch_2.o $(OBJDIR)/vrj_batch_3.o \
+             $(OBJDIR)/vrj_batch_4.o $(OBJDIR)/vrj_batch_5.o
+$(OBJDIR)/vanrijn_cuda.o: $(CSRC)/vanrijn_cuda.cu $(CSRC)/vrj_scene_prep.cuh $(CUDA_DEPS)
 	mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) $(EXTRA) -c -o $@ $(CSRC)/vanrijn_cuda.cu
-$(OBJDIR)/vrj_bvh_build.o: $(CSRC)/vrj_bvh_build.cu include/vanrijn_cuda.h
+$(OBJDIR)/vrj_batch_%.o: $(CSRC)/vrj_batch_inst.cu $(CUDA_DEPS)
+	mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(EXTRA) -DVRJ_INST=$* -c -o $@ $(CSRC)/vrj_batch_inst.cu
+$(OBJDIR)/vrj_bvh_build.o: $(CSRC)/vrj_bvh_build.cu $(CSRC)/vrj_internal.h include/vanrijn_cuda.h
 	mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) $(EXTRA) -c -o $@ $(CSRC)/vrj_bvh_build.cu
 
-$(LIBDIR)/libvanrijn_cuda.so: $(OBJDIR)/vanrijn_cuda.o $(OBJDIR)/vrj_bvh_build.o
+$(LIBDIR)/libvanrijn_cuda.so: $(OBJDIR)/vanrijn_cuda.o $(OBJDIR)/vrj_bvh_build.o $(BATCH_OBJS)
 	mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $^ -ldl
 
@@ -49,5 +54,6 @@ build/vanrijn: examples/vanrijn_main.cpp $(LIBDIR)/libvanrijn_host.so include/va
 
 clean:
 	rm -f $(LIBDIR)/*.so oracle/*.so
+	rm -rf $(OBJDIR) build/vanrijn build/drop_in_example
 
 .PHONY: all oracle clean examples

@@ -326,7 +326,12 @@ struct RenderOptions {
 };
 
 // camera.rs:95-100.  Throws std::runtime_error where the reference would panic or when CUDA fails.
+// The reference's signature: every call renders a sample nobody has rendered before (the reference draws from an
+// OS-seeded generator; here the sample index comes from next_sample_index()), so the main.rs loop -- call, merge_tile,
+// repeat -- converges.  For a reproducible render pass RenderOptions with an explicit sample_offset.
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width);
+// reserves `count` consecutive sample indices of the process-wide sequence and returns the first
+uint64_t next_sample_index(uint64_t count = 1);
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &options);
 
 // The frame's AccumulationBuffer kept in GPU memory between passes ("progressive preview").

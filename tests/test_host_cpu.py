@@ -75,6 +75,88 @@ def test_scene_validation_rejects_bad_descriptions():
     assert capi.cuda().vrj_scene_create(None, 0, C.byref(h)) == 1
 
 
+def test_scene_validation_rejects_malformed_trees():
+    """The C ABI is the trust boundary for caller-built trees: a child outside the BVH's own node range, a cycle, a node
+    with two parents, a leaf triangle outside the BVH's range, an understated depth or a tree that is not full must be
+    refused before anything reaches the device (the scene-prep kernels index per-BVH temporaries by child - first_node
+    and the traversal stacks hold 32 entries)."""
+    hs = V.build_scene(scenes.scene_main(subdivisions=1, obj=False))  # 80-triangle mesh, host-built tree
+    d = hs.desc()
+    nn = int(d.n_nodes)
+    assert nn == 2 * 80 - 1 and d.n_bvhs == 1
+    child0 = np.ctypeslib.as_array(d.node_child, (nn, 2)).copy()
+    bvh0 = capi.Bvh.from_buffer_copy(d.bvhs[0])
+    h = C.c_void_p()
+    L = capi.cuda()
+
+    def create(child, bvh=None):
+        bad = capi.SceneDesc.from_buffer_copy(d)
+        child = np.ascontiguousarray(child, np.int32)
+        bad.node_child = child.ctypes.data_as(C.POINTER(C.c_int32))
+        b = (capi.Bvh * 1)(bvh if bvh is not None else capi.Bvh.from_buffer_copy(bvh0))
+        bad.bvhs = b
+        st = L.vrj_scene_create(C.byref(bad), 0, C.byref(h))
+        return st, L.vrj_last_error().decode()
+
+    internal = np.flatnonzero(child0[:, 0] >= 0)
+    leaves = np.flatnonzero(child0[:, 0] < 0)
+    # the untouched description passes validation (status 2 = no CUDA device here; 0 on a GPU box)
+    st, msg = create(child0)
+    assert st in (0, 2), msg
+    if st == 0:
+        L.vrj_scene_destroy(h)
+    for name, mutate in [
+        ("child before its parent (cycle)", lambda c: c.__setitem__((int(internal[3]), 0), 0)),
+        ("child equal to the node itself", lambda c: c.__setitem__((int(internal[2]), 1), int(internal[2]))),
+        ("child past the bvh's node range", lambda c: c.__setitem__((int(internal[1]), 1), nn)),
+        ("two parents", lambda c: c.__setitem__((int(internal[0]), 1), int(c[internal[1], 0]))),
+        ("leaf triangle outside the bvh", lambda c: c.__setitem__((int(leaves[0]), 0), ~80)),
+        ("leaf with two triangles", lambda c: c.__setitem__((int(leaves[1]), 1), 2)),
+        ("triangles out of leaf order", lambda c: (c.__setitem__((int(leaves[0]), 0), int(child0[leaves[1], 0])),
+                                                   c.__setitem__((int(leaves[1]), 0), int(child0[leaves[0], 0])))),
+        ("internal node turned into a leaf (tree not full)", lambda c: (c.__setitem__((int(internal[-1]), 0), int(child0[leaves[0], 0])),
+                                                                        c.__setitem__((int(internal[-1]), 1), 0))),
+    ]:
+        c = child0.copy()
+        mutate(c)
+        st, msg = create(c)
+        assert st in (1, 3), (name, st, msg)
+    # a bvh whose ranges lie outside the arrays, and one that claims nodes of another tree
+    b = capi.Bvh.from_buffer_copy(bvh0)
+    b.first_node = 1
+    assert create(child0, b)[0] == 1
+    b = capi.Bvh.from_buffer_copy(bvh0)
+    b.n_nodes = nn - 2
+    assert create(child0, b)[0] == 1
+    # `depth` is not trusted: a degenerate 40-level chain is refused whatever the field says
+    n_leaves = 41
+    chain = np.zeros((2 * n_leaves - 1, 2), np.int32)
+    k = 0
+    for lvl in range(n_leaves - 1):  # internal node k: left = leaf k+1, right = next internal k+2
+        chain[k] = (k + 1, k + 2)
+        chain[k + 1] = (~lvl, 1)
+        k += 2
+    chain[k] = (~(n_leaves - 1), 1)
+    bad = capi.SceneDesc.from_buffer_copy(d)
+    assert n_leaves <= d.n_triangles and len(chain) <= nn
+    b = capi.Bvh.from_buffer_copy(bvh0)
+    b.n_nodes, b.n_triangles, b.depth = len(chain), n_leaves, 3
+    full = child0.copy()
+    full[:len(chain)] = chain
+    st, msg = create(full, b)
+    assert st == 3 and "deeper" in msg, (st, msg)
+
+
+def test_same_signature_call_draws_fresh_sample_indices():
+    """partial_render_scene(scene, tile, h, w) must not repeat samples (main.rs:199-217 merges call after call): its
+    sample indices come from one process-wide counter."""
+    H = capi.host()
+    a = H.vrjh_next_sample_index(1)
+    b = H.vrjh_next_sample_index(5)
+    c = H.vrjh_next_sample_index(1)
+    assert b == a + 1 and c == b + 5
+
+
 def _flat_arrays(d):
     nt, nn = d.n_triangles, d.n_nodes
     tri = [np.ctypeslib.as_array(getattr(d, k), (nt, 4)) for k in ("tri_v0", "tri_v1", "tri_v2", "tri_n0", "tri_n1", "tri_n2")]

@@ -206,7 +206,8 @@ int vrjh_partial_render_scene(void *p, const uint64_t tile[4], uint64_t height, 
     HostScene *h = static_cast<HostScene *>(p);
     return guarded([&] {
         RenderOptions o;
-        o.seed = seed, o.sample_offset = sample_offset;
+        // UINT64_MAX: a fresh sample index, as the reference's same-signature call draws fresh random numbers
+        o.seed = seed, o.sample_offset = sample_offset == UINT64_MAX ? next_sample_index(o.spp) : sample_offset;
         Tile t{(size_t)tile[0], (size_t)tile[1], (size_t)tile[2], (size_t)tile[3]};
         AccumulationBuffer b = partial_render_scene(h->scene, t, (size_t)height, (size_t)width, o);
         size_t n = b.width() * b.height();
@@ -217,6 +218,7 @@ int vrjh_partial_render_scene(void *p, const uint64_t tile[4], uint64_t height, 
         if (weight_bias) std::memcpy(weight_bias, b.weight_bias.data(), n * sizeof(double));
     });
 }
+uint64_t vrjh_next_sample_index(uint64_t count) { return next_sample_index(count); }
 /* AccumulationBuffer::merge_tile on raw arrays (dst is dst_w x dst_h, src is the tile's size) */
 int vrjh_merge_tile(double *dst_colour, double *dst_weight, uint64_t dst_w, uint64_t dst_h, const uint64_t tile[4],
                     const double *src_colour, const double *src_weight) {

@@ -5,6 +5,7 @@
 #include "../../../include/vanrijn.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -713,8 +714,20 @@ const VrjScene *device_scene(const Scene &scene, int device) {
     return dev;
 }
 
+// The reference draws fresh `rand` values on every call (camera.rs:47-48, photon.rs:18-24), and main.rs:199-217 relies on
+// that: it calls partial_render_scene over and over and merge_tile()s the results so the image converges.  The
+// counter-based generator here is a pure function of (seed, pixel, sample index), so "fresh" means a sample index no
+// earlier call of this process has used: the same-signature overload takes its indices from one process-wide counter.
+// Reproducible renders go through the RenderOptions overload, which says which indices to use.
+uint64_t next_sample_index(uint64_t count) {
+    static std::atomic<uint64_t> counter{0};
+    return counter.fetch_add(count, std::memory_order_relaxed);
+}
+
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width) {
-    return partial_render_scene(scene, tile, height, width, RenderOptions());
+    RenderOptions o;
+    o.sample_offset = next_sample_index(o.spp);
+    return partial_render_scene(scene, tile, height, width, o);
 }
 
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &o) {

@@ -2,7 +2,7 @@
 // There is no CPU fallback anywhere in this library: without a CUDA device every entry
 // point that computes returns VRJ_ERR_CUDA.
 #include "../../include/vanrijn_cuda.h"
-#include "vrj_kernels.cuh"
+#include "vrj_batch.cuh"
 #include "vrj_scene_prep.cuh"
 #include "vrj_internal.h"
 
@@ -21,15 +21,21 @@
 #include <vector>
 
 using namespace vrj;
+using namespace vrjimpl;
 
 namespace {
-
 thread_local std::string g_error;
-VrjStatus fail(VrjStatus code, const std::string &msg) {
-    g_error = msg;
-    return code;
-}
 } // namespace
+
+// the six instantiations live in vrj_batch_inst.cu (one object file each)
+namespace vrjimpl {
+extern template VrjStatus run_batch<float, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
+extern template VrjStatus run_batch<float, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
+extern template VrjStatus run_batch<double, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
+extern template VrjStatus run_batch<double, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
+extern template VrjStatus run_batch<float, float, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
+extern template VrjStatus run_batch<float, float, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
+} // namespace vrjimpl
 // other translation units of the library (vrj_bvh_build.cu) report through the same thread-local message
 void vrj_set_error(const std::string &msg) { g_error = msg; }
 
@@ -118,94 +124,6 @@ void vrj_pool_free(void *p) {
     if (!keep) cudaFree(p);
 }
 namespace {
-#define VRJ_CUDA(expr)                                                                                      \
-    do {                                                                                                    \
-        cudaError_t e_ = (expr);                                                                            \
-        if (e_ != cudaSuccess)                                                                              \
-            return fail(e_ == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA,             \
-                        std::string(#expr) + ": " + cudaGetErrorString(e_));                                \
-    } while (0)
-
-struct DeviceBuffer {
-    void *p = nullptr;
-    size_t bytes = 0;
-    ~DeviceBuffer() { release(); }
-    void release() {
-        if (p) vrj_pool_free(p), p = nullptr;
-    }
-    cudaError_t alloc(size_t n) {
-        bytes = n;
-        return vrj_pool_alloc(&p, n);
-    }
-    template <typename T>
-    T *as() const { return static_cast<T *>(p); }
-};
-
-// per-call scratch: path queues, photon results, accumulators, counters
-struct Scratch {
-    size_t capacity = 0; // paths
-    size_t npix = 0;
-    uint32_t steps = 0;
-    DeviceBuffer queues[2][6];
-    DeviceBuffer photons, hits[2], tbest[2], list, counters, stats;
-    DeviceBuffer acc_colour, acc_sum, acc_bias, acc_weight, acc_wbias;
-    DeviceBuffer lights, light_samples, srgb8;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<cudaEvent_t> marks; // per-launch boundaries, reused across calls
-    std::vector<int> mark_class;    // class of the launch that ENDS at mark i (-1: start of a batch)
-    size_t n_marks = 0;
-    uint32_t *host_count = nullptr; // pinned
-    ~Scratch() {
-        if (stream) cudaStreamDestroy(stream);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-        for (cudaEvent_t e : marks) cudaEventDestroy(e);
-        if (host_count) cudaFreeHost(host_count);
-    }
-    // record a boundary event on the stream; cls = class of the launch it closes
-    cudaError_t mark(int cls) {
-        if (n_marks == marks.size()) {
-            cudaEvent_t e;
-            cudaError_t err = cudaEventCreate(&e);
-            if (err != cudaSuccess) return err;
-            marks.push_back(e), mark_class.push_back(cls);
-        }
-        mark_class[n_marks] = cls;
-        return cudaEventRecord(marks[n_marks++], stream);
-    }
-    TraceBuffers trace_buffers(int i) const {
-        TraceBuffers t;
-        t.hits = hits[i].as<int2>(), t.tbest = tbest[i].as<double>(), t.list = list.as<uint32_t>();
-        return t;
-    }
-    PathQueue queue(int i) const {
-        PathQueue q;
-        q.q0 = queues[i][0].as<double2>(), q.q1 = queues[i][1].as<double2>(), q.q2 = queues[i][2].as<double2>();
-        q.q3 = queues[i][3].as<double2>(), q.q4 = queues[i][4].as<double2>(), q.q5 = queues[i][5].as<uint4>();
-        return q;
-    }
-};
-
-} // namespace
-
-struct VrjScene {
-    int device = 0;
-    int sm_count = 0;
-    uint64_t device_bytes = 0;
-    uint64_t upload_bytes = 0;
-    DevScene dev{};
-    std::vector<DeviceBuffer *> owned;
-    uint32_t n_spectra = 0;
-    uint32_t tail_max = 1u << 18; // queue length at which k_tail finishes the batch in one launch (0 = never)
-    uint32_t tail_max_shallow = 0; // the same for recursion limits <= 12
-    uint64_t path_budget = 1ull << 27; // paths in flight per batch
-    ~VrjScene() {
-        for (auto *b : owned) delete b;
-    }
-};
-
-namespace {
 
 // next representable float above / below (bit arithmetic: this runs 12x per BVH node at scene upload)
 inline float float_up(float f) {
@@ -252,22 +170,51 @@ VrjStatus validate(const VrjSceneDesc *d) {
                      : it.kind == VRJ_ITEM_TRIANGLE ? d->n_triangles : it.kind == VRJ_ITEM_BVH ? d->n_bvhs : 0;
         if (it.index >= lim) return fail(VRJ_ERR_INVALID_ARGUMENT, "item index out of range");
     }
+    // The C ABI is a trust boundary (a Rust caller builds these arrays): the device code indexes per-BVH temporaries with
+    // `child - first_node`, walks with a 32-entry stack and breaks distance ties by triangle index, so every tree must be a
+    // proper binary tree in DFS pre-order inside its own node range, no deeper than the stack, with its triangles in leaf order.
+    std::vector<uint8_t> level; // 0 = not reached yet; the root is level 1
     for (uint32_t i = 0; i < d->n_bvhs; i++) {
         const VrjBvh &b = d->bvhs[i];
-        if (b.first_node + b.n_nodes > d->n_nodes || b.first_triangle + b.n_triangles > d->n_triangles)
+        if (b.first_node > d->n_nodes || b.n_nodes > d->n_nodes - b.first_node || b.first_triangle > d->n_triangles ||
+            b.n_triangles > d->n_triangles - b.first_triangle)
             return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh range out of bounds");
-        // n_nodes == 0 with triangles: the tree is built on the device at upload (median split: depth known from n)
-        const uint32_t depth = (b.n_nodes == 0 && b.n_triangles) ? vrj_build::tree_depth(b.n_triangles) : b.depth;
-        if (depth > 31) return fail(VRJ_ERR_UNSUPPORTED, "bvh deeper than the 32-entry traversal stack");
-        for (uint64_t n = b.first_node; n < b.first_node + b.n_nodes; n++) {
-            int32_t l = d->node_child[2 * n], r = d->node_child[2 * n + 1];
+        if (b.n_nodes == 0) {
+            // n_nodes == 0 with triangles: the tree is built on the device at upload (median split: depth known from n)
+            if (b.n_triangles && vrj_build::tree_depth(b.n_triangles) > 31) return fail(VRJ_ERR_UNSUPPORTED, "bvh deeper than the 32-entry traversal stack");
+            continue;
+        }
+        const uint64_t lo = b.first_node, hi = b.first_node + b.n_nodes;
+        const uint64_t tlo = b.first_triangle, thi = b.first_triangle + b.n_triangles;
+        level.assign((size_t)b.n_nodes, 0);
+        level[0] = 1;
+        uint64_t leaves = 0, leaf_triangles = 0;
+        int64_t last_triangle = -1;
+        for (uint64_t n = lo; n < hi; n++) {
+            const uint8_t lv = level[(size_t)(n - lo)];
+            if (lv == 0) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh node is not reachable from the root (nodes must be in DFS pre-order)");
+            const int32_t l = d->node_child[2 * n], r = d->node_child[2 * n + 1];
             if (l >= 0) {
-                if ((uint64_t)l >= d->n_nodes || r < 0 || (uint64_t)r >= d->n_nodes) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh child out of range");
+                // pre-order: both children come after their parent, inside this tree's range; each node has one parent
+                if (r < 0 || (uint64_t)l <= n || (uint64_t)l >= hi || (uint64_t)r <= n || (uint64_t)r >= hi || l == r)
+                    return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh child out of range (children must follow their parent inside the bvh's own node range)");
+                if (lv >= 31) return fail(VRJ_ERR_UNSUPPORTED, "bvh deeper than the 32-entry traversal stack");
+                uint8_t &ll = level[(size_t)((uint64_t)l - lo)], &rl = level[(size_t)((uint64_t)r - lo)];
+                if (ll || rl) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh node has two parents");
+                ll = rl = (uint8_t)(lv + 1);
             } else {
+                leaves++;
                 if (r < 0 || r > 1) return fail(VRJ_ERR_UNSUPPORTED, "bvh leaves hold at most one triangle (as the reference builds them)");
-                if (r == 1 && (uint64_t)(~l) >= d->n_triangles) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh leaf triangle out of range");
+                if (r == 1) {
+                    const uint64_t t = (uint64_t)(~l);
+                    if (t < tlo || t >= thi) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh leaf triangle outside the bvh's own triangle range");
+                    if ((int64_t)t <= last_triangle) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh triangles must be stored in leaf (DFS) order");
+                    last_triangle = (int64_t)t, leaf_triangles++;
+                }
             }
         }
+        if (b.n_nodes != 2 * leaves - 1) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh is not a full binary tree (n_nodes != 2 * leaves - 1)");
+        if (leaf_triangles != b.n_triangles) return fail(VRJ_ERR_INVALID_ARGUMENT, "bvh leaves do not cover the bvh's triangle range");
     }
     return VRJ_OK;
 }
@@ -349,15 +296,30 @@ void release_scratch(VrjScene *sc, Scratch *s) {
     else delete s;
 }
 
-VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t steps, uint32_t n_lights, size_t n_light_samples) {
+// `queue_oom` (optional): set when the allocation that failed was the path queues -- the only part a smaller batch shrinks
+VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t steps, uint32_t n_lights, size_t n_light_samples, bool *queue_oom = nullptr) {
+    if (queue_oom) *queue_oom = false;
     if (!s->stream) {
         VRJ_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         VRJ_CUDA(cudaEventCreate(&s->ev0));
         VRJ_CUDA(cudaEventCreate(&s->ev1));
         VRJ_CUDA(cudaMallocHost(&s->host_count, 64 * sizeof(uint32_t)));
     }
+    // every group below is all-or-nothing: a failed allocation leaves the group empty with its size field at 0 (never
+    // half-sized or stale), so the block can go back to the pool and the caller can retry
+    auto alloc_group = [](std::vector<std::pair<DeviceBuffer *, size_t>> &want, const char *what) -> VrjStatus {
+        for (auto &w : want) w.first->release();
+        for (auto &w : want) {
+            cudaError_t e = w.first->alloc(w.second);
+            if (e != cudaSuccess) {
+                for (auto &v : want) v.first->release();
+                cudaGetLastError();
+                return fail(e == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+            }
+        }
+        return VRJ_OK;
+    };
     if (s->capacity < capacity) {
-        // all-or-nothing: a failed allocation leaves the block empty (capacity 0), never half-sized, so the caller can retry smaller
         s->capacity = 0;
         std::vector<std::pair<DeviceBuffer *, size_t>> want;
         for (int i = 0; i < 2; i++)
@@ -365,29 +327,26 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
         want.push_back({&s->photons, capacity * sizeof(double2)});
         for (int i = 0; i < 2; i++) want.push_back({&s->hits[i], capacity * sizeof(int2)}), want.push_back({&s->tbest[i], capacity * sizeof(double)});
         want.push_back({&s->list, capacity * sizeof(uint32_t)});
-        for (auto &w : want) w.first->release();
-        for (auto &w : want) {
-            cudaError_t e = w.first->alloc(w.second);
-            if (e != cudaSuccess) {
-                for (auto &v : want) v.first->release();
-                cudaGetLastError();
-                return fail(e == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA, std::string("path queues: ") + cudaGetErrorString(e));
-            }
+        VrjStatus st = alloc_group(want, "path queues");
+        if (st != VRJ_OK) {
+            if (queue_oom) *queue_oom = st == VRJ_ERR_OUT_OF_MEMORY;
+            return st;
         }
         s->capacity = capacity;
     }
     if (s->npix < npix) {
-        DeviceBuffer *bufs[5] = {&s->acc_colour, &s->acc_sum, &s->acc_bias, &s->acc_weight, &s->acc_wbias};
-        size_t per[5] = {3, 3, 3, 1, 1};
-        for (int i = 0; i < 5; i++) {
-            bufs[i]->release();
-            VRJ_CUDA(bufs[i]->alloc(npix * per[i] * sizeof(double)));
-        }
+        s->npix = 0;
+        std::vector<std::pair<DeviceBuffer *, size_t>> want = {{&s->acc_colour, npix * 24}, {&s->acc_sum, npix * 24}, {&s->acc_bias, npix * 24},
+                                                               {&s->acc_weight, npix * 8}, {&s->acc_wbias, npix * 8}};
+        VrjStatus st = alloc_group(want, "accumulators");
+        if (st != VRJ_OK) return st;
         s->npix = npix;
     }
     if (s->steps < steps) {
-        s->counters.release();
-        VRJ_CUDA(s->counters.alloc(((size_t)steps * 4 + 4) * sizeof(uint32_t)));
+        s->steps = 0;
+        std::vector<std::pair<DeviceBuffer *, size_t>> want = {{&s->counters, ((size_t)steps * 4 + 4) * sizeof(uint32_t)}};
+        VrjStatus st = alloc_group(want, "level counters");
+        if (st != VRJ_OK) return st;
         s->steps = steps;
     }
     if (!s->stats.p) VRJ_CUDA(s->stats.alloc(ST_COUNT * sizeof(unsigned long long)));
@@ -399,110 +358,6 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
         s->light_samples.release();
         VRJ_CUDA(s->light_samples.alloc(std::max<size_t>(2, n_light_samples) * sizeof(double)));
     }
-    return VRJ_OK;
-}
-
-// resident CTAs per SM of a kernel at 128 threads; asked once per kernel (the query costs tens of microseconds and a
-// 1-spp call makes five of them)
-template <typename K>
-int persistent_grid(const VrjScene *sc, K kernel) {
-    static std::mutex m;
-    static std::unordered_map<const void *, int> cache;
-    const void *key = reinterpret_cast<const void *>(kernel);
-    {
-        std::lock_guard<std::mutex> g(m);
-        auto it = cache.find(key);
-        if (it != cache.end()) return sc->sm_count * it->second;
-    }
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    std::lock_guard<std::mutex> g(m);
-    cache[key] = per_sm;
-    return sc->sm_count * per_sm;
-}
-
-template <typename NT, typename R, bool COUNT>
-VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, int walk, uint64_t *launches) {
-    const bool quad = walk == 1, q16 = walk == 2; // 0: the 2-wide tree in NT boxes; 1: 4-wide f32; 2: 2-wide on the 16-bit grid
-    // launch sequence: G T S_0 [X_k T_k S_k]*, k = 1..levels (X = k_tail, a no-op until the queue is short);
-    // SimpleRandom needs max_depth levels, Whitted one more (its limit-0 level still shades and traces);
-    // the final S only finishes paths.
-    const uint32_t levels = whitted ? rc.max_depth + 1 : rc.max_depth;
-    const uint32_t stride = rc.max_depth + 3;
-    uint32_t *qcount = s->counters.as<uint32_t>(); // qcount[k]: length of the queue S_{k-1} wrote (k >= 1)
-    uint32_t *lcount = qcount + stride;             // lcount[k]: rays of queue k staged for BVH traversal
-    uint32_t *work_t = lcount + stride;             // work-fetch counters of T_k
-    uint32_t *work_s = work_t + stride;             // ... of G (k = 0 only) / S_k
-    uint32_t *tail_done = work_s + stride;          // set by the k_tail launch that finished the batch
-    VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 4 + 1) * sizeof(uint32_t), s->stream));
-    unsigned long long *stats = s->stats.as<unsigned long long>();
-    double2 *photons = s->photons.as<double2>();
-    const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT, false>) : q16 ? persistent_grid(sc, k_traceq<COUNT, false>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
-    const int g_t0 = quad ? persistent_grid(sc, k_trace4<COUNT, true>) : q16 ? persistent_grid(sc, k_traceq<COUNT, true>) : persistent_grid(sc, k_trace_primary<NT, R, COUNT>);
-    const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, true>);
-    const int g_s = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, false>);
-    // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
-    // per-level latency it removes is smaller than what its one-thread-per-path traversal costs (measured)
-    const uint32_t tail_max = levels > 12 ? sc->tail_max : sc->tail_max_shallow;
-    const int g_x = (int)std::max<uint32_t>(1, (tail_max + 127) / 128);
-    const bool has_bvh = sc->dev.n_bvh_items > 0;
-    VRJ_CUDA(s->mark(-1));
-    // the raygen kernel uses work_s[0]; S_0 uses work_t[stride-1] (never used by a T)
-    k_raygen<R, COUNT><<<g_gen, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_s + 0, stats);
-    (*launches)++;
-    VRJ_CUDA(s->mark(4));
-    if (has_bvh) {
-        if (quad) k_trace4<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
-        else if (q16) k_traceq<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
-        else k_trace_primary<NT, R, COUNT><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->trace_buffers(0), lcount + 0, work_t + 0, stats);
-        (*launches)++;
-        VRJ_CUDA(s->mark(0));
-    }
-    uint32_t *work_s0 = work_t + (stride - 1);
-    if (whitted)
-        k_shade<NT, R, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
-    else
-        k_shade<NT, R, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
-    (*launches)++;
-    VRJ_CUDA(s->mark(3));
-    for (uint32_t k = 1; k <= levels; k++) {
-        const int ci = k & 1, ni = (k + 1) & 1;
-        if (tail_max) {
-            if (whitted)
-                k_tail<NT, R, COUNT, true><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
-            else
-                k_tail<NT, R, COUNT, false><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
-            (*launches)++;
-            VRJ_CUDA(s->mark(5));
-        }
-        if (has_bvh) {
-            if (quad) k_trace4<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
-            else if (q16) k_traceq<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
-            else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
-            (*launches)++;
-            VRJ_CUDA(s->mark(1));
-        }
-        if (whitted)
-            k_shade<NT, R, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
-        else
-            k_shade<NT, R, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
-        (*launches)++;
-        VRJ_CUDA(s->mark(3));
-        // stop launching once the batch has drained (queue empty, or finished by k_tail)
-        if (levels > 12 && k % 4 == 0 && k < levels) {
-            VRJ_CUDA(cudaMemcpyAsync(s->host_count, qcount + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-            VRJ_CUDA(cudaMemcpyAsync(s->host_count + 1, tail_done, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-            VRJ_CUDA(cudaStreamSynchronize(s->stream));
-            if (s->host_count[0] == 0 || s->host_count[1] != 0) break;
-        }
-    }
-    AccumDev acc;
-    acc.colour = s->acc_colour.as<double>(), acc.sum = s->acc_sum.as<double>(), acc.bias = s->acc_bias.as<double>();
-    acc.weight = s->acc_weight.as<double>(), acc.weight_bias = s->acc_wbias.as<double>();
-    k_resolve<R><<<(rc.npix + 255) / 256, 256, 0, s->stream>>>(acc, photons, rc.npix, rc.batch_samples);
-    (*launches)++;
-    VRJ_CUDA(s->mark(2));
-    VRJ_CUDA(cudaGetLastError());
     return VRJ_OK;
 }
 
@@ -531,6 +386,7 @@ int32_t vrj_device_count(void) {
 }
 
 VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out) {
+    DeviceGuard device_guard;
     if (!out) return fail(VRJ_ERR_INVALID_ARGUMENT, "out is NULL");
     *out = nullptr;
     auto t_start = std::chrono::steady_clock::now();
@@ -846,6 +702,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
 
 void vrj_scene_destroy(VrjScene *scene) {
     if (!scene) return;
+    DeviceGuard device_guard;
     cudaSetDevice(scene->device);
     delete scene;
 }
@@ -854,6 +711,7 @@ uint64_t vrj_scene_device_bytes(const VrjScene *scene) { return scene ? scene->d
 uint64_t vrj_scene_upload_bytes(const VrjScene *scene) { return scene ? scene->upload_bytes : 0; }
 
 void vrj_release_scratch(void) {
+    DeviceGuard device_guard;
     {
         std::lock_guard<std::mutex> g(g_pool_mutex);
         for (auto &e : g_pool) {
@@ -918,6 +776,7 @@ void vrj_free_host(void *p) {
 }
 
 void *vrj_alloc_device(int32_t device, uint64_t bytes) {
+    DeviceGuard device_guard;
     void *p = nullptr;
     if (cudaSetDevice(device) != cudaSuccess || vrj_pool_alloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess) {
         g_error = std::string("vrj_alloc_device: ") + cudaGetErrorString(cudaGetLastError());
@@ -928,6 +787,7 @@ void *vrj_alloc_device(int32_t device, uint64_t bytes) {
 }
 void vrj_free_device(void *p) { vrj_pool_free(p); }
 VrjStatus vrj_copy_to_host(int32_t device, void *host_dst, const void *device_src, uint64_t bytes) {
+    DeviceGuard device_guard;
     if (bytes && (!host_dst || !device_src)) return fail(VRJ_ERR_INVALID_ARGUMENT, "NULL argument");
     VRJ_CUDA(cudaSetDevice(device));
     VRJ_CUDA(cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
@@ -957,6 +817,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     }
     const uint64_t tw = tile->end_column - tile->start_column, th = tile->end_row - tile->start_row;
     const uint64_t npix = tw * th;
+    DeviceGuard device_guard;
     static const bool timing = std::getenv("VRJ_TIMING") != nullptr;
     const auto t_call0 = std::chrono::steady_clock::now();
     if (out->stats) std::memset(out->stats, 0, sizeof(VrjStats));
@@ -972,13 +833,23 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     struct Releaser {
         VrjScene *sc;
         Scratch *s;
-        ~Releaser() { release_scratch(sc, s); }
+        // whatever path leaves this function (an error in the middle of the batch loop included), nothing may still be
+        // running on the block's stream when another caller is handed the block
+        ~Releaser() {
+            if (s->stream) cudaStreamSynchronize(s->stream);
+            release_scratch(sc, s);
+        }
     } releaser{scene, s};
-    VrjStatus st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples);
-    while (st == VRJ_ERR_OUT_OF_MEMORY && batch > 1) { // 240 bytes per path in flight: halve the batch until the queues fit
+    bool queue_oom = false;
+    VrjStatus st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
+    while (st == VRJ_ERR_OUT_OF_MEMORY && queue_oom && batch > 1) { // 240 bytes per path in flight: halve the batch until the queues fit
         vrj_pool_trim();
         batch = (batch + 1) / 2;
-        st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples);
+        st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
+    }
+    if (st == VRJ_ERR_OUT_OF_MEMORY && !queue_oom) { // the accumulators do not shrink with the batch: give cached blocks back, once
+        vrj_pool_trim();
+        st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
     }
     if (st != VRJ_OK) return st;
 
@@ -1112,6 +983,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
 }
 
 VrjStatus vrj_tone_map(int32_t device, uint32_t memory, uint32_t source, const double *colour, uint64_t n, uint8_t *rgb8) {
+    DeviceGuard device_guard;
     if (n && (!colour || !rgb8)) return fail(VRJ_ERR_INVALID_ARGUMENT, "NULL argument");
     if (source > VRJ_TONEMAP_LINEAR_RGB || memory > VRJ_MEM_DEVICE) return fail(VRJ_ERR_INVALID_ARGUMENT, "unknown source / memory");
     if (n == 0) return VRJ_OK;
@@ -1141,6 +1013,7 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     if (stats) std::memset(stats, 0, sizeof(VrjStats));
     if (n == 0) return VRJ_OK;
     if (n > 0xfffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "more than 2^32 rays in one call");
+    DeviceGuard device_guard;
     VRJ_CUDA(cudaSetDevice(scene->device));
     DeviceBuffer d_o, d_d, d_obj, d_prim, d_t, d_stats, d_q[3], d_hits, d_tbest, d_list;
     VRJ_CUDA(d_o.alloc(n * 24));
@@ -1160,7 +1033,8 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     struct Cleanup {
         cudaStream_t s;
         cudaEvent_t a, b;
-        ~Cleanup() { cudaStreamDestroy(s), cudaEventDestroy(a), cudaEventDestroy(b); }
+        // runs before the DeviceBuffers above return to the pool: no kernel or copy may still be using them
+        ~Cleanup() { cudaStreamSynchronize(s), cudaStreamDestroy(s), cudaEventDestroy(a), cudaEventDestroy(b); }
     } cleanup{stream, e0, e1};
     VRJ_CUDA(cudaMemcpyAsync(d_o.p, origins, n * 24, cudaMemcpyHostToDevice, stream));
     VRJ_CUDA(cudaMemcpyAsync(d_d.p, directions, n * 24, cudaMemcpyHostToDevice, stream));
@@ -1263,6 +1137,7 @@ VrjStatus vrj_comm_create(int32_t n, const int32_t *devices, VrjComm **out) {
     if (!out || n < 1 || !devices) return fail(VRJ_ERR_INVALID_ARGUMENT, "vrj_comm_create: bad arguments");
     *out = nullptr;
     if (!g_nccl.load()) return fail(VRJ_ERR_UNSUPPORTED, "NCCL (libnccl.so.2) could not be loaded");
+    DeviceGuard device_guard;
     VrjComm *c = new VrjComm();
     c->devices.assign(devices, devices + n);
     c->comms.assign(n, nullptr);
@@ -1286,6 +1161,7 @@ VrjStatus vrj_comm_create(int32_t n, const int32_t *devices, VrjComm **out) {
 
 void vrj_comm_destroy(VrjComm *c) {
     if (!c) return;
+    DeviceGuard device_guard;
     for (size_t i = 0; i < c->streams.size(); i++) {
         cudaSetDevice(c->devices[i]);
         cudaStreamDestroy(c->streams[i]);
@@ -1297,6 +1173,7 @@ void vrj_comm_destroy(VrjComm *c) {
 
 void vrj_comm_scene_destroy(VrjMultiScene *m) {
     if (!m) return;
+    DeviceGuard device_guard;
     for (size_t i = 0; i < m->scenes.size(); i++) {
         cudaSetDevice(m->comm->devices[i]);
         vrj_scene_destroy(m->scenes[i]);
@@ -1336,6 +1213,7 @@ VrjStatus vrj_render_sharded(VrjMultiScene *m, const VrjTile *tile, uint64_t hei
     if (tile->end_column < tile->start_column || tile->end_row < tile->start_row) return fail(VRJ_ERR_INVALID_ARGUMENT, "bad tile");
     VrjComm *c = m->comm;
     const int G = (int)c->devices.size();
+    DeviceGuard device_guard;
     const size_t npix = (size_t)(tile->end_column - tile->start_column) * (tile->end_row - tile->start_row);
     if (out->stats) std::memset(out->stats, 0, sizeof(VrjStats));
     if (npix == 0 || p->spp == 0) return VRJ_OK;

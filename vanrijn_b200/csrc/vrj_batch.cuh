@@ -1,0 +1,216 @@
+// vrj_batch.cuh -- one wavefront batch (launch sequence of the kernels in vrj_kernels.cuh) and the host-side state it runs on.
+// Shared by vanrijn_cuda.cu (the C ABI) and vrj_batch_inst.cu, which is compiled once per (box type, real type, counting)
+// combination so the six instantiations of run_batch -- each with its own k_shade / k_tail / k_trace variants -- build in
+// parallel instead of in one translation unit.
+#pragma once
+#include "../../include/vanrijn_cuda.h"
+#include "vrj_kernels.cuh"
+#include "vrj_internal.h"
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace vrjimpl {
+using namespace vrj;
+
+inline VrjStatus fail(VrjStatus code, const std::string &msg) {
+    vrj_set_error(msg);
+    return code;
+}
+#define VRJ_CUDA(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(e_ == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA,             \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                                \
+    } while (0)
+
+struct DeviceBuffer {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DeviceBuffer() { release(); }
+    void release() {
+        if (p) vrj_pool_free(p), p = nullptr;
+    }
+    cudaError_t alloc(size_t n) {
+        bytes = n;
+        return vrj_pool_alloc(&p, n);
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+// per-call scratch: path queues, photon results, accumulators, counters
+struct Scratch {
+    size_t capacity = 0; // paths
+    size_t npix = 0;
+    uint32_t steps = 0;
+    DeviceBuffer queues[2][6];
+    DeviceBuffer photons, hits[2], tbest[2], list, counters, stats;
+    DeviceBuffer acc_colour, acc_sum, acc_bias, acc_weight, acc_wbias;
+    DeviceBuffer lights, light_samples, srgb8;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> marks; // per-launch boundaries, reused across calls
+    std::vector<int> mark_class;    // class of the launch that ENDS at mark i (-1: start of a batch)
+    size_t n_marks = 0;
+    uint32_t *host_count = nullptr; // pinned
+    ~Scratch() {
+        if (stream) cudaStreamDestroy(stream);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t e : marks) cudaEventDestroy(e);
+        if (host_count) cudaFreeHost(host_count);
+    }
+    // record a boundary event on the stream; cls = class of the launch it closes
+    cudaError_t mark(int cls) {
+        if (n_marks == marks.size()) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
+            marks.push_back(e), mark_class.push_back(cls);
+        }
+        mark_class[n_marks] = cls;
+        return cudaEventRecord(marks[n_marks++], stream);
+    }
+    TraceBuffers trace_buffers(int i) const {
+        TraceBuffers t;
+        t.hits = hits[i].as<int2>(), t.tbest = tbest[i].as<double>(), t.list = list.as<uint32_t>();
+        return t;
+    }
+    PathQueue queue(int i) const {
+        PathQueue q;
+        q.q0 = queues[i][0].as<double2>(), q.q1 = queues[i][1].as<double2>(), q.q2 = queues[i][2].as<double2>();
+        q.q3 = queues[i][3].as<double2>(), q.q4 = queues[i][4].as<double2>(), q.q5 = queues[i][5].as<uint4>();
+        return q;
+    }
+};
+
+} // namespace vrjimpl
+
+struct VrjScene {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t device_bytes = 0;
+    uint64_t upload_bytes = 0;
+    vrj::DevScene dev{};
+    std::vector<vrjimpl::DeviceBuffer *> owned;
+    uint32_t n_spectra = 0;
+    uint32_t tail_max = 1u << 18; // queue length at which k_tail finishes the batch in one launch (0 = never)
+    uint32_t tail_max_shallow = 0; // the same for recursion limits <= 12
+    uint64_t path_budget = 1ull << 27; // paths in flight per batch
+    ~VrjScene() {
+        for (auto *b : owned) delete b;
+    }
+};
+
+namespace vrjimpl {
+
+// resident CTAs per SM of a kernel at 128 threads; asked once per kernel (the query costs tens of microseconds and a
+// 1-spp call makes five of them)
+template <typename K>
+int persistent_grid(const VrjScene *sc, K kernel) {
+    static std::mutex m;
+    static std::unordered_map<const void *, int> cache;
+    const void *key = reinterpret_cast<const void *>(kernel);
+    {
+        std::lock_guard<std::mutex> g(m);
+        auto it = cache.find(key);
+        if (it != cache.end()) return sc->sm_count * it->second;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    std::lock_guard<std::mutex> g(m);
+    cache[key] = per_sm;
+    return sc->sm_count * per_sm;
+}
+
+template <typename NT, typename R, bool COUNT>
+VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, int walk, uint64_t *launches) {
+    const bool quad = walk == 1, q16 = walk == 2; // 0: the 2-wide tree in NT boxes; 1: 4-wide f32; 2: 2-wide on the 16-bit grid
+    // launch sequence: G T S_0 [X_k T_k S_k]*, k = 1..levels (X = k_tail, a no-op until the queue is short);
+    // SimpleRandom needs max_depth levels, Whitted one more (its limit-0 level still shades and traces);
+    // the final S only finishes paths.
+    const uint32_t levels = whitted ? rc.max_depth + 1 : rc.max_depth;
+    const uint32_t stride = rc.max_depth + 3;
+    uint32_t *qcount = s->counters.as<uint32_t>(); // qcount[k]: length of the queue S_{k-1} wrote (k >= 1)
+    uint32_t *lcount = qcount + stride;             // lcount[k]: rays of queue k staged for BVH traversal
+    uint32_t *work_t = lcount + stride;             // work-fetch counters of T_k
+    uint32_t *work_s = work_t + stride;             // ... of G (k = 0 only) / S_k
+    uint32_t *tail_done = work_s + stride;          // set by the k_tail launch that finished the batch
+    VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 4 + 1) * sizeof(uint32_t), s->stream));
+    unsigned long long *stats = s->stats.as<unsigned long long>();
+    double2 *photons = s->photons.as<double2>();
+    const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT, false>) : q16 ? persistent_grid(sc, k_traceq<COUNT, false>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
+    const int g_t0 = quad ? persistent_grid(sc, k_trace4<COUNT, true>) : q16 ? persistent_grid(sc, k_traceq<COUNT, true>) : persistent_grid(sc, k_trace_primary<NT, R, COUNT>);
+    const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, true>);
+    const int g_s = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, false>);
+    // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
+    // per-level latency it removes is smaller than what its one-thread-per-path traversal costs (measured)
+    const uint32_t tail_max = levels > 12 ? sc->tail_max : sc->tail_max_shallow;
+    const int g_x = (int)std::max<uint32_t>(1, (tail_max + 127) / 128);
+    const bool has_bvh = sc->dev.n_bvh_items > 0;
+    VRJ_CUDA(s->mark(-1));
+    // the raygen kernel uses work_s[0]; S_0 uses work_t[stride-1] (never used by a T)
+    k_raygen<R, COUNT><<<g_gen, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_s + 0, stats);
+    (*launches)++;
+    VRJ_CUDA(s->mark(4));
+    if (has_bvh) {
+        if (quad) k_trace4<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
+        else if (q16) k_traceq<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
+        else k_trace_primary<NT, R, COUNT><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->trace_buffers(0), lcount + 0, work_t + 0, stats);
+        (*launches)++;
+        VRJ_CUDA(s->mark(0));
+    }
+    uint32_t *work_s0 = work_t + (stride - 1);
+    if (whitted)
+        k_shade<NT, R, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
+    else
+        k_shade<NT, R, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
+    (*launches)++;
+    VRJ_CUDA(s->mark(3));
+    for (uint32_t k = 1; k <= levels; k++) {
+        const int ci = k & 1, ni = (k + 1) & 1;
+        if (tail_max) {
+            if (whitted)
+                k_tail<NT, R, COUNT, true><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
+            else
+                k_tail<NT, R, COUNT, false><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
+            (*launches)++;
+            VRJ_CUDA(s->mark(5));
+        }
+        if (has_bvh) {
+            if (quad) k_trace4<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            else if (q16) k_traceq<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            (*launches)++;
+            VRJ_CUDA(s->mark(1));
+        }
+        if (whitted)
+            k_shade<NT, R, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
+        else
+            k_shade<NT, R, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
+        (*launches)++;
+        VRJ_CUDA(s->mark(3));
+        // stop launching once the batch has drained (queue empty, or finished by k_tail)
+        if (levels > 12 && k % 4 == 0 && k < levels) {
+            VRJ_CUDA(cudaMemcpyAsync(s->host_count, qcount + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+            VRJ_CUDA(cudaMemcpyAsync(s->host_count + 1, tail_done, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+            VRJ_CUDA(cudaStreamSynchronize(s->stream));
+            if (s->host_count[0] == 0 || s->host_count[1] != 0) break;
+        }
+    }
+    AccumDev acc;
+    acc.colour = s->acc_colour.as<double>(), acc.sum = s->acc_sum.as<double>(), acc.bias = s->acc_bias.as<double>();
+    acc.weight = s->acc_weight.as<double>(), acc.weight_bias = s->acc_wbias.as<double>();
+    k_resolve<R><<<(rc.npix + 255) / 256, 256, 0, s->stream>>>(acc, photons, rc.npix, rc.batch_samples);
+    (*launches)++;
+    VRJ_CUDA(s->mark(2));
+    VRJ_CUDA(cudaGetLastError());
+    return VRJ_OK;
+}
+
+} // namespace vrjimpl

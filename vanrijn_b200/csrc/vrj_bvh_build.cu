@@ -616,6 +616,7 @@ extern "C" VRJ_API VrjStatus vrj_bvh_build(int32_t device, uint64_t n_triangles,
         return VRJ_ERR_UNSUPPORTED;
     }
     if (depth) *depth = tree_depth(n_triangles);
+    DeviceGuard device_guard;
     VRJB(cudaSetDevice(device)); // no device: VRJ_ERR_CUDA -- there is no CPU fallback behind this entry point
     if (n_triangles == 0) { // bounding_volume_hierarchy.rs:53-61: a single empty leaf with BoundingBox::empty()
         const double inf = std::numeric_limits<double>::infinity();

@@ -14,6 +14,20 @@ cudaError_t vrj_pool_alloc(void **out, size_t bytes);
 void vrj_pool_free(void *p);
 void vrj_pool_trim();
 
+// every exported function that switches devices puts the caller's current device back (a torch caller would otherwise
+// find itself on another GPU after vrj_render_sharded)
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1, cudaGetLastError();
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 namespace vrj_build {
 // BoundingVolumeHierarchy::build on the current device (vrj_bvh_build.cu).  d_vertices: 9 doubles per triangle in
 // input order.  Outputs (device memory): d_order[n] (leaf position -> input index), d_node_min / d_node_max

@@ -628,7 +628,7 @@ __global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t npix, u
 }
 
 // debug output (VrjAccumOut.photons) is sample-major: [(sample * npix + pixel)]
-__global__ void k_photons_sample_major(const double2 *__restrict__ photons, double2 *__restrict__ out, uint32_t npix, uint32_t batch_samples) {
+static __global__ void k_photons_sample_major(const double2 *__restrict__ photons, double2 *__restrict__ out, uint32_t npix, uint32_t batch_samples) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // output index
     if (i >= (size_t)npix * batch_samples) return;
     const uint32_t s = (uint32_t)(i / npix), p = (uint32_t)(i - (size_t)s * npix);
@@ -644,7 +644,7 @@ __device__ __forceinline__ unsigned char clamp_to_byte(double v) {
     double b = v * 255.0;
     return b != b ? (unsigned char)0 : (unsigned char)(int)b;
 }
-__global__ void k_tone_map(const double *colour, unsigned char *rgb8, uint64_t n, int source) {
+static __global__ void k_tone_map(const double *colour, unsigned char *rgb8, uint64_t n, int source) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     D3 c = d3(colour[3 * p], colour[3 * p + 1], colour[3 * p + 2]);
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(128) k_stage_ray_list(DevScene sc, uint32_t n,
     ls.flush(stats);
 }
 
-__global__ void k_hit_ids(DevScene sc, uint32_t n, TraceBuffers tb, int32_t *object_id, int32_t *prim_id, double *t,
+static __global__ void k_hit_ids(DevScene sc, uint32_t n, TraceBuffers tb, int32_t *object_id, int32_t *prim_id, double *t,
                           unsigned long long *stats) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -227,8 +227,12 @@ class HostScene:
         out["stats"] = st
         return out
 
-    def partial_render_scene(self, tile, height, width, seed=1, sample_offset=0):
-        """The reference call: partial_render_scene(&scene, tile, height, width) -> AccumulationBuffer."""
+    def partial_render_scene(self, tile, height, width, seed=1, sample_offset=None):
+        """The reference call: partial_render_scene(&scene, tile, height, width) -> AccumulationBuffer.
+        sample_offset=None is the reference's behaviour -- every call renders a fresh sample (the index comes from the
+        host library's process-wide counter, next_sample_index()); pass an index for a reproducible render."""
+        if sample_offset is None:
+            sample_offset = 0xFFFFFFFFFFFFFFFF
         sc, ec, sr, er = tile
         npix = (ec - sc) * (er - sr)
         out = {k: np.zeros(npix * 3) for k in ("colour", "colour_sum", "colour_bias")}
