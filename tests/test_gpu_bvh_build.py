@@ -4,10 +4,21 @@ numbering, same boxes -- so hit ids and tie-breaking cannot depend on where the 
 import numpy as np
 import pytest
 
+import helpers
+import oraclelib as O
 import vanrijn_b200 as V
 from vanrijn_b200 import capi, host, scenes
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c4():
+    """BASELINE config C4 (11 x 11 bunny copies = 9.9 M triangles + ground plane): the GPU scene with its tree built during
+    the upload, and the ORACLE's scene -- its tree built by the oracle's own restatement of
+    BoundingVolumeHierarchy::build (bounding_volume_hierarchy.rs:38-75), about 20-30 s on the host cores."""
+    spec = scenes.scene_grid(copies=11)
+    return spec, V.build_scene(spec, device_builder="upload"), O.OracleScene(spec)
 
 
 def host_tree(verts):
@@ -178,3 +189,42 @@ def test_c4_sized_scene_filters_agree_at_4k():
         else:
             assert np.array_equal(r["photons"], ref["photons"]), f
             assert r["stats"].rays == ref["stats"].rays
+
+
+def test_c4_full_size_against_the_oracle(c4):
+    """C4 at FULL size against the oracle (parity hole 1): bounding_volume_hierarchy.rs:95-119 on the 25-level
+    tree of 9.9 M triangles.  (i) 120 000 pixel-centre rays of the 3840x2160 frame: object id, primitive id and distance
+    BIT-exact against the oracle's reference-order, unpruned traversal (edge rays excluded as north_star says), in every
+    filter mode; (ii) a non-square tile in the middle of the meshes, at its 4K offsets, 2 spp, recursion limit 8: every
+    sample's wavelength bit-identical and its radiance within 1e-12 of the oracle's, ray counts equal."""
+    spec, hs, orc = c4
+    W, H = 3840, 2160
+    assert orc.L.orc_bvh_triangle_count(orc.h, 1) == 11 * 11 * 81920
+    assert orc.L.orc_bvh_depth(orc.h, 1) == 25
+    o, d = helpers.camera_rays(W, H, spec.camera)
+    rng = np.random.default_rng(5)
+    lower = np.flatnonzero(np.arange(W * H) // W >= 1284)          # the rows the meshes cover
+    idx = np.concatenate([rng.choice(lower, 100000, replace=False), rng.choice(W * H, 20000, replace=False)])
+    oo, dd = o[idx], d[idx]
+    r_obj, r_prim, r_t, _ = orc.trace(oo, dd, mode=O.TRAVERSE_REFERENCE)
+    ok = orc.edge_distance(oo, dd) > 1e-6
+    assert (r_obj[ok] == 1).sum() > 30000                          # tens of thousands of triangle hits, not plane hits
+    assert len(np.unique(r_prim[ok & (r_obj == 1)])) > 20000       # spread over the whole mesh
+    for f in (capi.FILTER_F32, capi.FILTER_F64, capi.FILTER_F32X4, capi.FILTER_Q16):
+        g_obj, g_prim, g_t, _ = hs.trace(oo, dd, bvh_filter=f)
+        assert np.array_equal(g_obj[ok], r_obj[ok]), f
+        assert np.array_equal(g_prim[ok], r_prim[ok]), f
+        assert np.array_equal(g_t[ok].view(np.uint64), r_t[ok].view(np.uint64)), f
+        assert ((g_obj != r_obj) | (g_prim != r_prim))[~ok].sum() <= 12
+    tile = (1900, 2003, 1450, 1497)                                 # 103 x 47, inside the grid of meshes
+    g = hs.render(tile, H, W, spp=2, max_depth=8, seed=9, want_photons=True)
+    r = orc.render(tile, H, W, spp=2, max_depth=8, seed=9, want_photons=True)
+    assert r["stats"].bounce_rays > 103 * 47                       # the crop is on the meshes: paths bounce
+    assert np.array_equal(g["photons"][..., 0], r["photons"][..., 0])
+    live = r["photons"][..., 0] != 0.0
+    gi, ri = g["photons"][..., 1][live], r["photons"][..., 1][live]
+    assert np.max(np.abs(gi - ri) / np.maximum(np.abs(ri), 1e-300)) < 1e-12
+    for k in ("primary_rays", "bounce_rays", "paths_missed", "paths_escaped", "paths_depth_limited"):
+        assert getattr(g["stats"], k) == getattr(r["stats"], k), k
+    np.testing.assert_allclose(g["colour_sum"], r["colour_sum"], rtol=1e-9, atol=1e-25)
+    assert np.all(g["weight"] == 2.0)

@@ -22,7 +22,8 @@ for i in range(a.reps):
                   bvh_filter=f, want=("colour_sum", "weight"), count_traversal=a.count,
                   precision=capi.PRECISION_F32_FAST if a.precision == "f32" else capi.PRECISION_F64)
     st = r["stats"]
-    print("rep %d: %.1f Mrays/s device (%.2f ms; primary %.2f bounce %.2f resolve %.2f), rays %d" % (
-        i, st.rays / st.device_ms / 1e3, st.device_ms, st.primary_ms, st.bounce_ms, st.resolve_ms, st.rays), flush=True)
+    print("rep %d: %.1f Mrays/s device (%.2f ms; trace primary %.2f bounce %.2f | raygen+shade %.2f | resolve %.2f | tail %.2f), rays %d, staged %d, launches %d" % (
+        i, st.rays / st.device_ms / 1e3, st.device_ms, st.primary_ms, st.bounce_ms, st.shade_ms, st.resolve_ms, st.tail_ms, st.rays,
+        st.staged_rays, st.kernel_launches), flush=True)
     if a.count:
         print("   node visits/ray %.2f  triangle tests/ray %.3f  staged %.3f of rays" % (st.node_visits / st.rays, st.triangle_tests / st.rays, st.staged_rays / st.rays))

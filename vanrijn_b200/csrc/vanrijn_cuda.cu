@@ -36,6 +36,34 @@ extern template VrjStatus run_batch<double, double, true>(const VrjScene *, Scra
 extern template VrjStatus run_batch<float, float, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
 extern template VrjStatus run_batch<float, float, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
 } // namespace vrjimpl
+// NVTX (optional): nvtxRangePushA / nvtxRangePop from libnvToolsExt.so.1, looked up once when VRJ_NVTX is set
+namespace {
+struct NvtxApi {
+    int (*push)(const char *) = nullptr;
+    int (*pop)() = nullptr;
+    NvtxApi() {
+        if (!std::getenv("VRJ_NVTX")) return;
+        for (const char *name : {"libnvToolsExt.so.1", "libnvToolsExt.so"}) {
+            if (void *lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL)) {
+                push = reinterpret_cast<int (*)(const char *)>(dlsym(lib, "nvtxRangePushA"));
+                pop = reinterpret_cast<int (*)()>(dlsym(lib, "nvtxRangePop"));
+                if (push && pop) return;
+                push = nullptr, pop = nullptr;
+            }
+        }
+    }
+};
+const NvtxApi &nvtx_api() {
+    static NvtxApi api;
+    return api;
+}
+} // namespace
+void vrj_nvtx_push(const char *name) {
+    if (nvtx_api().push) nvtx_api().push(name);
+}
+void vrj_nvtx_pop() {
+    if (nvtx_api().pop) nvtx_api().pop();
+}
 // other translation units of the library (vrj_bvh_build.cu) report through the same thread-local message
 void vrj_set_error(const std::string &msg) { g_error = msg; }
 
@@ -297,12 +325,13 @@ void release_scratch(VrjScene *sc, Scratch *s) {
 }
 
 // `queue_oom` (optional): set when the allocation that failed was the path queues -- the only part a smaller batch shrinks
-VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t steps, uint32_t n_lights, size_t n_light_samples, bool *queue_oom = nullptr) {
+VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t rec_capacity, size_t npix, uint32_t steps, uint32_t n_lights, size_t n_light_samples, bool *queue_oom = nullptr) {
     if (queue_oom) *queue_oom = false;
     if (!s->stream) {
         VRJ_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         VRJ_CUDA(cudaEventCreate(&s->ev0));
         VRJ_CUDA(cudaEventCreate(&s->ev1));
+        for (cudaEvent_t &e : s->drain_ev) VRJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         VRJ_CUDA(cudaMallocHost(&s->host_count, 64 * sizeof(uint32_t)));
     }
     // every group below is all-or-nothing: a failed allocation leaves the group empty with its size field at 0 (never
@@ -333,6 +362,16 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t npix, uint32_t step
             return st;
         }
         s->capacity = capacity;
+    }
+    if (s->rec_capacity < rec_capacity) {
+        s->rec_capacity = 0;
+        std::vector<std::pair<DeviceBuffer *, size_t>> want = {{&s->recs, rec_capacity * sizeof(TraceRec)}};
+        VrjStatus st = alloc_group(want, "trace records");
+        if (st != VRJ_OK) {
+            if (queue_oom) *queue_oom = st == VRJ_ERR_OUT_OF_MEMORY;
+            return st;
+        }
+        s->rec_capacity = rec_capacity;
     }
     if (s->npix < npix) {
         s->npix = 0;
@@ -461,6 +500,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     const Section s_sph = reserve_section(d->n_spheres * sizeof(SphereDev)), s_pl = reserve_section(d->n_planes * sizeof(PlaneDev));
     const Section s_mat = reserve_section(d->n_materials * sizeof(MaterialDev)), s_spc = reserve_section(d->n_spectra * sizeof(SpectrumDev));
     const Section s_smp = reserve_section(d->n_spectrum_samples * sizeof(double));
+    const Section s_grd = reserve_section(d->n_spectrum_samples * sizeof(double));
     const Section s_it = reserve_section(d->n_items * sizeof(ItemDev)), s_an = reserve_section(d->n_items * 4), s_bv = reserve_section(d->n_items * 4);
     const size_t small_bytes = std::max<size_t>(cursor, 256);
     const Section s_n32 = reserve_section(n_wide * 64), s_n64 = reserve_section(n_wide * 112);
@@ -626,6 +666,20 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     for (uint32_t i = 0; i < d->n_spectra; i++)
         spectra[i] = SpectrumDev{d->spectra[i].shortest_wavelength, d->spectra[i].longest_wavelength, d->spectra[i].first_sample, d->spectra[i].n_samples};
     if (d->n_spectrum_samples) std::memcpy(stage + s_smp.offset, d->spectrum_samples, d->n_spectrum_samples * sizeof(double));
+    // wavelength of every sample, with the operations of spectrum.rs:62,67 (`i as f64 / (n-1) as f64 * range + shortest`): the
+    // lookup on the device reads these instead of dividing twice per call (vrj_device.cuh, spectrum_lookup_grid)
+    {
+        volatile double *grid = reinterpret_cast<double *>(stage + s_grd.offset); // volatile: no contraction / reassociation by the host compiler
+        for (uint32_t i = 0; i < d->n_spectra; i++) {
+            const VrjSpectrum &sp = d->spectra[i];
+            const double range = sp.longest_wavelength - sp.shortest_wavelength, nm1 = (double)(sp.n_samples - 1);
+            for (uint32_t k = 0; k < sp.n_samples; k++) {
+                const double q = (double)k / nm1;
+                const double scaled = q * range;
+                grid[sp.first_sample + k] = scaled + sp.shortest_wavelength;
+            }
+        }
+    }
     MaterialDev *materials = reinterpret_cast<MaterialDev *>(stage + s_mat.offset);
     for (uint32_t i = 0; i < d->n_materials; i++)
         materials[i] = MaterialDev{d->materials[i].kind, d->materials[i].spectrum, d->materials[i].p0, d->materials[i].p1, d->materials[i].p2};
@@ -676,6 +730,12 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     sc->dev.materials = reinterpret_cast<const MaterialDev *>(base + s_mat.offset);
     sc->dev.spectra = reinterpret_cast<const SpectrumDev *>(base + s_spc.offset);
     sc->dev.spectrum_samples = reinterpret_cast<const double *>(base + s_smp.offset);
+    sc->dev.spectrum_grids = reinterpret_cast<const double *>(base + s_grd.offset);
+    sc->dev.material_mask = 0;
+    for (uint32_t i = 0; i < d->n_materials; i++) sc->dev.material_mask |= 1u << d->materials[i].kind;
+    sc->kernel_material_mask = sc->dev.material_mask == 1u ? 1u : (uint32_t)VRJ_MM_ALL;
+    if (const char *mm = std::getenv("VRJ_MATERIAL_MASK")) // experiments only: 15 = always the general kernels
+        if (std::atoi(mm) == VRJ_MM_ALL) sc->kernel_material_mask = VRJ_MM_ALL;
     sc->dev.items = reinterpret_cast<const ItemDev *>(base + s_it.offset);
     sc->dev.analytic_items = reinterpret_cast<const uint32_t *>(base + s_an.offset);
     sc->dev.bvh_items = reinterpret_cast<const uint32_t *>(base + s_bv.offset);
@@ -686,6 +746,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
         std::sscanf(tune, "%d,%d,%d,%d,%u,%d", &sc->dev.refill_threshold, &sc->dev.leaf_threshold, &sc->dev.node_batch, &sc->dev.max_iters, &sc->tail_max,
                     &sc->dev.node_batch4);
     if (const char *pb = std::getenv("VRJ_PATH_BUDGET_LOG2")) sc->path_budget = 1ull << std::min(std::max(std::atoi(pb), 16), 31); // experiments only
+    if (const char *r = std::getenv("VRJ_RECORDS")) sc->trace_records = std::atoi(r) != 0; // experiments only
     if (const char *ts = std::getenv("VRJ_TAIL_SHALLOW")) sc->tail_max_shallow = (uint32_t)std::strtoul(ts, nullptr, 10); // experiments only
     if (std::getenv("VRJ_TIMING")) {
         auto t_end = std::chrono::steady_clock::now();
@@ -841,15 +902,17 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         }
     } releaser{scene, s};
     bool queue_oom = false;
-    VrjStatus st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
+    // TraceRec records: only the calls that walk them need the extra 96 bytes per path in flight
+    const bool records = p->precision == VRJ_PRECISION_F64 && p->bvh_filter == VRJ_FILTER_F32 && scene->trace_records && scene->dev.n_bvh_items > 0;
+    VrjStatus st = ensure_scratch(s, npix * batch, records ? npix * batch : 0, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
     while (st == VRJ_ERR_OUT_OF_MEMORY && queue_oom && batch > 1) { // 240 bytes per path in flight: halve the batch until the queues fit
         vrj_pool_trim();
         batch = (batch + 1) / 2;
-        st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
+        st = ensure_scratch(s, npix * batch, records ? npix * batch : 0, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
     }
     if (st == VRJ_ERR_OUT_OF_MEMORY && !queue_oom) { // the accumulators do not shrink with the batch: give cached blocks back, once
         vrj_pool_trim();
-        st = ensure_scratch(s, npix * batch, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
+        st = ensure_scratch(s, npix * batch, records ? npix * batch : 0, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
     }
     if (st != VRJ_OK) return st;
 
@@ -916,6 +979,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     VRJ_CUDA(cudaEventRecord(s->ev0, s->stream));
     for (uint32_t done = 0; done < p->spp; done += batch) {
         rc.batch_samples = std::min(batch, p->spp - done);
+        rc.div_batch = FastDiv::make(rc.batch_samples), rc.div_tile_w = FastDiv::make(rc.tile_w);
         rc.first_sample = p->sample_offset + (uint64_t)done * rc.sample_stride;
         if (p->count_traversal) {
             st = fast ? run_batch<float, float, true>(scene, s, rc, whitted, 0, &launches)
@@ -1025,6 +1089,10 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     VRJ_CUDA(d_hits.alloc(n * 8));
     VRJ_CUDA(d_tbest.alloc(n * 8));
     VRJ_CUDA(d_list.alloc(n * 4));
+    // the default filter walks ready-made records, as the render path does (the id gate then tests the kernel that renders)
+    const bool records = bvh_filter == VRJ_FILTER_F32 && scene->trace_records && scene->dev.n_bvh_items > 0;
+    DeviceBuffer d_recs;
+    if (records) VRJ_CUDA(d_recs.alloc(n * sizeof(TraceRec)));
     VRJ_CUDA(d_stats.alloc((ST_COUNT + 1) * sizeof(unsigned long long)));
     cudaStream_t stream;
     VRJ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -1043,7 +1111,7 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
     uint32_t *d_lcount = reinterpret_cast<uint32_t *>(dstats + ST_COUNT), *d_work = d_lcount + 1;
     PathQueue q{};
     q.q0 = d_q[0].as<double2>(), q.q1 = d_q[1].as<double2>(), q.q2 = d_q[2].as<double2>();
-    TraceBuffers tb{d_hits.as<int2>(), d_tbest.as<double>(), d_list.as<uint32_t>()};
+    TraceBuffers tb{d_hits.as<int2>(), d_tbest.as<double>(), d_list.as<uint32_t>(), records ? d_recs.as<TraceRec>() : nullptr};
     const uint32_t n32 = (uint32_t)n;
     int grid_a = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)scene->sm_count * 16);
     VRJ_CUDA(cudaEventRecord(e0, stream));
@@ -1057,6 +1125,8 @@ VrjStatus vrj_trace_rays(const VrjScene *scene_c, uint64_t n, const double *orig
             k_trace4<true, false><<<persistent_grid(scene, k_trace4<true, false>), 128, 0, stream>>>(scene->dev, RenderConst{}, q, tb, d_lcount, d_work, dstats, nullptr);
         else if (bvh_filter == VRJ_FILTER_Q16)
             k_traceq<true, false><<<persistent_grid(scene, k_traceq<true, false>), 128, 0, stream>>>(scene->dev, RenderConst{}, q, tb, d_lcount, d_work, dstats, nullptr);
+        else if (records)
+            k_trace_rec<true><<<persistent_grid(scene, k_trace_rec<true>), 128, 0, stream>>>(scene->dev, tb, d_lcount, d_work, dstats, nullptr);
         else
             k_trace<float, double, true><<<persistent_grid(scene, k_trace<float, double, true>), 128, 0, stream>>>(scene->dev, q, tb, d_lcount, d_work, dstats, nullptr);
     }

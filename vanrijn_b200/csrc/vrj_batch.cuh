@@ -13,6 +13,16 @@
 #include <unordered_map>
 #include <vector>
 
+// NVTX ranges around the wavefront stages: libnvToolsExt is resolved at run time and only when
+// VRJ_NVTX is set in the environment, so the library carries no link-time dependency and the ranges cost one branch.
+void vrj_nvtx_push(const char *name);
+void vrj_nvtx_pop();
+struct VrjNvtxRange {
+    explicit VrjNvtxRange(const char *name) { vrj_nvtx_push(name); }
+    ~VrjNvtxRange() { vrj_nvtx_pop(); }
+};
+#define VRJ_NVTX_RANGE(var, name) VrjNvtxRange var(name)
+
 namespace vrjimpl {
 using namespace vrj;
 
@@ -50,10 +60,13 @@ struct Scratch {
     uint32_t steps = 0;
     DeviceBuffer queues[2][6];
     DeviceBuffer photons, hits[2], tbest[2], list, counters, stats;
+    DeviceBuffer recs;       // TraceRec per staged ray (rec_capacity of them); shared by the levels like `list`
+    size_t rec_capacity = 0;
     DeviceBuffer acc_colour, acc_sum, acc_bias, acc_weight, acc_wbias;
     DeviceBuffer lights, light_samples, srgb8;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t drain_ev[2] = {nullptr, nullptr}; // behind the pinned copies of the drain check (run_levels)
     std::vector<cudaEvent_t> marks; // per-launch boundaries, reused across calls
     std::vector<int> mark_class;    // class of the launch that ENDS at mark i (-1: start of a batch)
     size_t n_marks = 0;
@@ -62,6 +75,8 @@ struct Scratch {
         if (stream) cudaStreamDestroy(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t e : drain_ev)
+            if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : marks) cudaEventDestroy(e);
         if (host_count) cudaFreeHost(host_count);
     }
@@ -76,9 +91,10 @@ struct Scratch {
         mark_class[n_marks] = cls;
         return cudaEventRecord(marks[n_marks++], stream);
     }
-    TraceBuffers trace_buffers(int i) const {
+    TraceBuffers trace_buffers(int i, bool records = false) const {
         TraceBuffers t;
         t.hits = hits[i].as<int2>(), t.tbest = tbest[i].as<double>(), t.list = list.as<uint32_t>();
+        t.recs = records ? recs.as<TraceRec>() : nullptr;
         return t;
     }
     PathQueue queue(int i) const {
@@ -102,6 +118,8 @@ struct VrjScene {
     uint32_t tail_max = 1u << 18; // queue length at which k_tail finishes the batch in one launch (0 = never)
     uint32_t tail_max_shallow = 0; // the same for recursion limits <= 12
     uint64_t path_budget = 1ull << 27; // paths in flight per batch
+    bool trace_records = true; // staged rays carry their traversal constants (TraceRec); VRJ_RECORDS=0 turns it off (experiments)
+    uint32_t kernel_material_mask = VRJ_MM_ALL; // 1: every material is Lambertian (the Lambertian-only kernel variants run)
     ~VrjScene() {
         for (auto *b : owned) delete b;
     }
@@ -128,13 +146,20 @@ int persistent_grid(const VrjScene *sc, K kernel) {
     return sc->sm_count * per_sm;
 }
 
-template <typename NT, typename R, bool COUNT>
-VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, int walk, uint64_t *launches) {
+// which calls walk ready-made records: the 2-wide f32 walk of the binary64 path (the default and the bench's)
+template <typename NT, typename R>
+inline bool wants_records(const VrjScene *sc, int walk) {
+    return sizeof(NT) == 4 && sizeof(R) == 8 && walk == 0 && sc->trace_records && sc->dev.n_bvh_items > 0;
+}
+
+// One batch with the integrator (WHITTED) and the scene's material kinds (MM, see vrj_device.cuh) fixed at compile time.
+template <typename NT, typename R, bool COUNT, bool WHITTED, int MM>
+VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int walk, uint64_t *launches) {
     const bool quad = walk == 1, q16 = walk == 2; // 0: the 2-wide tree in NT boxes; 1: 4-wide f32; 2: 2-wide on the 16-bit grid
     // launch sequence: G T S_0 [X_k T_k S_k]*, k = 1..levels (X = k_tail, a no-op until the queue is short);
     // SimpleRandom needs max_depth levels, Whitted one more (its limit-0 level still shades and traces);
     // the final S only finishes paths.
-    const uint32_t levels = whitted ? rc.max_depth + 1 : rc.max_depth;
+    const uint32_t levels = WHITTED ? rc.max_depth + 1 : rc.max_depth;
     const uint32_t stride = rc.max_depth + 3;
     uint32_t *qcount = s->counters.as<uint32_t>(); // qcount[k]: length of the queue S_{k-1} wrote (k >= 1)
     uint32_t *lcount = qcount + stride;             // lcount[k]: rays of queue k staged for BVH traversal
@@ -146,61 +171,71 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     double2 *photons = s->photons.as<double2>();
     const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT, false>) : q16 ? persistent_grid(sc, k_traceq<COUNT, false>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
     const int g_t0 = quad ? persistent_grid(sc, k_trace4<COUNT, true>) : q16 ? persistent_grid(sc, k_traceq<COUNT, true>) : persistent_grid(sc, k_trace_primary<NT, R, COUNT>);
-    const int g_s0 = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, true>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, true>);
-    const int g_s = whitted ? persistent_grid(sc, k_shade<NT, R, COUNT, true, false>) : persistent_grid(sc, k_shade<NT, R, COUNT, false, false>);
+    const int g_s0 = persistent_grid(sc, k_shade<NT, R, COUNT, WHITTED, true, MM>);
+    const int g_s = persistent_grid(sc, k_shade<NT, R, COUNT, WHITTED, false, MM>);
     // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
     // per-level latency it removes is smaller than what its one-thread-per-path traversal costs (measured)
     const uint32_t tail_max = levels > 12 ? sc->tail_max : sc->tail_max_shallow;
     const int g_x = (int)std::max<uint32_t>(1, (tail_max + 127) / 128);
     const bool has_bvh = sc->dev.n_bvh_items > 0;
+    // the default walk of the parity path takes its rays as ready-to-walk records (TraceRec); the other walks form the
+    // traversal constants per lane from the queue entry
+    const bool rec = wants_records<NT, R>(sc, walk) && s->rec_capacity >= (size_t)rc.npix * rc.batch_samples;
+    const TraceBuffers tb0 = s->trace_buffers(0, rec), tb1 = s->trace_buffers(1, rec);
+    const int g_tr = rec ? persistent_grid(sc, k_trace_rec<COUNT>) : 0;
+    VRJ_NVTX_RANGE(batch_range, "vrj batch");
     VRJ_CUDA(s->mark(-1));
     // the raygen kernel uses work_s[0]; S_0 uses work_t[stride-1] (never used by a T)
-    k_raygen<R, COUNT><<<g_gen, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_s + 0, stats);
+    k_raygen<R, COUNT><<<g_gen, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), tb0, lcount + 0, work_s + 0, stats);
     (*launches)++;
     VRJ_CUDA(s->mark(4));
     if (has_bvh) {
-        if (quad) k_trace4<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
-        else if (q16) k_traceq<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), s->trace_buffers(0), lcount + 0, work_t + 0, stats, tail_done);
-        else k_trace_primary<NT, R, COUNT><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->trace_buffers(0), lcount + 0, work_t + 0, stats);
+        if (rec) k_trace_rec<COUNT><<<g_tr, 128, 0, s->stream>>>(sc->dev, tb0, lcount + 0, work_t + 0, stats, tail_done);
+        else if (quad) k_trace4<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), tb0, lcount + 0, work_t + 0, stats, tail_done);
+        else if (q16) k_traceq<COUNT, true><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), tb0, lcount + 0, work_t + 0, stats, tail_done);
+        else k_trace_primary<NT, R, COUNT><<<g_t0, 128, 0, s->stream>>>(sc->dev, rc, tb0, lcount + 0, work_t + 0, stats);
         (*launches)++;
         VRJ_CUDA(s->mark(0));
     }
     uint32_t *work_s0 = work_t + (stride - 1);
-    if (whitted)
-        k_shade<NT, R, COUNT, true, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
-    else
-        k_shade<NT, R, COUNT, false, true><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, s->trace_buffers(0), s->queue(1), qcount + 1, s->trace_buffers(1), lcount + 1, work_s0, photons, stats, tail_done);
+    k_shade<NT, R, COUNT, WHITTED, true, MM><<<g_s0, 128, 0, s->stream>>>(sc->dev, rc, s->queue(0), nullptr, tb0, s->queue(1), qcount + 1, tb1, lcount + 1, work_s0, photons, stats, tail_done);
     (*launches)++;
     VRJ_CUDA(s->mark(3));
+    bool drain_pending = false;
     for (uint32_t k = 1; k <= levels; k++) {
         const int ci = k & 1, ni = (k + 1) & 1;
         if (tail_max) {
-            if (whitted)
-                k_tail<NT, R, COUNT, true><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
-            else
-                k_tail<NT, R, COUNT, false><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
+            k_tail<NT, R, COUNT, WHITTED, MM><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
             (*launches)++;
             VRJ_CUDA(s->mark(5));
         }
         if (has_bvh) {
-            if (quad) k_trace4<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
-            else if (q16) k_traceq<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
-            else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), s->trace_buffers(ci), lcount + k, work_t + k, stats, tail_done);
+            const TraceBuffers &tbc = ci ? tb1 : tb0;
+            if (rec) k_trace_rec<COUNT><<<g_tr, 128, 0, s->stream>>>(sc->dev, tbc, lcount + k, work_t + k, stats, tail_done);
+            else if (quad) k_trace4<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), tbc, lcount + k, work_t + k, stats, tail_done);
+            else if (q16) k_traceq<COUNT, false><<<g_t, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), tbc, lcount + k, work_t + k, stats, tail_done);
+            else k_trace<NT, R, COUNT><<<g_t, 128, 0, s->stream>>>(sc->dev, s->queue(ci), tbc, lcount + k, work_t + k, stats, tail_done);
             (*launches)++;
             VRJ_CUDA(s->mark(1));
         }
-        if (whitted)
-            k_shade<NT, R, COUNT, true, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
-        else
-            k_shade<NT, R, COUNT, false, false><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, s->trace_buffers(ci), s->queue(ni), qcount + k + 1, s->trace_buffers(ni), lcount + k + 1, work_s + k, photons, stats, tail_done);
+        k_shade<NT, R, COUNT, WHITTED, false, MM><<<g_s, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, ci ? tb1 : tb0, s->queue(ni), qcount + k + 1, ni ? tb1 : tb0, lcount + k + 1, work_s + k, photons, stats, tail_done);
         (*launches)++;
         VRJ_CUDA(s->mark(3));
-        // stop launching once the batch has drained (queue empty, or finished by k_tail)
+        // Deep recursion limits (the reference's 128): stop launching once the batch has drained (queue empty, or finished
+        // by k_tail).  The check never stalls the launch pipeline: after a group of four levels the queue length and the tail
+        // flag are copied to a pinned slot behind an event, the next group is enqueued, and only then does the host look at
+        // the PREVIOUS group's slot -- the GPU always has a group queued while the host waits, at the price of at most one
+        // group of launches that return at once.
         if (levels > 12 && k % 4 == 0 && k < levels) {
-            VRJ_CUDA(cudaMemcpyAsync(s->host_count, qcount + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-            VRJ_CUDA(cudaMemcpyAsync(s->host_count + 1, tail_done, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-            VRJ_CUDA(cudaStreamSynchronize(s->stream));
-            if (s->host_count[0] == 0 || s->host_count[1] != 0) break;
+            const int slot = (int)(k / 4) & 1;
+            if (drain_pending) {
+                VRJ_CUDA(cudaEventSynchronize(s->drain_ev[slot ^ 1]));
+                if (s->host_count[2 * (slot ^ 1)] == 0 || s->host_count[2 * (slot ^ 1) + 1] != 0) break;
+            }
+            VRJ_CUDA(cudaMemcpyAsync(s->host_count + 2 * slot, qcount + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+            VRJ_CUDA(cudaMemcpyAsync(s->host_count + 2 * slot + 1, tail_done, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+            VRJ_CUDA(cudaEventRecord(s->drain_ev[slot], s->stream));
+            drain_pending = true;
         }
     }
     AccumDev acc;
@@ -211,6 +246,15 @@ VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool 
     VRJ_CUDA(s->mark(2));
     VRJ_CUDA(cudaGetLastError());
     return VRJ_OK;
+}
+
+// kernel variants exist for "Lambertian only" (the reference's own scenes: main.rs, benches/simple_scene.rs) and for
+// "any material"; VRJ_MATERIAL_MASK=15 in the environment forces the general variant (experiments)
+template <typename NT, typename R, bool COUNT>
+VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, int walk, uint64_t *launches) {
+    const bool lambert_only = sc->kernel_material_mask == 1u;
+    if (whitted) return lambert_only ? run_levels<NT, R, COUNT, true, 1>(sc, s, rc, walk, launches) : run_levels<NT, R, COUNT, true, VRJ_MM_ALL>(sc, s, rc, walk, launches);
+    return lambert_only ? run_levels<NT, R, COUNT, false, 1>(sc, s, rc, walk, launches) : run_levels<NT, R, COUNT, false, VRJ_MM_ALL>(sc, s, rc, walk, launches);
 }
 
 } // namespace vrjimpl

@@ -169,6 +169,11 @@ struct Rng {
     __device__ __forceinline__ R uniform();
     template <typename R>
     __device__ __forceinline__ R uniform_open();
+    // two consecutive Open01 draws.  EVEN: the caller knows the ordinal is even (both draws come from one Philox block), so
+    // the block is formed at ONE place in the code instead of behind each draw's "is it cached?" test -- the Philox rounds
+    // are the largest inlined piece of the shading kernels.  Same ordinals, same words, same values as two uniform_open calls.
+    template <typename R, bool EVEN>
+    __device__ __forceinline__ void open_pair(R &a, R &b);
 };
 template <>
 __device__ __forceinline__ double Rng::uniform<double>() { return f64(); }
@@ -178,6 +183,21 @@ template <>
 __device__ __forceinline__ float Rng::uniform<float>() { return (float)(bits() >> 40) * (1.0f / 16777216.0f); }
 template <>
 __device__ __forceinline__ float Rng::uniform_open<float>() { return ((float)(bits() >> 41) + 0.5f) * (1.0f / 8388608.0f); }
+template <typename R, bool EVEN>
+__device__ __forceinline__ void Rng::open_pair(R &a, R &b) {
+    if (EVEN) {
+        block(ordinal >> 1);
+        ordinal += 2;
+        const uint64_t lo = ((uint64_t)w[1] << 32) | w[0], hi = ((uint64_t)w[3] << 32) | w[2];
+        if (sizeof(R) == 8) {
+            a = (R)(((double)(lo >> 12) + 0.5) * (1.0 / 4503599627370496.0)), b = (R)(((double)(hi >> 12) + 0.5) * (1.0 / 4503599627370496.0));
+        } else {
+            a = (R)(((float)(lo >> 41) + 0.5f) * (1.0f / 8388608.0f)), b = (R)(((float)(hi >> 41) + 0.5f) * (1.0f / 8388608.0f));
+        }
+    } else {
+        a = uniform_open<R>(), b = uniform_open<R>();
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // colour/spectrum.rs
@@ -191,34 +211,59 @@ __device__ const double g_rgb_basis[7][32] = {
 };
 enum { B_WHITE = 0, B_CYAN, B_MAGENTA, B_YELLOW, B_RED, B_GREEN, B_BLUE };
 
-// spectrum.rs:50-79, `sample(i)` supplies sample i
-template <typename R, typename F>
-__device__ __forceinline__ R spectrum_lookup(R shortest, R longest, uint32_t n, R wavelength, F sample) {
+// spectrum.rs:50-79, `sample(i)` supplies sample i and `grid(i)` the wavelength of sample i, i / (n-1) * range + shortest
+// (spectrum.rs:62,67).  In binary64 the grid comes from a table written at scene upload with exactly those operations
+// (division, multiplication, addition of the same binary64 values round the same way on the host and here), which takes
+// two of the lookup's four divisions off the shading path; `compute_grid` forms it in place (binary32 fast mode, lights).
+template <typename R>
+struct ComputedGrid {
+    R shortest, range, nm1;
+    __device__ __forceinline__ R operator()(uint32_t i) const { return (R)i / nm1 * range + shortest; }
+};
+template <typename R, typename F, typename G>
+__device__ __forceinline__ R spectrum_lookup_grid(R shortest, R longest, uint32_t n, R wavelength, F sample, G grid) {
     if (wavelength < shortest || wavelength > longest) return R(0);
     R range = longest - shortest;
     R nm1 = (R)(n - 1);
     R fidx = nm1 * ((wavelength - shortest) / range);
     uint32_t before = (fidx != fidx || fidx < R(0)) ? 0u : (uint32_t)fidx;
     if (before > n - 1) before = n - 1; // cannot happen in binary64; guards binary32 rounding at the upper end
-    R wl_before = (R)before / nm1 * range + shortest;
+    R wl_before = grid(before);
     if (before == n - 1) return sample(before);
-    R wl_after = (R)(before + 1) / nm1 * range + shortest;
+    R wl_after = grid(before + 1);
     R delta = wl_after - wl_before;
     R ratio = (wavelength - wl_before) / delta;
     return sample(before) * (R(1) - ratio) + sample(before + 1) * ratio;
 }
-template <typename R>
-__device__ __forceinline__ R spectrum_intensity(const SpectrumDev *__restrict__ spectra, const double *__restrict__ samples,
-                                                uint32_t id, R wavelength) {
+template <typename R, typename F>
+__device__ __forceinline__ R spectrum_lookup(R shortest, R longest, uint32_t n, R wavelength, F sample) {
+    return spectrum_lookup_grid<R>(shortest, longest, n, wavelength, sample, ComputedGrid<R>{shortest, longest - shortest, (R)(n - 1)});
+}
+// `grids`: the table parallel to `samples` (same indices), binary64 only
+__device__ __forceinline__ double spectrum_intensity(const SpectrumDev *__restrict__ spectra, const double *__restrict__ samples,
+                                                     const double *__restrict__ grids, uint32_t id, double wavelength) {
+    SpectrumDev s = spectra[id];
+    const double *p = samples + s.first, *g = grids + s.first;
+    return spectrum_lookup_grid<double>(s.shortest, s.longest, s.n, wavelength, [p](uint32_t i) { return __ldg(p + i); },
+                                        [g](uint32_t i) { return __ldg(g + i); });
+}
+__device__ __forceinline__ float spectrum_intensity(const SpectrumDev *__restrict__ spectra, const double *__restrict__ samples,
+                                                    const double *__restrict__, uint32_t id, float wavelength) {
     SpectrumDev s = spectra[id];
     const double *p = samples + s.first;
-    return spectrum_lookup<R>((R)s.shortest, (R)s.longest, s.n, wavelength, [p](uint32_t i) { return (R)__ldg(p + i); });
+    return spectrum_lookup<float>((float)s.shortest, (float)s.longest, s.n, wavelength, [p](uint32_t i) { return (float)__ldg(p + i); });
 }
+// the sample wavelengths of the 32-entry rgb basis spectra (spectrum.rs:182-419 span 380..720 nm): i / 31 * 340 + 380,
+// folded by the host compiler in IEEE binary64 (round to nearest), i.e. the values the expression gives at run time
+#define VRJ_RGB_GRID(i) ((double)(i) / 31.0 * 340.0 + 380.0)
+__device__ const double g_rgb_grid[32] = {
+    VRJ_RGB_GRID(0),  VRJ_RGB_GRID(1),  VRJ_RGB_GRID(2),  VRJ_RGB_GRID(3),  VRJ_RGB_GRID(4),  VRJ_RGB_GRID(5),  VRJ_RGB_GRID(6),  VRJ_RGB_GRID(7),
+    VRJ_RGB_GRID(8),  VRJ_RGB_GRID(9),  VRJ_RGB_GRID(10), VRJ_RGB_GRID(11), VRJ_RGB_GRID(12), VRJ_RGB_GRID(13), VRJ_RGB_GRID(14), VRJ_RGB_GRID(15),
+    VRJ_RGB_GRID(16), VRJ_RGB_GRID(17), VRJ_RGB_GRID(18), VRJ_RGB_GRID(19), VRJ_RGB_GRID(20), VRJ_RGB_GRID(21), VRJ_RGB_GRID(22), VRJ_RGB_GRID(23),
+    VRJ_RGB_GRID(24), VRJ_RGB_GRID(25), VRJ_RGB_GRID(26), VRJ_RGB_GRID(27), VRJ_RGB_GRID(28), VRJ_RGB_GRID(29), VRJ_RGB_GRID(30), VRJ_RGB_GRID(31)};
 // spectrum.rs:81-165 evaluated lazily: only the (at most two) samples the lookup touches are formed
 template <typename R>
-__device__ __forceinline__ R rgb_reflection_intensity(R r, R g, R b, R wavelength) {
-    int second, third;
-    R c0, c1, c2;
+__device__ __forceinline__ void rgb_basis_split(R r, R g, R b, int &second, int &third, R &c0, R &c1, R &c2) {
     if (r <= g && r <= b) {
         if (g <= b) { second = B_CYAN, third = B_BLUE, c0 = r, c1 = g - r, c2 = b - g; }
         else        { second = B_CYAN, third = B_GREEN, c0 = r, c1 = b - r, c2 = g - b; }
@@ -229,8 +274,21 @@ __device__ __forceinline__ R rgb_reflection_intensity(R r, R g, R b, R wavelengt
         if (r <= g) { second = B_YELLOW, third = B_GREEN, c0 = b, c1 = r - b, c2 = g - r; }
         else        { second = B_YELLOW, third = B_RED, c0 = b, c1 = g - b, c2 = r - g; }
     }
-    return spectrum_lookup<R>(R(380), R(720), 32u, wavelength, [=](uint32_t i) {
-        return c0 * (R)g_rgb_basis[B_WHITE][i] + c1 * (R)g_rgb_basis[second][i] + c2 * (R)g_rgb_basis[third][i];
+}
+__device__ __forceinline__ double rgb_reflection_intensity(double r, double g, double b, double wavelength) {
+    int second, third;
+    double c0, c1, c2;
+    rgb_basis_split(r, g, b, second, third, c0, c1, c2);
+    return spectrum_lookup_grid<double>(380.0, 720.0, 32u, wavelength,
+                                        [=](uint32_t i) { return c0 * g_rgb_basis[B_WHITE][i] + c1 * g_rgb_basis[second][i] + c2 * g_rgb_basis[third][i]; },
+                                        [](uint32_t i) { return g_rgb_grid[i]; });
+}
+__device__ __forceinline__ float rgb_reflection_intensity(float r, float g, float b, float wavelength) {
+    int second, third;
+    float c0, c1, c2;
+    rgb_basis_split(r, g, b, second, third, c0, c1, c2);
+    return spectrum_lookup<float>(380.f, 720.f, 32u, wavelength, [=](uint32_t i) {
+        return c0 * (float)g_rgb_basis[B_WHITE][i] + c1 * (float)g_rgb_basis[second][i] + c2 * (float)g_rgb_basis[third][i];
     });
 }
 
@@ -414,33 +472,41 @@ __device__ __forceinline__ FresnelT<R> fresnel(V3<R> w_i, R eta1, R eta2) {
 
 #define VRJ_PI 3.14159265358979323846264338327950288
 
+// MM: bit k set = material kind k may occur in the scene (VrjScene knows its materials).  A kernel instantiated for the kinds
+// a scene really has carries no code for the others (Phong's pow, the reflective lobe's acos / exp, the dielectric's Fresnel
+// terms, the cosine-hemisphere sampler's sin / cos): less to fetch through the 32 KB instruction cache of an SM.
+#define VRJ_MM_ALL 15
+template <int MM>
+__device__ __forceinline__ bool is_kind(uint32_t kind, int k) { return (MM & (1 << k)) != 0 && (MM == (1 << k) || kind == (uint32_t)k); }
+
 // Material::sample: returns direction (BSDF space) and pdf, consuming draws from rng
-template <typename R>
+template <int MM, typename R>
 __device__ __forceinline__ void material_sample(const MaterialDev &m, R eta_or_zero, V3<R> w_i, Rng &rng, V3<R> &dir, R &pdf) {
     const R pi = R(VRJ_PI);
-    if (m.kind == 0) { // lambertian_material.rs:36-59 (rejection in the unit disc)
-        R x = R(2) * rng.uniform_open<R>() - R(1);
-        R y = R(2) * rng.uniform_open<R>() - R(1);
-        while (((R(0) + x * x) + y * y) + R(0) * R(0) > R(1)) {
-            x = R(2) * rng.uniform_open<R>() - R(1);
-            y = R(2) * rng.uniform_open<R>() - R(1);
-        }
+    if (is_kind<MM>(m.kind, 0)) { // lambertian_material.rs:36-59 (rejection in the unit disc)
+        // in a scene whose materials are all Lambertian every material draw comes in pairs, so the ordinal stays even
+        R x, y;
+        do {
+            R u, v;
+            rng.open_pair<R, MM == 1>(u, v);
+            x = R(2) * u - R(1), y = R(2) * v - R(1);
+        } while (((R(0) + x * x) + y * y) + R(0) * R(0) > R(1));
         R z = fmax(sqrt(R(1) - x * x - y * y), R(0));
         R cos_theta = ((R(0) + x * R(0)) + y * R(0)) + z * R(1);
         R sin_theta = sqrt(R(1) - cos_theta * cos_theta);
         dir = normalize(V3<R>{x, y, z});
         pdf = (cos_theta * sin_theta) / pi;
-    } else if (m.kind == 2) { // reflective_material.rs:42-47
+    } else if (is_kind<MM>(m.kind, 2)) { // reflective_material.rs:42-47
         dir = V3<R>{-w_i.x, -w_i.y, w_i.z};
         pdf = R(1);
-    } else if (m.kind == 3) { // smooth_transparent_dialectric.rs:91-114
+    } else if (is_kind<MM>(m.kind, 3)) { // smooth_transparent_dialectric.rs:91-114
         R eta1 = w_i.z >= R(0) ? R(1) : eta_or_zero, eta2 = w_i.z >= R(0) ? eta_or_zero : R(1);
         FresnelT<R> f = fresnel(w_i, eta1, eta2);
         pdf = R(0.5);
         if (f.transmission_strength <= R(0.0000000001)) dir = f.reflection_direction;
         else if (f.reflection_strength <= R(0.0000000001) || rng.boolean()) dir = f.transmission_direction;
         else dir = f.reflection_direction;
-    } else { // materials/mod.rs:28-33 -> cosine_weighted_hemisphere.rs:19-33, unit_disc.rs:27-44, uniform_square.rs:20-25
+    } else if (MM & 2) { // Phong: materials/mod.rs:28-33 -> cosine_weighted_hemisphere.rs:19-33, unit_disc.rs:27-44, uniform_square.rs:20-25
         R sx = R(-1) + rng.uniform_open<R>() * R(2);
         R sy = R(-1) + rng.uniform_open<R>() * R(2);
         R dx, dy;
@@ -455,17 +521,19 @@ __device__ __forceinline__ void material_sample(const MaterialDev &m, R eta_or_z
         R z = sqrt(fmax(R(0), R(1) - dx * dx - dy * dy));
         dir = V3<R>{dx, dy, z};
         pdf = sqrt(dx * dx + dy * dy) / pi;
+    } else { // a kind the scene was said not to contain: unreachable (vrj_scene_create forms the mask from the materials)
+        dir = V3<R>{R(0), R(0), R(1)}, pdf = R(0);
     }
 }
 
 // Material::bsdf as an affine map of the incoming intensity: out = a * in + b.
 // `s` is the material spectrum at the photon's wavelength (colour, or eta for the dielectric).
-template <typename R>
+template <int MM, typename R>
 __device__ __forceinline__ void material_bsdf_affine(const MaterialDev &m, R s, V3<R> w_o, V3<R> w_i, R &a, R &b) {
     const R p0 = (R)m.p0, p1 = (R)m.p1, p2 = (R)m.p2;
-    if (m.kind == 0) { // lambertian_material.rs:27-34
+    if (is_kind<MM>(m.kind, 0)) { // lambertian_material.rs:27-34
         a = s * p0, b = R(0);
-    } else if (m.kind == 1) { // phong_material.rs:16-36
+    } else if (is_kind<MM>(m.kind, 1)) { // phong_material.rs:16-36
         if (w_i.z < R(0) || w_o.z < R(0)) {
             a = R(0), b = R(0);
         } else {
@@ -473,7 +541,7 @@ __device__ __forceinline__ void material_bsdf_affine(const MaterialDev &m, R s, 
             a = s * p0;
             b = pow(fabs(dot(w_o, refl)), p2) * (p1 / dot(w_i, V3<R>{R(0), R(0), R(1)}));
         }
-    } else if (m.kind == 2) { // reflective_material.rs:15-40
+    } else if (is_kind<MM>(m.kind, 2)) { // reflective_material.rs:15-40
         if (w_i.z <= R(0) || w_o.z <= R(0)) {
             a = R(0), b = R(0);
         } else {
@@ -485,7 +553,7 @@ __device__ __forceinline__ void material_bsdf_affine(const MaterialDev &m, R s, 
             R rf = p1 * exp(-(theta * theta) / (two * sigma * sigma));
             a = (s * p0) * (R(1) - rf), b = rf;
         }
-    } else { // smooth_transparent_dialectric.rs:74-89
+    } else if (MM & 8) { // smooth_transparent_dialectric.rs:74-89
         R eta1 = w_i.z >= R(0) ? R(1) : s, eta2 = w_i.z >= R(0) ? s : R(1);
         FresnelT<R> f = fresnel(w_i, eta1, eta2);
         V3<R> dr = w_o - f.reflection_direction, dt = w_o - f.transmission_direction;
@@ -493,6 +561,8 @@ __device__ __forceinline__ void material_bsdf_affine(const MaterialDev &m, R s, 
         if (dot(dr, dr) < R(0.0000000001)) a = f.reflection_strength;
         else if (dot(dt, dt) < R(0.0000000001)) a = f.transmission_strength;
         else a = R(0);
+    } else {
+        a = R(0), b = R(0);
     }
 }
 

@@ -71,11 +71,31 @@ struct PathQueue {
     uint4 *q5;   // result slot, rng draw ordinal, recursion limit of the NEXT integrate level, flags (1 = terminal)
 };
 
+// n / d for a divisor fixed per call (Granlund-Montgomery round-up form, exact for every 32-bit n and d >= 1): one IMAD.HI,
+// one subtract, two shifts and an add instead of the ~20-instruction 32-bit division sequence; slot_to_pixel runs two of
+// them per camera ray and per shaded path
+struct FastDiv {
+    uint32_t m, s1, s2, d;
+    __host__ __device__ static FastDiv make(uint32_t d) {
+        FastDiv f;
+        uint32_t l = 0;
+        while (l < 32 && (1ull << l) < d) l++;
+        f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+        f.s1 = l < 1 ? l : 1, f.s2 = l > 1 ? l - 1 : 0, f.d = d;
+        return f;
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const {
+        const uint32_t t = __umulhi(m, n);
+        return (t + ((n - t) >> s1)) >> s2;
+    }
+};
+
 struct RenderConst {
     uint64_t width, height;             // full image
     uint64_t start_column, start_row;   // tile origin
     uint32_t tile_w, tile_h, npix;      // tile
     uint32_t batch_samples;             // samples in this batch
+    FastDiv div_batch, div_tile_w;      // division by batch_samples / tile_w
     uint64_t first_sample;              // sample index of batch slot 0
     uint64_t sample_stride;
     uint64_t seed;
@@ -152,8 +172,8 @@ __device__ __forceinline__ void biased_ray(V3<R> origin, V3<R> direction, R amou
 // (seed, pixel, sample index), so the order changes no result.
 __device__ __forceinline__ void slot_to_pixel(const RenderConst &rc, uint32_t slot, uint32_t &pixel_global,
                                               uint64_t &sample, uint64_t &grow, uint64_t &gcol) {
-    uint32_t p = slot / rc.batch_samples, s = slot - p * rc.batch_samples;
-    uint32_t row = p / rc.tile_w, col = p - row * rc.tile_w;
+    uint32_t p = rc.div_batch.div(slot), s = slot - p * rc.batch_samples;
+    uint32_t row = rc.div_tile_w.div(p), col = p - row * rc.tile_w;
     grow = rc.start_row + row, gcol = rc.start_column + col;
     pixel_global = (uint32_t)(grow * rc.width + gcol);
     sample = rc.first_sample + (uint64_t)s * rc.sample_stride;
@@ -164,6 +184,7 @@ struct TraceBuffers {
     int2 *hits;            // per queue entry: (item, triangle), -1 = miss
     double *tbest;         // per queue entry: distance of that hit (+inf on a miss)
     uint32_t *list;        // queue entries whose ray passed a BVH root pre-test
+    TraceRec *recs;        // non-NULL: those rays as ready-to-walk records instead (default f32 walk in binary64; see TraceRec)
 };
 
 // analytic objects + BVH root pre-test for the ray just written to queue entry `idx`; all 32 lanes call
@@ -171,16 +192,21 @@ template <bool COUNT, typename R>
 __device__ __forceinline__ void stage_ray(const DevScene &sc, bool have_ray, uint32_t idx, V3<R> o, V3<R> d, const TraceBuffers &tb,
                                           uint32_t *list_count, LocalStats &ls) {
     bool need = false;
+    HitT<R> best;
+    FilterRay<float> fr;
     if (have_ray) {
-        HitT<R> best;
         TraceCounters tc = {0, 0};
-        need = pretrace<COUNT>(sc, o, d, best, tc);
+        need = pretrace<COUNT>(sc, o, d, best, tc, fr);
         tb.hits[idx] = make_int2(best.item, best.tri);
         tb.tbest[idx] = (double)best.t;
         if (COUNT) ls.v[ST_TRIS] += tc.tri_tests;
     }
     uint32_t pos = queue_reserve(need, list_count);
-    if (need) tb.list[pos] = idx, ls.v[ST_STAGED]++;
+    if (need) {
+        ls.v[ST_STAGED]++;
+        if (sizeof(R) == 8 && tb.recs) store_trace_rec(tb.recs, pos, tri_ray(convert<double>(o), convert<double>(d)), fr, (double)best.t, best.item, idx);
+        else tb.list[pos] = idx;
+    }
 }
 
 // The camera ray of a result slot (camera.rs:45-66): two Philox draws, the film point, Ray::new.  It is a pure function of
@@ -242,6 +268,29 @@ struct ListRaySource {
         int2 h = tb.hits[j];
         best.item = h.x, best.tri = h.y, best.t = (R)tb.tbest[j];
     }
+    template <typename NT, typename R>
+    __device__ __forceinline__ uint32_t load_setup(uint32_t r, TriRayT<R> &tr, FilterRay<NT> &fr, HitT<R> &best) {
+        V3<R> o, d;
+        load(r, o, d, best);
+        tr = tri_ray(o, d);
+        fr = filter_ray<NT>(o, d);
+        return r;
+    }
+};
+// rays staged as records: nothing to compute, three 256-bit loads; the handle is the queue entry itself
+struct RecRaySource {
+    const TraceBuffers &tb;
+    __device__ __forceinline__ uint32_t load_setup(uint32_t r, TriRayT<double> &tr, FilterRay<float> &fr, HitT<double> &best) {
+        return load_trace_rec(tb.recs, r, tr, fr, best);
+    }
+};
+struct RecHitSink {
+    const TraceBuffers &tb;
+    __device__ __forceinline__ void store(uint32_t j, const HitT<double> &best, bool improved) {
+        if (!improved) return;
+        tb.hits[j] = make_int2(best.item, best.tri);
+        tb.tbest[j] = best.t;
+    }
 };
 // the same for the camera rays of a batch: the ray is formed from its slot, nothing is read from the queue
 struct PrimaryRaySource {
@@ -254,6 +303,14 @@ struct PrimaryRaySource {
         camera_ray(sc, rc, j, o, d);
         int2 h = tb.hits[j];
         best.item = h.x, best.tri = h.y, best.t = (R)tb.tbest[j];
+    }
+    template <typename NT, typename R>
+    __device__ __forceinline__ uint32_t load_setup(uint32_t r, TriRayT<R> &tr, FilterRay<NT> &fr, HitT<R> &best) {
+        V3<R> o, d;
+        load(r, o, d, best);
+        tr = tri_ray(o, d);
+        fr = filter_ray<NT>(o, d);
+        return r;
     }
 };
 struct ListHitSink {
@@ -293,6 +350,24 @@ __global__ void VRJ_TRACE_BOUNDS(R) k_trace_primary(DevScene sc, RenderConst rc,
     ListHitSink sink{tb};
     TraceCounters tc = {0, 0};
     trace_persistent<NT, R, COUNT>(sc, n, work, source, sink, tc);
+    if (COUNT) {
+        LocalStats ls;
+        ls.clear();
+        ls.v[ST_NODES] = tc.node_visits, ls.v[ST_TRIS] = tc.tri_tests;
+        ls.flush(stats);
+    }
+}
+
+// k_trace over ready-to-walk records (camera rays and bounce rays alike): the default walk of the parity path
+template <bool COUNT>
+__global__ void VRJ_TRACE_BOUNDS(double) k_trace_rec(DevScene sc, TraceBuffers tb, const uint32_t *list_count, uint32_t *work,
+                                                     unsigned long long *stats, const uint32_t *tail_done) {
+    if (tail_done && *tail_done) return;
+    const uint32_t n = *list_count;
+    RecRaySource source{tb};
+    RecHitSink sink{tb};
+    TraceCounters tc = {0, 0};
+    trace_persistent<float, double, COUNT>(sc, n, work, source, sink, tc);
     if (COUNT) {
         LocalStats ls;
         ls.clear();
@@ -363,7 +438,7 @@ __device__ __forceinline__ double2 photon_out(R wavelength, R intensity) { retur
 // shadow rays), update the affine accumulator -- leaves the bounce ray and the new state in p and returns true.
 // `first`: p.slot is set, the rest of the state is initialised here (camera.rs:108-119).
 // `load_ray(o, d)` fetches the ray only when it is needed.
-template <typename NT, bool COUNT, bool WHITTED, typename R, typename RayLoader>
+template <typename NT, bool COUNT, bool WHITTED, int MM, typename R, typename RayLoader>
 __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderConst &rc, PathRegsT<R> &p, int2 hit, R hit_t, bool first,
                                             RayLoader load_ray, double2 *photons, LocalStats &ls) {
     const R span = R(740.0) - R(380.0); // photon.rs:18-24, colour/mod.rs:13-14
@@ -394,7 +469,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
             return false;
         }
     } else if (hit.x < 0) {
-        R L = rgb_reflection_intensity<R>(p.aux, p.aux, R(1), p.wl); // sky(W): simple_random_integrator.rs:43-46,57-65
+        R L = rgb_reflection_intensity(p.aux, p.aux, R(1), p.wl); // sky(W): simple_random_integrator.rs:43-46,57-65
         photons[p.slot] = photon_out(p.wl, (p.A * L + p.B) * span);
         ls.v[ST_ESCAPED]++;
         return false;
@@ -416,7 +491,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
         return false;
     }
     MaterialDev m = sc.materials[h.material];
-    R s = spectrum_intensity<R>(sc.spectra, sc.spectrum_samples, m.spectrum, p.wl);
+    R s = spectrum_intensity(sc.spectra, sc.spectrum_samples, sc.spectrum_grids, m.spectrum, p.wl);
     V3<R> w_retro = mul(w2b, h.retro);
     if (WHITTED) {
         // whitted_integrator.rs:33-50: one shadow ray per light
@@ -436,7 +511,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
                 R emitted = light_intensity<R>(rc, Lt.spectrum, p.wl);
                 emitted = emitted * fabs(dot(ldir, h.normal));
                 R la, lb;
-                material_bsdf_affine(m, s, w_retro, mul(w2b, ldir), la, lb); // (retro, incoming) order
+                material_bsdf_affine<MM>(m, s, w_retro, mul(w2b, ldir), la, lb); // (retro, incoming) order
                 term = la * emitted + lb;
             }
             direct += term;
@@ -451,7 +526,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
     rng.init(rc.seed, pixel, sample, p.ordinal);
     V3<R> w_s;
     R pdf;
-    material_sample(m, s, w_retro, rng, w_s, pdf);
+    material_sample<MM>(m, s, w_retro, rng, w_s, pdf);
     p.ordinal = rng.ordinal;
     V3<R> W = mul(b2w, w_s);
     biased_ray(h.location, W, (R)rc.bias, p.o, p.d);
@@ -459,7 +534,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
     R ba, bb;
     if (WHITTED) {
         // bsdf(retro, sampled, L_in) * |W.n|, pdf unused; B before the bounce term is kept in aux
-        material_bsdf_affine(m, s, w_retro, w_s, ba, bb);
+        material_bsdf_affine<MM>(m, s, w_retro, w_s, ba, bb);
         p.aux = p.B;
         p.B += p.A * (bb * cosine);
         p.A *= ba * cosine;
@@ -467,7 +542,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
         p.limit = p.limit ? p.limit - 1 : 0;
     } else {
         // simple_random_integrator.rs:39-53: bsdf(sampled, retro, L_in * pdf * |W.n|)
-        material_bsdf_affine(m, s, w_s, w_retro, ba, bb);
+        material_bsdf_affine<MM>(m, s, w_s, w_retro, ba, bb);
         p.B += p.A * bb;
         p.A *= ba * (pdf * cosine);
         p.aux = W.y; // the sky uses the un-normalised W
@@ -478,7 +553,7 @@ __device__ __forceinline__ bool shade_entry(const DevScene &sc, const RenderCons
 }
 
 // ---- k_shade: consume the hits of a queue; survivors are enqueued warp-ballot compacted and staged ----
-template <typename NT, typename R, bool COUNT, bool WHITTED, bool FIRST>
+template <typename NT, typename R, bool COUNT, bool WHITTED, bool FIRST, int MM>
 __global__ void VRJ_SHADE_BOUNDS(R) k_shade(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
                                                TraceBuffers tb_in, PathQueue out, uint32_t *out_count, TraceBuffers tb_out,
                                                uint32_t *list_count, uint32_t *work, double2 *photons,
@@ -539,7 +614,7 @@ __global__ void VRJ_SHADE_BOUNDS(R) k_shade(DevScene sc, RenderConst rc, PathQue
                     p.wl = (R)a3.x, p.A = (R)a3.y, p.B = (R)a4.x, p.aux = (R)a4.y;
                     p.slot = a5.x, p.ordinal = a5.y, p.limit = a5.z, p.flags = a5.w;
                 }
-                alive = shade_entry<NT, COUNT, WHITTED>(
+                alive = shade_entry<NT, COUNT, WHITTED, MM>(
                     sc, rc, p, hit, hit.x >= 0 ? (R)tb_in.tbest[j] : R(0), FIRST,
                     [&in, &sc, &rc, j](V3<R> &o, V3<R> &d) {
                         if (FIRST) camera_ray(sc, rc, j, o, d); // never stored: see camera_ray
@@ -561,7 +636,7 @@ __global__ void VRJ_SHADE_BOUNDS(R) k_shade(DevScene sc, RenderConst rc, PathQue
 // here every thread follows one path (trace -> shade -> trace ...) to its end, so the remaining levels overlap.
 // Runs before T_k on queue k; does nothing unless the queue is at most `tail_max` long; sets *tail_done so the
 // remaining T / S launches of the batch return immediately.
-template <typename NT, typename R, bool COUNT, bool WHITTED>
+template <typename NT, typename R, bool COUNT, bool WHITTED, int MM>
 __global__ void __launch_bounds__(128, 2) k_tail(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
                                               uint32_t tail_max, double2 *photons, unsigned long long *stats,
                                               uint32_t *tail_done) {
@@ -584,7 +659,7 @@ __global__ void __launch_bounds__(128, 2) k_tail(DevScene sc, RenderConst rc, Pa
                 // one thread, one path: what it waits on is the chain of dependent node fetches, and the 4-wide tree halves it
                 HitT<R> h = trace_closest<NT, COUNT, false, R, VRJ_TAIL_QUAD != 0>(sc, p.o, p.d, tc);
                 if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
-                alive = shade_entry<NT, COUNT, WHITTED>(sc, rc, p, make_int2(h.item, h.tri), h.t, false, [](V3<R> &, V3<R> &) {}, photons, ls);
+                alive = shade_entry<NT, COUNT, WHITTED, MM>(sc, rc, p, make_int2(h.item, h.tri), h.t, false, [](V3<R> &, V3<R> &) {}, photons, ls);
             }
         }
     }
@@ -609,7 +684,11 @@ __global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t npix, u
     double w = acc.weight[p], wb = acc.weight_bias[p];
     for (uint32_t s = 0; s < batch_samples; s++) {
         double2 ph = photons[(size_t)p * batch_samples + s]; // pixel-major: a thread walks its own 16 * batch_samples bytes
-        D3 c = convert<double>(cmf<R>((R)ph.x) * (R)ph.y); // colour_xyz.rs:31-35
+        // colour_xyz.rs:31-35.  A sample of intensity +0 (every primary miss and depth-limited path: 45 % of the bench frame)
+        // contributes cmf * 0 = 0 whatever its wavelength; the seven exponentials are skipped and the Kahan update below,
+        // which still runs, leaves the same sums (adding +0 or -0 to an accumulator that started at +0 is the identity)
+        D3 c = d3(0.0, 0.0, 0.0);
+        if (__double_as_longlong(ph.y) != 0ll) c = convert<double>(cmf<R>((R)ph.x) * (R)ph.y);
         const double weight = 1.0;
         double wy = weight - wb;
         double wt = w + wy;

@@ -34,12 +34,14 @@ struct DevScene {
     const MaterialDev *__restrict__ materials;
     const SpectrumDev *__restrict__ spectra;
     const double *__restrict__ spectrum_samples;
+    const double *__restrict__ spectrum_grids; // wavelength of every sample (same indexing): i / (n-1) * range + shortest
     const ItemDev *__restrict__ items;
     uint32_t n_items;
     // the same items split by kind for the persistent traversal: indices into items[]
     const uint32_t *__restrict__ analytic_items; // spheres, planes, flat-list triangles
     const uint32_t *__restrict__ bvh_items;
     uint32_t n_analytic, n_bvh_items;
+    uint32_t material_mask; // bit k: a material of kind k exists (selects the kernel variant; the kernels do not read it)
     // persistent-traversal tuning (lanes): refill when this many lanes are idle; run postponed leaf tests when this many are parked
     int refill_threshold, leaf_threshold, node_batch, max_iters, node_batch4;
     double cam[3];
@@ -377,7 +379,7 @@ __device__ __forceinline__ HitT<R> trace_closest(const DevScene &sc, V3<R> o, V3
 // (spheres, planes, flat-list triangles) and a conservative pre-test of every BVH's root box.
 // Returns the best analytic hit and whether the ray has to be queued for BVH traversal.
 template <bool COUNT, typename R>
-__device__ __forceinline__ bool pretrace(const DevScene &sc, V3<R> o, V3<R> d, HitT<R> &best, TraceCounters &cnt) {
+__device__ __forceinline__ bool pretrace(const DevScene &sc, V3<R> o, V3<R> d, HitT<R> &best, TraceCounters &cnt, FilterRay<float> &fr) {
     best.t = real_inf<R>(), best.item = -1, best.tri = -1;
     for (uint32_t a = 0; a < sc.n_analytic; a++) {
         uint32_t i = sc.analytic_items[a];
@@ -402,7 +404,7 @@ __device__ __forceinline__ bool pretrace(const DevScene &sc, V3<R> o, V3<R> d, H
     }
     bool need = false;
     if (sc.n_bvh_items) {
-        FilterRay<float> fr = filter_ray<float>(o, d);
+        fr = filter_ray<float>(o, d);
         float limit = filter_limit<float>(best.t);
         for (uint32_t b = 0; b < sc.n_bvh_items; b++) {
             ItemDev it = sc.items[sc.bvh_items[b]];
@@ -411,6 +413,51 @@ __device__ __forceinline__ bool pretrace(const DevScene &sc, V3<R> o, V3<R> d, H
         }
     }
     return need;
+}
+
+// ------------------------------------------------------------------------------------------
+// A ray staged for BVH traversal, with everything the walk needs already formed by the kernel that produced the ray
+// (k_raygen / k_shade run with full warps; inside the persistent walk only the few lanes that have run dry would do this
+// work -- two binary64 divisions for the triangle test's shear, three for the slab filter -- at 8 to 16 lanes of 32).
+// 96 bytes = three 256-bit loads; records are written compacted, so the lanes that refill together read neighbours.
+//   v0: origin.x, origin.y, origin.z, shear x          (binary64)
+//   v1: shear y, distance of the best hit of the other objects (binary64); filter 1/d x, y, z, near-offset x (binary32)
+//   v2: near-offset y, z, far-offset x, y, z (binary32); flags (perm | sign(pd.z) << 2); queue entry; item of that best hit
+struct TraceRec {
+    double2 a0, a1, b0;
+    float4 b1;
+    float4 c0;
+    uint4 c1;
+};
+static_assert(sizeof(TraceRec) == 96, "TraceRec is three 32-byte vectors");
+__device__ __forceinline__ void store_trace_rec(TraceRec *recs, uint32_t pos, const TriRayT<double> &tr, const FilterRay<float> &fr,
+                                                double t_best, int item, uint32_t j) {
+    double2 *p = reinterpret_cast<double2 *>(recs + pos);
+    p[0] = make_double2(tr.o.x, tr.o.y);
+    p[1] = make_double2(tr.o.z, tr.sx);
+    p[2] = make_double2(tr.sy, t_best);
+    reinterpret_cast<float4 *>(p)[3] = make_float4(fr.id[0], fr.id[1], fr.id[2], fr.cn[0]);
+    reinterpret_cast<float4 *>(p)[4] = make_float4(fr.cn[1], fr.cn[2], fr.cf[0], fr.cf[1]);
+    reinterpret_cast<uint4 *>(p)[5] = make_uint4(__float_as_uint(fr.cf[2]), (uint32_t)tr.perm | (sign_bit(tr.pdz) ? 4u : 0u), j, (uint32_t)item);
+}
+__device__ __forceinline__ uint32_t load_trace_rec(const TraceRec *recs, uint32_t r, TriRayT<double> &tr, FilterRay<float> &fr, HitT<double> &best) {
+    const double2 *p = reinterpret_cast<const double2 *>(recs + r);
+    double2 a0, a1, b0, b1d, c0d, c1d;
+    ldg256(p, a0, a1);
+    ldg256(p + 2, b0, b1d);
+    ldg256(p + 4, c0d, c1d);
+    tr.o = d3(a0.x, a0.y, a1.x), tr.sx = a1.y, tr.sy = b0.x;
+    best.t = b0.y;
+    const float id0 = __int_as_float(__double2loint(b1d.x)), id1 = __int_as_float(__double2hiint(b1d.x));
+    const float id2 = __int_as_float(__double2loint(b1d.y)), cn0 = __int_as_float(__double2hiint(b1d.y));
+    const float cn1 = __int_as_float(__double2loint(c0d.x)), cn2 = __int_as_float(__double2hiint(c0d.x));
+    const float cf0 = __int_as_float(__double2loint(c0d.y)), cf1 = __int_as_float(__double2hiint(c0d.y));
+    const float cf2 = __int_as_float(__double2loint(c1d.x));
+    const uint32_t flags = (uint32_t)__double2hiint(c1d.x);
+    fr.id[0] = id0, fr.id[1] = id1, fr.id[2] = id2, fr.cn[0] = cn0, fr.cn[1] = cn1, fr.cn[2] = cn2, fr.cf[0] = cf0, fr.cf[1] = cf1, fr.cf[2] = cf2;
+    tr.perm = (int)(flags & 3u), tr.pdz = (flags & 4u) ? -1.0 : 1.0; // only the sign of pd.z is used (triangle.rs:63)
+    best.item = __double2hiint(c1d.y), best.tri = -1; // the triangle of an analytic hit stays in hits[]: it is only rewritten on improvement
+    return (uint32_t)__double2loint(c1d.y);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -423,8 +470,10 @@ __device__ __forceinline__ bool pretrace(const DevScene &sc, V3<R> o, V3<R> d, H
 // Semantics: objects compete with "smaller distance wins, earlier object wins ties" (sampler.rs:14-19),
 // triangles inside one BVH with "later DFS leaf wins ties" (bounding_volume_hierarchy.rs:77-92).
 //
-// Source:  void load(uint32_t r, D3 &o, D3 &d, Hit &best)   -- ray r of the list and its best analytic hit
-// Sink:    void store(uint32_t r, const Hit &best, bool improved)
+// Source:  uint32_t load_setup(uint32_t r, TriRay &tr, FilterRay &fr, Hit &best) -- staged ray r: the constants of the exact
+//          triangle test and of the slab filter, and the best hit of the other objects; returns the sink's handle
+//          (the 4-wide and 16-bit engines below use  void load(uint32_t r, D3 &o, D3 &d, Hit &best)  and form the constants)
+// Sink:    void store(uint32_t handle, const Hit &best, bool improved)
 template <typename NT, typename R, bool COUNT, typename Source, typename Sink>
 __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n, uint32_t *work, Source &source, Sink &sink,
                                                  TraceCounters &cnt) {
@@ -510,11 +559,8 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
                 if (idle) {
                     uint32_t my = base + (uint32_t)__popc(idle_mask & ((1u << lane) - 1u));
                     if (my < n) {
-                        V3<R> o, d;
-                        source.load(my, o, d, best);
-                        r = my, improved = false;
-                        tr = tri_ray(o, d);
-                        fr = filter_ray<NT>(o, d);
+                        r = source.load_setup(my, tr, fr, best); // the handle the sink stores the result under
+                        improved = false;
                         bcur = 0;
                         cur = (int)sc.items[sc.bvh_items[0]].root;
                         sp = 0, loc_t = real_inf<R>(), loc_tri = -1;
