@@ -15,7 +15,7 @@ CUDA_DEPS = $(CSRC)/vrj_batch.cuh $(CSRC)/vrj_kernels.cuh $(CSRC)/vrj_traverse.c
             $(CSRC)/vrj_internal.h $(CSRC)/rgb_basis_tables.inc include/vanrijn_cuda.h
 HOST_DEPS = $(CSRC)/host/vanrijn_host.cpp $(CSRC)/host/host_capi.cpp include/vanrijn.hpp include/vanrijn_cuda.h
 
-all: $(LIBDIR)/libvanrijn_cuda.so $(LIBDIR)/libvanrijn_host.so oracle examples
+all: $(LIBDIR)/libvanrijn_cuda.so $(LIBDIR)/libvanrijn_host.so oracle examples tools
 
 # translation units: the C ABI + scene upload; the device BVH builder; and one object per instantiation of the wavefront
 # batch (vrj_batch_inst.cu with -DVRJ_INST=0..5), so `make -j` compiles the kernel variants in parallel
@@ -52,8 +52,14 @@ build/vanrijn: examples/vanrijn_main.cpp $(LIBDIR)/libvanrijn_host.so include/va
 	mkdir -p build
 	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lvanrijn_host -lvanrijn_cuda -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 
+# microbenchmark behind roofline.k_trace: dependent 64-byte gathers from L2 / HBM (profiles/r02_l2_gather_peak.json)
+tools: build/l2_gather_peak
+build/l2_gather_peak: tools/l2_gather_peak.cu
+	mkdir -p build
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o $@ $<
+
 clean:
 	rm -f $(LIBDIR)/*.so oracle/*.so
 	rm -rf $(OBJDIR) build/vanrijn build/drop_in_example
 
-.PHONY: all oracle clean examples
+.PHONY: all oracle clean examples tools

@@ -334,6 +334,19 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
 uint64_t next_sample_index(uint64_t count = 1);
 AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t height, size_t width, const RenderOptions &options);
 
+// main.rs:192-217 as a function: `workers` threads (the reference: rayon's pool through par_bridge) take the tiles of
+// TileIterator(width, height, tile_size) round and round, call partial_render_scene on each and hand the result to the
+// calling thread, which merge_tile()s it into `rendered_image` as it arrives (main.rs:214-216).  `options` defaults to what
+// the reference hard-codes (1 spp, RECURSION_LIMIT 128); with `fresh_samples` every call takes its sample indices from
+// next_sample_index() like the same-signature call, otherwise pass k over the tiles uses options.sample_offset + k * spp.
+// Stops after `calls` calls.  At most `workers` finished tiles wait for the merge.
+struct MainLoopStats {
+    double wall_s = 0, call_s = 0, merge_s = 0, device_ms = 0; // call_s: summed over the workers
+    uint64_t rays = 0, calls = 0, bytes_to_host = 0;
+};
+MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, size_t tile_size, uint64_t calls, unsigned workers,
+                               const RenderOptions &options, bool fresh_samples, AccumulationBuffer &rendered_image);
+
 // The frame's AccumulationBuffer kept in GPU memory between passes ("progressive preview").
 // main.rs:199-225 merges a freshly downloaded 1-spp buffer per tile into the frame on the host (merge_tile's weighted
 // mean) and tone-maps on the host; here every pass continues the Kahan accumulators where the last one stopped

@@ -1079,6 +1079,13 @@ int orc_bvh_depth(const OrcScene *s, int object_id) {
     const Object &o = s->objects[object_id];
     return o.is_bvh ? o.bvh->depth : -1;
 }
+/* prim_id (index in the order the mesh was handed over) of the triangle at each leaf, in DFS order */
+int64_t orc_bvh_leaf_order(const OrcScene *s, int object_id, int32_t *out) {
+    const Object &o = s->objects[object_id];
+    if (!o.is_bvh) return -1;
+    for (size_t i = 0; i < o.bvh->tris.size(); i++) out[i] = (int32_t)o.bvh->tris[i].prim_id;
+    return (int64_t)o.bvh->tris.size();
+}
 int64_t orc_load_obj(const char *path, double **verts, double **normals) {
     std::vector<Triangle> tris;
     if (!load_obj(path, &tris)) return -1;

@@ -55,6 +55,7 @@ int orc_add_bvh(OrcScene *, int64_t ntri, const double *verts, const double *nor
 int orc_add_bvh_obj(OrcScene *, const char *path, int material);
 int64_t orc_bvh_triangle_count(const OrcScene *, int object_id);
 int orc_bvh_depth(const OrcScene *, int object_id);
+int64_t orc_bvh_leaf_order(const OrcScene *, int object_id, int32_t *prim_ids); /* DFS leaf order */
 /* load_obj only: returns triangle count, fills verts/normals (caller frees with orc_free) */
 int64_t orc_load_obj(const char *path, double **verts, double **normals);
 void orc_free(void *);

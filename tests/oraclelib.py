@@ -72,6 +72,8 @@ def lib():
     L.orc_bvh_triangle_count.restype = C.c_int64
     L.orc_bvh_triangle_count.argtypes = [C.c_void_p, C.c_int]
     L.orc_bvh_depth.argtypes = [C.c_void_p, C.c_int]
+    L.orc_bvh_leaf_order.restype = C.c_int64
+    L.orc_bvh_leaf_order.argtypes = [C.c_void_p, C.c_int, ip]
     L.orc_load_obj.restype = C.c_int64
     L.orc_load_obj.argtypes = [C.c_char_p, C.POINTER(dp), C.POINTER(dp)]
     L.orc_free.argtypes = [C.c_void_p]

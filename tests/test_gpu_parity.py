@@ -136,6 +136,7 @@ def test_path_traced_samples_phong(variant):
     g = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=5, want_photons=True)
     r = orc.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=5, want_photons=True)
     diverged = photons_close(g["photons"], r["photons"], 1e-9, max_diverged=30)   # of 10 800 samples (0.3 %)
+    print("phong[%s]: %d of %d samples follow a different path than the oracle (CUDA vs glibc sin/cos/pow ulps)" % (variant, diverged, g["photons"].shape[0] * g["photons"].shape[1]))
     assert g["stats"].primary_rays == r["stats"].primary_rays and g["stats"].paths_missed == r["stats"].paths_missed
     if diverged == 0:
         np.testing.assert_allclose(g["colour_sum"], r["colour_sum"], rtol=1e-8, atol=1e-20)

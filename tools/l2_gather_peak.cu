@@ -1,0 +1,110 @@
+// l2_gather_peak.cu -- what bounds k_trace: the rate at which an SM array can fetch 64-byte records at data-dependent
+// addresses from a table that lives in L2 (the bench scene's 5.2 MB of BVH nodes) or in HBM (config C4's 3.6 GB).
+//
+// Every lane follows its own chain: it loads a 64-byte record with two 256-bit read-only loads (ld.global.nc.v8, exactly
+// what load_node issues) and the record holds the index of the next one -- like a traversal step, the next address is not
+// known before the data arrives.  CHAINS independent chains per lane model the instruction-level parallelism a smarter
+// walk could expose.  The grid is k_trace's (148 SMs x RES CTAs of 128 threads).
+//
+//   build/l2_gather_peak            prints one JSON object: GB/s and records/s per table size x chains x resident CTAs
+//
+// Used by bench.py as the denominator of roofline.k_trace (profiles/r02_l2_gather_peak.json holds the committed result).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#define CK(x)                                                                                  \
+    do {                                                                                       \
+        cudaError_t e_ = (x);                                                                  \
+        if (e_ != cudaSuccess) {                                                               \
+            std::fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_));                      \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+__device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+
+template <int CHAINS>
+__global__ void __launch_bounds__(128) k_chase(const uint4 *__restrict__ table, uint32_t n_records, int steps, uint32_t *sink) {
+    uint32_t idx[CHAINS], acc = 0;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) idx[c] = (uint32_t)(((uint64_t)(tid * CHAINS + c) * 2654435761u) % n_records);
+    for (int s = 0; s < steps; s++) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; c++) {
+            uint4 a, b, d, e;
+            const uint4 *p = table + (size_t)idx[c] * 4;
+            ldg256(p, a, b);
+            ldg256(p + 2, d, e);
+            idx[c] = a.x;                                  // the next record: known only once the data is here
+            acc += b.y ^ d.z ^ e.w;                        // every part of the record is consumed
+        }
+    }
+    if (acc == 0x12345678u) sink[0] = acc; // keeps the loads alive
+}
+
+template <int CHAINS>
+static int run(const uint4 *d_table, uint32_t n_records, int grid, int steps, uint32_t *d_sink, double *gbs, double *grecs) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_chase<CHAINS><<<grid, 128>>>(d_table, n_records, steps / 4, d_sink); // warm-up: pulls the table into L2
+    CK(cudaEventRecord(e0));
+    k_chase<CHAINS><<<grid, 128>>>(d_table, n_records, steps, d_sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double records = (double)grid * 128.0 * CHAINS * steps;
+    *grecs = records / (ms * 1e-3) / 1e9;
+    *gbs = *grecs * 64.0;
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    return 0;
+}
+
+int main() {
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    const size_t sizes_mb[] = {5, 32, 96, 1024, 3648};
+    uint32_t *d_sink;
+    CK(cudaMalloc(&d_sink, 4));
+    std::printf("{\"what\": \"dependent 64-byte gathers (2 x ld.global.nc.v8 per record), one chain per lane unless stated\", \"sms\": %d, \"results\": [", sms);
+    bool first = true;
+    for (size_t mb : sizes_mb) {
+        const uint32_t n = (uint32_t)(mb * 1024 * 1024 / 64);
+        // a random cyclic permutation: record i names the record that follows it
+        std::vector<uint32_t> perm(n);
+        for (uint32_t i = 0; i < n; i++) perm[i] = i;
+        std::mt19937_64 rng(12345 + mb);
+        for (uint32_t i = n - 1; i > 0; i--) std::swap(perm[i], perm[rng() % (i + 1)]);
+        std::vector<uint32_t> host((size_t)n * 16, 0x9e3779b9u);
+        for (uint32_t i = 0; i < n; i++) host[(size_t)perm[i] * 16] = perm[(i + 1) % n];
+        uint4 *d_table;
+        CK(cudaMalloc(&d_table, (size_t)n * 64));
+        CK(cudaMemcpy(d_table, host.data(), (size_t)n * 64, cudaMemcpyHostToDevice));
+        for (int res : {6, 8, 16}) {
+            const int grid = sms * res;
+            const int steps = mb >= 1024 ? 256 : 1024;
+            double gbs[3], gr[3];
+            if (run<1>(d_table, n, grid, steps, d_sink, &gbs[0], &gr[0])) return 1;
+            if (run<2>(d_table, n, grid, steps, d_sink, &gbs[1], &gr[1])) return 1;
+            if (run<4>(d_table, n, grid, steps / 2, d_sink, &gbs[2], &gr[2])) return 1;
+            std::printf("%s\n {\"table_mb\": %zu, \"ctas_per_sm\": %d, \"GBps_1chain\": %.1f, \"GBps_2chains\": %.1f, \"GBps_4chains\": %.1f, "
+                        "\"Grecords_per_s_1chain\": %.2f}",
+                        first ? "" : ",", mb, res, gbs[0], gbs[1], gbs[2], gr[0]);
+            first = false;
+        }
+        CK(cudaFree(d_table));
+    }
+    std::printf("\n]}\n");
+    return 0;
+}

@@ -215,6 +215,9 @@ def host():
         if hasattr(L, "vrjh_next_sample_index"):  # absent only from older kernel-variant builds (VRJ_LIBDIR experiments)
             L.vrjh_next_sample_index.restype = C.c_uint64
             L.vrjh_next_sample_index.argtypes = [C.c_uint64]
+        if hasattr(L, "vrjh_render_like_main"):
+            L.vrjh_render_like_main.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_int, dp, dp, dp]
         L.vrjh_merge_tile.argtypes = [dp, dp, C.c_uint64, C.c_uint64, u64p, dp, dp]
         L.vrjh_scene_save_cache.argtypes = [C.c_void_p, C.c_char_p]
         L.vrjh_scene_load_cache.restype = C.c_void_p

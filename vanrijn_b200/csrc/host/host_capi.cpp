@@ -219,6 +219,32 @@ int vrjh_partial_render_scene(void *p, const uint64_t tile[4], uint64_t height, 
     });
 }
 uint64_t vrjh_next_sample_index(uint64_t count) { return next_sample_index(count); }
+/* render_like_main (main.rs:192-217): `calls` partial_render_scene calls from `workers` threads, merged into the caller's
+ * width x height colour / weight arrays (which hold the image so far; zero weight = empty).  spp == 0: the reference's own
+ * call (1 spp, limit 128, fresh samples); otherwise spp / max_depth / seed as given, samples counted from sample_offset.
+ * kahan_state: whether each call also brings its Kahan arrays back (the reference's AccumulationBuffer has them; merge_tile
+ * never reads them).  stats8: wall_s, call_s, merge_s, device_ms, rays, calls, bytes_to_host, 0. */
+int vrjh_render_like_main(void *p, uint64_t width, uint64_t height, uint64_t tile_size, uint64_t calls, uint32_t workers,
+                          uint32_t spp, uint32_t max_depth, uint64_t seed, uint64_t sample_offset, int kahan_state, int device,
+                          double *colour, double *weight, double *stats8) {
+    HostScene *h = static_cast<HostScene *>(p);
+    return guarded([&] {
+        AccumulationBuffer image(width, height);
+        const size_t n = width * height;
+        std::memcpy(image.colour.data(), colour, 3 * n * sizeof(double));
+        std::memcpy(image.weight.data(), weight, n * sizeof(double));
+        RenderOptions o; // defaults = what the reference hard-codes
+        if (spp) o.spp = spp, o.max_depth = max_depth, o.seed = seed, o.sample_offset = sample_offset;
+        o.kahan_state = kahan_state != 0, o.device = device;
+        MainLoopStats st = render_like_main(h->scene, width, height, tile_size, calls, workers, o, spp == 0, image);
+        std::memcpy(colour, image.colour.data(), 3 * n * sizeof(double));
+        std::memcpy(weight, image.weight.data(), n * sizeof(double));
+        if (stats8) {
+            stats8[0] = st.wall_s, stats8[1] = st.call_s, stats8[2] = st.merge_s, stats8[3] = st.device_ms;
+            stats8[4] = (double)st.rays, stats8[5] = (double)st.calls, stats8[6] = (double)st.bytes_to_host, stats8[7] = 0.0;
+        }
+    });
+}
 /* AccumulationBuffer::merge_tile on raw arrays (dst is dst_w x dst_h, src is the tile's size) */
 int vrjh_merge_tile(double *dst_colour, double *dst_weight, uint64_t dst_w, uint64_t dst_h, const uint64_t tile[4],
                     const double *src_colour, const double *src_weight) {

@@ -6,7 +6,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -760,6 +762,89 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
     out.stats = o.stats;
     if (vrj_render_tile(dev, &t, height, width, &p, &out) != VRJ_OK) throw std::runtime_error(std::string("vrj_render_tile: ") + vrj_last_error());
     return buffer;
+}
+
+// ------------------------------------------------------------------------------ main.rs:192-217
+MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, size_t tile_size, uint64_t calls, unsigned workers,
+                               const RenderOptions &options, bool fresh_samples, AccumulationBuffer &rendered_image) {
+    if (rendered_image.width() != width || rendered_image.height() != height) throw std::runtime_error("render_like_main: image size mismatch");
+    std::vector<Tile> tiles;
+    {
+        TileIterator it(width, height, tile_size);
+        Tile t;
+        while (it.next(t)) tiles.push_back(t);
+    }
+    MainLoopStats total;
+    if (tiles.empty() || calls == 0) return total;
+    workers = std::max(1u, workers);
+    device_scene(scene, options.device); // flatten + upload before the clock starts (main.rs builds the scene first)
+    struct Item {
+        Tile tile;
+        AccumulationBuffer buffer;
+    };
+    std::mutex m;
+    std::condition_variable ready, room;
+    std::vector<std::unique_ptr<Item>> queue; // the mpsc channel of main.rs:195, bounded so finished tiles cannot pile up
+    std::atomic<uint64_t> next{0};
+    std::string error;
+    unsigned live = workers;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto seconds = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < workers; w++) {
+        pool.emplace_back([&]() {
+            double my_call = 0, my_ms = 0;
+            uint64_t my_rays = 0, my_calls = 0, my_bytes = 0;
+            try {
+                for (;;) {
+                    const uint64_t k = next.fetch_add(1);
+                    if (k >= calls) break;
+                    const Tile tile = tiles[k % tiles.size()]; // .cycle()
+                    RenderOptions o = options;
+                    VrjStats stats{};
+                    o.stats = &stats;
+                    o.sample_offset = fresh_samples ? next_sample_index(o.spp) : options.sample_offset + (k / tiles.size()) * (uint64_t)o.spp * o.sample_stride;
+                    const auto tc = std::chrono::steady_clock::now();
+                    std::unique_ptr<Item> item(new Item{tile, partial_render_scene(scene, tile, height, width, o)});
+                    my_call += seconds(tc);
+                    my_rays += stats.primary_rays + stats.bounce_rays + stats.shadow_rays, my_ms += stats.device_ms, my_calls++;
+                    my_bytes += 8 * (item->buffer.colour.size() + item->buffer.colour_sum.size() + item->buffer.colour_bias.size() +
+                                     item->buffer.weight.size() + item->buffer.weight_bias.size());
+                    std::unique_lock<std::mutex> lock(m);
+                    room.wait(lock, [&] { return queue.size() < workers || !error.empty(); });
+                    if (!error.empty()) break;
+                    queue.push_back(std::move(item));
+                    ready.notify_one();
+                }
+            } catch (const std::exception &e) {
+                std::lock_guard<std::mutex> lock(m);
+                if (error.empty()) error = e.what();
+            }
+            std::lock_guard<std::mutex> lock(m);
+            total.call_s += my_call, total.device_ms += my_ms, total.rays += my_rays, total.calls += my_calls, total.bytes_to_host += my_bytes;
+            live--;
+            ready.notify_one();
+            room.notify_all();
+        });
+    }
+    for (;;) { // the 'running loop of main.rs:211-218 without the window
+        std::unique_ptr<Item> item;
+        {
+            std::unique_lock<std::mutex> lock(m);
+            ready.wait(lock, [&] { return !queue.empty() || live == 0; });
+            if (queue.empty()) break;
+            item = std::move(queue.front());
+            queue.erase(queue.begin());
+            room.notify_one();
+        }
+        const auto tm = std::chrono::steady_clock::now();
+        rendered_image.merge_tile(item->tile, item->buffer);
+        total.merge_s += seconds(tm);
+    }
+    for (auto &t : pool) t.join();
+    total.wall_s = seconds(t0);
+    if (!error.empty()) throw std::runtime_error("render_like_main: " + error);
+    return total;
 }
 
 // ------------------------------------------------------------------------------ device-resident frame

@@ -7,6 +7,7 @@
 #include "vrj_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -306,21 +307,37 @@ std::mutex g_host_pool_mutex;
 std::vector<HostBlock> g_host_pool_free;
 std::unordered_map<void *, size_t> g_host_pool_live;
 
-Scratch *acquire_scratch(VrjScene *sc) {
+// Blocks are kept for concurrent callers (main.rs:197-209 drives the entry point from a pool of workers, each call needing
+// its own block): up to 16 per device as long as what the pool holds stays under 48 GB -- sixteen 1-spp 1080p blocks are
+// 14 GB, one 64-spp block is 45 GB.  A caller is handed the smallest pooled block that is large enough, else the largest.
+size_t scratch_bytes(const Scratch *s) { return s->capacity * 240 + s->rec_capacity * sizeof(TraceRec) + s->npix * 88; }
+std::atomic<int> g_active_calls[64];
+Scratch *acquire_scratch(VrjScene *sc, size_t want_capacity) {
     std::lock_guard<std::mutex> g(g_pool_mutex);
-    for (size_t i = 0; i < g_pool.size(); i++)
-        if (g_pool[i].first == sc->device) {
-            Scratch *s = g_pool[i].second;
-            g_pool.erase(g_pool.begin() + i);
-            return s;
+    size_t best = g_pool.size();
+    for (size_t i = 0; i < g_pool.size(); i++) {
+        if (g_pool[i].first != sc->device) continue;
+        if (best == g_pool.size()) {
+            best = i;
+            continue;
         }
+        const size_t c = g_pool[i].second->capacity, b = g_pool[best].second->capacity;
+        const bool c_fits = c >= want_capacity, b_fits = b >= want_capacity;
+        if ((c_fits && (!b_fits || c < b)) || (!c_fits && !b_fits && c > b)) best = i;
+    }
+    if (best != g_pool.size()) {
+        Scratch *s = g_pool[best].second;
+        g_pool.erase(g_pool.begin() + best);
+        return s;
+    }
     return new Scratch();
 }
 void release_scratch(VrjScene *sc, Scratch *s) {
     std::lock_guard<std::mutex> g(g_pool_mutex);
-    size_t same = 0;
-    for (auto &e : g_pool) same += e.first == sc->device;
-    if (same < 2) g_pool.push_back({sc->device, s});
+    size_t same = 0, bytes = scratch_bytes(s);
+    for (auto &e : g_pool)
+        if (e.first == sc->device) same++, bytes += scratch_bytes(e.second);
+    if (same < 16 && (same < 2 || bytes <= (size_t(48) << 30))) g_pool.push_back({sc->device, s});
     else delete s;
 }
 
@@ -383,7 +400,7 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t rec_capacity, size_
     }
     if (s->steps < steps) {
         s->steps = 0;
-        std::vector<std::pair<DeviceBuffer *, size_t>> want = {{&s->counters, ((size_t)steps * 4 + 4) * sizeof(uint32_t)}};
+        std::vector<std::pair<DeviceBuffer *, size_t>> want = {{&s->counters, ((size_t)steps * 5 + 4) * sizeof(uint32_t)}};
         VrjStatus st = alloc_group(want, "level counters");
         if (st != VRJ_OK) return st;
         s->steps = steps;
@@ -885,12 +902,20 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     if (npix == 0 || p->spp == 0) return VRJ_OK;
     VRJ_CUDA(cudaSetDevice(scene->device));
 
-    // batch: as many samples of the whole tile in flight as fit the path budget
-    const uint64_t path_budget = scene->path_budget; // paths in flight: 128 Mi by default = ~31 GB of queue state (sized for 180 GB of HBM)
+    // batch: as many samples of the whole tile in flight as fit the path budget -- 128 Mi paths by default = 45 GB of queue
+    // state (sized for 180 GB of HBM) -- shared between the calls running on this device right now, so several callers asking
+    // for many samples each do not have to find out through failed allocations that they cannot all have a full budget
+    struct ActiveCall {
+        std::atomic<int> &n;
+        int others;
+        explicit ActiveCall(std::atomic<int> &c) : n(c), others(c.fetch_add(1)) {}
+        ~ActiveCall() { n.fetch_sub(1); }
+    } active(g_active_calls[(unsigned)scene->device % 64]);
+    const uint64_t path_budget = std::max<uint64_t>(scene->path_budget / (uint64_t)(active.others + 1), std::min<uint64_t>(scene->path_budget, uint64_t(1) << 22));
     uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(p->spp, path_budget / npix));
     if (npix * (uint64_t)batch > 0xfffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "tile too large");
     const bool whitted = p->integrator == VRJ_INTEGRATOR_WHITTED;
-    Scratch *s = acquire_scratch(scene);
+    Scratch *s = acquire_scratch(scene, npix * batch);
     struct Releaser {
         VrjScene *sc;
         Scratch *s;

@@ -166,7 +166,7 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
     uint32_t *work_t = lcount + stride;             // work-fetch counters of T_k
     uint32_t *work_s = work_t + stride;             // ... of G (k = 0 only) / S_k
     uint32_t *tail_done = work_s + stride;          // set by the k_tail launch that finished the batch
-    VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 4 + 1) * sizeof(uint32_t), s->stream));
+    VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 5 + 1) * sizeof(uint32_t), s->stream));
     unsigned long long *stats = s->stats.as<unsigned long long>();
     double2 *photons = s->photons.as<double2>();
     const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT, false>) : q16 ? persistent_grid(sc, k_traceq<COUNT, false>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
@@ -202,8 +202,17 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
     (*launches)++;
     VRJ_CUDA(s->mark(3));
     bool drain_pending = false;
+#if VRJ_SPLIT_STAGE
+    const int g_st = persistent_grid(sc, k_stage<R, COUNT>);
+    uint32_t *work_st = tail_done + 1; // work-fetch counters of the k_stage launches (stride entries)
+#endif
     for (uint32_t k = 1; k <= levels; k++) {
         const int ci = k & 1, ni = (k + 1) & 1;
+#if VRJ_SPLIT_STAGE
+        k_stage<R, COUNT><<<g_st, 128, 0, s->stream>>>(sc->dev, s->queue(ci), qcount + k, ci ? tb1 : tb0, lcount + k, work_st + k, stats, tail_done);
+        (*launches)++;
+        VRJ_CUDA(s->mark(4));
+#endif
         if (tail_max) {
             k_tail<NT, R, COUNT, WHITTED, MM><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
             (*launches)++;

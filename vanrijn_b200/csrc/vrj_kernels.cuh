@@ -29,6 +29,18 @@
 #ifndef VRJ_RAYGEN_CHUNK
 #define VRJ_RAYGEN_CHUNK 1024
 #endif
+// 1: the closest-hit stage 1 of a bounce ray (analytic objects, root pre-test, traversal record) runs in its own streaming
+// kernel, k_stage, instead of at the end of k_shade: k_shade loses a quarter of its code (it is bound by instruction fetch and
+// binary64 latency at 5 CTAs per SM) and the stage work runs at twice the occupancy; the price is re-reading the ray (48 B)
+#ifndef VRJ_SPLIT_STAGE
+#define VRJ_SPLIT_STAGE 0
+#endif
+#ifndef VRJ_STAGE_MINB
+#define VRJ_STAGE_MINB 8
+#endif
+#ifndef VRJ_RAYGEN_MINB
+#define VRJ_RAYGEN_MINB VRJ_SHADE_MINB
+#endif
 #ifndef VRJ_FIRST_UNSORTED
 #define VRJ_FIRST_UNSORTED 1
 #endif
@@ -229,7 +241,7 @@ __device__ __forceinline__ void camera_ray(const DevScene &sc, const RenderConst
 
 // ---- k_raygen: camera rays (camera.rs:45-66), staged for traversal ----
 template <typename R, bool COUNT>
-__global__ void VRJ_SHADE_BOUNDS(R) k_raygen(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, uint32_t *list_count,
+__global__ void __launch_bounds__(128, sizeof(R) == 4 ? VRJ_SHADE_MINB_F32 : VRJ_RAYGEN_MINB) k_raygen(DevScene sc, RenderConst rc, PathQueue q, TraceBuffers tb, uint32_t *list_count,
                                                 uint32_t *work, unsigned long long *stats) {
     const uint32_t n = rc.npix * rc.batch_samples;
     LocalStats ls;
@@ -624,9 +636,38 @@ __global__ void VRJ_SHADE_BOUNDS(R) k_shade(DevScene sc, RenderConst rc, PathQue
             }
             uint32_t idx = queue_reserve(alive, out_count);
             if (alive) queue_store(out, idx, p.o, p.d, p.wl, p.A, p.B, p.aux, p.slot, p.ordinal, p.limit, p.flags);
+#if !VRJ_SPLIT_STAGE
             stage_ray<COUNT>(sc, alive, idx, p.o, p.d, tb_out, list_count, ls);
+#endif
         }
         __syncthreads(); // s_sorted / s_count are reused by the next chunk
+    }
+    ls.flush(stats);
+}
+
+// ---- k_stage: stage 1 of the closest hit for the bounce rays k_shade just enqueued (VRJ_SPLIT_STAGE) ----
+template <typename R, bool COUNT>
+__global__ void __launch_bounds__(128, VRJ_STAGE_MINB) k_stage(DevScene sc, PathQueue q, const uint32_t *count, TraceBuffers tb, uint32_t *list_count,
+                                                               uint32_t *work, unsigned long long *stats, const uint32_t *tail_done) {
+    if (*tail_done) return;
+    const uint32_t n = *count;
+    LocalStats ls;
+    ls.clear();
+    __shared__ uint32_t s_base;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = atomicAdd(work, (uint32_t)VRJ_RAYGEN_CHUNK);
+        __syncthreads();
+        const uint32_t base = s_base;
+        if (base >= n) break;
+#pragma unroll 1
+        for (uint32_t k = threadIdx.x; k < (uint32_t)VRJ_RAYGEN_CHUNK; k += 128) {
+            const uint32_t j = base + k;
+            if (base + (k & ~31u) >= n) break; // the whole warp is past the end
+            V3<R> o = V3<R>{R(0), R(0), R(0)}, d = V3<R>{R(0), R(0), R(1)};
+            if (j < n) queue_load_ray(q, j, o, d);
+            stage_ray<COUNT>(sc, j < n, j, o, d, tb, list_count, ls);
+        }
     }
     ls.flush(stats);
 }

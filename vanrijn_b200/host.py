@@ -246,6 +246,24 @@ class HostScene:
         return out
 
 
+def render_like_main(hs, width, height, calls, workers, tile_size=2048, spp=0, max_depth=128, seed=1, sample_offset=0,
+                     kahan_state=True, device=0, colour=None, weight=None):
+    """main.rs:192-217 through the C++ mirror (render_like_main): `workers` threads call partial_render_scene on the cycled
+    tiles, the calling thread merge_tile()s.  spp=0: the reference's own call (1 spp, limit 128, fresh samples).
+    Returns (colour, weight, stats dict)."""
+    n = width * height
+    colour = np.zeros(n * 3) if colour is None else colour
+    weight = np.zeros(n) if weight is None else weight
+    st = np.zeros(8)
+    r = hs.H.vrjh_render_like_main(hs.h, width, height, tile_size, calls, workers, spp, max_depth, seed, sample_offset,
+                                   1 if kahan_state else 0, device, colour.ctypes.data_as(dp), weight.ctypes.data_as(dp),
+                                   st.ctypes.data_as(dp))
+    if r != 0:
+        raise capi.VrjError(hs.H.vrjh_last_error().decode())
+    keys = ("wall_s", "call_s", "merge_s", "device_ms", "rays", "calls", "bytes_to_host")
+    return colour, weight, dict(zip(keys, [float(x) for x in st[:7]]))
+
+
 def tone_map(colour, source=capi.TONEMAP_XYZ, device=0):
     """ClampingToneMapper on host arrays through the device (vrj_tone_map): (n,3) float64 -> (n,3) uint8."""
     c = np.ascontiguousarray(colour, dtype=np.float64).reshape(-1, 3)
