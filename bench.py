@@ -542,7 +542,7 @@ def main():
     if os.path.exists(gpath):
         try:
             g = json.load(open(gpath))
-            cands = [r for r in g["results"] if r["table_mb"] == 5 and r["ctas_per_sm"] == 6]
+            cands = [r for r in g["results"] if r.get("record_bytes", 64) == 64 and r["table_mb"] == 5 and r["ctas_per_sm"] == 6]
             l2_peak = cands[0]["GBps_1chain"]
             l2_src = "measured: dependent 64-byte gathers, 5 MB table, 6 CTAs/SM, one chain per lane (profiles/r02_l2_gather_peak.json)"
         except Exception:

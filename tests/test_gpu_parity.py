@@ -135,7 +135,10 @@ def test_path_traced_samples_phong(variant):
     W, H, spp = 80, 45, 3
     g = hs.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=5, want_photons=True)
     r = orc.render((0, W, 0, H), H, W, spp=spp, max_depth=128, seed=5, want_photons=True)
-    diverged = photons_close(g["photons"], r["photons"], 1e-9, max_diverged=30)   # of 10 800 samples (0.3 %)
+    # of 10 800 samples.  Measured on B200 (round 2): 0 (all-Lambertian surroundings) and 6 (mirror / glass surroundings, where
+    # a last-ulp difference of CUDA's sin / cos against glibc's is amplified by the specular chain); the second-source vectors
+    # (tests/test_second_source.py) pin the sampler's arithmetic itself, so the allowance only has to cover libm
+    diverged = photons_close(g["photons"], r["photons"], 1e-9, max_diverged=12)
     print("phong[%s]: %d of %d samples follow a different path than the oracle (CUDA vs glibc sin/cos/pow ulps)" % (variant, diverged, g["photons"].shape[0] * g["photons"].shape[1]))
     assert g["stats"].primary_rays == r["stats"].primary_rays and g["stats"].paths_missed == r["stats"].paths_missed
     if diverged == 0:

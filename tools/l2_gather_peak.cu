@@ -32,7 +32,7 @@ __device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
                  : "l"(p));
 }
 
-template <int CHAINS>
+template <int CHAINS, int REC> // REC: record size in bytes (32, 64 or 128), read with REC / 32 256-bit loads
 __global__ void __launch_bounds__(128) k_chase(const uint4 *__restrict__ table, uint32_t n_records, int steps, uint32_t *sink) {
     uint32_t idx[CHAINS], acc = 0;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,34 +41,49 @@ __global__ void __launch_bounds__(128) k_chase(const uint4 *__restrict__ table, 
     for (int s = 0; s < steps; s++) {
 #pragma unroll
         for (int c = 0; c < CHAINS; c++) {
-            uint4 a, b, d, e;
-            const uint4 *p = table + (size_t)idx[c] * 4;
-            ldg256(p, a, b);
-            ldg256(p + 2, d, e);
-            idx[c] = a.x;                                  // the next record: known only once the data is here
-            acc += b.y ^ d.z ^ e.w;                        // every part of the record is consumed
+            const uint4 *p = table + (size_t)idx[c] * (REC / 16);
+            uint32_t next = 0;
+#pragma unroll
+            for (int q = 0; q < REC / 32; q++) {
+                uint4 a, b;
+                ldg256(p + 2 * q, a, b);
+                if (q == 0) next = a.x;                    // the next record: known only once the data is here
+                acc += a.y ^ b.z ^ b.w;                    // every part of the record is consumed
+            }
+            idx[c] = next;
         }
     }
     if (acc == 0x12345678u) sink[0] = acc; // keeps the loads alive
 }
 
-template <int CHAINS>
+template <int CHAINS, int REC>
 static int run(const uint4 *d_table, uint32_t n_records, int grid, int steps, uint32_t *d_sink, double *gbs, double *grecs) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    k_chase<CHAINS><<<grid, 128>>>(d_table, n_records, steps / 4, d_sink); // warm-up: pulls the table into L2
+    k_chase<CHAINS, REC><<<grid, 128>>>(d_table, n_records, steps / 4, d_sink); // warm-up: pulls the table into L2
     CK(cudaEventRecord(e0));
-    k_chase<CHAINS><<<grid, 128>>>(d_table, n_records, steps, d_sink);
+    k_chase<CHAINS, REC><<<grid, 128>>>(d_table, n_records, steps, d_sink);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double records = (double)grid * 128.0 * CHAINS * steps;
     *grecs = records / (ms * 1e-3) / 1e9;
-    *gbs = *grecs * 64.0;
+    *gbs = *grecs * REC;
     cudaEventDestroy(e0), cudaEventDestroy(e1);
     return 0;
+}
+
+// a random cyclic permutation over n records of `rec` bytes: the first word of record i names the record that follows it
+static std::vector<uint32_t> make_table(uint32_t n, int rec, uint64_t seed) {
+    std::vector<uint32_t> perm(n);
+    for (uint32_t i = 0; i < n; i++) perm[i] = i;
+    std::mt19937_64 rng(seed);
+    for (uint32_t i = n - 1; i > 0; i--) std::swap(perm[i], perm[rng() % (i + 1)]);
+    std::vector<uint32_t> host((size_t)n * (rec / 4), 0x9e3779b9u);
+    for (uint32_t i = 0; i < n; i++) host[(size_t)perm[i] * (rec / 4)] = perm[(i + 1) % n];
+    return host;
 }
 
 int main() {
@@ -77,17 +92,12 @@ int main() {
     const size_t sizes_mb[] = {5, 32, 96, 1024, 3648};
     uint32_t *d_sink;
     CK(cudaMalloc(&d_sink, 4));
-    std::printf("{\"what\": \"dependent 64-byte gathers (2 x ld.global.nc.v8 per record), one chain per lane unless stated\", \"sms\": %d, \"results\": [", sms);
+    std::printf("{\"what\": \"dependent gathers of whole records (256-bit ld.global.nc.v8 loads), one chain per lane unless stated; "
+                "record_bytes 64 = a BVH node as k_trace reads it\", \"sms\": %d, \"results\": [", sms);
     bool first = true;
     for (size_t mb : sizes_mb) {
         const uint32_t n = (uint32_t)(mb * 1024 * 1024 / 64);
-        // a random cyclic permutation: record i names the record that follows it
-        std::vector<uint32_t> perm(n);
-        for (uint32_t i = 0; i < n; i++) perm[i] = i;
-        std::mt19937_64 rng(12345 + mb);
-        for (uint32_t i = n - 1; i > 0; i--) std::swap(perm[i], perm[rng() % (i + 1)]);
-        std::vector<uint32_t> host((size_t)n * 16, 0x9e3779b9u);
-        for (uint32_t i = 0; i < n; i++) host[(size_t)perm[i] * 16] = perm[(i + 1) % n];
+        std::vector<uint32_t> host = make_table(n, 64, 12345 + mb);
         uint4 *d_table;
         CK(cudaMalloc(&d_table, (size_t)n * 64));
         CK(cudaMemcpy(d_table, host.data(), (size_t)n * 64, cudaMemcpyHostToDevice));
@@ -95,14 +105,27 @@ int main() {
             const int grid = sms * res;
             const int steps = mb >= 1024 ? 256 : 1024;
             double gbs[3], gr[3];
-            if (run<1>(d_table, n, grid, steps, d_sink, &gbs[0], &gr[0])) return 1;
-            if (run<2>(d_table, n, grid, steps, d_sink, &gbs[1], &gr[1])) return 1;
-            if (run<4>(d_table, n, grid, steps / 2, d_sink, &gbs[2], &gr[2])) return 1;
-            std::printf("%s\n {\"table_mb\": %zu, \"ctas_per_sm\": %d, \"GBps_1chain\": %.1f, \"GBps_2chains\": %.1f, \"GBps_4chains\": %.1f, "
+            if (run<1, 64>(d_table, n, grid, steps, d_sink, &gbs[0], &gr[0])) return 1;
+            if (run<2, 64>(d_table, n, grid, steps, d_sink, &gbs[1], &gr[1])) return 1;
+            if (run<4, 64>(d_table, n, grid, steps / 2, d_sink, &gbs[2], &gr[2])) return 1;
+            std::printf("%s\n {\"record_bytes\": 64, \"table_mb\": %zu, \"ctas_per_sm\": %d, \"GBps_1chain\": %.1f, \"GBps_2chains\": %.1f, \"GBps_4chains\": %.1f, "
                         "\"Grecords_per_s_1chain\": %.2f}",
                         first ? "" : ",", mb, res, gbs[0], gbs[1], gbs[2], gr[0]);
             first = false;
         }
+        CK(cudaFree(d_table));
+    }
+    // is the L2-resident rate a byte rate or a request rate?  32-byte (the 16-bit nodes) and 128-byte (the 4-wide nodes) records
+    for (int rec : {32, 128}) {
+        const size_t mb = 32;
+        const uint32_t n = (uint32_t)(mb * 1024 * 1024 / rec);
+        std::vector<uint32_t> host = make_table(n, rec, 777 + rec);
+        uint4 *d_table;
+        CK(cudaMalloc(&d_table, (size_t)n * rec));
+        CK(cudaMemcpy(d_table, host.data(), (size_t)n * rec, cudaMemcpyHostToDevice));
+        double gbs = 0, gr = 0;
+        if (rec == 32 ? run<1, 32>(d_table, n, sms * 6, 1024, d_sink, &gbs, &gr) : run<1, 128>(d_table, n, sms * 6, 1024, d_sink, &gbs, &gr)) return 1;
+        std::printf(",\n {\"record_bytes\": %d, \"table_mb\": %zu, \"ctas_per_sm\": 6, \"GBps_1chain\": %.1f, \"Grecords_per_s_1chain\": %.2f}", rec, mb, gbs, gr);
         CK(cudaFree(d_table));
     }
     std::printf("\n]}\n");

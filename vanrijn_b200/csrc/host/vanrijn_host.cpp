@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <mutex>
 #include <numeric>
@@ -541,6 +542,78 @@ void ImageRgbU8::write_png(const std::string &filename) const {
     if (std::fclose(f) != 0 || !ok) throw std::runtime_error("write_png: write failed: " + filename);
 }
 
+namespace {
+// A few resident threads for merge_tile: a whole 1080p frame is 200 MB of reads and writes per merge, and the reference's
+// loop (main.rs:214-216) merges on ONE thread once per partial_render_scene call -- with the rendering on the GPU that
+// single thread is what bounds the loop, so big tiles are split by rows over a pool that lives as long as the process
+// (starting threads per call cost as much as a quarter of the merge).
+class RowPool {
+  public:
+    static RowPool &instance() {
+        static RowPool pool;
+        return pool;
+    }
+    // runs fn(r0, r1) over [0, rows) split into one piece per thread (the caller takes a piece too); returns when all are done
+    void run(size_t rows, const std::function<void(size_t, size_t)> &fn) {
+        std::lock_guard<std::mutex> serial(serial_); // one merge at a time owns the pool
+        if (rows == 0) return;
+        const size_t want = std::min(rows, workers_.size() + 1);
+        const size_t per = (rows + want - 1) / want;
+        const size_t pieces = (rows + per - 1) / per; // rounding can leave fewer pieces than threads
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn, rows_ = rows, per_ = per, next_ = 1, pending_ = pieces - 1, generation_++;
+        }
+        wake_.notify_all();
+        fn(0, std::min(rows, per));
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    RowPool() {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n = std::min(15u, hw > 2 ? hw / 2 : 1u); // + the calling thread
+        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
+    }
+    ~RowPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+        }
+        wake_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            size_t piece;
+            const std::function<void(size_t, size_t)> *fn;
+            size_t rows, per;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                wake_.wait(g, [&] { return stop_ || (generation_ != seen && fn_ && next_ * per_ < rows_); });
+                if (stop_) return;
+                piece = next_++;
+                if (next_ * per_ >= rows_) seen = generation_;
+                fn = fn_, rows = rows_, per = per_;
+            }
+            (*fn)(piece * per, std::min(rows, (piece + 1) * per));
+            std::lock_guard<std::mutex> g(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, serial_;
+    std::condition_variable wake_, done_;
+    const std::function<void(size_t, size_t)> *fn_ = nullptr;
+    size_t rows_ = 0, per_ = 1, next_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+} // namespace
+
 void AccumulationBuffer::merge_tile(const Tile &tile, const AccumulationBuffer &src) {
     if (tile.width() != src.width() || tile.height() != src.height()) throw std::runtime_error("merge_tile: tile and source sizes differ");
     if (tile.end_row > height_ || tile.end_column > width_) throw std::runtime_error("merge_tile: tile outside the buffer");
@@ -554,16 +627,9 @@ void AccumulationBuffer::merge_tile(const Tile &tile, const AccumulationBuffer &
                 weight[d] += w2;
             }
     };
-    // pixels are independent: big tiles are merged by a few threads (a 1080p frame: 9 ms -> 3 ms per pass)
-    const size_t n_threads = tile.width() * tile.height() >= (size_t(1) << 18) ? std::min<size_t>(4, std::max(1u, std::thread::hardware_concurrency())) : 1;
-    if (n_threads <= 1) return rows(0, tile.height());
-    std::vector<std::thread> pool;
-    const size_t per = (tile.height() + n_threads - 1) / n_threads;
-    for (size_t t = 0; t < n_threads; t++) {
-        const size_t r0 = t * per, r1 = std::min(tile.height(), r0 + per);
-        if (r0 < r1) pool.emplace_back(rows, r0, r1);
-    }
-    for (auto &th : pool) th.join();
+    // pixels are independent: big tiles are merged by the resident row pool (a 1080p frame: 9 ms on one thread)
+    if (tile.width() * tile.height() < (size_t(1) << 18)) return rows(0, tile.height());
+    RowPool::instance().run(tile.height(), rows);
 }
 
 // ------------------------------------------------------------------------------ scene cache

@@ -845,7 +845,8 @@ void vrj_free_host(void *p) {
         if (it != g_host_pool_live.end()) {
             size_t cached = 0;
             for (const HostBlock &b : g_host_pool_free) cached += b.bytes;
-            keep = cached + it->second <= (size_t(8) << 30) && g_host_pool_free.size() < 64;
+            // room for the buffers of a pool of concurrent callers (main.rs:197-209): 16 in flight x 5 arrays
+            keep = cached + it->second <= (size_t(16) << 30) && g_host_pool_free.size() < 256;
             if (keep) g_host_pool_free.push_back(HostBlock{p, it->second});
             g_host_pool_live.erase(it);
         }

@@ -50,6 +50,14 @@ struct DevScene {
 #ifndef VRJ_TRACE_TRIRAY_SMEM
 #define VRJ_TRACE_TRIRAY_SMEM 0
 #endif
+// Experiment (north_star: "node loads staged through shared memory"): K > 0 keeps the top K levels of the first mesh's
+// tree (2^K - 1 wide nodes of 64 bytes, heap-ordered) in shared memory; each CTA copies them in at kernel start and the
+// walk reads those nodes with LDS instead of LDG.  Off by default: measured no faster (profiles/README.md, round 2) --
+// the top of the tree already hits L1, and both paths go through the same load/store unit.
+#ifndef VRJ_TRACE_SMEM_LEVELS
+#define VRJ_TRACE_SMEM_LEVELS 0
+#endif
+#define VRJ_SMEM_TAG 0x40000000
 template <typename R>
 struct HitT {
     R t;
@@ -519,9 +527,53 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
             cur = VRJ_LEAF_DONE;
         }
     };
+#if VRJ_TRACE_SMEM_LEVELS
+    constexpr int NTOP = (1 << VRJ_TRACE_SMEM_LEVELS) - 1;
+    __shared__ float4 s_top[sizeof(NT) == 4 ? NTOP * 4 : 1];
+    __shared__ int s_ref[sizeof(NT) == 4 ? NTOP * 2 : 1];
+    if (sizeof(NT) == 4) {
+        // heap-ordered copy of the top levels: node i has children 2i+1, 2i+2; s_ref holds their GLOBAL references
+        // (VRJ_LEAF_DONE = no such node), rewritten to tagged shared-memory references at the end
+        const float4 *nodes = reinterpret_cast<const float4 *>(sc.nodes32);
+        if (threadIdx.x == 0) {
+            const int root = (int)sc.items[sc.bvh_items[0]].root;
+            for (int q = 0; q < 4; q++) s_top[q] = nodes[(size_t)root * 4 + q];
+            s_ref[0] = __float_as_int(s_top[3].x), s_ref[1] = __float_as_int(s_top[3].y);
+        }
+        for (int level = 1; level < VRJ_TRACE_SMEM_LEVELS; level++) {
+            __syncthreads();
+            const int first = (1 << level) - 1, count = 1 << level;
+            for (int k = threadIdx.x; k < count; k += blockDim.x) {
+                const int i = first + k, parent = (i - 1) >> 1;
+                const int ref = s_ref[2 * parent + ((i - 1) & 1)];
+                if (ref >= 0) {
+                    for (int q = 0; q < 4; q++) s_top[i * 4 + q] = nodes[(size_t)ref * 4 + q];
+                    s_ref[2 * i] = __float_as_int(s_top[i * 4 + 3].x), s_ref[2 * i + 1] = __float_as_int(s_top[i * 4 + 3].y);
+                } else {
+                    s_ref[2 * i] = s_ref[2 * i + 1] = VRJ_LEAF_DONE;
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < (NTOP >> 1); i += blockDim.x) { // nodes whose children are in the table too
+            if (s_ref[2 * i] >= 0) s_top[i * 4 + 3].x = __int_as_float(VRJ_SMEM_TAG | (2 * i + 1));
+            if (s_ref[2 * i + 1] >= 0) s_top[i * 4 + 3].y = __int_as_float(VRJ_SMEM_TAG | (2 * i + 2));
+        }
+        __syncthreads();
+    }
+#endif
     auto node_step = [&]() {
         WideNode<NT> nd;
-        load_node(sc, cur, nd);
+#if VRJ_TRACE_SMEM_LEVELS
+        if (sizeof(NT) == 4 && (cur & VRJ_SMEM_TAG)) {
+            const float4 *p = s_top + (cur & ~VRJ_SMEM_TAG) * 4;
+            const float4 a = p[0], b = p[1], c = p[2], kf = p[3];
+            nd.c0[0] = (NT)a.x, nd.c0[1] = (NT)a.y, nd.c0[2] = (NT)a.z, nd.c0[3] = (NT)a.w, nd.c0[4] = (NT)c.x, nd.c0[5] = (NT)c.y;
+            nd.c1[0] = (NT)b.x, nd.c1[1] = (NT)b.y, nd.c1[2] = (NT)b.z, nd.c1[3] = (NT)b.w, nd.c1[4] = (NT)c.z, nd.c1[5] = (NT)c.w;
+            nd.left = __float_as_int(kf.x), nd.right = __float_as_int(kf.y);
+        } else
+#endif
+            load_node(sc, cur, nd);
         if (COUNT) cnt.node_visits += 2;
         NT e0, e1;
         bool h0 = box_filter(fr, nd.c0[0], nd.c0[1], nd.c0[2], nd.c0[3], nd.c0[4], nd.c0[5], limit, e0);
@@ -562,7 +614,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene &sc, uint32_t n,
                         r = source.load_setup(my, tr, fr, best); // the handle the sink stores the result under
                         improved = false;
                         bcur = 0;
-                        cur = (int)sc.items[sc.bvh_items[0]].root;
+                        cur = (VRJ_TRACE_SMEM_LEVELS && sizeof(NT) == 4) ? VRJ_SMEM_TAG : (int)sc.items[sc.bvh_items[0]].root;
                         sp = 0, loc_t = real_inf<R>(), loc_tri = -1;
                         limit = filter_limit<NT>(best.t);
                     }
