@@ -823,10 +823,15 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
     VrjTile t{tile.start_column, tile.end_column, tile.start_row, tile.end_row};
     VrjAccumOut out{};
     out.memory = VRJ_MEM_HOST;
-    out.colour = buffer.colour.data(), out.weight = buffer.weight.data();
-    if (!buffer.colour_sum.empty()) out.colour_sum = buffer.colour_sum.data(), out.colour_bias = buffer.colour_bias.data(), out.weight_bias = buffer.weight_bias.data();
+    out.colour = buffer.colour.data();
+    const bool full_state = !buffer.colour_sum.empty();
+    if (full_state) out.weight = buffer.weight.data(), out.colour_sum = buffer.colour_sum.data(), out.colour_bias = buffer.colour_bias.data(), out.weight_bias = buffer.weight_bias.data();
     out.stats = o.stats;
     if (vrj_render_tile(dev, &t, height, width, &p, &out) != VRJ_OK) throw std::runtime_error(std::string("vrj_render_tile: ") + vrj_last_error());
+    // A fresh buffer's weight is known without asking the device: every sample, hit or miss, enters update_pixel with weight
+    // 1.0 (camera.rs:121-127) and a sum of spp ones is exact, so the colour-and-weight-only buffer brings back the colours
+    // alone (a quarter less over PCIe per call) and the weights are written here
+    if (!full_state && o.spp) std::fill(buffer.weight.begin(), buffer.weight.end(), (double)o.spp);
     return buffer;
 }
 
@@ -874,8 +879,10 @@ MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, 
                     std::unique_ptr<Item> item(new Item{tile, partial_render_scene(scene, tile, height, width, o)});
                     my_call += seconds(tc);
                     my_rays += stats.primary_rays + stats.bounce_rays + stats.shadow_rays, my_ms += stats.device_ms, my_calls++;
-                    my_bytes += 8 * (item->buffer.colour.size() + item->buffer.colour_sum.size() + item->buffer.colour_bias.size() +
-                                     item->buffer.weight.size() + item->buffer.weight_bias.size());
+                    // what crossed PCIe: all five arrays, or the colours alone (the weights of a colour-and-weight-only buffer are written on the host)
+                    my_bytes += 8 * (item->buffer.colour_sum.empty() ? item->buffer.colour.size()
+                                                                      : item->buffer.colour.size() + item->buffer.colour_sum.size() + item->buffer.colour_bias.size() +
+                                                                            item->buffer.weight.size() + item->buffer.weight_bias.size());
                     std::unique_lock<std::mutex> lock(m);
                     room.wait(lock, [&] { return queue.size() < workers || !error.empty(); });
                     if (!error.empty()) break;
