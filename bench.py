@@ -483,19 +483,26 @@ def main():
     ref_sig = None
     if world == 1 and not args.no_extra:
         try:
-            ref_sig = {"what": "8 worker threads x partial_render_scene(scene, tile, h, w) [1 spp, RECURSION_LIMIT 128] + merge_tile on the "
-                               "calling thread, as src/main.rs:192-217; wall clock of the whole loop", "threads": 8}
-            for key, kahan, calls in (("colour_weight_only", False, 96), ("five_arrays", True, 48)):
-                host.render_like_main(hs, W, H, 16, 8, kahan_state=kahan, device=local)          # warm-up: scratch blocks, pinned pool
-                colour, weight, st = host.render_like_main(hs, W, H, calls, 8, kahan_state=kahan, device=local)
-                if not np.all(weight == calls):
-                    raise AssertionError("merged weights differ from %d" % calls)
-                ref_sig[key] = {"value": st["rays"] / st["wall_s"] / 1e6, "unit": "Mrays/s", "calls": calls,
-                                "ms_per_call": 1e3 * st["wall_s"] / calls, "d2h_bytes_per_call": st["bytes_to_host"] / calls,
-                                "merge_tile_ms_per_call": 1e3 * st["merge_s"] / calls, "device_ms_per_call": st["device_ms"] / calls,
-                                "worker_ms_per_call": 1e3 * st["call_s"] / calls, "spp_per_s": calls / st["wall_s"]}
-            ref_sig["value"] = ref_sig["colour_weight_only"]["value"]
-            ref_sig["unit"] = "Mrays/s"
+            ref_sig = {"what": "N worker threads x partial_render_scene(scene, tile, h, w) [1 spp, RECURSION_LIMIT 128, whole-frame tile] + "
+                               "merge_tile on the calling thread, as src/main.rs:192-217; wall clock of the whole loop.  colour_only: the "
+                               "tile buffer carries what merge_tile reads (colours + one weight); five_arrays: the reference type's five arrays",
+                       "bounds_per_call": {"d2h_colour_only_bytes": npix * 24, "d2h_five_arrays_bytes": npix * 88,
+                                           "merge_tile_bytes_read_written": npix * (32 + 24 + 32)}}
+            best = None
+            for key, kahan, calls in (("colour_only", False, 96), ("five_arrays", True, 48)):
+                for workers in (4, 8):
+                    host.render_like_main(hs, W, H, 2 * workers, workers, kahan_state=kahan, device=local)   # warm-up: scratch blocks, pinned pool
+                    colour, weight, st = host.render_like_main(hs, W, H, calls, workers, kahan_state=kahan, device=local)
+                    if not np.all(weight == calls):
+                        raise AssertionError("merged weights differ from %d" % calls)
+                    r = {"value": st["rays"] / st["wall_s"] / 1e6, "unit": "Mrays/s", "threads": workers, "calls": calls,
+                         "ms_per_call": 1e3 * st["wall_s"] / calls, "d2h_bytes_per_call": st["bytes_to_host"] / calls,
+                         "merge_tile_ms_per_call": 1e3 * st["merge_s"] / calls, "device_ms_per_call": st["device_ms"] / calls,
+                         "worker_ms_per_call": 1e3 * st["call_s"] / calls, "spp_per_s": calls / st["wall_s"]}
+                    ref_sig["%s_%d_threads" % (key, workers)] = r
+                    if key == "colour_only" and (best is None or r["value"] > best["value"]):
+                        best = r
+            ref_sig["value"], ref_sig["unit"], ref_sig["threads"] = best["value"], "Mrays/s", best["threads"]
         except Exception as e:
             ref_sig = {"status": "FAILED: %s" % e}
 

@@ -288,6 +288,9 @@ class AccumulationBuffer {
     void merge_tile(const Tile &tile, const AccumulationBuffer &src);
     UploadVector<double> colour, colour_sum, colour_bias; // 3 per pixel (XYZ)
     UploadVector<double> weight, weight_bias;             // 1 per pixel
+    // > 0: a buffer rendered with RenderOptions::kahan_state = false -- every pixel carries this weight (the samples per pixel of
+    // the call; hit or miss, each sample enters update_pixel with weight 1.0, camera.rs:121-127) and `weight` is left empty
+    double uniform_weight = 0.0;
 
   private:
     friend AccumulationBuffer partial_render_scene(const Scene &, Tile, size_t, size_t, const struct RenderOptions &);
@@ -316,9 +319,10 @@ struct RenderOptions {
     uint32_t bvh_filter = VRJ_FILTER_F32;
     uint32_t sample_stride = 1;
     int device = 0;
-    // false: the returned buffer carries only `colour` and `weight` -- all that merge_tile (accumulation_buffer.rs:62-85) and
-    // to_image_rgb_u8 read; the Kahan arrays (colour_sum, colour_bias, weight_bias: 7 of the 11 doubles per pixel) stay empty
-    // and are not copied back.  Such a buffer cannot be continued with update_pixel.
+    // false: the returned buffer carries only `colour` and one weight for all pixels (`uniform_weight`) -- all that merge_tile
+    // (accumulation_buffer.rs:62-85) and to_image_rgb_u8 read; the per-pixel weights and the Kahan arrays (8 of the 11 doubles
+    // per pixel) stay empty and are not copied back: 50 MB instead of 182 MB per 1080p call.  Such a buffer cannot be continued
+    // with update_pixel.
     bool kahan_state = true;
     std::vector<DirectionalLight> lights; // Whitted
     Spectrum ambient_light = Spectrum::black();

@@ -1,0 +1,20 @@
+"""The reference's calling pattern (main.rs:192-217: worker threads x 1-spp partial_render_scene + merge_tile on the calling
+thread) at several worker counts: wall time per call and where it goes.  python tools/ref_signature_scaling.py [calls]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import vanrijn_b200 as V
+from vanrijn_b200 import scenes, host
+calls = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+hs = V.build_scene(scenes.scene_main(subdivisions=6, obj=True))
+W, H = 1920, 1080
+for kahan in (False, True):
+    for workers in (1, 2, 4, 8, 12):
+        host.render_like_main(hs, W, H, 2 * workers, workers, kahan_state=kahan)   # warm-up
+        colour, weight, st = host.render_like_main(hs, W, H, calls, workers, kahan_state=kahan)
+        assert np.all(weight == calls)
+        print("%s workers %2d: %.2f ms/call  %.0f Mrays/s | merge %.2f ms/call, worker wall %.2f ms/call (/%d = %.2f), device events %.2f ms/call, D2H %.0f MB/call" % (
+            "five arrays " if kahan else "colour+weight", workers, 1e3 * st["wall_s"] / calls, st["rays"] / st["wall_s"] / 1e6,
+            1e3 * st["merge_s"] / calls, 1e3 * st["call_s"] / calls, workers, 1e3 * st["call_s"] / calls / workers,
+            st["device_ms"] / calls, st["bytes_to_host"] / calls / 1e6), flush=True)

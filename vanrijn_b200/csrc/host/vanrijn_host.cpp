@@ -460,7 +460,7 @@ AccumulationBuffer::AccumulationBuffer(size_t width, size_t height)
 
 AccumulationBuffer::AccumulationBuffer(size_t width, size_t height, Uninitialized, bool kahan_state)
     : colour(3 * width * height), colour_sum(kahan_state ? 3 * width * height : 0), colour_bias(kahan_state ? 3 * width * height : 0),
-      weight(width * height), weight_bias(kahan_state ? width * height : 0), width_(width), height_(height) {}
+      weight(kahan_state ? width * height : 0), weight_bias(kahan_state ? width * height : 0), width_(width), height_(height) {}
 
 ImageRgbU8 AccumulationBuffer::to_image_rgb_u8(int device) const {
     ImageRgbU8 image(width_, height_);
@@ -617,11 +617,13 @@ class RowPool {
 void AccumulationBuffer::merge_tile(const Tile &tile, const AccumulationBuffer &src) {
     if (tile.width() != src.width() || tile.height() != src.height()) throw std::runtime_error("merge_tile: tile and source sizes differ");
     if (tile.end_row > height_ || tile.end_column > width_) throw std::runtime_error("merge_tile: tile outside the buffer");
+    if (weight.empty()) throw std::runtime_error("merge_tile: the destination needs per-pixel weights");
+    const bool uniform_src = src.weight.empty(); // a colour-only tile: one weight for all its pixels
     auto rows = [&](size_t r0, size_t r1) {
         for (size_t i = r0; i < r1; i++)
             for (size_t j = 0; j < tile.width(); j++) {
                 size_t d = (tile.start_row + i) * width_ + tile.start_column + j, s = i * src.width_ + j;
-                double w1 = weight[d], w2 = src.weight[s];
+                double w1 = weight[d], w2 = uniform_src ? src.uniform_weight : src.weight[s];
                 double inv = 1.0 / (w1 + w2); // accumulation_buffer.rs:81-85
                 for (int k = 0; k < 3; k++) colour[3 * d + k] = (colour[3 * d + k] * w1 + src.colour[3 * s + k] * w2) * inv;
                 weight[d] += w2;
@@ -829,9 +831,8 @@ AccumulationBuffer partial_render_scene(const Scene &scene, Tile tile, size_t he
     out.stats = o.stats;
     if (vrj_render_tile(dev, &t, height, width, &p, &out) != VRJ_OK) throw std::runtime_error(std::string("vrj_render_tile: ") + vrj_last_error());
     // A fresh buffer's weight is known without asking the device: every sample, hit or miss, enters update_pixel with weight
-    // 1.0 (camera.rs:121-127) and a sum of spp ones is exact, so the colour-and-weight-only buffer brings back the colours
-    // alone (a quarter less over PCIe per call) and the weights are written here
-    if (!full_state && o.spp) std::fill(buffer.weight.begin(), buffer.weight.end(), (double)o.spp);
+    // 1.0 (camera.rs:121-127) and a sum of spp ones is exact, so the colour-only buffer brings back the colours alone
+    if (!full_state) buffer.uniform_weight = (double)o.spp;
     return buffer;
 }
 

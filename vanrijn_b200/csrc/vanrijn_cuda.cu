@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
 #include <thread>
 #include <unordered_map>
 #include <limits>
@@ -37,34 +38,10 @@ extern template VrjStatus run_batch<double, double, true>(const VrjScene *, Scra
 extern template VrjStatus run_batch<float, float, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
 extern template VrjStatus run_batch<float, float, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
 } // namespace vrjimpl
-// NVTX (optional): nvtxRangePushA / nvtxRangePop from libnvToolsExt.so.1, looked up once when VRJ_NVTX is set
-namespace {
-struct NvtxApi {
-    int (*push)(const char *) = nullptr;
-    int (*pop)() = nullptr;
-    NvtxApi() {
-        if (!std::getenv("VRJ_NVTX")) return;
-        for (const char *name : {"libnvToolsExt.so.1", "libnvToolsExt.so"}) {
-            if (void *lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL)) {
-                push = reinterpret_cast<int (*)(const char *)>(dlsym(lib, "nvtxRangePushA"));
-                pop = reinterpret_cast<int (*)()>(dlsym(lib, "nvtxRangePop"));
-                if (push && pop) return;
-                push = nullptr, pop = nullptr;
-            }
-        }
-    }
-};
-const NvtxApi &nvtx_api() {
-    static NvtxApi api;
-    return api;
-}
-} // namespace
-void vrj_nvtx_push(const char *name) {
-    if (nvtx_api().push) nvtx_api().push(name);
-}
-void vrj_nvtx_pop() {
-    if (nvtx_api().pop) nvtx_api().pop();
-}
+// NVTX ranges through the header-only NVTX 3: no library to link or load -- the calls are no-ops until a
+// tool (ncu --nvtx, nsys) injects itself
+void vrj_nvtx_push(const char *name) { nvtxRangePushA(name); }
+void vrj_nvtx_pop() { nvtxRangePop(); }
 // other translation units of the library (vrj_bvh_build.cu) report through the same thread-local message
 void vrj_set_error(const std::string &msg) { g_error = msg; }
 
@@ -445,6 +422,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     DeviceGuard device_guard;
     if (!out) return fail(VRJ_ERR_INVALID_ARGUMENT, "out is NULL");
     *out = nullptr;
+    VRJ_NVTX_RANGE(create_range, "vrj_scene_create");
     auto t_start = std::chrono::steady_clock::now();
     VrjStatus st = validate(d);
     if (st != VRJ_OK) return st;
@@ -898,6 +876,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     const uint64_t npix = tw * th;
     DeviceGuard device_guard;
     static const bool timing = std::getenv("VRJ_TIMING") != nullptr;
+    VRJ_NVTX_RANGE(call_range, "vrj_render_tile");
     const auto t_call0 = std::chrono::steady_clock::now();
     if (out->stats) std::memset(out->stats, 0, sizeof(VrjStats));
     if (npix == 0 || p->spp == 0) return VRJ_OK;

@@ -13,8 +13,7 @@
 #include <unordered_map>
 #include <vector>
 
-// NVTX ranges around the wavefront stages: libnvToolsExt is resolved at run time and only when
-// VRJ_NVTX is set in the environment, so the library carries no link-time dependency and the ranges cost one branch.
+// NVTX ranges around the wavefront stages: header-only NVTX 3 (vanrijn_cuda.cu), no-ops unless a tool is attached.
 void vrj_nvtx_push(const char *name);
 void vrj_nvtx_pop();
 struct VrjNvtxRange {
@@ -208,6 +207,7 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
 #endif
     for (uint32_t k = 1; k <= levels; k++) {
         const int ci = k & 1, ni = (k + 1) & 1;
+        VRJ_NVTX_RANGE(level_range, "vrj level: tail / trace / shade");
 #if VRJ_SPLIT_STAGE
         k_stage<R, COUNT><<<g_st, 128, 0, s->stream>>>(sc->dev, s->queue(ci), qcount + k, ci ? tb1 : tb0, lcount + k, work_st + k, stats, tail_done);
         (*launches)++;
@@ -247,6 +247,7 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
             drain_pending = true;
         }
     }
+    VRJ_NVTX_RANGE(resolve_range, "vrj resolve");
     AccumDev acc;
     acc.colour = s->acc_colour.as<double>(), acc.sum = s->acc_sum.as<double>(), acc.bias = s->acc_bias.as<double>();
     acc.weight = s->acc_weight.as<double>(), acc.weight_bias = s->acc_wbias.as<double>();
