@@ -44,8 +44,11 @@ oracle:
 	$(MAKE) -s -C oracle
 
 # build/vanrijn: the reference's harness (src/main.rs) over the host mirror; build/drop_in_example: doc-test + bench scene
-examples: build/vanrijn build/drop_in_example
+examples: build/vanrijn build/drop_in_example build/merge_bench
 build/%: examples/%.cpp $(LIBDIR)/libvanrijn_host.so include/vanrijn.hpp
+	mkdir -p build
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lvanrijn_host -lvanrijn_cuda -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+build/merge_bench: tools/merge_bench.cpp $(LIBDIR)/libvanrijn_host.so include/vanrijn.hpp
 	mkdir -p build
 	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -lvanrijn_host -lvanrijn_cuda -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 build/vanrijn: examples/vanrijn_main.cpp $(LIBDIR)/libvanrijn_host.so include/vanrijn.hpp

@@ -489,9 +489,9 @@ def main():
                        "bounds_per_call": {"d2h_colour_only_bytes": npix * 24, "d2h_five_arrays_bytes": npix * 88,
                                            "merge_tile_bytes_read_written": npix * (32 + 24 + 32)}}
             best = None
-            for key, kahan, calls in (("colour_only", False, 96), ("five_arrays", True, 48)):
+            for key, kahan, calls in (("colour_only", False, 192), ("five_arrays", True, 48)):
                 for workers in (4, 8):
-                    host.render_like_main(hs, W, H, 2 * workers, workers, kahan_state=kahan, device=local)   # warm-up: scratch blocks, pinned pool
+                    host.render_like_main(hs, W, H, 6 * workers, workers, kahan_state=kahan, device=local)   # warm-up: scratch blocks, pinned pool
                     colour, weight, st = host.render_like_main(hs, W, H, calls, workers, kahan_state=kahan, device=local)
                     if not np.all(weight == calls):
                         raise AssertionError("merged weights differ from %d" % calls)

@@ -286,6 +286,10 @@ class AccumulationBuffer {
     size_t height() const { return height_; }
     // accumulation_buffer.rs:62-85 -- touches only colour and weight of the destination
     void merge_tile(const Tile &tile, const AccumulationBuffer &src);
+    // merge_tile(tile, *srcs[0]); merge_tile(tile, *srcs[1]); ... in ONE pass over the destination: per pixel the same
+    // operations in the same order (bit-identical), but the frame's colours and weights cross the memory bus once instead
+    // of once per buffer -- what main.rs:213-216 does when several messages are waiting in the channel
+    void merge_tiles(const Tile &tile, const std::vector<const AccumulationBuffer *> &srcs);
     UploadVector<double> colour, colour_sum, colour_bias; // 3 per pixel (XYZ)
     UploadVector<double> weight, weight_bias;             // 1 per pixel
     // > 0: a buffer rendered with RenderOptions::kahan_state = false -- every pixel carries this weight (the samples per pixel of
@@ -295,6 +299,8 @@ class AccumulationBuffer {
   private:
     friend AccumulationBuffer partial_render_scene(const Scene &, Tile, size_t, size_t, const struct RenderOptions &);
     friend class DeviceAccumulationBuffer;
+    friend struct MainLoopStats render_like_main(const struct Scene &, size_t, size_t, size_t, uint64_t, unsigned, const struct RenderOptions &, bool,
+                                                 AccumulationBuffer &);
     struct Uninitialized {};
     AccumulationBuffer(size_t width, size_t height, Uninitialized, bool kahan_state = true); // arrays about to be overwritten by a render
     size_t width_, height_;

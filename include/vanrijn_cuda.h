@@ -29,7 +29,12 @@
  *
  * Thread safety: a VrjScene is immutable after creation; vrj_render_tile / vrj_trace_rays
  * may be called concurrently from several host threads on one scene (mirrors the rayon
- * use at src/main.rs:197-209); each call uses its own stream and scratch block.
+ * use at src/main.rs:197-209); each call uses its own stream and scratch block.  At most a few
+ * calls render on one device at the same moment (a FIFO gate; the others' copies back to the
+ * host overlap), and small host-memory calls of the reference's kind (SimpleRandom, <= 4 samples,
+ * fresh buffer) that queue up behind it and differ only in sample indices and output buffers are
+ * rendered as ONE wavefront, each receiving bit for bit the buffer it would have received alone
+ * (VrjStats.coalesced_calls).
  */
 #ifndef VANRIJN_CUDA_H
 #define VANRIJN_CUDA_H
@@ -40,7 +45,7 @@
 extern "C" {
 #endif
 
-#define VRJ_ABI_VERSION 1
+#define VRJ_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VRJ_API __attribute__((visibility("default")))
@@ -209,6 +214,9 @@ typedef struct VrjStats {
     uint64_t staged_rays;                       /* rays that passed a BVH root pre-test and went through k_trace */
     double tail_ms;                             /* k_tail (all launches, including the no-op ones) */
     uint64_t tail_launches;
+    uint64_t coalesced_calls;                   /* calls that shared this call's wavefront (1 = alone).  When > 1 the ray counters
+                                                   and times above are this call's even share of the wavefront's totals (sums over
+                                                   the calls stay exact); see vrj_render_tile */
 } VrjStats;
 
 /* The five arrays of AccumulationBuffer (accumulation_buffer.rs:6-12), tile-local, row-major like

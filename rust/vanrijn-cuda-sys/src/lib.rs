@@ -4,7 +4,7 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_void};
 
-pub const VRJ_ABI_VERSION: u32 = 1;
+pub const VRJ_ABI_VERSION: u32 = 2;
 pub const VRJ_OK: i32 = 0;
 pub const VRJ_MAT_LAMBERTIAN: u32 = 0;
 pub const VRJ_MAT_PHONG: u32 = 1;
@@ -90,6 +90,7 @@ pub struct VrjStats {
     pub primary_launches: u64, pub bounce_launches: u64, pub resolve_launches: u64,
     pub shade_ms: f64, pub shade_launches: u64, pub staged_rays: u64,
     pub tail_ms: f64, pub tail_launches: u64,
+    pub coalesced_calls: u64,
 }
 
 #[repr(C)]

@@ -287,6 +287,46 @@ def test_concurrent_calls_on_one_scene():
         assert np.array_equal(got[i], serial[i])
 
 
+def test_coalesced_calls_bit_identical():
+    """Small host-memory calls that queue up behind a busy device are rendered as ONE wavefront (vanrijn_cuda.cu,
+    "coalesced calls"): every caller must still receive bit for bit the five arrays it would have received alone, the shared
+    wavefront's ray counters must add up, and at least one wavefront must really have been shared.  The stand-alone result
+    comes from the non-coalescing path (a call that also asks for its photons is never coalesced)."""
+    import threading
+    spec = scenes.scene_main(subdivisions=3, obj=False, variant="mixed")
+    hs = V.build_scene(spec)
+    W, H, tile = 320, 200, (16, 300, 8, 190)
+    hs.device_scene(0)
+    names = ("colour", "colour_sum", "colour_bias", "weight", "weight_bias")
+    n_calls = 12
+    spps = [1 + (i % 3) for i in range(n_calls)]           # calls of 1, 2 and 3 samples share wavefronts
+    offsets = [1000 + 7 * i for i in range(n_calls)]       # non-contiguous sample indices
+    alone = [hs.render(tile, H, W, spp=spps[i], max_depth=128, seed=5, sample_offset=offsets[i], want_photons=True) for i in range(n_calls)]
+    assert all(a["stats"].coalesced_calls == 1 for a in alone)
+    shared_seen = 0
+    for want in (names, ("colour",)):
+        for _ in range(3):
+            got = [None] * n_calls
+            start = threading.Barrier(n_calls)
+
+            def work(i):
+                start.wait()
+                got[i] = hs.render(tile, H, W, spp=spps[i], max_depth=128, seed=5, sample_offset=offsets[i], want=want)
+
+            threads = [threading.Thread(target=work, args=(i,)) for i in range(n_calls)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            for i in range(n_calls):
+                for k in want:
+                    assert np.array_equal(got[i][k], alone[i][k]), (i, k)
+            for k in ("primary_rays", "bounce_rays", "paths_missed", "paths_escaped", "paths_depth_limited"):
+                assert sum(getattr(g["stats"], k) for g in got) == sum(getattr(a["stats"], k) for a in alone), k
+            shared_seen = max(shared_seen, max(g["stats"].coalesced_calls for g in got))
+    assert shared_seen >= 2
+
+
 def test_deep_recursion_tail_kernel_matches_oracle():
     """Recursion limit 128 takes the k_tail path (remaining levels of a short queue finished in one launch):
     same per-sample results as the oracle's recursion, and far fewer launches than 2 x 128."""

@@ -22,7 +22,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     lib = capi.cuda()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vrj_abi_version() == 1
+    assert lib.vrj_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):
@@ -270,23 +270,25 @@ def test_tile_iterator_and_merge_tile_match_the_oracle():
         assert n == O.lib().orc_tile_iterator(w, h, ts, b, cap)
         assert list(a[:4 * n]) == list(b[:4 * n])
     rng = np.random.default_rng(1)
-    W, H, tile = 16, 12, (3, 7, 4, 9)
-    dc, dw = rng.random((H, W, 3)), rng.random((H, W)) + 0.1
-    sc_, sw = rng.random((5, 4, 3)), rng.random((5, 4)) + 0.1
-    got_c, got_w = dc.copy(), dw.copy()
-    t4 = (C.c_uint64 * 4)(*tile)
-    assert capi.host().vrjh_merge_tile(got_c.ctypes.data_as(capi.dp), got_w.ctypes.data_as(capi.dp), W, H, t4,
-                                       np.ascontiguousarray(sc_).ctypes.data_as(capi.dp), np.ascontiguousarray(sw).ctypes.data_as(capi.dp)) == 0
-    for i in range(5):
-        for j in range(4):
-            out = np.zeros(3)
-            O.lib().orc_accum_blend(dc[4 + i, 3 + j].copy().ctypes.data_as(O.dp), dw[4 + i, 3 + j],
-                                    sc_[i, j].copy().ctypes.data_as(O.dp), sw[i, j], out.ctypes.data_as(O.dp))
-            assert np.array_equal(got_c[4 + i, 3 + j], out)
-            assert got_w[4 + i, 3 + j] == dw[4 + i, 3 + j] + sw[i, j]
-    mask = np.ones((H, W), bool)
-    mask[4:9, 3:7] = False
-    assert np.array_equal(got_c[mask], dc[mask]) and np.array_equal(got_w[mask], dw[mask])
+    # widths 4 and 11: whole 4-pixel vectors, and vectors + a scalar remainder (the AVX2 row of merge_tile)
+    for W, H, tile in [(16, 12, (3, 7, 4, 9)), (16, 12, (1, 12, 2, 9))]:
+        tw, th = tile[1] - tile[0], tile[3] - tile[2]
+        dc, dw = rng.random((H, W, 3)), rng.random((H, W)) + 0.1
+        sc_, sw = rng.random((th, tw, 3)), rng.random((th, tw)) + 0.1
+        got_c, got_w = dc.copy(), dw.copy()
+        t4 = (C.c_uint64 * 4)(*tile)
+        assert capi.host().vrjh_merge_tile(got_c.ctypes.data_as(capi.dp), got_w.ctypes.data_as(capi.dp), W, H, t4,
+                                           np.ascontiguousarray(sc_).ctypes.data_as(capi.dp), np.ascontiguousarray(sw).ctypes.data_as(capi.dp)) == 0
+        for i in range(th):
+            for j in range(tw):
+                out = np.zeros(3)
+                O.lib().orc_accum_blend(dc[tile[2] + i, tile[0] + j].copy().ctypes.data_as(O.dp), dw[tile[2] + i, tile[0] + j],
+                                        sc_[i, j].copy().ctypes.data_as(O.dp), sw[i, j], out.ctypes.data_as(O.dp))
+                assert np.array_equal(got_c[tile[2] + i, tile[0] + j], out)
+                assert got_w[tile[2] + i, tile[0] + j] == dw[tile[2] + i, tile[0] + j] + sw[i, j]
+        mask = np.ones((H, W), bool)
+        mask[tile[2]:tile[3], tile[0]:tile[1]] = False
+        assert np.array_equal(got_c[mask], dc[mask]) and np.array_equal(got_w[mask], dw[mask])
     # a tile that leaves the destination is an error (the reference panics on the Array2D index, array2d.rs:58-66)
     t_bad = (C.c_uint64 * 4)(14, 18, 4, 9)
     assert capi.host().vrjh_merge_tile(got_c.ctypes.data_as(capi.dp), got_w.ctypes.data_as(capi.dp), W, H, t_bad,
@@ -399,3 +401,33 @@ def test_rust_sys_crate_declares_every_header_symbol():
     for const in re.findall(r"\b(VRJ_(?:FILTER|PRECISION|MEM|ITEM|MAT|INTEGRATOR|TONEMAP)_\w+)\s*=\s*(\d+)", header):
         m = re.search(r"pub const %s: u32 = (\d+);" % const[0], crate)
         assert m and m.group(1) == const[1], const
+
+
+def test_merge_tiles_equals_consecutive_merge_tile_calls():
+    """merge_tiles(tile, [a, b, c]) -- what the main.rs loop does with several waiting messages -- must equal
+    merge_tile(a); merge_tile(b); merge_tile(c) bit for bit (accumulation_buffer.rs:62-85 per pixel, in arrival order), for
+    buffers with per-pixel weights and for colour-only buffers that carry one weight; small (single-thread) and large tiles."""
+    rng = np.random.default_rng(9)
+    H = capi.host()
+    for W, Hh, tile in [(40, 30, (3, 34, 2, 29)), (700, 520, (20, 659, 10, 510))]:
+        tw, th = tile[1] - tile[0], tile[3] - tile[2]
+        t4 = (C.c_uint64 * 4)(*tile)
+        for n, uniform in [(1, False), (3, False), (5, True)]:
+            dc, dw = rng.random((Hh, W, 3)), rng.random((Hh, W)) + 0.1
+            sc_ = rng.random((n, th, tw, 3))
+            sw = np.full((n, th, tw), 2.0) if uniform else rng.random((n, th, tw)) + 0.1
+            seq_c, seq_w = dc.copy(), dw.copy()
+            for k in range(n):
+                assert H.vrjh_merge_tile(seq_c.ctypes.data_as(capi.dp), seq_w.ctypes.data_as(capi.dp), W, Hh, t4,
+                                         np.ascontiguousarray(sc_[k]).ctypes.data_as(capi.dp), np.ascontiguousarray(sw[k]).ctypes.data_as(capi.dp)) == 0
+            got_c, got_w = dc.copy(), dw.copy()
+            assert H.vrjh_merge_tiles(got_c.ctypes.data_as(capi.dp), got_w.ctypes.data_as(capi.dp), W, Hh, t4, n, sc_.ctypes.data_as(capi.dp),
+                                      None if uniform else sw.ctypes.data_as(capi.dp), 2.0) == 0
+            assert np.array_equal(got_c, seq_c) and np.array_equal(got_w, seq_w)
+            # and against the expression itself, in numpy (binary64, same order)
+            want_c, want_w = dc[tile[2]:tile[3], tile[0]:tile[1]].copy(), dw[tile[2]:tile[3], tile[0]:tile[1]].copy()
+            for k in range(n):
+                inv = 1.0 / (want_w + sw[k])
+                want_c = (want_c * want_w[..., None] + sc_[k] * sw[k][..., None]) * inv[..., None]
+                want_w = want_w + sw[k]
+            assert np.array_equal(got_c[tile[2]:tile[3], tile[0]:tile[1]], want_c) and np.array_equal(got_w[tile[2]:tile[3], tile[0]:tile[1]], want_w)

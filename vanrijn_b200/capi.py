@@ -102,7 +102,7 @@ class Stats(C.Structure):
                [("device_ms", C.c_double), ("primary_ms", C.c_double), ("bounce_ms", C.c_double), ("resolve_ms", C.c_double),
                 ("primary_launches", C.c_uint64), ("bounce_launches", C.c_uint64), ("resolve_launches", C.c_uint64),
                 ("shade_ms", C.c_double), ("shade_launches", C.c_uint64), ("staged_rays", C.c_uint64),
-                ("tail_ms", C.c_double), ("tail_launches", C.c_uint64)]
+                ("tail_ms", C.c_double), ("tail_launches", C.c_uint64), ("coalesced_calls", C.c_uint64)]
 
     @property
     def rays(self):
@@ -219,6 +219,8 @@ def host():
             L.vrjh_render_like_main.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
                                                 C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_int, dp, dp, dp]
         L.vrjh_merge_tile.argtypes = [dp, dp, C.c_uint64, C.c_uint64, u64p, dp, dp]
+        if hasattr(L, "vrjh_merge_tiles"):
+            L.vrjh_merge_tiles.argtypes = [dp, dp, C.c_uint64, C.c_uint64, u64p, C.c_uint32, dp, dp, C.c_double]
         L.vrjh_scene_save_cache.argtypes = [C.c_void_p, C.c_char_p]
         L.vrjh_scene_load_cache.restype = C.c_void_p
         L.vrjh_scene_load_cache.argtypes = [C.c_char_p]

@@ -260,6 +260,30 @@ int vrjh_merge_tile(double *dst_colour, double *dst_weight, uint64_t dst_w, uint
         std::memcpy(dst_weight, dst.weight.data(), dst_w * dst_h * sizeof(double));
     });
 }
+/* AccumulationBuffer::merge_tiles: `n` source buffers (concatenated in src_colour / src_weight) merged in order in one pass;
+ * src_weight == NULL: colour-only buffers that all carry `uniform_weight` */
+int vrjh_merge_tiles(double *dst_colour, double *dst_weight, uint64_t dst_w, uint64_t dst_h, const uint64_t tile[4], uint32_t n,
+                     const double *src_colour, const double *src_weight, double uniform_weight) {
+    return guarded([&] {
+        Tile t{(size_t)tile[0], (size_t)tile[1], (size_t)tile[2], (size_t)tile[3]};
+        const size_t npix = t.width() * t.height();
+        AccumulationBuffer dst(dst_w, dst_h);
+        std::memcpy(dst.colour.data(), dst_colour, 3 * dst_w * dst_h * sizeof(double));
+        std::memcpy(dst.weight.data(), dst_weight, dst_w * dst_h * sizeof(double));
+        std::vector<AccumulationBuffer> srcs;
+        for (uint32_t k = 0; k < n; k++) {
+            srcs.emplace_back(t.width(), t.height());
+            std::memcpy(srcs[k].colour.data(), src_colour + 3 * npix * k, 3 * npix * sizeof(double));
+            if (src_weight) std::memcpy(srcs[k].weight.data(), src_weight + npix * k, npix * sizeof(double));
+            else srcs[k].weight.clear(), srcs[k].uniform_weight = uniform_weight;
+        }
+        std::vector<const AccumulationBuffer *> ptrs;
+        for (const AccumulationBuffer &b : srcs) ptrs.push_back(&b);
+        dst.merge_tiles(t, ptrs);
+        std::memcpy(dst_colour, dst.colour.data(), 3 * dst_w * dst_h * sizeof(double));
+        std::memcpy(dst_weight, dst.weight.data(), dst_w * dst_h * sizeof(double));
+    });
+}
 /* save_scene_cache / load_scene_cache: the flattened scene on disk.  vrjh_scene_load_cache returns a new scene handle or NULL. */
 int vrjh_scene_save_cache(void *p, const char *path) {
     HostScene *h = static_cast<HostScene *>(p);

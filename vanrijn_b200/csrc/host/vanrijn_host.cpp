@@ -5,6 +5,9 @@
 #include "../../../include/vanrijn.hpp"
 
 #include <algorithm>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -574,7 +577,11 @@ class RowPool {
   private:
     RowPool() {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const unsigned n = std::min(15u, hw > 2 ? hw / 2 : 1u); // + the calling thread
+        // + the calling thread = half the cores: a 1080p merge runs at 180 GB/s with 8 threads and gains nothing from 16
+        // (build/merge_bench), and the other half stays free for the workers that enqueue the device's kernels -- a worker
+        // that loses its core while it launches a wavefront leaves the GPU idle
+        unsigned n = std::min(15u, hw > 3 ? hw / 2 - 1 : 1u);
+        if (const char *e = std::getenv("VRJ_MERGE_THREADS")) n = (unsigned)std::max(0, std::atoi(e) - 1); // experiments
         for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
     }
     ~RowPool() {
@@ -614,22 +621,85 @@ class RowPool {
 };
 } // namespace
 
-void AccumulationBuffer::merge_tile(const Tile &tile, const AccumulationBuffer &src) {
-    if (tile.width() != src.width() || tile.height() != src.height()) throw std::runtime_error("merge_tile: tile and source sizes differ");
+// One row of merge_tile (accumulation_buffer.rs:62-85) for `ns` source buffers applied in order: per pixel and buffer
+// inv = 1/(w1+w2); c = (c*w1 + s*w2)*inv per channel; w = w1+w2.  The destination's colour and weight are read and written
+// once whatever `ns` is.  On AVX2 hosts four pixels go through the same operations at once: the weights are expanded to one
+// value per channel with lane permutes, which turns the interleaved XYZ triples into three flat vectors.  Every lane performs
+// the same IEEE binary64 operation on the same operands as the scalar form (separate multiply and add: no FMA), so the result
+// is bit-identical (tests/test_host_cpu.py compares both paths with the oracle's blend).
+struct MergeSource {
+    const double *colour; // first pixel of the row
+    const double *weight; // NULL: `uniform`
+    double uniform;
+};
+static void merge_row_scalar(double *colour, double *weight, const MergeSource *src, size_t ns, size_t j0, size_t n) {
+    for (size_t j = j0; j < n; j++) {
+        double w1 = weight[j], c0 = colour[3 * j], c1 = colour[3 * j + 1], c2 = colour[3 * j + 2];
+        for (size_t k = 0; k < ns; k++) {
+            const double w2 = src[k].weight ? src[k].weight[j] : src[k].uniform;
+            const double inv = 1.0 / (w1 + w2); // accumulation_buffer.rs:81-85
+            const double *sc = src[k].colour + 3 * j;
+            c0 = (c0 * w1 + sc[0] * w2) * inv, c1 = (c1 * w1 + sc[1] * w2) * inv, c2 = (c2 * w1 + sc[2] * w2) * inv;
+            w1 += w2;
+        }
+        colour[3 * j] = c0, colour[3 * j + 1] = c1, colour[3 * j + 2] = c2, weight[j] = w1;
+    }
+}
+#if defined(__x86_64__)
+__attribute__((target("avx2")))
+static void merge_row_avx2(double *colour, double *weight, const MergeSource *src, size_t ns, size_t n) {
+    const __m256d one = _mm256_set1_pd(1.0);
+    size_t j = 0;
+    for (; j + 4 <= n; j += 4) {
+        __m256d w1 = _mm256_loadu_pd(weight + j);
+        __m256d c0 = _mm256_loadu_pd(colour + 3 * j), c1 = _mm256_loadu_pd(colour + 3 * j + 4), c2 = _mm256_loadu_pd(colour + 3 * j + 8);
+        for (size_t k = 0; k < ns; k++) {
+            const __m256d w2 = src[k].weight ? _mm256_loadu_pd(src[k].weight + j) : _mm256_set1_pd(src[k].uniform);
+            const __m256d sum = _mm256_add_pd(w1, w2), inv = _mm256_div_pd(one, sum);
+            const double *sc = src[k].colour + 3 * j;
+            // pixels a b c d -> channel vectors [a a a b] [b b c c] [c d d d]
+#define VRJ_BLEND(c, off, imm)                                                                                                   \
+    c = _mm256_mul_pd(_mm256_add_pd(_mm256_mul_pd(c, _mm256_permute4x64_pd(w1, imm)),                                            \
+                                    _mm256_mul_pd(_mm256_loadu_pd(sc + off), _mm256_permute4x64_pd(w2, imm))),                   \
+                      _mm256_permute4x64_pd(inv, imm))
+            VRJ_BLEND(c0, 0, 0x40);
+            VRJ_BLEND(c1, 4, 0xA5);
+            VRJ_BLEND(c2, 8, 0xFE);
+#undef VRJ_BLEND
+            w1 = sum;
+        }
+        _mm256_storeu_pd(weight + j, w1);
+        _mm256_storeu_pd(colour + 3 * j, c0), _mm256_storeu_pd(colour + 3 * j + 4, c1), _mm256_storeu_pd(colour + 3 * j + 8, c2);
+    }
+    merge_row_scalar(colour, weight, src, ns, j, n);
+}
+#endif
+static void merge_row(double *colour, double *weight, const MergeSource *src, size_t ns, size_t n) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !std::getenv("VRJ_MERGE_SCALAR");
+    if (avx2) return merge_row_avx2(colour, weight, src, ns, n);
+#endif
+    merge_row_scalar(colour, weight, src, ns, 0, n);
+}
+
+void AccumulationBuffer::merge_tile(const Tile &tile, const AccumulationBuffer &src) { merge_tiles(tile, {&src}); }
+
+void AccumulationBuffer::merge_tiles(const Tile &tile, const std::vector<const AccumulationBuffer *> &srcs) {
+    for (const AccumulationBuffer *src : srcs)
+        if (tile.width() != src->width() || tile.height() != src->height()) throw std::runtime_error("merge_tile: tile and source sizes differ");
     if (tile.end_row > height_ || tile.end_column > width_) throw std::runtime_error("merge_tile: tile outside the buffer");
     if (weight.empty()) throw std::runtime_error("merge_tile: the destination needs per-pixel weights");
-    const bool uniform_src = src.weight.empty(); // a colour-only tile: one weight for all its pixels
+    if (srcs.empty()) return;
     auto rows = [&](size_t r0, size_t r1) {
-        for (size_t i = r0; i < r1; i++)
-            for (size_t j = 0; j < tile.width(); j++) {
-                size_t d = (tile.start_row + i) * width_ + tile.start_column + j, s = i * src.width_ + j;
-                double w1 = weight[d], w2 = uniform_src ? src.uniform_weight : src.weight[s];
-                double inv = 1.0 / (w1 + w2); // accumulation_buffer.rs:81-85
-                for (int k = 0; k < 3; k++) colour[3 * d + k] = (colour[3 * d + k] * w1 + src.colour[3 * s + k] * w2) * inv;
-                weight[d] += w2;
-            }
+        std::vector<MergeSource> ms(srcs.size());
+        for (size_t i = r0; i < r1; i++) {
+            const size_t d = (tile.start_row + i) * width_ + tile.start_column, s = i * tile.width();
+            for (size_t k = 0; k < srcs.size(); k++) // a colour-only tile carries one weight for all its pixels
+                ms[k] = MergeSource{srcs[k]->colour.data() + 3 * s, srcs[k]->weight.empty() ? nullptr : srcs[k]->weight.data() + s, srcs[k]->uniform_weight};
+            merge_row(colour.data() + 3 * d, weight.data() + d, ms.data(), ms.size(), tile.width());
+        }
     };
-    // pixels are independent: big tiles are merged by the resident row pool (a 1080p frame: 9 ms on one thread)
+    // pixels are independent: big tiles are merged by the resident row pool
     if (tile.width() * tile.height() < (size_t(1) << 18)) return rows(0, tile.height());
     RowPool::instance().run(tile.height(), rows);
 }
@@ -850,6 +920,14 @@ MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, 
     if (tiles.empty() || calls == 0) return total;
     workers = std::max(1u, workers);
     device_scene(scene, options.device); // flatten + upload before the clock starts (main.rs builds the scene first)
+    {
+        // The buffers partial_render_scene returns live in pooled page-locked memory.  Up to three per worker exist at the same
+        // moment (being rendered, waiting in the channel, being merged); growing the pool costs ~40 ms of cudaMallocHost per
+        // buffer during which the device cannot be fed, so the pool is brought to that size once, before the loop starts.
+        std::vector<AccumulationBuffer> warm;
+        const size_t want = (size_t)std::min<uint64_t>(calls, 3ull * workers);
+        for (size_t i = 0; i < want; i++) warm.push_back(AccumulationBuffer(tiles[0].width(), tiles[0].height(), AccumulationBuffer::Uninitialized{}, options.kahan_state));
+    }
     struct Item {
         Tile tile;
         AccumulationBuffer buffer;
@@ -902,17 +980,29 @@ MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, 
         });
     }
     for (;;) { // the 'running loop of main.rs:211-218 without the window
-        std::unique_ptr<Item> item;
+        // `for message in tile_rx.try_iter()` (main.rs:213): everything that is waiting is taken; messages for the same tile are
+        // merged in arrival order in one pass over the frame (merge_tiles == consecutive merge_tile calls, bit for bit)
+        std::vector<std::unique_ptr<Item>> items;
         {
             std::unique_lock<std::mutex> lock(m);
             ready.wait(lock, [&] { return !queue.empty() || live == 0; });
             if (queue.empty()) break;
-            item = std::move(queue.front());
-            queue.erase(queue.begin());
-            room.notify_one();
+            items.swap(queue);
+            room.notify_all();
         }
         const auto tm = std::chrono::steady_clock::now();
-        rendered_image.merge_tile(item->tile, item->buffer);
+        for (size_t i = 0; i < items.size();) {
+            std::vector<const AccumulationBuffer *> same{&items[i]->buffer};
+            size_t j = i + 1;
+            const Tile &t = items[i]->tile;
+            for (; j < items.size() && same.size() < 8; j++) {
+                const Tile &u = items[j]->tile;
+                if (u.start_column != t.start_column || u.end_column != t.end_column || u.start_row != t.start_row || u.end_row != t.end_row) break;
+                same.push_back(&items[j]->buffer);
+            }
+            rendered_image.merge_tiles(t, same);
+            i = j;
+        }
         total.merge_s += seconds(tm);
     }
     for (auto &t : pool) t.join();

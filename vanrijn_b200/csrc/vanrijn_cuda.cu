@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,12 +32,12 @@ thread_local std::string g_error;
 
 // the six instantiations live in vrj_batch_inst.cu (one object file each)
 namespace vrjimpl {
-extern template VrjStatus run_batch<float, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
-extern template VrjStatus run_batch<float, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
-extern template VrjStatus run_batch<double, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
-extern template VrjStatus run_batch<double, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
-extern template VrjStatus run_batch<float, float, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
-extern template VrjStatus run_batch<float, float, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *);
+extern template VrjStatus run_batch<float, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
+extern template VrjStatus run_batch<float, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
+extern template VrjStatus run_batch<double, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
+extern template VrjStatus run_batch<double, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
+extern template VrjStatus run_batch<float, float, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
+extern template VrjStatus run_batch<float, float, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
 } // namespace vrjimpl
 // NVTX ranges through the header-only NVTX 3: no library to link or load -- the calls are no-ops until a
 // tool (ncu --nvtx, nsys) injects itself
@@ -75,6 +76,15 @@ void vrj_pool_trim() {
     }
     cudaSetDevice(cur);
 }
+// allocations that went to the driver (VRJ_TIMING prints them at exit: in a steady state both stay flat)
+std::atomic<uint64_t> g_n_device_mallocs{0}, g_n_host_mallocs{0};
+struct AllocReport {
+    ~AllocReport() {
+        if (std::getenv("VRJ_TIMING"))
+            std::fprintf(stderr, "vanrijn_cuda: %llu cudaMalloc, %llu cudaMallocHost calls\n", (unsigned long long)g_n_device_mallocs.load(),
+                         (unsigned long long)g_n_host_mallocs.load());
+    }
+} g_alloc_report;
 cudaError_t vrj_pool_alloc(void **out, size_t bytes) {
     *out = nullptr;
     bytes = (std::max<size_t>(bytes, 256) + 255) & ~size_t(255);
@@ -99,6 +109,7 @@ cudaError_t vrj_pool_alloc(void **out, size_t bytes) {
         }
     }
     void *p = nullptr;
+    g_n_device_mallocs++;
     e = cudaMalloc(&p, bytes);
     if (e == cudaErrorMemoryAllocation) { // give the cached blocks back and try once more
         cudaGetLastError();
@@ -289,6 +300,60 @@ std::unordered_map<void *, size_t> g_host_pool_live;
 // 14 GB, one 64-spp block is 45 GB.  A caller is handed the smallest pooled block that is large enough, else the largest.
 size_t scratch_bytes(const Scratch *s) { return s->capacity * 240 + s->rec_capacity * sizeof(TraceRec) + s->npix * 88; }
 std::atomic<int> g_active_calls[64];
+
+// Render gate: how many calls may have their wavefronts on one device at the same moment.  main.rs:197-209 drives the entry
+// point from a pool of workers; every call's kernels are persistent grids sized to fill all 148 SMs, so eight of them
+// interleaved gain nothing over two and evict each other's queues from L2 (measured, 1-spp 1080p calls: 1.33 ms of device
+// time per call with two in flight, 1.73 with four, 2.07 with eight).  Callers past the gate's width wait their turn (FIFO)
+// before enqueueing; the gate opens again when the call's last kernel has finished, so its copy back to the host overlaps
+// the next caller's rendering.  VRJ_CONCURRENT_RENDERS overrides the width (experiments).
+struct RenderGate {
+    std::mutex m;
+    std::condition_variable cv;
+    int running = 0;
+    uint64_t next_ticket = 0, serving = 0;
+};
+RenderGate g_render_gate[64];
+int render_gate_width() {
+    static const int width = [] {
+        const char *e = std::getenv("VRJ_CONCURRENT_RENDERS");
+        return e ? std::max(1, std::atoi(e)) : 2;
+    }();
+    return width;
+}
+struct RenderTurn {
+    RenderGate &g;
+    bool held = false;
+    explicit RenderTurn(int device) : g(g_render_gate[(unsigned)device % 64]) {}
+    void acquire() {
+        std::unique_lock<std::mutex> lock(g.m);
+        const uint64_t ticket = g.next_ticket++;
+        g.cv.wait(lock, [&] { return ticket == g.serving && g.running < render_gate_width(); });
+        g.serving++, g.running++, held = true;
+        g.cv.notify_all();
+    }
+    void release() {
+        if (!held) return;
+        {
+            std::lock_guard<std::mutex> lock(g.m);
+            g.running--, held = false;
+        }
+        g.cv.notify_all();
+    }
+    ~RenderTurn() { release(); }
+};
+
+// Waiting for the device: a lone caller spins on the event (lowest latency); when several calls are in flight on the device
+// (main.rs's worker pool) a waiting thread sleeps until the GPU's interrupt instead -- eight workers spinning on their copies
+// would take the cores the host's merge_tile threads need (measured: the loop of main.rs:192-217 collapsed from 1.6 to 3-17 ms
+// per call once workers + merge threads exceeded the host's cores).  Events that may be slept on carry cudaEventBlockingSync.
+cudaError_t wait_event(cudaEvent_t e, int device) {
+    if (g_active_calls[(unsigned)device % 64].load(std::memory_order_relaxed) > 1) return cudaEventSynchronize(e);
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(e);
+        if (q != cudaErrorNotReady) return q;
+    }
+}
 Scratch *acquire_scratch(VrjScene *sc, size_t want_capacity) {
     std::lock_guard<std::mutex> g(g_pool_mutex);
     size_t best = g_pool.size();
@@ -324,21 +389,31 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t rec_capacity, size_
     if (!s->stream) {
         VRJ_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         VRJ_CUDA(cudaEventCreate(&s->ev0));
-        VRJ_CUDA(cudaEventCreate(&s->ev1));
+        VRJ_CUDA(cudaEventCreateWithFlags(&s->ev1, cudaEventBlockingSync)); // timing stays enabled; see wait_event
+        VRJ_CUDA(cudaEventCreateWithFlags(&s->ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
+        for (cudaEvent_t &e : s->call_ev) VRJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventBlockingSync | cudaEventDisableTiming));
         for (cudaEvent_t &e : s->drain_ev) VRJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        VRJ_CUDA(cudaMallocHost(&s->host_count, 64 * sizeof(uint32_t)));
+        VRJ_CUDA(cudaMallocHost(&s->host_count, 256 * sizeof(uint32_t))); // drain-check slots + the sample table of coalesced calls
     }
     // every group below is all-or-nothing: a failed allocation leaves the group empty with its size field at 0 (never
     // half-sized or stale), so the block can go back to the pool and the caller can retry
-    auto alloc_group = [](std::vector<std::pair<DeviceBuffer *, size_t>> &want, const char *what) -> VrjStatus {
+    // ... and ONE allocation: cudaMalloc waits for a gap in the device's work, so with another caller's persistent kernels
+    // running the 25 buffers of a block cost 30 ms each (measured: 840 ms for the second block of a worker pool)
+    auto alloc_group = [](DeviceBuffer &slab, std::vector<std::pair<DeviceBuffer *, size_t>> &want, const char *what) -> VrjStatus {
         for (auto &w : want) w.first->release();
+        slab.release();
+        size_t total = 0;
+        for (auto &w : want) total += (w.second + 255) & ~size_t(255);
+        cudaError_t e = slab.alloc(total);
+        if (e != cudaSuccess) {
+            slab.release();
+            cudaGetLastError();
+            return fail(e == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        }
+        size_t at = 0;
         for (auto &w : want) {
-            cudaError_t e = w.first->alloc(w.second);
-            if (e != cudaSuccess) {
-                for (auto &v : want) v.first->release();
-                cudaGetLastError();
-                return fail(e == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
-            }
+            w.first->borrow(static_cast<char *>(slab.p) + at, w.second);
+            at += (w.second + 255) & ~size_t(255);
         }
         return VRJ_OK;
     };
@@ -350,7 +425,7 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t rec_capacity, size_
         want.push_back({&s->photons, capacity * sizeof(double2)});
         for (int i = 0; i < 2; i++) want.push_back({&s->hits[i], capacity * sizeof(int2)}), want.push_back({&s->tbest[i], capacity * sizeof(double)});
         want.push_back({&s->list, capacity * sizeof(uint32_t)});
-        VrjStatus st = alloc_group(want, "path queues");
+        VrjStatus st = alloc_group(s->queue_slab, want, "path queues");
         if (st != VRJ_OK) {
             if (queue_oom) *queue_oom = st == VRJ_ERR_OUT_OF_MEMORY;
             return st;
@@ -360,7 +435,7 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t rec_capacity, size_
     if (s->rec_capacity < rec_capacity) {
         s->rec_capacity = 0;
         std::vector<std::pair<DeviceBuffer *, size_t>> want = {{&s->recs, rec_capacity * sizeof(TraceRec)}};
-        VrjStatus st = alloc_group(want, "trace records");
+        VrjStatus st = alloc_group(s->rec_slab, want, "trace records");
         if (st != VRJ_OK) {
             if (queue_oom) *queue_oom = st == VRJ_ERR_OUT_OF_MEMORY;
             return st;
@@ -371,15 +446,18 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t rec_capacity, size_
         s->npix = 0;
         std::vector<std::pair<DeviceBuffer *, size_t>> want = {{&s->acc_colour, npix * 24}, {&s->acc_sum, npix * 24}, {&s->acc_bias, npix * 24},
                                                                {&s->acc_weight, npix * 8}, {&s->acc_wbias, npix * 8}};
-        VrjStatus st = alloc_group(want, "accumulators");
+        VrjStatus st = alloc_group(s->acc_slab, want, "accumulators");
         if (st != VRJ_OK) return st;
         s->npix = npix;
     }
     if (s->steps < steps) {
         s->steps = 0;
-        std::vector<std::pair<DeviceBuffer *, size_t>> want = {{&s->counters, ((size_t)steps * 5 + 4) * sizeof(uint32_t)}};
-        VrjStatus st = alloc_group(want, "level counters");
-        if (st != VRJ_OK) return st;
+        cudaError_t e = s->counters.alloc(((size_t)steps * 5 + 4) * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            s->counters.release();
+            cudaGetLastError();
+            return fail(e == cudaErrorMemoryAllocation ? VRJ_ERR_OUT_OF_MEMORY : VRJ_ERR_CUDA, std::string("level counters: ") + cudaGetErrorString(e));
+        }
         s->steps = steps;
     }
     if (!s->stats.p) VRJ_CUDA(s->stats.alloc(ST_COUNT * sizeof(unsigned long long)));
@@ -394,6 +472,27 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t rec_capacity, size_
     return VRJ_OK;
 }
 
+// the per-call constants of the kernels (camera.rs:24-34 for the film size)
+RenderConst make_render_const(const VrjTile *tile, uint64_t height, uint64_t width, const VrjRenderParams *p) {
+    RenderConst rc{};
+    rc.width = width, rc.height = height;
+    rc.start_column = tile->start_column, rc.start_row = tile->start_row;
+    rc.tile_w = (uint32_t)(tile->end_column - tile->start_column), rc.tile_h = (uint32_t)(tile->end_row - tile->start_row);
+    rc.npix = rc.tile_w * rc.tile_h;
+    rc.sample_stride = p->sample_stride ? p->sample_stride : 1;
+    rc.seed = p->seed;
+    rc.max_depth = p->max_depth, rc.n_lights = p->n_lights, rc.has_ambient = p->ambient_light ? 1u : 0u;
+    // binary32 cannot represent origin + 1e-7 * direction at scene scale (ulp(5) = 4.8e-7): the fast mode needs a bias of a
+    // few hundred ulps or every bounce ray re-hits the surface it leaves
+    rc.bias = p->precision == VRJ_PRECISION_F32_FAST ? std::max(p->bias, 1e-4) : p->bias;
+    { // camera.rs:24-34
+        double w = (double)width, h = (double)height;
+        if (w > h) rc.film_w = w / h, rc.film_h = 1.0;
+        else rc.film_w = 1.0, rc.film_h = w / h;
+    }
+    return rc;
+}
+
 void fill_stats(VrjStats *st, const unsigned long long *h, uint64_t launches, float ms) {
     st->primary_rays = h[ST_PRIMARY], st->bounce_rays = h[ST_BOUNCE], st->shadow_rays = h[ST_SHADOW];
     st->paths_missed = h[ST_MISSED], st->paths_escaped = h[ST_ESCAPED], st->paths_depth_limited = h[ST_LIMITED];
@@ -401,6 +500,248 @@ void fill_stats(VrjStats *st, const unsigned long long *h, uint64_t launches, fl
     st->staged_rays = h[ST_STAGED];
     st->kernel_launches = launches;
     st->device_ms = ms;
+}
+
+
+// ---------------------------------------------------------------------------------------------- coalesced calls
+// main.rs:197-209 calls partial_render_scene once per one-sample pass from a pool of workers.  Each such call is a small
+// wavefront (2 M paths at 1080p) whose ~28 launches do not fill 148 SMs: 1.7 ms of device time against 0.52 ms per sample
+// when 64 samples share a wavefront.  Calls that arrive while the device is busy and differ only in their sample indices and
+// output buffers are therefore rendered TOGETHER: one of the waiting callers (the leader) takes its turn at the render gate,
+// collects every compatible caller that has queued up behind it, runs one wavefront over all their samples (the batch's slots
+// carry their sample indices in a table, RenderConst::sample_table), resolves each call's samples into that call's own
+// fresh buffer (k_resolve_multi) and copies every buffer back.  A sample is a pure function of (seed, pixel, sample index)
+// and each call's samples are applied to its buffer in sample order, so every caller receives bit for bit what it would have
+// received alone (tests/test_gpu_parity.py::test_coalesced_calls_bit_identical).  The ray counters of a shared wavefront are
+// split evenly over its calls (the remainder goes to the first; sums stay exact) and VrjStats.coalesced_calls says how many
+// shared it.  VRJ_COALESCE=0 turns this off (experiments).
+struct CoalesceRequest {
+    const VrjScene *scene;
+    VrjTile tile;
+    uint64_t height, width;
+    VrjRenderParams params;
+    VrjAccumOut *out;
+    VrjStatus status = VRJ_OK;
+    std::string error;
+    bool done = false;     // a leader failed before launching anything: `status` / `error` say why
+    bool launched = false; // rendered by a leader: stats are filled, the buffers are on their way, `wait_ev` fires on arrival
+    cudaEvent_t wait_ev = nullptr;
+    uint32_t wanted() const {
+        return (out->colour ? 1u : 0u) | (out->colour_sum ? 2u : 0u) | (out->colour_bias ? 4u : 0u) | (out->weight ? 8u : 0u) | (out->weight_bias ? 16u : 0u);
+    }
+    bool compatible(const CoalesceRequest &o) const {
+        return scene == o.scene && tile.start_column == o.tile.start_column && tile.end_column == o.tile.end_column &&
+               tile.start_row == o.tile.start_row && tile.end_row == o.tile.end_row && height == o.height && width == o.width &&
+               params.max_depth == o.params.max_depth && params.seed == o.params.seed && params.bvh_filter == o.params.bvh_filter &&
+               params.precision == o.params.precision && params.bias == o.params.bias &&
+               (params.sample_stride ? params.sample_stride : 1u) == (o.params.sample_stride ? o.params.sample_stride : 1u) && wanted() == o.wanted();
+    }
+};
+struct Coalescer {
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<CoalesceRequest *> waiting;
+    bool collecting = false; // a leader is waiting for its turn at the gate; arrivals pile up behind it
+};
+Coalescer g_coalescer[64];
+constexpr uint64_t kCoalesceMaxPaths = uint64_t(1) << 25; // 32 Mi paths = 11 GB of queue state per shared wavefront
+
+bool coalescing_enabled() {
+    static const bool on = [] {
+        const char *e = std::getenv("VRJ_COALESCE");
+        return !e || std::atoi(e) != 0;
+    }();
+    return on;
+}
+bool coalescable(const VrjRenderParams *p, const VrjAccumOut *out, uint64_t npix) {
+    return coalescing_enabled() && out->memory == VRJ_MEM_HOST && !out->accumulate && !out->photons && !out->srgb8 && out->colour &&
+           p->integrator == VRJ_INTEGRATOR_SIMPLE_RANDOM && p->n_lights == 0 && !p->ambient_light && !p->count_traversal &&
+           p->spp >= 1 && p->spp <= 4 && npix * p->spp * 2 <= kCoalesceMaxPaths;
+}
+
+// one wavefront for `n` compatible requests; fills their buffers and stats; the status applies to all of them
+VrjStatus render_group(Coalescer &co, CoalesceRequest *const *reqs, uint32_t n, RenderTurn &turn, bool *published) {
+    static const bool timing = std::getenv("VRJ_TIMING") != nullptr;
+    const auto t1 = std::chrono::steady_clock::now();
+    const CoalesceRequest &r0 = *reqs[0];
+    VrjScene *scene = const_cast<VrjScene *>(r0.scene);
+    const VrjRenderParams *p = &r0.params;
+    RenderConst rc = make_render_const(&r0.tile, r0.height, r0.width, p);
+    const uint64_t npix = rc.npix;
+    uint32_t total = 0;
+    MultiCalls mc{};
+    mc.n = n, mc.full = (r0.wanted() & ~1u) ? 1u : 0u;
+    std::vector<uint64_t> table;
+    for (uint32_t c = 0; c < n; c++) {
+        mc.first[c] = total, mc.count[c] = reqs[c]->params.spp;
+        for (uint32_t i = 0; i < reqs[c]->params.spp; i++) table.push_back(reqs[c]->params.sample_offset + (uint64_t)i * rc.sample_stride);
+        total += reqs[c]->params.spp;
+    }
+    VRJ_NVTX_RANGE(call_range, "vrj_render_tile (coalesced)");
+    // group sizes vary from wavefront to wavefront: blocks are sized in steps of eight 1-sample calls so that a block taken
+    // from the pool almost never has to grow (growing re-allocates every queue: tens of milliseconds)
+    const size_t capacity = npix * (size_t)((total + 7u) / 8u * 8u);
+    Scratch *s = acquire_scratch(scene, capacity);
+    struct Releaser {
+        VrjScene *sc;
+        Scratch *s;
+        ~Releaser() {
+            if (s->stream) cudaStreamSynchronize(s->stream);
+            release_scratch(sc, s);
+        }
+    } releaser{scene, s};
+    const bool records = p->precision == VRJ_PRECISION_F64 && p->bvh_filter == VRJ_FILTER_F32 && scene->trace_records && scene->dev.n_bvh_items > 0;
+    VrjStatus st = ensure_scratch(s, capacity, records ? capacity : 0, 0, p->max_depth + 3, 0, 0);
+    if (st == VRJ_ERR_OUT_OF_MEMORY) { // fall back to exactly what this wavefront needs
+        vrj_pool_trim();
+        st = ensure_scratch(s, npix * total, records ? npix * total : 0, 0, p->max_depth + 3, 0, 0);
+    }
+    if (st != VRJ_OK) return st;
+    const auto t1b = std::chrono::steady_clock::now();
+    const size_t per_call = npix * (mc.full ? 11 : 3) * sizeof(double);
+    if (s->multi_out.bytes < per_call * n || !s->multi_out.p) {
+        s->multi_out.release();
+        VRJ_CUDA(s->multi_out.alloc(per_call * MULTI_MAX_CALLS)); // sized once for the largest group
+    }
+    if (!s->sample_table.p) VRJ_CUDA(s->sample_table.alloc(4 * MULTI_MAX_CALLS * sizeof(uint64_t)));
+    double *base = s->multi_out.as<double>();
+    mc.out.colour = base;
+    if (mc.full) {
+        mc.out.sum = base + 3 * npix * n, mc.out.bias = base + 6 * npix * n;
+        mc.out.weight = base + 9 * npix * n, mc.out.weight_bias = base + 10 * npix * n;
+    }
+    // the table goes through the block's pinned slot (entries 8.. of host_count; the drain check uses 0..3)
+    uint64_t *pinned_table = reinterpret_cast<uint64_t *>(s->host_count + 8);
+    std::memcpy(pinned_table, table.data(), table.size() * sizeof(uint64_t));
+    VRJ_CUDA(cudaMemcpyAsync(s->sample_table.p, pinned_table, table.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+    VRJ_CUDA(cudaMemsetAsync(s->stats.p, 0, ST_COUNT * sizeof(unsigned long long), s->stream));
+    rc.sample_table = s->sample_table.as<uint64_t>();
+    rc.lights = s->lights.as<LightDev>(), rc.light_samples = s->light_samples.as<double>();
+    rc.batch_samples = total;
+    rc.div_batch = FastDiv::make(total), rc.div_tile_w = FastDiv::make(rc.tile_w);
+    rc.first_sample = 0;
+    const int quad = p->bvh_filter == VRJ_FILTER_F32X4 ? 1 : p->bvh_filter == VRJ_FILTER_Q16 ? 2 : 0;
+    uint64_t launches = 0;
+    s->n_marks = 0;
+    VRJ_CUDA(cudaEventRecord(s->ev0, s->stream));
+    st = p->precision == VRJ_PRECISION_F32_FAST ? run_batch<float, float, false>(scene, s, rc, false, 0, &launches, &mc)
+         : p->bvh_filter == VRJ_FILTER_F64     ? run_batch<double, double, false>(scene, s, rc, false, 0, &launches, &mc)
+                                               : run_batch<float, double, false>(scene, s, rc, false, quad, &launches, &mc);
+    if (st != VRJ_OK) return st;
+    unsigned long long *hstats = reinterpret_cast<unsigned long long *>(s->host_count + 160); // pinned, see vrj_render_tile
+    VRJ_CUDA(cudaMemcpyAsync(hstats, s->stats.p, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    VRJ_CUDA(cudaEventRecord(s->ev1, s->stream));
+    // every call's arrays cross PCIe behind an event of their own, the leader's (call 0) last: a caller returns as soon as ITS
+    // buffer has arrived, so the host's merge of the first buffer overlaps the copies of the others
+    const double *dev_arr[5] = {mc.out.colour, mc.out.sum, mc.out.bias, mc.out.weight, mc.out.weight_bias};
+    const size_t per[5] = {3, 3, 3, 1, 1};
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t c = (k + 1) % n;
+        double *user[5] = {reqs[c]->out->colour, reqs[c]->out->colour_sum, reqs[c]->out->colour_bias, reqs[c]->out->weight, reqs[c]->out->weight_bias};
+        for (int i = 0; i < 5; i++)
+            if (user[i]) VRJ_CUDA(cudaMemcpyAsync(user[i], dev_arr[i] + (size_t)c * npix * per[i], npix * per[i] * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        VRJ_CUDA(cudaEventRecord(s->call_ev[c], s->stream));
+    }
+    const auto t2 = std::chrono::steady_clock::now();
+    VRJ_CUDA(wait_event(s->ev1, scene->device));
+    turn.release(); // the next wavefront may start while this one's buffers cross PCIe
+    float ms = 0.f;
+    VRJ_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    double cls_ms[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t cls_n[6] = {0, 0, 0, 0, 0, 0};
+    for (size_t i = 1; i < s->n_marks; i++) {
+        int c = s->mark_class[i];
+        float seg = 0.f;
+        if (c >= 0 && cudaEventElapsedTime(&seg, s->marks[i - 1], s->marks[i]) == cudaSuccess) cls_ms[c] += seg, cls_n[c]++;
+    }
+    for (uint32_t c = 0; c < n; c++) {
+        VrjStats *o = reqs[c]->out->stats;
+        if (!o) continue;
+        unsigned long long share[ST_COUNT];
+        for (int k = 0; k < ST_COUNT; k++) share[k] = hstats[k] / n + (c == 0 ? hstats[k] % n : 0);
+        std::memset(o, 0, sizeof *o);
+        fill_stats(o, share, launches, ms / (float)n); // device time: the call's share of the wavefront
+        o->primary_ms = cls_ms[0] / n, o->bounce_ms = cls_ms[1] / n, o->resolve_ms = cls_ms[2] / n;
+        o->shade_ms = (cls_ms[3] + cls_ms[4]) / n, o->tail_ms = cls_ms[5] / n;
+        o->primary_launches = cls_n[0], o->bounce_launches = cls_n[1], o->resolve_launches = cls_n[2];
+        o->shade_launches = cls_n[3] + cls_n[4], o->tail_launches = cls_n[5];
+        o->coalesced_calls = n;
+    }
+    // the other callers wait for their own buffers from here on
+    {
+        std::lock_guard<std::mutex> lock(co.m);
+        for (uint32_t c = 1; c < n; c++) reqs[c]->wait_ev = s->call_ev[c], reqs[c]->launched = true;
+        *published = true; // from here on those requests belong to their callers again
+    }
+    co.cv.notify_all();
+    VRJ_CUDA(wait_event(s->call_ev[0], scene->device)); // recorded last: everything queued on the stream has finished
+    if (timing) {
+        auto msd = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        std::fprintf(stderr, "vrj_render_tile (coalesced): %u calls, %u samples: scratch %.3f ms, enqueue %.3f ms, wait %.3f ms (device %.3f ms, %llu launches), mallocs %llu / %llu\n", n, total,
+                     msd(t1, t1b), msd(t1b, t2), msd(t2, std::chrono::steady_clock::now()), ms, (unsigned long long)launches,
+                     (unsigned long long)g_n_device_mallocs.load(), (unsigned long long)g_n_host_mallocs.load());
+    }
+    return VRJ_OK;
+}
+
+// entry of a coalescable call: queue up, then either be served by a leader or become one
+VrjStatus render_coalesced(const VrjScene *scene, const VrjTile *tile, uint64_t height, uint64_t width, const VrjRenderParams *p, VrjAccumOut *out) {
+    CoalesceRequest req;
+    req.scene = scene, req.tile = *tile, req.height = height, req.width = width, req.params = *p, req.out = out;
+    Coalescer &co = g_coalescer[(unsigned)scene->device % 64];
+    const uint64_t npix = (tile->end_column - tile->start_column) * (tile->end_row - tile->start_row);
+    std::unique_lock<std::mutex> lock(co.m);
+    co.waiting.push_back(&req);
+    co.cv.wait(lock, [&] { return req.done || req.launched || (!co.collecting && !co.waiting.empty() && co.waiting.front() == &req); });
+    if (req.launched) { // a leader rendered this call with its own and will not touch `req` again: wait for the buffers
+        const cudaEvent_t ev = req.wait_ev;
+        lock.unlock();
+        const cudaError_t e = wait_event(ev, scene->device);
+        if (e != cudaSuccess) return fail(VRJ_ERR_CUDA, std::string("coalesced call: ") + cudaGetErrorString(e));
+        return VRJ_OK;
+    }
+    if (req.done) { // the leader failed before anything was launched
+        vrj_set_error(req.error);
+        return req.status;
+    }
+    co.collecting = true;
+    lock.unlock();
+    RenderTurn turn(scene->device);
+    turn.acquire(); // callers that arrive while this one waits for the device join its wavefront
+    lock.lock();
+    std::vector<CoalesceRequest *> group{&req};
+    uint64_t paths = npix * p->spp;
+    for (size_t i = 0; i < co.waiting.size();) {
+        CoalesceRequest *w = co.waiting[i];
+        if (w == &req) {
+            co.waiting.erase(co.waiting.begin() + i);
+            continue;
+        }
+        if (group.size() < (size_t)MULTI_MAX_CALLS && w->compatible(req) && paths + npix * w->params.spp <= kCoalesceMaxPaths) {
+            paths += npix * w->params.spp;
+            group.push_back(w);
+            co.waiting.erase(co.waiting.begin() + i);
+            continue;
+        }
+        i++;
+    }
+    co.collecting = false;
+    lock.unlock();
+    co.cv.notify_all(); // the next caller in line may start collecting
+    bool published = false; // true once the other callers have been told to wait for their buffers (they may return at any moment)
+    const VrjStatus st = render_group(co, group.data(), (uint32_t)group.size(), turn, &published);
+    turn.release();
+    if (!published) {
+        const std::string err = st != VRJ_OK ? std::string(vrj_last_error()) : std::string("coalesced call: not rendered");
+        lock.lock();
+        for (CoalesceRequest *g : group)
+            if (g != &req) g->status = st != VRJ_OK ? st : VRJ_ERR_CUDA, g->error = err, g->done = true;
+        lock.unlock();
+        co.cv.notify_all();
+    }
+    return st;
 }
 
 } // namespace
@@ -805,6 +1146,7 @@ void *vrj_alloc_host(uint64_t bytes) {
         }
     }
     void *p = nullptr;
+    g_n_host_mallocs++;
     if (cudaMallocHost(&p, want) != cudaSuccess) {
         g_error = "cudaMallocHost failed";
         cudaGetLastError();
@@ -891,6 +1233,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         explicit ActiveCall(std::atomic<int> &c) : n(c), others(c.fetch_add(1)) {}
         ~ActiveCall() { n.fetch_sub(1); }
     } active(g_active_calls[(unsigned)scene->device % 64]);
+    if (coalescable(p, out, npix)) return render_coalesced(scene, tile, height, width, p, out);
     const uint64_t path_budget = std::max<uint64_t>(scene->path_budget / (uint64_t)(active.others + 1), std::min<uint64_t>(scene->path_budget, uint64_t(1) << 22));
     uint32_t batch = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(p->spp, path_budget / npix));
     if (npix * (uint64_t)batch > 0xfffffff0ull) return fail(VRJ_ERR_UNSUPPORTED, "tile too large");
@@ -956,21 +1299,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         VRJ_CUDA(cudaStreamSynchronize(s->stream)); // the staging vectors are locals
     }
 
-    RenderConst rc{};
-    rc.width = width, rc.height = height;
-    rc.start_column = tile->start_column, rc.start_row = tile->start_row;
-    rc.tile_w = (uint32_t)tw, rc.tile_h = (uint32_t)th, rc.npix = (uint32_t)npix;
-    rc.sample_stride = p->sample_stride ? p->sample_stride : 1;
-    rc.seed = p->seed;
-    rc.max_depth = p->max_depth, rc.n_lights = p->n_lights, rc.has_ambient = p->ambient_light ? 1u : 0u;
-    // binary32 cannot represent origin + 1e-7 * direction at scene scale (ulp(5) = 4.8e-7): the fast mode needs a bias of a
-    // few hundred ulps or every bounce ray re-hits the surface it leaves
-    rc.bias = p->precision == VRJ_PRECISION_F32_FAST ? std::max(p->bias, 1e-4) : p->bias;
-    { // camera.rs:24-34
-        double w = (double)width, h = (double)height;
-        if (w > h) rc.film_w = w / h, rc.film_h = 1.0;
-        else rc.film_w = 1.0, rc.film_h = w / h;
-    }
+    RenderConst rc = make_render_const(tile, height, width, p);
     rc.lights = s->lights.as<LightDev>();
     rc.light_samples = s->light_samples.as<double>();
 
@@ -980,6 +1309,8 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     const bool fast = p->precision == VRJ_PRECISION_F32_FAST;
     uint64_t launches = 0;
     s->n_marks = 0;
+    RenderTurn turn(scene->device); // declared after `releaser`: an early return gives the turn back before the block
+    turn.acquire();
     const auto t_call1 = std::chrono::steady_clock::now();
     VRJ_CUDA(cudaEventRecord(s->ev0, s->stream));
     for (uint32_t done = 0; done < p->spp; done += batch) {
@@ -1006,6 +1337,10 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
             VRJ_CUDA(cudaMemcpyAsync(out->photons + (size_t)done * npix * 2, tmp, count * sizeof(double2), out_kind, s->stream));
         }
     }
+    // the counters go through the block's pinned slot: a copy into pageable memory would hold this thread until everything
+    // queued before it -- the copies of the result included -- had finished, and the gate could not open early
+    unsigned long long *hstats = reinterpret_cast<unsigned long long *>(s->host_count + 160);
+    VRJ_CUDA(cudaMemcpyAsync(hstats, s->stats.p, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     VRJ_CUDA(cudaEventRecord(s->ev1, s->stream));
     for (int i = 0; i < 5; i++)
         if (arrs[i].user)
@@ -1019,10 +1354,11 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         launches++;
         VRJ_CUDA(cudaMemcpyAsync(out->srgb8, s->srgb8.p, npix * 3, out_kind, s->stream));
     }
-    unsigned long long hstats[ST_COUNT];
-    VRJ_CUDA(cudaMemcpyAsync(hstats, s->stats.p, sizeof hstats, cudaMemcpyDeviceToHost, s->stream));
     const auto t_call2 = std::chrono::steady_clock::now();
-    VRJ_CUDA(cudaStreamSynchronize(s->stream));
+    VRJ_CUDA(cudaEventRecord(s->ev_done, s->stream));
+    VRJ_CUDA(wait_event(s->ev1, scene->device)); // the last kernel is done: the next caller may render while this one's copies run
+    turn.release();
+    VRJ_CUDA(wait_event(s->ev_done, scene->device));
     const auto t_call3 = std::chrono::steady_clock::now();
     float ms = 0.f;
     VRJ_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
@@ -1047,6 +1383,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         out->stats->primary_launches = cls_n[0], out->stats->bounce_launches = cls_n[1], out->stats->resolve_launches = cls_n[2];
         out->stats->shade_ms = cls_ms[3] + cls_ms[4], out->stats->shade_launches = cls_n[3] + cls_n[4];
         out->stats->tail_ms = cls_ms[5], out->stats->tail_launches = cls_n[5];
+        out->stats->coalesced_calls = 1;
     }
     return VRJ_OK;
 }

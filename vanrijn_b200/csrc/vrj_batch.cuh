@@ -40,13 +40,20 @@ inline VrjStatus fail(VrjStatus code, const std::string &msg) {
 struct DeviceBuffer {
     void *p = nullptr;
     size_t bytes = 0;
+    bool borrowed = false; // p points into another buffer's block (a Scratch slab); nothing to free
     ~DeviceBuffer() { release(); }
     void release() {
-        if (p) vrj_pool_free(p), p = nullptr;
+        if (p && !borrowed) vrj_pool_free(p);
+        p = nullptr, borrowed = false;
     }
     cudaError_t alloc(size_t n) {
+        release();
         bytes = n;
         return vrj_pool_alloc(&p, n);
+    }
+    void borrow(void *q, size_t n) {
+        release();
+        p = q, bytes = n, borrowed = true;
     }
     template <typename T>
     T *as() const { return static_cast<T *>(p); }
@@ -62,9 +69,13 @@ struct Scratch {
     DeviceBuffer recs;       // TraceRec per staged ray (rec_capacity of them); shared by the levels like `list`
     size_t rec_capacity = 0;
     DeviceBuffer acc_colour, acc_sum, acc_bias, acc_weight, acc_wbias;
+    DeviceBuffer queue_slab, rec_slab, acc_slab; // the groups above live in one allocation each (see ensure_scratch)
+    DeviceBuffer multi_out, sample_table; // coalesced calls: their output arrays (call-major pieces) and the batch's sample indices
     DeviceBuffer lights, light_samples, srgb8;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; // first / last kernel of a call
+    cudaEvent_t ev_done = nullptr;             // behind the call's last copy
+    cudaEvent_t call_ev[16] = {};              // coalesced calls: behind the copies of call c (MULTI_MAX_CALLS)
     cudaEvent_t drain_ev[2] = {nullptr, nullptr}; // behind the pinned copies of the drain check (run_levels)
     std::vector<cudaEvent_t> marks; // per-launch boundaries, reused across calls
     std::vector<int> mark_class;    // class of the launch that ENDS at mark i (-1: start of a batch)
@@ -74,6 +85,9 @@ struct Scratch {
         if (stream) cudaStreamDestroy(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_done) cudaEventDestroy(ev_done);
+        for (cudaEvent_t e : call_ev)
+            if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : drain_ev)
             if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : marks) cudaEventDestroy(e);
@@ -153,7 +167,7 @@ inline bool wants_records(const VrjScene *sc, int walk) {
 
 // One batch with the integrator (WHITTED) and the scene's material kinds (MM, see vrj_device.cuh) fixed at compile time.
 template <typename NT, typename R, bool COUNT, bool WHITTED, int MM>
-VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int walk, uint64_t *launches) {
+VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int walk, uint64_t *launches, const MultiCalls *multi) {
     const bool quad = walk == 1, q16 = walk == 2; // 0: the 2-wide tree in NT boxes; 1: 4-wide f32; 2: 2-wide on the 16-bit grid
     // launch sequence: G T S_0 [X_k T_k S_k]*, k = 1..levels (X = k_tail, a no-op until the queue is short);
     // SimpleRandom needs max_depth levels, Whitted one more (its limit-0 level still shades and traces);
@@ -165,7 +179,7 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
     uint32_t *work_t = lcount + stride;             // work-fetch counters of T_k
     uint32_t *work_s = work_t + stride;             // ... of G (k = 0 only) / S_k
     uint32_t *tail_done = work_s + stride;          // set by the k_tail launch that finished the batch
-    VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 5 + 1) * sizeof(uint32_t), s->stream));
+    VRJ_CUDA(cudaMemsetAsync(qcount, 0, ((size_t)stride * 5 + 2) * sizeof(uint32_t), s->stream));
     unsigned long long *stats = s->stats.as<unsigned long long>();
     double2 *photons = s->photons.as<double2>();
     const int g_gen = persistent_grid(sc, k_raygen<R, COUNT>), g_t = quad ? persistent_grid(sc, k_trace4<COUNT, false>) : q16 ? persistent_grid(sc, k_traceq<COUNT, false>) : persistent_grid(sc, k_trace<NT, R, COUNT>);
@@ -175,7 +189,8 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
     // k_tail pays off for deep recursion limits (the reference's 128: 260 launches -> 28); at depth <= 12 the
     // per-level latency it removes is smaller than what its one-thread-per-path traversal costs (measured)
     const uint32_t tail_max = levels > 12 ? sc->tail_max : sc->tail_max_shallow;
-    const int g_x = (int)std::max<uint32_t>(1, (tail_max + 127) / 128);
+    const int g_x = tail_max ? persistent_grid(sc, k_tail<NT, R, COUNT, WHITTED, MM>) : 0; // persistent warps, per-lane refill
+    uint32_t *tail_work = tail_done + 1 + stride;   // k_tail's work-fetch counter (after the k_stage counters)
     const bool has_bvh = sc->dev.n_bvh_items > 0;
     // the default walk of the parity path takes its rays as ready-to-walk records (TraceRec); the other walks form the
     // traversal constants per lane from the queue entry
@@ -214,7 +229,7 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
         VRJ_CUDA(s->mark(4));
 #endif
         if (tail_max) {
-            k_tail<NT, R, COUNT, WHITTED, MM><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done);
+            k_tail<NT, R, COUNT, WHITTED, MM><<<g_x, 128, 0, s->stream>>>(sc->dev, rc, s->queue(ci), qcount + k, tail_max, photons, stats, tail_done, tail_work);
             (*launches)++;
             VRJ_CUDA(s->mark(5));
         }
@@ -251,7 +266,8 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
     AccumDev acc;
     acc.colour = s->acc_colour.as<double>(), acc.sum = s->acc_sum.as<double>(), acc.bias = s->acc_bias.as<double>();
     acc.weight = s->acc_weight.as<double>(), acc.weight_bias = s->acc_wbias.as<double>();
-    k_resolve<R><<<(rc.npix + 255) / 256, 256, 0, s->stream>>>(acc, photons, rc.npix, rc.batch_samples);
+    if (multi) k_resolve_multi<R><<<(rc.npix * multi->n + 255) / 256, 256, 0, s->stream>>>(*multi, photons, rc.npix, rc.batch_samples);
+    else k_resolve<R><<<(rc.npix + 255) / 256, 256, 0, s->stream>>>(acc, photons, rc.npix, rc.batch_samples);
     (*launches)++;
     VRJ_CUDA(s->mark(2));
     VRJ_CUDA(cudaGetLastError());
@@ -261,10 +277,10 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
 // kernel variants exist for "Lambertian only" (the reference's own scenes: main.rs, benches/simple_scene.rs) and for
 // "any material"; VRJ_MATERIAL_MASK=15 in the environment forces the general variant (experiments)
 template <typename NT, typename R, bool COUNT>
-VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, int walk, uint64_t *launches) {
+VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, int walk, uint64_t *launches, const MultiCalls *multi = nullptr) {
     const bool lambert_only = sc->kernel_material_mask == 1u;
-    if (whitted) return lambert_only ? run_levels<NT, R, COUNT, true, 1>(sc, s, rc, walk, launches) : run_levels<NT, R, COUNT, true, VRJ_MM_ALL>(sc, s, rc, walk, launches);
-    return lambert_only ? run_levels<NT, R, COUNT, false, 1>(sc, s, rc, walk, launches) : run_levels<NT, R, COUNT, false, VRJ_MM_ALL>(sc, s, rc, walk, launches);
+    if (whitted) return lambert_only ? run_levels<NT, R, COUNT, true, 1>(sc, s, rc, walk, launches, multi) : run_levels<NT, R, COUNT, true, VRJ_MM_ALL>(sc, s, rc, walk, launches, multi);
+    return lambert_only ? run_levels<NT, R, COUNT, false, 1>(sc, s, rc, walk, launches, multi) : run_levels<NT, R, COUNT, false, VRJ_MM_ALL>(sc, s, rc, walk, launches, multi);
 }
 
 } // namespace vrjimpl

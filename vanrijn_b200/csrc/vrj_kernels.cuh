@@ -110,6 +110,7 @@ struct RenderConst {
     FastDiv div_batch, div_tile_w;      // division by batch_samples / tile_w
     uint64_t first_sample;              // sample index of batch slot 0
     uint64_t sample_stride;
+    const uint64_t *sample_table;       // non-NULL: sample index of batch slot s is sample_table[s] (coalesced calls, MultiCalls)
     uint64_t seed;
     uint32_t max_depth, n_lights;
     uint32_t has_ambient, pad;
@@ -188,7 +189,7 @@ __device__ __forceinline__ void slot_to_pixel(const RenderConst &rc, uint32_t sl
     uint32_t row = rc.div_tile_w.div(p), col = p - row * rc.tile_w;
     grow = rc.start_row + row, gcol = rc.start_column + col;
     pixel_global = (uint32_t)(grow * rc.width + gcol);
-    sample = rc.first_sample + (uint64_t)s * rc.sample_stride;
+    sample = rc.sample_table ? __ldg(rc.sample_table + s) : rc.first_sample + (uint64_t)s * rc.sample_stride;
 }
 
 // Stage-1 results of one ray + the list of rays that still need BVH traversal
@@ -674,34 +675,58 @@ __global__ void __launch_bounds__(128, VRJ_STAGE_MINB) k_stage(DevScene sc, Path
 
 // ---- k_tail: when few paths are left, finish ALL their remaining levels in one launch ----
 // A wavefront level costs at least the latency of its longest traversal (~100 us) however few rays it carries;
-// here every thread follows one path (trace -> shade -> trace ...) to its end, so the remaining levels overlap.
+// here every lane follows one path (trace -> shade -> trace ...) to its end, so the remaining levels overlap.
 // Runs before T_k on queue k; does nothing unless the queue is at most `tail_max` long; sets *tail_done so the
 // remaining T / S launches of the batch return immediately.
+// Persistent warps with per-lane refill: path lengths are geometric (most paths end after one or two more bounces, a few
+// run for dozens), so a lane whose path has ended takes the next queue entry at once (one warp-aggregated atomic) instead
+// of idling until the longest path of its warp is done -- in the one-path-per-thread form a warp ran ~6 bounces for ~1.7
+// useful ones per lane.
 template <typename NT, typename R, bool COUNT, bool WHITTED, int MM>
 __global__ void __launch_bounds__(128, 2) k_tail(DevScene sc, RenderConst rc, PathQueue in, const uint32_t *in_count,
                                               uint32_t tail_max, double2 *photons, unsigned long long *stats,
-                                              uint32_t *tail_done) {
+                                              uint32_t *tail_done, uint32_t *work) {
     const uint32_t n = *in_count;
     if (n > tail_max || *tail_done == 1u) return;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
     LocalStats ls;
     ls.clear();
-    const uint32_t padded = (n + 31u) & ~31u;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < padded; j += gridDim.x * blockDim.x) {
-        if (j < n) {
-            PathRegsT<R> p;
-            double2 a3 = in.q3[j], a4 = in.q4[j];
-            uint4 a5 = in.q5[j];
-            queue_load_ray(in, j, p.o, p.d);
-            p.wl = (R)a3.x, p.A = (R)a3.y, p.B = (R)a4.x, p.aux = (R)a4.y;
-            p.slot = a5.x, p.ordinal = a5.y, p.limit = a5.z, p.flags = a5.w;
-            bool alive = true;
-            while (alive) {
-                TraceCounters tc = {0, 0};
-                // one thread, one path: what it waits on is the chain of dependent node fetches, and the 4-wide tree halves it
-                HitT<R> h = trace_closest<NT, COUNT, false, R, VRJ_TAIL_QUAD != 0>(sc, p.o, p.d, tc);
-                if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
-                alive = shade_entry<NT, COUNT, WHITTED, MM>(sc, rc, p, make_int2(h.item, h.tri), h.t, false, [](V3<R> &, V3<R> &) {}, photons, ls);
+    PathRegsT<R> p;
+    p.o = V3<R>{R(0), R(0), R(0)}, p.d = V3<R>{R(0), R(0), R(1)};
+    p.wl = p.A = p.B = p.aux = R(0);
+    p.slot = p.ordinal = p.limit = p.flags = 0;
+    bool alive = false, exhausted = false;
+    while (true) {
+        const unsigned idle_mask = __ballot_sync(FULL, !alive);
+        if (idle_mask) {
+            if (!exhausted) {
+                const uint32_t want = (uint32_t)__popc(idle_mask);
+                const int leader = __ffs(idle_mask) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(work, want);
+                base = __shfl_sync(FULL, base, leader);
+                if (base + want >= n) exhausted = true;
+                if (!alive) {
+                    const uint32_t j = base + (uint32_t)__popc(idle_mask & ((1u << lane) - 1u));
+                    if (j < n) {
+                        double2 a3 = in.q3[j], a4 = in.q4[j];
+                        uint4 a5 = in.q5[j];
+                        queue_load_ray(in, j, p.o, p.d);
+                        p.wl = (R)a3.x, p.A = (R)a3.y, p.B = (R)a4.x, p.aux = (R)a4.y;
+                        p.slot = a5.x, p.ordinal = a5.y, p.limit = a5.z, p.flags = a5.w;
+                        alive = true;
+                    }
+                }
             }
+            if (exhausted && __ballot_sync(FULL, alive) == 0u) break;
+        }
+        if (alive) {
+            TraceCounters tc = {0, 0};
+            // one lane, one path: what it waits on is the chain of dependent node fetches, and the 4-wide tree halves it
+            HitT<R> h = trace_closest<NT, COUNT, false, R, VRJ_TAIL_QUAD != 0>(sc, p.o, p.d, tc);
+            if (COUNT) ls.v[ST_NODES] += tc.node_visits, ls.v[ST_TRIS] += tc.tri_tests;
+            alive = shade_entry<NT, COUNT, WHITTED, MM>(sc, rc, p, make_int2(h.item, h.tri), h.t, false, [](V3<R> &, V3<R> &) {}, photons, ls);
         }
     }
     ls.flush(stats);
@@ -745,6 +770,47 @@ __global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t npix, u
     acc.weight[p] = w, acc.weight_bias[p] = wb;
     double inv = 1.0 / w;
     acc.colour[3 * p] = sx * inv, acc.colour[3 * p + 1] = sy * inv, acc.colour[3 * p + 2] = sz * inv;
+}
+
+// Several calls rendered as ONE wavefront (vanrijn_cuda.cu, "coalesced calls"): the batch's samples [first[c], first[c] +
+// count[c]) belong to call c, whose buffer starts from zero like a fresh AccumulationBuffer (camera.rs:101).  Call c's arrays
+// are the c-th npix-sized piece of each output array; `full` = 0: only the colours are wanted.
+constexpr int MULTI_MAX_CALLS = 16;
+struct MultiCalls {
+    uint32_t n, full;
+    uint32_t first[MULTI_MAX_CALLS], count[MULTI_MAX_CALLS];
+    AccumDev out;
+};
+// one thread per (pixel, call), call fastest: a warp reads consecutive photons and writes runs of whole pixels per call
+template <typename R>
+__global__ void k_resolve_multi(MultiCalls mc, const double2 *photons, uint32_t npix, uint32_t batch_samples) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix * mc.n) return; // npix * n <= 2^32 is checked by the host
+    const uint32_t p = i / mc.n, c = i - p * mc.n;
+    double sx = 0.0, sy = 0.0, sz = 0.0, bx = 0.0, by = 0.0, bz = 0.0, w = 0.0, wb = 0.0;
+    const uint32_t s0 = mc.first[c], s1 = s0 + mc.count[c];
+    for (uint32_t s = s0; s < s1; s++) { // accumulation_buffer.rs:44-60, as in k_resolve
+        double2 ph = photons[(size_t)p * batch_samples + s];
+        D3 col = d3(0.0, 0.0, 0.0);
+        if (__double_as_longlong(ph.y) != 0ll) col = convert<double>(cmf<R>((R)ph.x) * (R)ph.y);
+        const double weight = 1.0;
+        double wy = weight - wb;
+        double wt = w + wy;
+        wb = (wt - w) - wy;
+        w = wt;
+        double yx = col.x * weight - bx, yy = col.y * weight - by, yz = col.z * weight - bz;
+        double tx = sx + yx, ty = sy + yy, tz = sz + yz;
+        bx = (tx - sx) - yx, by = (ty - sy) - yy, bz = (tz - sz) - yz;
+        sx = tx, sy = ty, sz = tz;
+    }
+    const size_t q = (size_t)c * npix + p;
+    double inv = 1.0 / w;
+    mc.out.colour[3 * q] = sx * inv, mc.out.colour[3 * q + 1] = sy * inv, mc.out.colour[3 * q + 2] = sz * inv;
+    if (mc.full) {
+        mc.out.sum[3 * q] = sx, mc.out.sum[3 * q + 1] = sy, mc.out.sum[3 * q + 2] = sz;
+        mc.out.bias[3 * q] = bx, mc.out.bias[3 * q + 1] = by, mc.out.bias[3 * q + 2] = bz;
+        mc.out.weight[q] = w, mc.out.weight_bias[q] = wb;
+    }
 }
 
 // debug output (VrjAccumOut.photons) is sample-major: [(sample * npix + pixel)]
