@@ -549,9 +549,14 @@ def main():
     if os.path.exists(gpath):
         try:
             g = json.load(open(gpath))
-            cands = [r for r in g["results"] if r.get("record_bytes", 64) == 64 and r["table_mb"] == 5 and r["ctas_per_sm"] == 6]
-            l2_peak = cands[0]["GBps_1chain"]
-            l2_src = "measured: dependent 64-byte gathers, 5 MB table, 6 CTAs/SM, one chain per lane (profiles/r02_l2_gather_peak.json)"
+            # the traversal's own access pattern without its arithmetic: root-to-leaf walks of a median-split tree of the bench
+            # mesh's size (top levels from L1, the rest from L2), every lane on a path of its own
+            walk = [r for r in g["tree_walk"]["results"] if r["leaves"] == 81920 and r["ctas_per_sm"] == 6]
+            l2_peak = walk[0]["GBps"]
+            l2_src = ("measured: root-to-leaf walks of a 5 MB median-split tree, one 64-byte record per step, one walk per lane, 6 CTAs/SM "
+                      "(tools/l2_gather_peak.cu -> profiles/r02_l2_gather_peak.json tree_walk); uniform dependent gathers from L2 reach "
+                      "%.0f GB/s.  Lanes of a warp that fetch the same record share one access, which the walk on incoherent paths "
+                      "does not model: camera rays can exceed it" % [r for r in g["results"] if r.get("record_bytes", 64) == 64 and r["table_mb"] == 5 and r["ctas_per_sm"] == 6][0]["GBps_1chain"])
         except Exception:
             pass
     step_achieved = bytes_per_ray * agg["rays"] / (agg["device_ms"] / 1e3) / 1e9

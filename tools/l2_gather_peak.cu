@@ -56,6 +56,57 @@ __global__ void __launch_bounds__(128) k_chase(const uint4 *__restrict__ table, 
     if (acc == 0x12345678u) sink[0] = acc; // keeps the loads alive
 }
 
+// The access pattern of a traversal rather than of a uniform gather: every lane walks from the root of a median-split binary
+// tree (records in DFS pre-order, like the product's wide nodes: n - 1 records of 64 bytes for n leaves) to a leaf, choosing a
+// child at random once the record has arrived, and starts again at the root.  The top levels are shared by all lanes and stay
+// in L1, the bottom levels come from L2 (or HBM for config C4's tree) -- the mix k_trace sees, without any of its arithmetic.
+__global__ void __launch_bounds__(128) k_tree_walk(const uint4 *__restrict__ table, int steps, uint32_t *sink) {
+    uint32_t acc = 0, node = 0;
+    uint32_t rng = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int s = 0; s < steps; s++) {
+        uint4 a, b;
+        ldg256(table + (size_t)node * 4, a, b);
+        uint4 c, d;
+        ldg256(table + (size_t)node * 4 + 2, c, d);
+        acc += a.z ^ b.w ^ c.x ^ d.y;
+        rng = rng * 1664525u + 1013904223u;
+        const uint32_t child = (rng >> 16) & 1u ? a.y : a.x; // known only once the record is here
+        node = child == 0xffffffffu ? 0u : child;             // a leaf: back to the root
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+// records of the tree over `n` leaves, DFS pre-order: word 0 / 1 = left / right child record, ~0 = that child is a leaf
+static uint32_t build_tree(std::vector<uint32_t> &host, uint32_t &next, uint32_t n) {
+    if (n <= 1) return 0xffffffffu;
+    const uint32_t me = next++;
+    const uint32_t l = build_tree(host, next, n / 2), r = build_tree(host, next, n - n / 2);
+    host[(size_t)me * 16] = l, host[(size_t)me * 16 + 1] = r;
+    return me;
+}
+static int run_tree(uint32_t leaves, int grid, int steps, uint32_t *d_sink, double *gbs, double *grecs) {
+    std::vector<uint32_t> host((size_t)(leaves - 1) * 16, 0x9e3779b9u);
+    uint32_t next = 0;
+    build_tree(host, next, leaves);
+    uint4 *d_table;
+    CK(cudaMalloc(&d_table, host.size() * 4));
+    CK(cudaMemcpy(d_table, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_tree_walk<<<grid, 128>>>(d_table, steps / 4, d_sink);
+    CK(cudaEventRecord(e0));
+    k_tree_walk<<<grid, 128>>>(d_table, steps, d_sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *grecs = (double)grid * 128.0 * steps / (ms * 1e-3) / 1e9;
+    *gbs = *grecs * 64;
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    CK(cudaFree(d_table));
+    return 0;
+}
+
 template <int CHAINS, int REC>
 static int run(const uint4 *d_table, uint32_t n_records, int grid, int steps, uint32_t *d_sink, double *gbs, double *grecs) {
     cudaEvent_t e0, e1;
@@ -128,6 +179,18 @@ int main() {
         std::printf(",\n {\"record_bytes\": %d, \"table_mb\": %zu, \"ctas_per_sm\": 6, \"GBps_1chain\": %.1f, \"Grecords_per_s_1chain\": %.2f}", rec, mb, gbs, gr);
         CK(cudaFree(d_table));
     }
-    std::printf("\n]}\n");
+    std::printf("\n],\n \"tree_walk\": {\"what\": \"root-to-leaf walks of a median-split tree in DFS pre-order, one 64-byte record per step, random child, "
+                "one walk per lane, 148 x ctas_per_sm CTAs of 128 threads\", \"results\": [");
+    first = true;
+    for (uint32_t leaves : {81920u, 9912320u}) { // the bench mesh (5.2 MB of records) and config C4's (634 MB)
+        for (int res : {6, 8}) {
+            double gbs = 0, gr = 0;
+            if (run_tree(leaves, sms * res, leaves > 1000000u ? 512 : 2048, d_sink, &gbs, &gr)) return 1;
+            std::printf("%s\n  {\"leaves\": %u, \"table_mb\": %.1f, \"ctas_per_sm\": %d, \"GBps\": %.1f, \"Grecords_per_s\": %.2f}", first ? "" : ",", leaves,
+                        (leaves - 1) * 64.0 / 1048576.0, res, gbs, gr);
+            first = false;
+        }
+    }
+    std::printf("\n ]}\n}\n");
     return 0;
 }

@@ -17,7 +17,7 @@ for kahan in kahans:
         host.render_like_main(hs, W, H, 8 * workers, workers, kahan_state=kahan)   # warm-up: scratch blocks, pinned pool
         colour, weight, st = host.render_like_main(hs, W, H, calls, workers, kahan_state=kahan)
         assert np.all(weight == calls)
-        print("%s workers %2d: %.2f ms/call  %.0f Mrays/s | merge %.2f ms/call, worker wall %.2f ms/call (/%d = %.2f), device events %.2f ms/call, D2H %.0f MB/call" % (
+        print("%s workers %2d: %.2f ms/call  %.0f Mrays/s | merge %.2f ms/call, worker wall %.2f ms/call (/%d = %.2f), device events %.2f ms/call, D2H %.0f MB/call, %d merge passes" % (
             "five arrays " if kahan else "colour+weight", workers, 1e3 * st["wall_s"] / calls, st["rays"] / st["wall_s"] / 1e6,
             1e3 * st["merge_s"] / calls, 1e3 * st["call_s"] / calls, workers, 1e3 * st["call_s"] / calls / workers,
-            st["device_ms"] / calls, st["bytes_to_host"] / calls / 1e6), flush=True)
+            st["device_ms"] / calls, st["bytes_to_host"] / calls / 1e6, st["merge_passes"]), flush=True)

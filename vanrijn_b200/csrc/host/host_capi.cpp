@@ -241,7 +241,7 @@ int vrjh_render_like_main(void *p, uint64_t width, uint64_t height, uint64_t til
         std::memcpy(weight, image.weight.data(), n * sizeof(double));
         if (stats8) {
             stats8[0] = st.wall_s, stats8[1] = st.call_s, stats8[2] = st.merge_s, stats8[3] = st.device_ms;
-            stats8[4] = (double)st.rays, stats8[5] = (double)st.calls, stats8[6] = (double)st.bytes_to_host, stats8[7] = 0.0;
+            stats8[4] = (double)st.rays, stats8[5] = (double)st.calls, stats8[6] = (double)st.bytes_to_host, stats8[7] = (double)st.merge_passes;
         }
     });
 }

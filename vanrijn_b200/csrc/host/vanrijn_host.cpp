@@ -556,21 +556,22 @@ class RowPool {
         static RowPool pool;
         return pool;
     }
-    // runs fn(r0, r1) over [0, rows) split into one piece per thread (the caller takes a piece too); returns when all are done
+    // runs fn(r0, r1) over [0, rows) in pieces of a few rows that the pool's threads and the caller take one after another;
+    // returns when all are done.  Small pieces, handed out on demand: the threads do not run at the same speed (a sibling
+    // hyper-thread may be busy feeding the GPU), and with one fixed share per thread the slowest one set the time of the pass.
     void run(size_t rows, const std::function<void(size_t, size_t)> &fn) {
         std::lock_guard<std::mutex> serial(serial_); // one merge at a time owns the pool
         if (rows == 0) return;
-        const size_t want = std::min(rows, workers_.size() + 1);
-        const size_t per = (rows + want - 1) / want;
-        const size_t pieces = (rows + per - 1) / per; // rounding can leave fewer pieces than threads
+        uint64_t gen;
         {
             std::lock_guard<std::mutex> g(m_);
-            fn_ = &fn, rows_ = rows, per_ = per, next_ = 1, pending_ = pieces - 1, generation_++;
+            fn_ = &fn, rows_ = rows, per_ = std::max<size_t>(1, rows / ((workers_.size() + 1) * 8));
+            pieces_ = (rows + per_ - 1) / per_, next_ = 0, finished_ = 0, gen = ++generation_;
         }
         wake_.notify_all();
-        fn(0, std::min(rows, per));
+        work(gen);
         std::unique_lock<std::mutex> g(m_);
-        done_.wait(g, [&] { return pending_ == 0; });
+        done_.wait(g, [&] { return finished_ == pieces_; });
         fn_ = nullptr;
     }
 
@@ -592,30 +593,39 @@ class RowPool {
         wake_.notify_all();
         for (auto &t : workers_) t.join();
     }
+    // take pieces of generation `gen` until none is left (or the pool has moved on)
+    void work(uint64_t gen) {
+        for (;;) {
+            size_t piece, rows, per;
+            const std::function<void(size_t, size_t)> *fn;
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (generation_ != gen || !fn_ || next_ >= pieces_) return;
+                piece = next_++, rows = rows_, per = per_, fn = fn_;
+            }
+            (*fn)(piece * per, std::min(rows, (piece + 1) * per)); // run() cannot return before this piece is counted below
+            std::lock_guard<std::mutex> g(m_);
+            if (++finished_ == pieces_) done_.notify_one();
+        }
+    }
     void loop() {
         uint64_t seen = 0;
         for (;;) {
-            size_t piece;
-            const std::function<void(size_t, size_t)> *fn;
-            size_t rows, per;
+            uint64_t gen;
             {
                 std::unique_lock<std::mutex> g(m_);
-                wake_.wait(g, [&] { return stop_ || (generation_ != seen && fn_ && next_ * per_ < rows_); });
+                wake_.wait(g, [&] { return stop_ || (generation_ != seen && fn_); });
                 if (stop_) return;
-                piece = next_++;
-                if (next_ * per_ >= rows_) seen = generation_;
-                fn = fn_, rows = rows_, per = per_;
+                gen = seen = generation_;
             }
-            (*fn)(piece * per, std::min(rows, (piece + 1) * per));
-            std::lock_guard<std::mutex> g(m_);
-            if (--pending_ == 0) done_.notify_one();
+            work(gen);
         }
     }
     std::vector<std::thread> workers_;
     std::mutex m_, serial_;
     std::condition_variable wake_, done_;
     const std::function<void(size_t, size_t)> *fn_ = nullptr;
-    size_t rows_ = 0, per_ = 1, next_ = 0, pending_ = 0;
+    size_t rows_ = 0, per_ = 1, pieces_ = 0, next_ = 0, finished_ = 0;
     uint64_t generation_ = 0;
     bool stop_ = false;
 };
@@ -1001,6 +1011,7 @@ MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, 
                 same.push_back(&items[j]->buffer);
             }
             rendered_image.merge_tiles(t, same);
+            total.merge_passes++;
             i = j;
         }
         total.merge_s += seconds(tm);

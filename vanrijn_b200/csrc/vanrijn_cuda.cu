@@ -600,8 +600,10 @@ VrjStatus render_group(Coalescer &co, CoalesceRequest *const *reqs, uint32_t n, 
     const auto t1b = std::chrono::steady_clock::now();
     const size_t per_call = npix * (mc.full ? 11 : 3) * sizeof(double);
     if (s->multi_out.bytes < per_call * n || !s->multi_out.p) {
+        // sized once for the largest group this tile size can form (1-sample calls up to the path limit)
+        const size_t max_calls = std::max<size_t>(n, std::min<size_t>(MULTI_MAX_CALLS, kCoalesceMaxPaths / std::max<uint64_t>(npix, 1)));
         s->multi_out.release();
-        VRJ_CUDA(s->multi_out.alloc(per_call * MULTI_MAX_CALLS)); // sized once for the largest group
+        VRJ_CUDA(s->multi_out.alloc(per_call * max_calls));
     }
     if (!s->sample_table.p) VRJ_CUDA(s->sample_table.alloc(4 * MULTI_MAX_CALLS * sizeof(uint64_t)));
     double *base = s->multi_out.as<double>();

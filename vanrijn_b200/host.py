@@ -260,8 +260,8 @@ def render_like_main(hs, width, height, calls, workers, tile_size=2048, spp=0, m
                                    st.ctypes.data_as(dp))
     if r != 0:
         raise capi.VrjError(hs.H.vrjh_last_error().decode())
-    keys = ("wall_s", "call_s", "merge_s", "device_ms", "rays", "calls", "bytes_to_host")
-    return colour, weight, dict(zip(keys, [float(x) for x in st[:7]]))
+    keys = ("wall_s", "call_s", "merge_s", "device_ms", "rays", "calls", "bytes_to_host", "merge_passes")
+    return colour, weight, dict(zip(keys, [float(x) for x in st[:8]]))
 
 
 def tone_map(colour, source=capi.TONEMAP_XYZ, device=0):
