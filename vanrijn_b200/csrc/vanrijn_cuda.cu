@@ -472,6 +472,15 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t rec_capacity, size_
     return VRJ_OK;
 }
 
+// Which walk a call takes.  VRJ_FILTER_F32 is the default; for scenes whose f32 nodes do not fit L2 (config C4: 634 MB) the
+// library walks the 16-bit nodes instead -- half the bytes per step, +2-4 % on C4 (profiles/r02_ab_variants.txt), slower on an
+// L2-resident scene.  The filter only decides which boxes are opened, never a result (every walk is bit-identical to every
+// other: tests/test_gpu_parity.py, tests/test_gpu_bvh_build.py), so this is a scheduling decision.  VRJ_AUTO_Q16=0 turns it off.
+uint32_t effective_filter(const VrjScene *scene, const VrjRenderParams *p) {
+    if (p->bvh_filter == VRJ_FILTER_F32 && p->precision == VRJ_PRECISION_F64 && scene->auto_q16) return VRJ_FILTER_Q16;
+    return p->bvh_filter;
+}
+
 // the per-call constants of the kernels (camera.rs:24-34 for the film size)
 RenderConst make_render_const(const VrjTile *tile, uint64_t height, uint64_t width, const VrjRenderParams *p) {
     RenderConst rc{};
@@ -590,7 +599,8 @@ VrjStatus render_group(Coalescer &co, CoalesceRequest *const *reqs, uint32_t n, 
             release_scratch(sc, s);
         }
     } releaser{scene, s};
-    const bool records = p->precision == VRJ_PRECISION_F64 && p->bvh_filter == VRJ_FILTER_F32 && scene->trace_records && scene->dev.n_bvh_items > 0;
+    const uint32_t filter = effective_filter(scene, p);
+    const bool records = p->precision == VRJ_PRECISION_F64 && filter == VRJ_FILTER_F32 && scene->trace_records && scene->dev.n_bvh_items > 0;
     VrjStatus st = ensure_scratch(s, capacity, records ? capacity : 0, 0, p->max_depth + 3, 0, 0);
     if (st == VRJ_ERR_OUT_OF_MEMORY) { // fall back to exactly what this wavefront needs
         vrj_pool_trim();
@@ -622,12 +632,12 @@ VrjStatus render_group(Coalescer &co, CoalesceRequest *const *reqs, uint32_t n, 
     rc.batch_samples = total;
     rc.div_batch = FastDiv::make(total), rc.div_tile_w = FastDiv::make(rc.tile_w);
     rc.first_sample = 0;
-    const int quad = p->bvh_filter == VRJ_FILTER_F32X4 ? 1 : p->bvh_filter == VRJ_FILTER_Q16 ? 2 : 0;
+    const int quad = filter == VRJ_FILTER_F32X4 ? 1 : filter == VRJ_FILTER_Q16 ? 2 : 0;
     uint64_t launches = 0;
     s->n_marks = 0;
     VRJ_CUDA(cudaEventRecord(s->ev0, s->stream));
     st = p->precision == VRJ_PRECISION_F32_FAST ? run_batch<float, float, false>(scene, s, rc, false, 0, &launches, &mc)
-         : p->bvh_filter == VRJ_FILTER_F64     ? run_batch<double, double, false>(scene, s, rc, false, 0, &launches, &mc)
+         : filter == VRJ_FILTER_F64            ? run_batch<double, double, false>(scene, s, rc, false, 0, &launches, &mc)
                                                : run_batch<float, double, false>(scene, s, rc, false, quad, &launches, &mc);
     if (st != VRJ_OK) return st;
     unsigned long long *hstats = reinterpret_cast<unsigned long long *>(s->host_count + 160); // pinned, see vrj_render_tile
@@ -1085,6 +1095,8 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
                     &sc->dev.node_batch4);
     if (const char *pb = std::getenv("VRJ_PATH_BUDGET_LOG2")) sc->path_budget = 1ull << std::min(std::max(std::atoi(pb), 16), 31); // experiments only
     if (const char *r = std::getenv("VRJ_RECORDS")) sc->trace_records = std::atoi(r) != 0; // experiments only
+    sc->auto_q16 = (size_t)d->n_triangles * 64 > (size_t(96) << 20); // the f32 nodes (64 bytes per triangle) against the 126 MB L2
+    if (const char *aq = std::getenv("VRJ_AUTO_Q16")) sc->auto_q16 = std::atoi(aq) != 0; // experiments only
     if (const char *ts = std::getenv("VRJ_TAIL_SHALLOW")) sc->tail_max_shallow = (uint32_t)std::strtoul(ts, nullptr, 10); // experiments only
     if (std::getenv("VRJ_TIMING")) {
         auto t_end = std::chrono::steady_clock::now();
@@ -1253,7 +1265,8 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     } releaser{scene, s};
     bool queue_oom = false;
     // TraceRec records: only the calls that walk them need the extra 96 bytes per path in flight
-    const bool records = p->precision == VRJ_PRECISION_F64 && p->bvh_filter == VRJ_FILTER_F32 && scene->trace_records && scene->dev.n_bvh_items > 0;
+    const uint32_t filter = effective_filter(scene, p);
+    const bool records = p->precision == VRJ_PRECISION_F64 && filter == VRJ_FILTER_F32 && scene->trace_records && scene->dev.n_bvh_items > 0;
     VrjStatus st = ensure_scratch(s, npix * batch, records ? npix * batch : 0, npix, p->max_depth + 3, p->n_lights, n_light_samples, &queue_oom);
     while (st == VRJ_ERR_OUT_OF_MEMORY && queue_oom && batch > 1) { // 240 bytes per path in flight: halve the batch until the queues fit
         vrj_pool_trim();
@@ -1306,7 +1319,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     rc.light_samples = s->light_samples.as<double>();
 
     // F32X4: the staged rays walk the 4-wide tree; inline any-hit queries (Whitted shadow rays, k_tail) use the 2-wide f32 tree
-    const int quad = p->bvh_filter == VRJ_FILTER_F32X4 ? 1 : p->bvh_filter == VRJ_FILTER_Q16 ? 2 : 0;
+    const int quad = filter == VRJ_FILTER_F32X4 ? 1 : filter == VRJ_FILTER_Q16 ? 2 : 0;
     // VRJ_PRECISION_F32_FAST: the whole sample in binary32 over the 2-wide f32 tree (no reference counterpart; not a parity mode)
     const bool fast = p->precision == VRJ_PRECISION_F32_FAST;
     uint64_t launches = 0;
@@ -1321,11 +1334,11 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         rc.first_sample = p->sample_offset + (uint64_t)done * rc.sample_stride;
         if (p->count_traversal) {
             st = fast ? run_batch<float, float, true>(scene, s, rc, whitted, 0, &launches)
-                 : p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, double, true>(scene, s, rc, whitted, 0, &launches)
+                 : filter == VRJ_FILTER_F64 ? run_batch<double, double, true>(scene, s, rc, whitted, 0, &launches)
                                                    : run_batch<float, double, true>(scene, s, rc, whitted, quad, &launches);
         } else {
             st = fast ? run_batch<float, float, false>(scene, s, rc, whitted, 0, &launches)
-                 : p->bvh_filter == VRJ_FILTER_F64 ? run_batch<double, double, false>(scene, s, rc, whitted, 0, &launches)
+                 : filter == VRJ_FILTER_F64 ? run_batch<double, double, false>(scene, s, rc, whitted, 0, &launches)
                                                    : run_batch<float, double, false>(scene, s, rc, whitted, quad, &launches);
         }
         if (st != VRJ_OK) return st;

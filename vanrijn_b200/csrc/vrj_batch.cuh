@@ -131,6 +131,7 @@ struct VrjScene {
     uint32_t tail_max = 1u << 18; // queue length at which k_tail finishes the batch in one launch (0 = never)
     uint32_t tail_max_shallow = 0; // the same for recursion limits <= 12
     uint64_t path_budget = 1ull << 27; // paths in flight per batch
+    bool auto_q16 = false; // VRJ_FILTER_F32 calls walk the 16-bit nodes: set for scenes whose f32 nodes exceed L2 (effective_filter)
     bool trace_records = true; // staged rays carry their traversal constants (TraceRec); VRJ_RECORDS=0 turns it off (experiments)
     uint32_t kernel_material_mask = VRJ_MM_ALL; // 1: every material is Lambertian (the Lambertian-only kernel variants run)
     ~VrjScene() {
