@@ -195,7 +195,7 @@ def extra_config(name, V, capi, scenes, np, device):
     pinned = {"colour": pinned_array(capi, np, npix * 3), "weight": pinned_array(capi, np, npix)}
     tile = (0, W, 0, H)
     best, e2e_best, st = None, None, None
-    for i in range(4):
+    for i in range(10 if name == "C2" else 4):  # C2 is one 1-spp frame per call (2.4 ms): more calls for a stable best-of
         t = time.perf_counter()
         r = hs.render(tile, H, W, spp=spp, sample_offset=i * spp, want=("colour", "weight"), buffers=pinned, device=device, **kw)
         dt = time.perf_counter() - t
@@ -498,7 +498,8 @@ def main():
                     r = {"value": st["rays"] / st["wall_s"] / 1e6, "unit": "Mrays/s", "threads": workers, "calls": calls,
                          "ms_per_call": 1e3 * st["wall_s"] / calls, "d2h_bytes_per_call": st["bytes_to_host"] / calls,
                          "merge_tile_ms_per_call": 1e3 * st["merge_s"] / calls, "device_ms_per_call": st["device_ms"] / calls,
-                         "worker_ms_per_call": 1e3 * st["call_s"] / calls, "spp_per_s": calls / st["wall_s"]}
+                         "worker_ms_per_call": 1e3 * st["call_s"] / calls, "spp_per_s": calls / st["wall_s"],
+                         "merge_passes": int(st["merge_passes"]), "calls_per_wavefront": st["wavefront_calls"] / calls}
                     ref_sig["%s_%d_threads" % (key, workers)] = r
                     if key == "colour_only" and (best is None or r["value"] > best["value"]):
                         best = r

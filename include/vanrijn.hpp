@@ -354,6 +354,7 @@ struct MainLoopStats {
     double wall_s = 0, call_s = 0, merge_s = 0, device_ms = 0; // call_s: summed over the workers
     uint64_t rays = 0, calls = 0, bytes_to_host = 0;
     uint64_t merge_passes = 0; // passes over the frame: messages that were waiting together were merged in one (merge_tiles)
+    uint64_t wavefront_calls = 0; // sum over the calls of VrjStats.coalesced_calls (/ calls = mean calls per shared wavefront)
 };
 MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, size_t tile_size, uint64_t calls, unsigned workers,
                                const RenderOptions &options, bool fresh_samples, AccumulationBuffer &rendered_image);

@@ -266,7 +266,17 @@ VRJ_API void *vrj_alloc_device(int32_t device, uint64_t bytes);
 VRJ_API void vrj_free_device(void *p);
 VRJ_API VrjStatus vrj_copy_to_host(int32_t device, void *host_dst, const void *device_src, uint64_t bytes);
 
-/* partial_render_scene: render `tile` of a width x height image, params->spp samples per pixel. */
+/* partial_render_scene (src/camera.rs:95-130): render `tile` of a width x height image, params->spp samples per pixel.
+ * Blocks until the output arrays are filled.  Safe to call from many threads on one scene; the library schedules the calls:
+ * at most a few render on a device at the same moment, and calls of the reference's kind -- VRJ_INTEGRATOR_SIMPLE_RANDOM,
+ * 1..4 samples, a fresh (accumulate == 0) host buffer that asks for `colour`, no photons / srgb8 / count_traversal -- that
+ * are waiting at that moment and agree in scene, tile, image size, max_depth, seed, bvh_filter, precision, bias,
+ * sample_stride and in WHICH arrays they ask for are rendered as one wavefront.  Every such call receives bit for bit the
+ * arrays it would have received alone (a sample is a pure function of seed, pixel and sample index, and each call's samples
+ * are applied to its own zeroed buffer in sample order); out->stats->coalesced_calls reports how many calls shared the
+ * wavefront.  Environment (experiments): VRJ_COALESCE=0, VRJ_CONCURRENT_RENDERS=<n>.
+ * VRJ_FILTER_F32 (the default) lets the library take the 16-bit walk for scenes whose f32 nodes exceed L2; no walk can change
+ * a result. */
 VRJ_API VrjStatus vrj_render_tile(const VrjScene *scene, const VrjTile *tile, uint64_t height, uint64_t width,
                           const VrjRenderParams *params, VrjAccumOut *out);
 

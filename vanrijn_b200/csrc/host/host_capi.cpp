@@ -223,10 +223,10 @@ uint64_t vrjh_next_sample_index(uint64_t count) { return next_sample_index(count
  * width x height colour / weight arrays (which hold the image so far; zero weight = empty).  spp == 0: the reference's own
  * call (1 spp, limit 128, fresh samples); otherwise spp / max_depth / seed as given, samples counted from sample_offset.
  * kahan_state: whether each call also brings its Kahan arrays back (the reference's AccumulationBuffer has them; merge_tile
- * never reads them).  stats8: wall_s, call_s, merge_s, device_ms, rays, calls, bytes_to_host, 0. */
+ * never reads them).  stats8 (9 doubles): wall_s, call_s, merge_s, device_ms, rays, calls, bytes_to_host, merge_passes, wavefront_calls. */
 int vrjh_render_like_main(void *p, uint64_t width, uint64_t height, uint64_t tile_size, uint64_t calls, uint32_t workers,
                           uint32_t spp, uint32_t max_depth, uint64_t seed, uint64_t sample_offset, int kahan_state, int device,
-                          double *colour, double *weight, double *stats8) {
+                          double *colour, double *weight, double *stats8) { /* stats8: 9 doubles */
     HostScene *h = static_cast<HostScene *>(p);
     return guarded([&] {
         AccumulationBuffer image(width, height);
@@ -241,7 +241,7 @@ int vrjh_render_like_main(void *p, uint64_t width, uint64_t height, uint64_t til
         std::memcpy(weight, image.weight.data(), n * sizeof(double));
         if (stats8) {
             stats8[0] = st.wall_s, stats8[1] = st.call_s, stats8[2] = st.merge_s, stats8[3] = st.device_ms;
-            stats8[4] = (double)st.rays, stats8[5] = (double)st.calls, stats8[6] = (double)st.bytes_to_host, stats8[7] = (double)st.merge_passes;
+            stats8[4] = (double)st.rays, stats8[5] = (double)st.calls, stats8[6] = (double)st.bytes_to_host, stats8[7] = (double)st.merge_passes, stats8[8] = (double)st.wavefront_calls;
         }
     });
 }

@@ -948,17 +948,22 @@ MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, 
     std::atomic<uint64_t> next{0};
     std::string error;
     unsigned live = workers;
+    uint64_t pending = 0; // calls a worker has started and not yet delivered (guarded by m)
     const auto t0 = std::chrono::steady_clock::now();
     auto seconds = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
     std::vector<std::thread> pool;
     for (unsigned w = 0; w < workers; w++) {
         pool.emplace_back([&]() {
             double my_call = 0, my_ms = 0;
-            uint64_t my_rays = 0, my_calls = 0, my_bytes = 0;
+            uint64_t my_rays = 0, my_calls = 0, my_bytes = 0, my_shared = 0;
             try {
                 for (;;) {
                     const uint64_t k = next.fetch_add(1);
                     if (k >= calls) break;
+                    {
+                        std::lock_guard<std::mutex> lock(m);
+                        pending++;
+                    }
                     const Tile tile = tiles[k % tiles.size()]; // .cycle()
                     RenderOptions o = options;
                     VrjStats stats{};
@@ -967,23 +972,25 @@ MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, 
                     const auto tc = std::chrono::steady_clock::now();
                     std::unique_ptr<Item> item(new Item{tile, partial_render_scene(scene, tile, height, width, o)});
                     my_call += seconds(tc);
-                    my_rays += stats.primary_rays + stats.bounce_rays + stats.shadow_rays, my_ms += stats.device_ms, my_calls++;
+                    my_rays += stats.primary_rays + stats.bounce_rays + stats.shadow_rays, my_ms += stats.device_ms, my_calls++, my_shared += stats.coalesced_calls;
                     // what crossed PCIe: all five arrays, or the colours alone (the weights of a colour-and-weight-only buffer are written on the host)
                     my_bytes += 8 * (item->buffer.colour_sum.empty() ? item->buffer.colour.size()
                                                                       : item->buffer.colour.size() + item->buffer.colour_sum.size() + item->buffer.colour_bias.size() +
                                                                             item->buffer.weight.size() + item->buffer.weight_bias.size());
                     std::unique_lock<std::mutex> lock(m);
                     room.wait(lock, [&] { return queue.size() < workers || !error.empty(); });
+                    pending--;
                     if (!error.empty()) break;
                     queue.push_back(std::move(item));
                     ready.notify_one();
                 }
-            } catch (const std::exception &e) {
+            } catch (const std::exception &e) { // partial_render_scene threw: its call was counted in `pending`
                 std::lock_guard<std::mutex> lock(m);
+                pending--;
                 if (error.empty()) error = e.what();
             }
             std::lock_guard<std::mutex> lock(m);
-            total.call_s += my_call, total.device_ms += my_ms, total.rays += my_rays, total.calls += my_calls, total.bytes_to_host += my_bytes;
+            total.call_s += my_call, total.device_ms += my_ms, total.rays += my_rays, total.calls += my_calls, total.bytes_to_host += my_bytes, total.wavefront_calls += my_shared;
             live--;
             ready.notify_one();
             room.notify_all();
@@ -992,11 +999,19 @@ MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, 
     for (;;) { // the 'running loop of main.rs:211-218 without the window
         // `for message in tile_rx.try_iter()` (main.rs:213): everything that is waiting is taken; messages for the same tile are
         // merged in arrival order in one pass over the frame (merge_tiles == consecutive merge_tile calls, bit for bit)
+        // main.rs sleeps 1/60 s between two drains of the channel (main.rs:236), so its passes always find many messages.
+        // Here the thread does not sleep; it waits until a few messages are there -- as long as calls that will deliver one
+        // are still in flight -- because one pass over the frame per message costs twice the memory traffic of one pass per
+        // four (the frame's 133 MB are read and written once per pass).
+        const size_t want = std::max<size_t>(1, std::min<size_t>(4, workers / 2));
         std::vector<std::unique_ptr<Item>> items;
         {
             std::unique_lock<std::mutex> lock(m);
-            ready.wait(lock, [&] { return !queue.empty() || live == 0; });
-            if (queue.empty()) break;
+            ready.wait(lock, [&] { return queue.size() >= want || (!queue.empty() && pending == 0) || live == 0 || !error.empty(); });
+            if (queue.empty()) {
+                if (live == 0) break;
+                continue; // an error is on its way: the workers are leaving
+            }
             items.swap(queue);
             room.notify_all();
         }

@@ -254,14 +254,14 @@ def render_like_main(hs, width, height, calls, workers, tile_size=2048, spp=0, m
     n = width * height
     colour = np.zeros(n * 3) if colour is None else colour
     weight = np.zeros(n) if weight is None else weight
-    st = np.zeros(8)
+    st = np.zeros(9)
     r = hs.H.vrjh_render_like_main(hs.h, width, height, tile_size, calls, workers, spp, max_depth, seed, sample_offset,
                                    1 if kahan_state else 0, device, colour.ctypes.data_as(dp), weight.ctypes.data_as(dp),
                                    st.ctypes.data_as(dp))
     if r != 0:
         raise capi.VrjError(hs.H.vrjh_last_error().decode())
-    keys = ("wall_s", "call_s", "merge_s", "device_ms", "rays", "calls", "bytes_to_host", "merge_passes")
-    return colour, weight, dict(zip(keys, [float(x) for x in st[:8]]))
+    keys = ("wall_s", "call_s", "merge_s", "device_ms", "rays", "calls", "bytes_to_host", "merge_passes", "wavefront_calls")
+    return colour, weight, dict(zip(keys, [float(x) for x in st[:9]]))
 
 
 def tone_map(colour, source=capi.TONEMAP_XYZ, device=0):
