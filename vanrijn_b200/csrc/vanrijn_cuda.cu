@@ -302,11 +302,14 @@ size_t scratch_bytes(const Scratch *s) { return s->capacity * 240 + s->rec_capac
 std::atomic<int> g_active_calls[64];
 
 // Render gate: how many calls may have their wavefronts on one device at the same moment.  main.rs:197-209 drives the entry
-// point from a pool of workers; every call's kernels are persistent grids sized to fill all 148 SMs, so eight of them
-// interleaved gain nothing over two and evict each other's queues from L2 (measured, 1-spp 1080p calls: 1.33 ms of device
-// time per call with two in flight, 1.73 with four, 2.07 with eight).  Callers past the gate's width wait their turn (FIFO)
-// before enqueueing; the gate opens again when the call's last kernel has finished, so its copy back to the host overlaps
-// the next caller's rendering.  VRJ_CONCURRENT_RENDERS overrides the width (experiments).
+// point from a pool of workers; every call's kernels are persistent grids sized to fill all 148 SMs, so many of them
+// interleaved only evict each other's queues from L2 (1-spp 1080p calls, device time per call: 1.33 ms with two in flight,
+// 1.73 with four, 2.07 with eight) -- but a few in flight pay, because a wavefront ends in a latency-bound tail (the last
+// levels carry a handful of long paths) that another wavefront's bulk fills.  Callers past the gate's width wait their turn
+// (FIFO) before enqueueing, and while they wait, compatible calls pile up behind them and are rendered together (see
+// "coalesced calls"); the gate opens again when the call's last kernel has finished, so its copy back to the host overlaps
+// the next caller's rendering.  Width 4 measured best at 4 to 16 workers once calls are coalesced (8 workers: 3.3 / 3.5 / 3.5
+// Grays/s through the loop of main.rs at widths 2 / 3 / 4).  VRJ_CONCURRENT_RENDERS overrides the width (experiments).
 struct RenderGate {
     std::mutex m;
     std::condition_variable cv;
@@ -317,7 +320,7 @@ RenderGate g_render_gate[64];
 int render_gate_width() {
     static const int width = [] {
         const char *e = std::getenv("VRJ_CONCURRENT_RENDERS");
-        return e ? std::max(1, std::atoi(e)) : 2;
+        return e ? std::max(1, std::atoi(e)) : 4;
     }();
     return width;
 }
