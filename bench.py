@@ -179,14 +179,14 @@ def extra_config(name, V, capi, scenes, np, device):
         what = "bunny BVH, Whitted, max_depth 0, one directional light + ambient, 1 spp"
     elif name == "C4":
         spec = scenes.scene_grid(copies=11)
-        W, H, spp = 3840, 2160, 4
+        W, H, spp = 3840, 2160, 15  # 15 spp at 4K = the 128 Mi-path budget of one wavefront batch
         kw.update(max_depth=8)
-        what = "11 x 11 bunny copies (9 912 320 triangles) + plane, SimpleRandom, depth 8, 4 spp per call"
+        what = "11 x 11 bunny copies (9 912 320 triangles) + plane, SimpleRandom, depth 8, 15 spp per call (one wavefront batch)"
     else:
         spec = scenes.scene_main(subdivisions=6, obj=True, variant="mixed")
-        W, H, spp = 1920, 1080, 16
-        kw.update(max_depth=128)
-        what = "main.rs scene with mirror sphere, diamond sphere, reflective bunny; SimpleRandom, recursion limit 128, 16 spp per call"
+        W, H, spp = 1920, 1080, 64  # one wavefront batch, like the bench step: the latency-bound tail (the few paths that run to
+        kw.update(max_depth=128)    # the limit: ~5 ms whatever the batch size) is paid once per batch
+        what = "main.rs scene with mirror sphere, diamond sphere, reflective bunny; SimpleRandom, recursion limit 128, 64 spp per call (one wavefront batch)"
     hs = V.build_scene(spec, device_builder="upload")
     t1 = time.perf_counter()
     hs.device_scene(device)
