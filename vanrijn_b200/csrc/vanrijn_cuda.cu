@@ -32,12 +32,12 @@ thread_local std::string g_error;
 
 // the six instantiations live in vrj_batch_inst.cu (one object file each)
 namespace vrjimpl {
-extern template VrjStatus run_batch<float, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
-extern template VrjStatus run_batch<float, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
-extern template VrjStatus run_batch<double, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
-extern template VrjStatus run_batch<double, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
-extern template VrjStatus run_batch<float, float, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
-extern template VrjStatus run_batch<float, float, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *);
+extern template VrjStatus run_batch<float, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *, const ResolveCopy *);
+extern template VrjStatus run_batch<float, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *, const ResolveCopy *);
+extern template VrjStatus run_batch<double, double, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *, const ResolveCopy *);
+extern template VrjStatus run_batch<double, double, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *, const ResolveCopy *);
+extern template VrjStatus run_batch<float, float, false>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *, const ResolveCopy *);
+extern template VrjStatus run_batch<float, float, true>(const VrjScene *, Scratch *, const RenderConst &, bool, int, uint64_t *, const MultiCalls *, const ResolveCopy *);
 } // namespace vrjimpl
 // NVTX ranges through the header-only NVTX 3: no library to link or load -- the calls are no-ops until a
 // tool (ncu --nvtx, nsys) injects itself
@@ -395,6 +395,9 @@ VrjStatus ensure_scratch(Scratch *s, size_t capacity, size_t rec_capacity, size_
         VRJ_CUDA(cudaEventCreateWithFlags(&s->ev1, cudaEventBlockingSync)); // timing stays enabled; see wait_event
         VRJ_CUDA(cudaEventCreateWithFlags(&s->ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
         for (cudaEvent_t &e : s->call_ev) VRJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventBlockingSync | cudaEventDisableTiming));
+        VRJ_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        VRJ_CUDA(cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming));
+        for (cudaEvent_t &e : s->piece_ev) VRJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (cudaEvent_t &e : s->drain_ev) VRJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         VRJ_CUDA(cudaMallocHost(&s->host_count, 256 * sizeof(uint32_t))); // drain-check slots + the sample table of coalesced calls
     }
@@ -1263,6 +1266,7 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
         // running on the block's stream when another caller is handed the block
         ~Releaser() {
             if (s->stream) cudaStreamSynchronize(s->stream);
+            if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
             release_scratch(sc, s);
         }
     } releaser{scene, s};
@@ -1331,18 +1335,25 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     turn.acquire();
     const auto t_call1 = std::chrono::steady_clock::now();
     VRJ_CUDA(cudaEventRecord(s->ev0, s->stream));
+    // the last batch's resolve runs in pieces whose parts of the arrays start for the host at once (ResolveCopy); small tiles
+    // and device-memory outputs (copies at HBM speed) keep the single resolve
+    ResolveCopy rcopy{{arrs[0].user, arrs[1].user, arrs[2].user, arrs[3].user, arrs[4].user}, out_kind, 4u};
+    const bool piecewise = out->memory == VRJ_MEM_HOST && npix >= (uint64_t(1) << 18) && !std::getenv("VRJ_NO_PIECEWISE_COPY");
+    bool copied = false;
     for (uint32_t done = 0; done < p->spp; done += batch) {
         rc.batch_samples = std::min(batch, p->spp - done);
+        const ResolveCopy *copy = piecewise && done + batch >= p->spp ? &rcopy : nullptr;
+        copied = copied || copy != nullptr;
         rc.div_batch = FastDiv::make(rc.batch_samples), rc.div_tile_w = FastDiv::make(rc.tile_w);
         rc.first_sample = p->sample_offset + (uint64_t)done * rc.sample_stride;
         if (p->count_traversal) {
-            st = fast ? run_batch<float, float, true>(scene, s, rc, whitted, 0, &launches)
-                 : filter == VRJ_FILTER_F64 ? run_batch<double, double, true>(scene, s, rc, whitted, 0, &launches)
-                                                   : run_batch<float, double, true>(scene, s, rc, whitted, quad, &launches);
+            st = fast ? run_batch<float, float, true>(scene, s, rc, whitted, 0, &launches, nullptr, copy)
+                 : filter == VRJ_FILTER_F64 ? run_batch<double, double, true>(scene, s, rc, whitted, 0, &launches, nullptr, copy)
+                                            : run_batch<float, double, true>(scene, s, rc, whitted, quad, &launches, nullptr, copy);
         } else {
-            st = fast ? run_batch<float, float, false>(scene, s, rc, whitted, 0, &launches)
-                 : filter == VRJ_FILTER_F64 ? run_batch<double, double, false>(scene, s, rc, whitted, 0, &launches)
-                                                   : run_batch<float, double, false>(scene, s, rc, whitted, quad, &launches);
+            st = fast ? run_batch<float, float, false>(scene, s, rc, whitted, 0, &launches, nullptr, copy)
+                 : filter == VRJ_FILTER_F64 ? run_batch<double, double, false>(scene, s, rc, whitted, 0, &launches, nullptr, copy)
+                                            : run_batch<float, double, false>(scene, s, rc, whitted, quad, &launches, nullptr, copy);
         }
         if (st != VRJ_OK) return st;
         if (out->photons) {
@@ -1360,9 +1371,13 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     unsigned long long *hstats = reinterpret_cast<unsigned long long *>(s->host_count + 160);
     VRJ_CUDA(cudaMemcpyAsync(hstats, s->stats.p, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     VRJ_CUDA(cudaEventRecord(s->ev1, s->stream));
-    for (int i = 0; i < 5; i++)
-        if (arrs[i].user)
-            VRJ_CUDA(cudaMemcpyAsync(arrs[i].user, arrs[i].dev->p, npix * arrs[i].per * sizeof(double), out_kind, s->stream));
+    if (copied) {
+        VRJ_CUDA(cudaStreamWaitEvent(s->stream, s->copy_done, 0)); // ev_done below then stands behind the pieces' copies too
+    } else {
+        for (int i = 0; i < 5; i++)
+            if (arrs[i].user)
+                VRJ_CUDA(cudaMemcpyAsync(arrs[i].user, arrs[i].dev->p, npix * arrs[i].per * sizeof(double), out_kind, s->stream));
+    }
     if (out->srgb8) {
         if (s->srgb8.bytes < npix * 3) {
             s->srgb8.release();

@@ -59,6 +59,15 @@ struct DeviceBuffer {
     T *as() const { return static_cast<T *>(p); }
 };
 
+// Where the resolved arrays of a call's LAST batch go.  k_resolve then runs in `pieces` row-aligned pieces, and each piece's
+// part of the arrays is copied to the caller on a second stream as soon as it is resolved: at 1080p the copy back (66 MB,
+// 1.25 ms over PCIe) hides behind the 1.6 ms the seven exponentials per sample take, instead of following them.
+struct ResolveCopy {
+    double *user[5];      // colour, colour_sum, colour_bias, weight, weight_bias (NULL: not wanted)
+    cudaMemcpyKind kind;
+    uint32_t pieces;
+};
+
 // per-call scratch: path queues, photon results, accumulators, counters
 struct Scratch {
     size_t capacity = 0; // paths
@@ -75,6 +84,9 @@ struct Scratch {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; // first / last kernel of a call
     cudaEvent_t ev_done = nullptr;             // behind the call's last copy
+    cudaStream_t copy_stream = nullptr;        // copies of resolved pieces (ResolveCopy) run here, next to the resolve kernels
+    cudaEvent_t piece_ev[8] = {};              // behind the resolve of piece i
+    cudaEvent_t copy_done = nullptr;           // behind the last of those copies
     cudaEvent_t call_ev[16] = {};              // coalesced calls: behind the copies of call c (MULTI_MAX_CALLS)
     cudaEvent_t drain_ev[2] = {nullptr, nullptr}; // behind the pinned copies of the drain check (run_levels)
     std::vector<cudaEvent_t> marks; // per-launch boundaries, reused across calls
@@ -86,6 +98,10 @@ struct Scratch {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_done) cudaEventDestroy(ev_done);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (copy_done) cudaEventDestroy(copy_done);
+        for (cudaEvent_t e : piece_ev)
+            if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : call_ev)
             if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : drain_ev)
@@ -168,7 +184,8 @@ inline bool wants_records(const VrjScene *sc, int walk) {
 
 // One batch with the integrator (WHITTED) and the scene's material kinds (MM, see vrj_device.cuh) fixed at compile time.
 template <typename NT, typename R, bool COUNT, bool WHITTED, int MM>
-VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int walk, uint64_t *launches, const MultiCalls *multi) {
+VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int walk, uint64_t *launches, const MultiCalls *multi,
+                     const ResolveCopy *copy) {
     const bool quad = walk == 1, q16 = walk == 2; // 0: the 2-wide tree in NT boxes; 1: 4-wide f32; 2: 2-wide on the 16-bit grid
     // launch sequence: G T S_0 [X_k T_k S_k]*, k = 1..levels (X = k_tail, a no-op until the queue is short);
     // SimpleRandom needs max_depth levels, Whitted one more (its limit-0 level still shades and traces);
@@ -267,9 +284,30 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
     AccumDev acc;
     acc.colour = s->acc_colour.as<double>(), acc.sum = s->acc_sum.as<double>(), acc.bias = s->acc_bias.as<double>();
     acc.weight = s->acc_weight.as<double>(), acc.weight_bias = s->acc_wbias.as<double>();
-    if (multi) k_resolve_multi<R><<<(rc.npix * multi->n + 255) / 256, 256, 0, s->stream>>>(*multi, photons, rc.npix, rc.batch_samples);
-    else k_resolve<R><<<(rc.npix + 255) / 256, 256, 0, s->stream>>>(acc, photons, rc.npix, rc.batch_samples);
-    (*launches)++;
+    if (multi) {
+        k_resolve_multi<R><<<(rc.npix * multi->n + 255) / 256, 256, 0, s->stream>>>(*multi, photons, rc.npix, rc.batch_samples);
+        (*launches)++;
+    } else if (copy && copy->pieces > 1) {
+        const double *dev[5] = {acc.colour, acc.sum, acc.bias, acc.weight, acc.weight_bias};
+        const size_t per[5] = {3, 3, 3, 1, 1};
+        const uint32_t step = ((rc.npix + copy->pieces - 1) / copy->pieces + 255u) & ~255u; // whole CTAs per piece
+        uint32_t piece = 0;
+        for (uint32_t first = 0; first < rc.npix; first += step, piece++) {
+            const uint32_t end = std::min(rc.npix, first + step);
+            k_resolve<R><<<(end - first + 255) / 256, 256, 0, s->stream>>>(acc, photons, first, end, rc.batch_samples);
+            (*launches)++;
+            VRJ_CUDA(cudaEventRecord(s->piece_ev[piece], s->stream));
+            VRJ_CUDA(cudaStreamWaitEvent(s->copy_stream, s->piece_ev[piece], 0));
+            for (int i = 0; i < 5; i++)
+                if (copy->user[i])
+                    VRJ_CUDA(cudaMemcpyAsync(copy->user[i] + (size_t)first * per[i], dev[i] + (size_t)first * per[i], (size_t)(end - first) * per[i] * sizeof(double),
+                                             copy->kind, s->copy_stream));
+        }
+        VRJ_CUDA(cudaEventRecord(s->copy_done, s->copy_stream));
+    } else {
+        k_resolve<R><<<(rc.npix + 255) / 256, 256, 0, s->stream>>>(acc, photons, 0u, rc.npix, rc.batch_samples);
+        (*launches)++;
+    }
     VRJ_CUDA(s->mark(2));
     VRJ_CUDA(cudaGetLastError());
     return VRJ_OK;
@@ -278,10 +316,14 @@ VrjStatus run_levels(const VrjScene *sc, Scratch *s, const RenderConst &rc, int 
 // kernel variants exist for "Lambertian only" (the reference's own scenes: main.rs, benches/simple_scene.rs) and for
 // "any material"; VRJ_MATERIAL_MASK=15 in the environment forces the general variant (experiments)
 template <typename NT, typename R, bool COUNT>
-VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, int walk, uint64_t *launches, const MultiCalls *multi = nullptr) {
+VrjStatus run_batch(const VrjScene *sc, Scratch *s, const RenderConst &rc, bool whitted, int walk, uint64_t *launches, const MultiCalls *multi = nullptr,
+                    const ResolveCopy *copy = nullptr) {
     const bool lambert_only = sc->kernel_material_mask == 1u;
-    if (whitted) return lambert_only ? run_levels<NT, R, COUNT, true, 1>(sc, s, rc, walk, launches, multi) : run_levels<NT, R, COUNT, true, VRJ_MM_ALL>(sc, s, rc, walk, launches, multi);
-    return lambert_only ? run_levels<NT, R, COUNT, false, 1>(sc, s, rc, walk, launches, multi) : run_levels<NT, R, COUNT, false, VRJ_MM_ALL>(sc, s, rc, walk, launches, multi);
+    if (whitted)
+        return lambert_only ? run_levels<NT, R, COUNT, true, 1>(sc, s, rc, walk, launches, multi, copy)
+                            : run_levels<NT, R, COUNT, true, VRJ_MM_ALL>(sc, s, rc, walk, launches, multi, copy);
+    return lambert_only ? run_levels<NT, R, COUNT, false, 1>(sc, s, rc, walk, launches, multi, copy)
+                        : run_levels<NT, R, COUNT, false, VRJ_MM_ALL>(sc, s, rc, walk, launches, multi, copy);
 }
 
 } // namespace vrjimpl

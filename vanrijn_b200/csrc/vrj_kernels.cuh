@@ -742,8 +742,8 @@ struct AccumDev {
 // accumulation_buffer.rs:44-60 applied for the batch's samples in sample order
 // R: precision of ColourXyz::from_photon (the colour matching functions); the accumulators are binary64 in both modes
 template <typename R>
-__global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t npix, uint32_t batch_samples) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_resolve(AccumDev acc, const double2 *photons, uint32_t first, uint32_t npix, uint32_t batch_samples) {
+    uint32_t p = first + blockIdx.x * blockDim.x + threadIdx.x; // pixels [first, npix): a call's last batch resolves in pieces
     if (p >= npix) return;
     double sx = acc.sum[3 * p], sy = acc.sum[3 * p + 1], sz = acc.sum[3 * p + 2];
     double bx = acc.bias[3 * p], by = acc.bias[3 * p + 1], bz = acc.bias[3 * p + 2];
