@@ -1338,7 +1338,13 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     // the last batch's resolve runs in pieces whose parts of the arrays start for the host at once (ResolveCopy); small tiles
     // and device-memory outputs (copies at HBM speed) keep the single resolve
     ResolveCopy rcopy{{arrs[0].user, arrs[1].user, arrs[2].user, arrs[3].user, arrs[4].user}, out_kind, 4u};
-    const bool piecewise = out->memory == VRJ_MEM_HOST && npix >= (uint64_t(1) << 18) && !std::getenv("VRJ_NO_PIECEWISE_COPY");
+    // (worth it when the resolve is long enough to hide a copy behind: with a sample or two per pixel it is 0.06 ms against 1.25 ms)
+    bool piecewise = out->memory == VRJ_MEM_HOST && npix >= (uint64_t(1) << 18) && std::min(batch, p->spp) >= 8 && !std::getenv("VRJ_NO_PIECEWISE_COPY");
+    for (int i = 0; i < 5 && piecewise; i++) { // page-locked destinations only: a copy into pageable memory holds the enqueueing thread
+        cudaPointerAttributes attr{};
+        if (arrs[i].user && (cudaPointerGetAttributes(&attr, arrs[i].user) != cudaSuccess || attr.type != cudaMemoryTypeHost)) piecewise = false;
+    }
+    cudaGetLastError();
     bool copied = false;
     for (uint32_t done = 0; done < p->spp; done += batch) {
         rc.batch_samples = std::min(batch, p->spp - done);
@@ -1369,8 +1375,8 @@ VrjStatus vrj_render_tile(const VrjScene *scene_c, const VrjTile *tile, uint64_t
     // the counters go through the block's pinned slot: a copy into pageable memory would hold this thread until everything
     // queued before it -- the copies of the result included -- had finished, and the gate could not open early
     unsigned long long *hstats = reinterpret_cast<unsigned long long *>(s->host_count + 160);
+    VRJ_CUDA(cudaEventRecord(s->ev1, s->stream)); // before the counters' copy: that one queues up behind the pieces' copies on the copy engine
     VRJ_CUDA(cudaMemcpyAsync(hstats, s->stats.p, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
-    VRJ_CUDA(cudaEventRecord(s->ev1, s->stream));
     if (copied) {
         VRJ_CUDA(cudaStreamWaitEvent(s->stream, s->copy_done, 0)); // ev_done below then stands behind the pieces' copies too
     } else {
