@@ -288,7 +288,7 @@ class AccumulationBuffer {
     void merge_tile(const Tile &tile, const AccumulationBuffer &src);
     // merge_tile(tile, *srcs[0]); merge_tile(tile, *srcs[1]); ... in ONE pass over the destination: per pixel the same
     // operations in the same order (bit-identical), but the frame's colours and weights cross the memory bus once instead
-    // of once per buffer -- what main.rs:213-216 does when several messages are waiting in the channel
+    // of once per buffer -- what main.rs:215-217 does when several messages are waiting in the channel
     void merge_tiles(const Tile &tile, const std::vector<const AccumulationBuffer *> &srcs);
     UploadVector<double> colour, colour_sum, colour_bias; // 3 per pixel (XYZ)
     UploadVector<double> weight, weight_bias;             // 1 per pixel

@@ -547,7 +547,7 @@ void ImageRgbU8::write_png(const std::string &filename) const {
 
 namespace {
 // A few resident threads for merge_tile: a whole 1080p frame is 200 MB of reads and writes per merge, and the reference's
-// loop (main.rs:214-216) merges on ONE thread once per partial_render_scene call -- with the rendering on the GPU that
+// loop (main.rs:215-217) merges on ONE thread once per partial_render_scene call -- with the rendering on the GPU that
 // single thread is what bounds the loop, so big tiles are split by rows over a pool that lives as long as the process
 // (starting threads per call cost as much as a quarter of the merge).
 class RowPool {
@@ -997,9 +997,9 @@ MainLoopStats render_like_main(const Scene &scene, size_t width, size_t height, 
         });
     }
     for (;;) { // the 'running loop of main.rs:211-218 without the window
-        // `for message in tile_rx.try_iter()` (main.rs:213): everything that is waiting is taken; messages for the same tile are
+        // `for message in tile_rx.try_iter()` (main.rs:215): everything that is waiting is taken; messages for the same tile are
         // merged in arrival order in one pass over the frame (merge_tiles == consecutive merge_tile calls, bit for bit)
-        // main.rs sleeps 1/60 s between two drains of the channel (main.rs:236), so its passes always find many messages.
+        // main.rs sleeps 1/60 s between two drains of the channel (main.rs:242), so its passes always find many messages.
         // Here the thread does not sleep; it waits until a few messages are there -- as long as calls that will deliver one
         // are still in flight -- because one pass over the frame per message costs twice the memory traffic of one pass per
         // four (the frame's 133 MB are read and written once per pass).
