@@ -241,17 +241,30 @@ VrjStatus validate(const VrjSceneDesc *d) {
 // Host arrays reach the device through one page-locked staging block kept for the life of the process (a pageable
 // cudaMemcpy ran at 0.2-2 GB/s on the B200 boxes; memcpy into pinned memory + one async copy runs at PCIe speed).
 // Arrays that are already page-locked (vrj_alloc_host) skip the staging copy.
-std::mutex g_staging_mutex;
-char *g_staging = nullptr;
-size_t g_staging_bytes = 0;
+// One staging block, one stream and one lock PER DEVICE: scenes for different GPUs (vrj_comm_scene_create, or one host thread
+// per GPU) are prepared side by side, and nothing here touches the legacy default stream.
+struct StagingArea {
+    std::mutex mutex;
+    char *block = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr; // non-blocking; created with the first scene for the device
+};
+StagingArea g_staging_area[64];
 struct Stager {
+    StagingArea &area;
     size_t cursor = 0, copied = 0;
     cudaStream_t stream = nullptr;
+    explicit Stager(StagingArea &a) : area(a) {}
     cudaError_t reserve(size_t bytes) {
-        if (g_staging_bytes >= bytes) return cudaSuccess;
-        if (g_staging) cudaFreeHost(g_staging), g_staging = nullptr, g_staging_bytes = 0;
-        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&g_staging), bytes);
-        if (e == cudaSuccess) g_staging_bytes = bytes;
+        if (!area.stream) {
+            cudaError_t e = cudaStreamCreateWithFlags(&area.stream, cudaStreamNonBlocking);
+            if (e != cudaSuccess) return e;
+        }
+        stream = area.stream;
+        if (area.bytes >= bytes) return cudaSuccess;
+        if (area.block) cudaFreeHost(area.block), area.block = nullptr, area.bytes = 0;
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&area.block), bytes);
+        if (e == cudaSuccess) area.bytes = bytes;
         return e;
     }
     static void parallel_memcpy(char *dst, const char *src, size_t bytes) {
@@ -278,7 +291,7 @@ struct Stager {
         if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost)
             return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
         cudaGetLastError();
-        char *st = g_staging + cursor;
+        char *st = area.block + cursor;
         cursor += (bytes + 255) & ~size_t(255);
         parallel_memcpy(st, static_cast<const char *>(src), bytes);
         return cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, stream);
@@ -907,12 +920,12 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     DeviceBuffer raw;
     VRJ_TRY_CUDA(raw.alloc(std::max<size_t>(rcur, 256)));
     char *rb = raw.as<char>();
-    cudaStream_t stream = nullptr; // the legacy default stream: scene creation is synchronous
     auto t_alloc = std::chrono::steady_clock::now();
-    std::lock_guard<std::mutex> staging_guard(g_staging_mutex);
-    Stager stager;
-    stager.stream = stream;
+    StagingArea &area = g_staging_area[(unsigned)device % 64];
+    std::lock_guard<std::mutex> staging_guard(area.mutex); // scene creation is synchronous; one at a time per device
+    Stager stager(area);
     VRJ_TRY_CUDA(stager.reserve(nt * (6 * 32 + 8) + (size_t)d->n_nodes * 72 + small_bytes + 16 * 256));
+    cudaStream_t stream = stager.stream; // the device's preparation stream
     if (nt) {
         const double *src[6] = {d->tri_v0, d->tri_v1, d->tri_v2, d->tri_n0, d->tri_n1, d->tri_n2};
         for (int k = 0; k < 6; k++) VRJ_TRY_CUDA(stager.copy(rb + r_v[k], src[k], nt * 32));
@@ -1014,7 +1027,7 @@ VrjStatus vrj_scene_create(const VrjSceneDesc *d, int32_t device, VrjScene **out
     VRJ_TRY_CUDA(cudaStreamSynchronize(stream)); // built_root is read below
 
     // ---- the small tables ----
-    char *stage = g_staging + stager.cursor; // the staged arrays before it were copied before the synchronize above
+    char *stage = area.block + stager.cursor; // the staged arrays before it were copied before the synchronize above
     std::memset(stage, 0, small_bytes);
     SpectrumDev *spectra = reinterpret_cast<SpectrumDev *>(stage + s_spc.offset);
     for (uint32_t i = 0; i < d->n_spectra; i++)
@@ -1640,18 +1653,29 @@ VrjStatus vrj_comm_scene_create(VrjComm *c, const VrjSceneDesc *desc, VrjMultiSc
     *out = nullptr;
     VrjMultiScene *m = new VrjMultiScene();
     m->comm = c;
-    for (int dev : c->devices) {
-        VrjScene *s = nullptr;
-        VrjStatus st = vrj_scene_create(desc, dev, &s);
-        if (st != VRJ_OK) {
-            std::string keep = g_error;
-            vrj_comm_scene_destroy(m);
-            return fail(st, keep);
-        }
-        m->scenes.push_back(s);
+    // one thread per GPU: every device has its own staging block, preparation stream and lock, so the replicas upload and
+    // build side by side
+    const size_t n = c->devices.size();
+    std::vector<VrjScene *> scenes(n, nullptr);
+    std::vector<VrjStatus> status(n, VRJ_OK);
+    std::vector<std::string> errors(n);
+    std::vector<std::thread> workers;
+    for (size_t i = 0; i < n; i++)
+        workers.emplace_back([&, i] {
+            status[i] = vrj_scene_create(desc, c->devices[i], &scenes[i]);
+            if (status[i] != VRJ_OK) errors[i] = g_error; // the message is thread-local
+        });
+    for (auto &w : workers) w.join();
+    for (size_t i = 0; i < n; i++) {
+        m->scenes.push_back(scenes[i]);
         m->sum.push_back(new DeviceBuffer());
         m->weight.push_back(new DeviceBuffer());
     }
+    for (size_t i = 0; i < n; i++)
+        if (status[i] != VRJ_OK) {
+            vrj_comm_scene_destroy(m);
+            return fail(status[i], errors[i]);
+        }
     *out = m;
     return VRJ_OK;
 }
